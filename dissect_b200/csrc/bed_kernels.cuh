@@ -1,0 +1,305 @@
+// PLINK .bed 2-bit decode, per-SNP statistics, standardisation and operand staging.
+//
+// Reference being replaced (all in genotype.cpp):
+//   parseSNPbyte :741-787   2-bit pattern -> code {00:1 hom A1, 01:0 missing, 10:2 het, 11:3 hom A2},
+//                           frequencies[code]++, missings = (code != 0)
+//   parseSNP     :726-739   nNonMissing, p1, p2, standardDev
+//   normalizeGenotypes :888-961   z = (code - 1*(1 + 2*p2)) / sd, missing stays 0
+// The fp64 genotype / missing matrices the reference materialises (16 bytes per genotype) never
+// exist here: the device keeps the packed 2-bit rows and writes tensor-core operand tiles directly.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dgrm {
+
+// ------------------------------------------------------------------------------------------------
+// Row / individual gather into the aligned chunk buffer.
+// dst row r (pitch dst_pitch, a multiple of 128) <- src row rows[r] (or row0 + r when rows == NULL).
+// src_ind == NULL: plain byte copy of nbytes per row.  Otherwise output individual i takes the 2-bit
+// field of .fam individual src_ind[i] (individualBEDIdxsMaskToKeep compaction, genotype.cpp:750-781).
+// ------------------------------------------------------------------------------------------------
+__global__ void bed_gather_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const int32_t* __restrict__ rows,
+                                  int64_t row0, int nrows, uint8_t* __restrict__ dst, int64_t dst_pitch,
+                                  int nbytes, const int32_t* __restrict__ src_ind, int n) {
+  const int r = blockIdx.y;
+  if (r >= nrows) return;
+  const int64_t srow = rows ? (int64_t)rows[r] : row0 + r;
+  const uint8_t* s = src + srow * src_pitch;
+  uint8_t* d = dst + (int64_t)r * dst_pitch;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbytes; b += gridDim.x * blockDim.x) {
+    if (src_ind == nullptr) {
+      d[b] = s[b];
+    } else {
+      uint32_t o = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = 4 * b + j;
+        if (i < n) {
+          const int f = src_ind[i];
+          o |= (uint32_t)((s[f >> 2] >> (2 * (f & 3))) & 3) << (2 * j);
+        }
+      }
+      d[b] = (uint8_t)o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a: per-SNP allele / missing counts and statistics.  One warp per SNP row, 128-bit loads,
+// popcount on the lo/hi bit planes, warp-shuffle reduction, lane 0 does the fp64 arithmetic in the
+// reference's operation order (no FMA contraction: explicit round-to-nearest intrinsics).
+//   zt[row][pattern] = standardised value for .bed bit pattern {00, 01, 10, 11}
+// ------------------------------------------------------------------------------------------------
+struct SnpStatsOut {
+  int32_t* freq;  // [m][4]
+  int32_t* nn;    // [m]
+  double* p1;
+  double* p2;
+  double* sd;
+  int32_t* bad_count;  // [2]: {sd == 0, no non-missing}
+  int64_t* bad_list;   // first bad_cap offenders (global SNP index, negative-coded for NaN)
+  int bad_cap;
+};
+
+__global__ void __launch_bounds__(256)
+bed_count_stats_kernel(const uint8_t* __restrict__ chunk, int64_t pitch, int nrows, int n, int64_t snp0,
+                       SnpStatsOut o, double* __restrict__ zt) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const uint4* p = reinterpret_cast<const uint4*>(chunk + (int64_t)row * pitch);
+  const int nvec = (n + 63) >> 6;  // 64 individuals per 16-byte vector
+  int c0 = 0, c2 = 0, c3 = 0;
+  for (int j = lane; j < nvec; j += 32) {
+    const uint4 d = __ldg(p + j);
+    const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i0 = (j * 4 + t) * 16;
+      int valid = n - i0;
+      valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
+      const uint32_t km = (valid == 16) ? 0x55555555u : (((1u << (2 * valid)) - 1u) & 0x55555555u);
+      const uint32_t lo = w[t] & 0x55555555u;
+      const uint32_t hi = (w[t] >> 1) & 0x55555555u;
+      c3 += __popc(lo & hi & km);   // 11 hom A2
+      c2 += __popc(hi & ~lo & km);  // 10 het
+      c0 += __popc(lo & ~hi & km);  // 01 missing
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, s);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, s);
+    c3 += __shfl_xor_sync(0xffffffffu, c3, s);
+  }
+  if (lane == 0) {
+    const int c1 = n - c0 - c2 - c3;  // 00 hom A1
+    const int64_t g = snp0 + row;
+    o.freq[g * 4 + 0] = c0;
+    o.freq[g * 4 + 1] = c1;
+    o.freq[g * 4 + 2] = c2;
+    o.freq[g * 4 + 3] = c3;
+    const int nn = c1 + c2 + c3;
+    o.nn[g] = nn;
+    // genotype.cpp:735-738
+    const double den = __dmul_rn(2., (double)nn);
+    const double p1 = __ddiv_rn(__dadd_rn(__dmul_rn(2., (double)c1), (double)c2), den);
+    const double p2 = __ddiv_rn(__dadd_rn(__dmul_rn(2., (double)c3), (double)c2), den);
+    const double sd = __dsqrt_rn(__dmul_rn(__dmul_rn(2., p1), __dsub_rn(1., p1)));
+    o.p1[g] = p1;
+    o.p2[g] = p2;
+    o.sd[g] = sd;
+    // genotype.cpp:922-923, 948-949, 959
+    const double shift = __dadd_rn(1., __dmul_rn(2., p2));
+    double z1 = __ddiv_rn(__dsub_rn(1., shift), sd);
+    double z2 = __ddiv_rn(__dsub_rn(2., shift), sd);
+    double z3 = __ddiv_rn(__dsub_rn(3., shift), sd);
+    const bool nan_snp = (nn == 0);
+    const bool zero_sd = !nan_snp && (sd == 0.);
+    if (nan_snp || zero_sd) {
+      z1 = z2 = z3 = 0.;  // keep NaN/Inf out of the accumulators; dgrm_finish reports the error
+      const int slot = atomicAdd(&o.bad_count[nan_snp ? 1 : 0], 1);
+      const int total = atomicAdd(&o.bad_count[2], 1);
+      (void)slot;
+      if (total < o.bad_cap) o.bad_list[total] = nan_snp ? -(g + 1) : g;
+    }
+    double* z = zt + (int64_t)row * 4;
+    z[0] = z1;  // 00
+    z[1] = 0.;  // 01 missing
+    z[2] = z2;  // 10
+    z[3] = z3;  // 11
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1c: expand one chunk into tensor-core operands.
+//   Z  [n_pad][z_pitch] 16-bit, K-major: Z[i][k] = round16(zt[k][pattern(k,i)])         (hi part)
+//      with SPLIT also Z[i][lo_off + k] = round16(zt - hi)                                 (lo part)
+//   Q  [n_pad][q_pitch] e4m3 0/1, K-major: Q[i][k] = (pattern != 01)                      (missings)
+//   MB [n_pad][mb_pitch] bit k of row i = (pattern != 01)                                  (popcount path)
+//   diag_part[ktile][i] = sum over the tile's SNPs of zt^2 in fp64 (exact diagonal of S)
+// Block = 128 SNPs x 128 individuals, 256 threads; lanes run along individuals so every smem access
+// is conflict free, the transposed tile is staged in smem and written out in full 128/256-byte rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int kExpK = 128;          // SNPs per block
+constexpr int kExpI = 128;          // individuals per block
+constexpr int kExpZPitch = 272;     // bytes per staged Z row (256 + 16 pad)
+constexpr int kExpQPitch = 136;     // bytes per staged Q row (128 + 8 pad)
+
+struct ExpandSmem {
+  uint8_t pk[kExpK][32];            // packed genotypes: row = SNP, 32 bytes = 128 individuals
+  uint16_t lut_hi[kExpK][4];
+  uint16_t lut_lo[kExpK][4];
+  double lut_sq[kExpK][4];
+  double dpart[2][kExpI];
+  uint8_t outz[kExpI * kExpZPitch];
+  uint8_t outq[kExpI * kExpQPitch];
+  uint32_t outm[kExpI][4];          // 128 mask bits per individual
+};
+
+template <bool BF16>
+__device__ __forceinline__ uint16_t round16(double v) {
+  if constexpr (BF16) {
+    return __bfloat16_as_ushort(__double2bfloat16(v));
+  } else {
+    return __half_as_ushort(__double2half(v));
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ double widen16(uint16_t b) {
+  if constexpr (BF16) {
+    return (double)__bfloat162float(__ushort_as_bfloat16(b));
+  } else {
+    return (double)__half2float(__ushort_as_half(b));
+  }
+}
+
+struct ExpandArgs {
+  const uint8_t* chunk;
+  int64_t pitch;
+  int kc;            // valid SNP rows in the chunk
+  int n;             // individuals
+  const double* zt;  // [kc][4]
+  uint16_t* Z;
+  int64_t z_pitch;   // elements
+  int64_t lo_off;    // element offset of the lo part (SPLIT)
+  uint8_t* Q;        // may be NULL (flat norm / popcount)
+  int64_t q_pitch;
+  uint32_t* MB;      // may be NULL
+  int64_t mb_pitch;  // 32-bit words
+  double* diag_part; // [ktiles][n_pad]
+  int n_pad;
+};
+
+template <bool BF16, bool SPLIT>
+__global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
+  extern __shared__ __align__(16) uint8_t expand_smem_raw[];
+  ExpandSmem& sm = *reinterpret_cast<ExpandSmem*>(expand_smem_raw);
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * kExpI;
+  const int k0 = blockIdx.y * kExpK;
+
+  // packed tile: 128 rows x 32 bytes = 256 uint4... one 16-byte piece per thread
+  {
+    const int r = tid >> 1, h = tid & 1;
+    uint4 v = make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);  // all missing
+    if (k0 + r < a.kc) {
+      const int64_t off = (int64_t)(k0 + r) * a.pitch + (i0 >> 2) + h * 16;
+      if ((i0 >> 2) + h * 16 < a.pitch) v = __ldg(reinterpret_cast<const uint4*>(a.chunk + off));
+    }
+    *reinterpret_cast<uint4*>(&sm.pk[r][h * 16]) = v;
+  }
+  if (tid < kExpK) {
+    double z[4] = {0., 0., 0., 0.};
+    if (k0 + tid < a.kc) {
+      const double* zp = a.zt + (int64_t)(k0 + tid) * 4;
+      z[0] = zp[0]; z[2] = zp[2]; z[3] = zp[3];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint16_t hi = round16<BF16>(z[c]);
+      sm.lut_hi[tid][c] = hi;
+      sm.lut_lo[tid][c] = SPLIT ? round16<BF16>(z[c] - widen16<BF16>(hi)) : (uint16_t)0;
+      sm.lut_sq[tid][c] = __dmul_rn(z[c], z[c]);
+    }
+  }
+  __syncthreads();
+
+  const int il = tid & (kExpI - 1);
+  const int kh = tid >> 7;
+  const bool live = (i0 + il) < a.n;
+  const int bsel = il >> 2;
+  const int bshift = 2 * (il & 3);
+  double dsum = 0.;
+#pragma unroll 1
+  for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+#pragma unroll 2
+    for (int j = 0; j < 8; ++j) {
+      const int kg = kh + 2 * j;
+      uint32_t h[4];
+      uint32_t ql = 0, qh = 0, mb = 0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int k = kg * 8 + t;
+        const uint32_t code = live ? ((sm.pk[k][bsel] >> bshift) & 3u) : 1u;
+        const uint32_t v = part == 0 ? sm.lut_hi[k][code] : sm.lut_lo[k][code];
+        if (t & 1) h[t >> 1] |= v << 16; else h[t >> 1] = v;
+        if (part == 0) {
+          const uint32_t present = (code != 1u);
+          if (t < 4) ql |= (present * 0x38u) << (8 * t); else qh |= (present * 0x38u) << (8 * (t - 4));
+          mb |= present << t;
+          dsum = __dadd_rn(dsum, sm.lut_sq[k][code]);
+        }
+      }
+      *reinterpret_cast<uint4*>(&sm.outz[il * kExpZPitch + kg * 16]) = make_uint4(h[0], h[1], h[2], h[3]);
+      if (part == 0) {
+        *reinterpret_cast<uint2*>(&sm.outq[il * kExpQPitch + kg * 8]) = make_uint2(ql, qh);
+        reinterpret_cast<uint8_t*>(&sm.outm[il][0])[kg] = (uint8_t)mb;
+      }
+    }
+    if (part == 0) sm.dpart[kh][il] = dsum;
+    __syncthreads();
+    // write-out: full rows, 16 lanes per row
+    {
+      const int c = tid & 15;
+      uint16_t* zbase = a.Z + (part == 0 ? 0 : a.lo_off) + k0;
+#pragma unroll
+      for (int ps = 0; ps < kExpI / 16; ++ps) {
+        const int r = ps * 16 + (tid >> 4);
+        const uint4 v = *reinterpret_cast<const uint4*>(&sm.outz[r * kExpZPitch + c * 16]);
+        *reinterpret_cast<uint4*>(zbase + (int64_t)(i0 + r) * a.z_pitch + c * 8) = v;
+      }
+      if (part == 0) {
+        if (a.Q) {
+#pragma unroll
+          for (int ps = 0; ps < kExpI / 16; ++ps) {
+            const int r = ps * 16 + (tid >> 4);
+            const uint2 v = *reinterpret_cast<const uint2*>(&sm.outq[r * kExpQPitch + c * 8]);
+            *reinterpret_cast<uint2*>(a.Q + (int64_t)(i0 + r) * a.q_pitch + k0 + c * 8) = v;
+          }
+        }
+        if (a.MB && tid < kExpI) {
+          const uint4 v = *reinterpret_cast<const uint4*>(&sm.outm[tid][0]);
+          *reinterpret_cast<uint4*>(a.MB + (int64_t)(i0 + tid) * a.mb_pitch + (k0 >> 5)) = v;
+        }
+        if (tid < kExpI)
+          a.diag_part[(int64_t)blockIdx.y * a.n_pad + i0 + tid] = __dadd_rn(sm.dpart[0][tid], sm.dpart[1][tid]);
+      }
+    }
+    if (SPLIT) __syncthreads();
+  }
+}
+
+// diag[i] += sum_kt diag_part[kt][i], fixed order (deterministic).
+__global__ void diag_reduce_kernel(const double* __restrict__ part, int nkt, int n_pad, double* __restrict__ diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  double s = diag[i];
+  for (int kt = 0; kt < nkt; ++kt) s = __dadd_rn(s, part[(int64_t)kt * n_pad + i]);
+  diag[i] = s;
+}
+
+}  // namespace dgrm

@@ -1,0 +1,1070 @@
+// libdgrm: C-ABI engine around the sm_100a kernels (see include/dgrm.h for the contract and the
+// reference file:line each entry point replaces).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dgrm.h"
+#include "bed_kernels.cuh"
+#include "finalize_kernels.cuh"
+#include "paircount_popc.cuh"
+#include "syrk_tcgen05.cuh"
+
+using namespace dgrm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct EventPair {
+  cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct dgrm_engine {
+  dgrm_config cfg;
+  std::string err;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  EncodeTiledFn encode = nullptr;
+
+  // cohort geometry
+  int64_t n_fam = 0, n = 0, n_pad = 0;
+  int64_t b_fam = 0;        // bytes per raw .bed row
+  int64_t b_row = 0;        // bytes per compacted row
+  int64_t chunk_pitch = 0;  // device chunk row pitch (multiple of 128)
+  int32_t* d_src_ind = nullptr;
+
+  // tile store
+  int nrb = 0, ncp = 0;
+  std::vector<int4> work;       // launch work list (CG form)
+  std::vector<int4> work_cg1;   // 128x256 form (popcount kernel)
+  std::vector<int32_t> tile_rc; // [ntiles][2]
+  int4* d_work = nullptr;
+  int4* d_work_cg1 = nullptr;
+  int32_t* d_index = nullptr;
+  int64_t ntiles = 0;
+  double* d_S = nullptr;
+  int32_t* d_N = nullptr;
+  double* d_diag = nullptr;
+
+  // chunk state
+  int kc_max = 0;
+  uint8_t* d_chunk = nullptr;
+  int fill = 0;
+  uint16_t* d_Z = nullptr;
+  int64_t z_pitch = 0;
+  uint8_t* d_Q = nullptr;
+  int64_t q_pitch = 0;
+  uint32_t* d_MB = nullptr;
+  int64_t mb_pitch = 0;
+  double* d_zt = nullptr;
+  double* d_diag_part = nullptr;
+  CUtensorMap tmap_z, tmap_q;
+  int64_t chunks_done = 0;
+
+  // per-SNP statistics
+  int64_t m_cap = 0, m = 0;
+  int32_t* d_freq = nullptr;
+  int32_t* d_nn = nullptr;
+  double *d_p1 = nullptr, *d_p2 = nullptr, *d_sd = nullptr;
+  int32_t* d_bad_count = nullptr;
+  int64_t* d_bad_list = nullptr;
+  static constexpr int kBadCap = 65536;
+
+  // host -> device staging (double buffered)
+  uint8_t* d_stage[2] = {nullptr, nullptr};
+  int64_t stage_pitch = 0;
+  int stage_rows = 0;
+  cudaEvent_t stage_copied[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+  int stage_i = 0;
+  int32_t* h_rowidx[2] = {nullptr, nullptr};
+  int32_t* d_rowidx[2] = {nullptr, nullptr};
+  cudaEvent_t rowidx_free[2] = {nullptr, nullptr};
+  int rowidx_i = 0;
+  cudaEvent_t producer_ev = nullptr;
+
+  bool have_ind = false, begun = false, finished = false;
+
+  // profiling
+  std::vector<EventPair> ev[DGRM_K_NUM];
+  std::vector<EventPair> ev_pool;
+  double ms_acc[DGRM_K_NUM] = {0};
+  int64_t launches[DGRM_K_NUM] = {0};
+};
+
+namespace {
+
+int fail(dgrm_engine* e, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _st = (call);                                                                            \
+    if (_st != cudaSuccess)                                                                              \
+      return fail(e, _st == cudaErrorMemoryAllocation ? DGRM_E_NOMEM : DGRM_E_CUDA, "%s failed: %s (%s:%d)", #call, \
+                  cudaGetErrorString(_st), __FILE__, __LINE__);                                          \
+  } while (0)
+
+struct Prof {
+  dgrm_engine* e;
+  int k;
+  EventPair p{nullptr, nullptr};
+  Prof(dgrm_engine* e_, int k_) : e(e_), k(k_) {
+    e->launches[k]++;
+    if (!e->cfg.profile) return;
+    if (!e->ev_pool.empty()) {
+      p = e->ev_pool.back();
+      e->ev_pool.pop_back();
+    } else {
+      cudaEventCreate(&p.a);
+      cudaEventCreate(&p.b);
+    }
+    cudaEventRecord(p.a, e->stream);
+  }
+  ~Prof() {
+    if (!e->cfg.profile) return;
+    cudaEventRecord(p.b, e->stream);
+    e->ev[k].push_back(p);
+  }
+};
+
+void free_dev(void* p) {
+  if (p) cudaFree(p);
+}
+
+void release_geometry(dgrm_engine* e) {
+  free_dev(e->d_src_ind); e->d_src_ind = nullptr;
+  free_dev(e->d_work); e->d_work = nullptr;
+  free_dev(e->d_work_cg1); e->d_work_cg1 = nullptr;
+  free_dev(e->d_index); e->d_index = nullptr;
+  free_dev(e->d_S); e->d_S = nullptr;
+  free_dev(e->d_N); e->d_N = nullptr;
+  free_dev(e->d_diag); e->d_diag = nullptr;
+  free_dev(e->d_chunk); e->d_chunk = nullptr;
+  free_dev(e->d_Z); e->d_Z = nullptr;
+  free_dev(e->d_Q); e->d_Q = nullptr;
+  free_dev(e->d_MB); e->d_MB = nullptr;
+  free_dev(e->d_zt); e->d_zt = nullptr;
+  free_dev(e->d_diag_part); e->d_diag_part = nullptr;
+  for (int i = 0; i < 2; ++i) {
+    free_dev(e->d_stage[i]); e->d_stage[i] = nullptr;
+    free_dev(e->d_rowidx[i]); e->d_rowidx[i] = nullptr;
+    if (e->h_rowidx[i]) cudaFreeHost(e->h_rowidx[i]);
+    e->h_rowidx[i] = nullptr;
+  }
+  e->have_ind = false;
+}
+
+void release_stats(dgrm_engine* e) {
+  free_dev(e->d_freq); e->d_freq = nullptr;
+  free_dev(e->d_nn); e->d_nn = nullptr;
+  free_dev(e->d_p1); e->d_p1 = nullptr;
+  free_dev(e->d_p2); e->d_p2 = nullptr;
+  free_dev(e->d_sd); e->d_sd = nullptr;
+  e->m_cap = 0;
+}
+
+int make_tmap(dgrm_engine* e, CUtensorMap* map, void* base, int elem_bytes, int64_t cols, int64_t rows,
+              int64_t pitch_bytes) {
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), 128u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = e->encode(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                               base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(e, DGRM_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return DGRM_OK;
+}
+
+// Lower-triangle supertiles (256x256) in an L2-friendly raster: groups of 8 supertile rows, swept
+// column by column, dealt round-robin to the engines of the partition.
+void build_tiles(dgrm_engine* e) {
+  const int T = (int)(e->n_pad / 256);
+  const int GR = 8;
+  e->nrb = 2 * T;
+  e->ncp = T;
+  e->work.clear();
+  e->work_cg1.clear();
+  e->tile_rc.clear();
+  std::vector<int32_t> index((size_t)e->nrb * e->ncp, -1);
+  int64_t s = 0, ls = 0;
+  for (int g = 0; g < T; g += GR) {
+    const int imax = std::min(g + GR, T) - 1;
+    for (int J = 0; J <= imax; ++J) {
+      for (int I = std::max(g, J); I <= imax; ++I, ++s) {
+        if ((int)(s % e->cfg.world) != e->cfg.rank) continue;
+        const int s0 = (int)(2 * ls), s1 = (int)(2 * ls + 1);
+        index[(size_t)(2 * I) * e->ncp + J] = s0;
+        index[(size_t)(2 * I + 1) * e->ncp + J] = s1;
+        e->tile_rc.push_back(2 * I); e->tile_rc.push_back(J);
+        e->tile_rc.push_back(2 * I + 1); e->tile_rc.push_back(J);
+        e->work_cg1.push_back(make_int4(I * 256, J * 256, s0, s0));
+        e->work_cg1.push_back(make_int4(I * 256 + 128, J * 256, s1, s1));
+        if (e->cfg.cta_group == 2) e->work.push_back(make_int4(I * 256, J * 256, s0, s1));
+        ++ls;
+      }
+    }
+  }
+  if (e->cfg.cta_group == 1) e->work = e->work_cg1;
+  e->ntiles = 2 * ls;
+  // upload
+  cudaMalloc(&e->d_index, index.size() * sizeof(int32_t));
+  cudaMemcpy(e->d_index, index.data(), index.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (!e->work.empty()) {
+    cudaMalloc(&e->d_work, e->work.size() * sizeof(int4));
+    cudaMemcpy(e->d_work, e->work.data(), e->work.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    cudaMalloc(&e->d_work_cg1, e->work_cg1.size() * sizeof(int4));
+    cudaMemcpy(e->d_work_cg1, e->work_cg1.data(), e->work_cg1.size() * sizeof(int4), cudaMemcpyHostToDevice);
+  }
+}
+
+TileStore tile_store(const dgrm_engine* e) {
+  TileStore ts;
+  ts.S = e->d_S;
+  ts.N = e->cfg.flat_norm ? nullptr : e->d_N;
+  ts.index = e->d_index;
+  ts.ncp = e->ncp;
+  ts.n = (int)e->n;
+  ts.flat_n = (double)e->m;
+  return ts;
+}
+
+template <int CG, bool KIND8, typename OutT>
+int launch_syrk(dgrm_engine* e, const CUtensorMap& tmap, const SyrkParams& p) {
+  using Cfg = SyrkCfg<CG>;
+  auto kern = grm_syrk_kernel<CG, KIND8, OutT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int units = std::min<int>(p.num_work, CG == 2 ? e->sm_count / 2 : e->sm_count);
+  if (units <= 0) return DGRM_OK;
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(units * CG);
+  lc.blockDim = dim3(Cfg::kThreads);
+  lc.dynamicSmemBytes = Cfg::kSmemBytes;
+  lc.stream = e->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&lc, kern, tmap, p));
+  return DGRM_OK;
+}
+
+int process_chunk(dgrm_engine* e) {
+  const int kc = e->fill;
+  if (kc == 0) return DGRM_OK;
+  const int kc_pad = (int)round_up(kc, 128);
+  const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
+  const bool bf16 = e->cfg.operand == DGRM_OPERAND_BF16;
+  const bool count_mma = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_MMA;
+  const bool count_popc = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_POPC;
+
+  {
+    Prof pr(e, DGRM_K_COUNT);
+    SnpStatsOut so{e->d_freq, e->d_nn, e->d_p1, e->d_p2, e->d_sd, e->d_bad_count, e->d_bad_list, dgrm_engine::kBadCap};
+    const int blocks = (kc * 32 + 255) / 256;
+    bed_count_stats_kernel<<<blocks, 256, 0, e->stream>>>(e->d_chunk, e->chunk_pitch, kc, (int)e->n, e->m, so, e->d_zt);
+    CK(cudaGetLastError());
+  }
+  {
+    Prof pr(e, DGRM_K_EXPAND);
+    ExpandArgs a;
+    a.chunk = e->d_chunk; a.pitch = e->chunk_pitch; a.kc = kc; a.n = (int)e->n; a.zt = e->d_zt;
+    a.Z = e->d_Z; a.z_pitch = e->z_pitch; a.lo_off = e->kc_max;
+    a.Q = count_mma ? e->d_Q : nullptr; a.q_pitch = e->q_pitch;
+    a.MB = count_popc ? e->d_MB : nullptr; a.mb_pitch = e->mb_pitch;
+    a.diag_part = e->d_diag_part; a.n_pad = (int)e->n_pad;
+    const dim3 grid((unsigned)(e->n_pad / kExpI), (unsigned)(kc_pad / kExpK));
+    const size_t smem = sizeof(ExpandSmem);
+    if (bf16) bed_expand_kernel<true, false><<<grid, 256, smem, e->stream>>>(a);
+    else if (split) bed_expand_kernel<false, true><<<grid, 256, smem, e->stream>>>(a);
+    else bed_expand_kernel<false, false><<<grid, 256, smem, e->stream>>>(a);
+    CK(cudaGetLastError());
+    diag_reduce_kernel<<<(unsigned)((e->n_pad + 255) / 256), 256, 0, e->stream>>>(e->d_diag_part, kc_pad / kExpK,
+                                                                                (int)e->n_pad, e->d_diag);
+    CK(cudaGetLastError());
+  }
+  if (!e->work.empty()) {
+    SyrkParams p{};
+    p.work = e->d_work;
+    p.num_work = (int)e->work.size();
+    p.accumulate = e->chunks_done > 0;
+    {
+      Prof pr(e, DGRM_K_SYRK);
+      p.num_kblocks = kc_pad / 64;
+      p.npass = split ? 3 : 1;
+      p.a_off[0] = 0; p.a_off[1] = e->kc_max; p.a_off[2] = 0;
+      p.b_off[0] = 0; p.b_off[1] = 0; p.b_off[2] = e->kc_max;
+      p.out = e->d_S;
+      p.idesc = make_idesc(e->cfg.cta_group, bf16 ? 1 : 0);
+      const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, false, double>(e, e->tmap_z, p)
+                                           : launch_syrk<1, false, double>(e, e->tmap_z, p);
+      if (rc) return rc;
+    }
+    if (count_mma) {
+      Prof pr(e, DGRM_K_PAIRCNT);
+      p.num_kblocks = kc_pad / 128;
+      p.npass = 1;
+      p.a_off[0] = p.b_off[0] = 0;
+      p.out = e->d_N;
+      p.idesc = make_idesc(e->cfg.cta_group, 0 /* e4m3 */);
+      const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, true, int>(e, e->tmap_q, p)
+                                           : launch_syrk<1, true, int>(e, e->tmap_q, p);
+      if (rc) return rc;
+    } else if (count_popc) {
+      Prof pr(e, DGRM_K_PAIRCNT);
+      const int nw = (int)e->work_cg1.size();
+      pair_count_popc_kernel<<<std::min(nw, e->sm_count * 2), 256, 0, e->stream>>>(
+          e->d_MB, e->mb_pitch, kc_pad / 32, e->d_work_cg1, nw, e->d_N, e->chunks_done > 0);
+      CK(cudaGetLastError());
+    }
+  }
+  e->m += kc;
+  e->chunks_done++;
+  e->fill = 0;
+  return DGRM_OK;
+}
+
+// append rows of a device-resident block to the chunk buffer, contracting whenever it fills up
+int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64_t nrows, const uint8_t* row_keep) {
+  std::vector<int32_t> idx;
+  int64_t kept = nrows;
+  if (row_keep) {
+    idx.reserve(nrows);
+    for (int64_t r = 0; r < nrows; ++r)
+      if (row_keep[r]) idx.push_back((int32_t)r);
+    kept = (int64_t)idx.size();
+  }
+  if (e->m + e->fill + kept > e->m_cap)
+    return fail(e, DGRM_E_INVALID, "more SNPs pushed (%lld) than dgrm_begin's capacity (%lld)",
+                (long long)(e->m + e->fill + kept), (long long)e->m_cap);
+  int64_t pos = 0;
+  while (pos < kept) {
+    const int take = (int)std::min<int64_t>(kept - pos, e->kc_max - e->fill);
+    const int32_t* d_idx = nullptr;
+    if (row_keep) {
+      const int s = e->rowidx_i;
+      e->rowidx_i ^= 1;
+      CK(cudaEventSynchronize(e->rowidx_free[s]));
+      memcpy(e->h_rowidx[s], idx.data() + pos, (size_t)take * sizeof(int32_t));
+      CK(cudaMemcpyAsync(e->d_rowidx[s], e->h_rowidx[s], (size_t)take * sizeof(int32_t), cudaMemcpyHostToDevice,
+                         e->stream));
+      d_idx = e->d_rowidx[s];
+    }
+    {
+      const int nbytes = (int)(e->d_src_ind ? e->b_row : e->b_fam);
+      const dim3 grid((unsigned)std::min<int64_t>((nbytes + 255) / 256, 64), (unsigned)take);
+      bed_gather_kernel<<<grid, 256, 0, e->stream>>>(d_rows, pitch, d_idx, pos, take,
+                                                     e->d_chunk + (int64_t)e->fill * e->chunk_pitch, e->chunk_pitch,
+                                                     nbytes, e->d_src_ind, (int)e->n);
+      CK(cudaGetLastError());
+      if (row_keep) CK(cudaEventRecord(e->rowidx_free[e->rowidx_i ^ 1], e->stream));
+    }
+    e->fill += take;
+    pos += take;
+    if (e->fill == e->kc_max) {
+      const int rc = process_chunk(e);
+      if (rc) return rc;
+    }
+  }
+  return DGRM_OK;
+}
+
+int check_ready(dgrm_engine* e, bool need_finished) {
+  if (!e) return DGRM_E_INVALID;
+  if (!e->have_ind) return fail(e, DGRM_E_INVALID, "dgrm_set_individuals has not been called");
+  if (!e->begun) return fail(e, DGRM_E_INVALID, "dgrm_begin has not been called");
+  if (need_finished && !e->finished) return fail(e, DGRM_E_INVALID, "dgrm_finish has not been called");
+  return DGRM_OK;
+}
+
+int numroc(int n, int nb, int iproc, int nprocs) {
+  // ScaLAPACK numroc_ with isrcproc = 0 (matrix.cpp:1748-1749)
+  const int nblocks = n / nb;
+  int r = (nblocks / nprocs) * nb;
+  const int extra = nblocks % nprocs;
+  if (iproc < extra) r += nb;
+  else if (iproc == extra) r += n % nb;
+  return r;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int dgrm_abi_version(void) { return DGRM_ABI_VERSION; }
+
+int dgrm_default_config(dgrm_config* cfg) {
+  if (!cfg) return DGRM_E_INVALID;
+  memset(cfg, 0, sizeof *cfg);
+  cfg->device = 0;
+  cfg->rank = 0;
+  cfg->world = 1;
+  cfg->operand = DGRM_OPERAND_FP16;
+  cfg->count_method = DGRM_COUNT_MMA;
+  cfg->flat_norm = 0;
+  cfg->chunk_snps = 8192;
+  cfg->cta_group = 2;
+  cfg->profile = 0;
+  return DGRM_OK;
+}
+
+const char* dgrm_last_error(const dgrm_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
+  dgrm_engine* e = nullptr;
+  if (!cfg || !out) return fail(nullptr, DGRM_E_INVALID, "dgrm_create: null argument");
+  *out = nullptr;
+  if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world)
+    return fail(nullptr, DGRM_E_INVALID, "dgrm_create: bad rank/world %d/%d", cfg->rank, cfg->world);
+  if (cfg->chunk_snps < 128 || cfg->chunk_snps % 128 != 0 || cfg->chunk_snps > 32768)
+    return fail(nullptr, DGRM_E_INVALID, "dgrm_create: chunk_snps must be a multiple of 128 in [128, 32768]");
+  if (cfg->cta_group != 1 && cfg->cta_group != 2)
+    return fail(nullptr, DGRM_E_INVALID, "dgrm_create: cta_group must be 1 or 2");
+  if (cfg->operand < 0 || cfg->operand > DGRM_OPERAND_FP16X2 || cfg->count_method < 0 ||
+      cfg->count_method > DGRM_COUNT_POPC)
+    return fail(nullptr, DGRM_E_INVALID, "dgrm_create: bad operand/count_method");
+  int ndev = 0;
+  cudaError_t st = cudaGetDeviceCount(&ndev);
+  if (st != cudaSuccess || ndev == 0)
+    return fail(nullptr, DGRM_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)",
+                cudaGetErrorString(st));
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(nullptr, DGRM_E_INVALID, "dgrm_create: device %d out of range (%d devices)", cfg->device, ndev);
+  cudaDeviceProp prop;
+  st = cudaGetDeviceProperties(&prop, cfg->device);
+  if (st != cudaSuccess) return fail(nullptr, DGRM_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(st));
+  if (prop.major != 10)
+    return fail(nullptr, DGRM_E_CUDA, "device %d is sm_%d%d; libdgrm is built for sm_100a only (no fallback path)",
+                cfg->device, prop.major, prop.minor);
+  e = new dgrm_engine();
+  e->cfg = *cfg;
+  e->sm_count = prop.multiProcessorCount;
+  e->kc_max = cfg->chunk_snps;
+#define CKC(call)                                                                          \
+  do {                                                                                     \
+    cudaError_t _s = (call);                                                               \
+    if (_s != cudaSuccess) {                                                               \
+      fail(nullptr, DGRM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_s));          \
+      delete e;                                                                            \
+      return DGRM_E_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CKC(cudaEventCreateWithFlags(&e->stage_copied[i], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&e->stage_free[i], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&e->rowidx_free[i], cudaEventDisableTiming));
+  }
+  CKC(cudaEventCreateWithFlags(&e->producer_ev, cudaEventDisableTiming));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CKC(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) {
+    fail(nullptr, DGRM_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    delete e;
+    return DGRM_E_CUDA;
+  }
+  e->encode = (EncodeTiledFn)fn;
+  CKC(cudaFuncSetAttribute(bed_expand_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(ExpandSmem)));
+  CKC(cudaFuncSetAttribute(bed_expand_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(ExpandSmem)));
+  CKC(cudaFuncSetAttribute(bed_expand_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(ExpandSmem)));
+#undef CKC
+  *out = e;
+  return DGRM_OK;
+}
+
+void dgrm_destroy(dgrm_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  release_geometry(e);
+  release_stats(e);
+  free_dev(e->d_bad_count);
+  free_dev(e->d_bad_list);
+  for (int k = 0; k < DGRM_K_NUM; ++k)
+    for (auto& p : e->ev[k]) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto& p : e->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (int i = 0; i < 2; ++i) {
+    if (e->stage_copied[i]) cudaEventDestroy(e->stage_copied[i]);
+    if (e->stage_free[i]) cudaEventDestroy(e->stage_free[i]);
+    if (e->rowidx_free[i]) cudaEventDestroy(e->rowidx_free[i]);
+  }
+  if (e->producer_ev) cudaEventDestroy(e->producer_ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  delete e;
+}
+
+int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask) {
+  if (!e) return DGRM_E_INVALID;
+  if (n_fam <= 0 || n_fam > (1 << 30)) return fail(e, DGRM_E_INVALID, "dgrm_set_individuals: bad n_fam");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->stream));
+  release_geometry(e);
+  e->begun = e->finished = false;
+  std::vector<int32_t> src;
+  bool identity = true;
+  if (keep_mask) {
+    for (int64_t f = 0; f < n_fam; ++f)
+      if (keep_mask[f]) src.push_back((int32_t)f); else identity = false;
+  }
+  e->n_fam = n_fam;
+  e->n = (keep_mask && !identity) ? (int64_t)src.size() : n_fam;
+  if (e->n <= 0) return fail(e, DGRM_E_INVALID, "dgrm_set_individuals: no individual kept");
+  e->n_pad = round_up(e->n, 256);
+  e->b_fam = (n_fam + 3) / 4;
+  e->b_row = (e->n + 3) / 4;
+  e->chunk_pitch = round_up(std::max(e->b_fam, e->b_row), 128);
+  if (keep_mask && !identity) {
+    CK(cudaMalloc(&e->d_src_ind, src.size() * sizeof(int32_t)));
+    CK(cudaMemcpy(e->d_src_ind, src.data(), src.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  build_tiles(e);
+  CK(cudaGetLastError());
+  const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
+  const int kc = e->kc_max;
+  e->z_pitch = (int64_t)kc * (split ? 2 : 1);
+  e->q_pitch = kc;
+  e->mb_pitch = kc / 32;
+  if (e->ntiles > 0) {
+    CK(cudaMalloc(&e->d_S, (size_t)e->ntiles * kTileElems * sizeof(double)));
+    if (!e->cfg.flat_norm) CK(cudaMalloc(&e->d_N, (size_t)e->ntiles * kTileElems * sizeof(int32_t)));
+  }
+  CK(cudaMalloc(&e->d_diag, (size_t)e->n_pad * sizeof(double)));
+  CK(cudaMalloc(&e->d_chunk, (size_t)kc * e->chunk_pitch));
+  CK(cudaMemset(e->d_chunk, 0x55, (size_t)kc * e->chunk_pitch));
+  CK(cudaMalloc(&e->d_Z, (size_t)e->n_pad * e->z_pitch * sizeof(uint16_t)));
+  CK(cudaMemset(e->d_Z, 0, (size_t)e->n_pad * e->z_pitch * sizeof(uint16_t)));
+  if (!e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_MMA) {
+    CK(cudaMalloc(&e->d_Q, (size_t)e->n_pad * e->q_pitch));
+    CK(cudaMemset(e->d_Q, 0, (size_t)e->n_pad * e->q_pitch));
+  }
+  if (!e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_POPC) {
+    CK(cudaMalloc(&e->d_MB, (size_t)e->n_pad * e->mb_pitch * sizeof(uint32_t)));
+    CK(cudaMemset(e->d_MB, 0, (size_t)e->n_pad * e->mb_pitch * sizeof(uint32_t)));
+  }
+  CK(cudaMalloc(&e->d_zt, (size_t)kc * 4 * sizeof(double)));
+  CK(cudaMalloc(&e->d_diag_part, (size_t)(kc / kExpK) * e->n_pad * sizeof(double)));
+  int rc = make_tmap(e, &e->tmap_z, e->d_Z, 2, e->z_pitch, e->n_pad, e->z_pitch * 2);
+  if (rc) return rc;
+  if (e->d_Q) {
+    rc = make_tmap(e, &e->tmap_q, e->d_Q, 1, e->q_pitch, e->n_pad, e->q_pitch);
+    if (rc) return rc;
+  }
+  // host staging: slabs of up to kc rows
+  e->stage_rows = kc;
+  e->stage_pitch = round_up(e->b_fam, 16);
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc(&e->d_stage[i], (size_t)e->stage_rows * e->stage_pitch));
+    CK(cudaMalloc(&e->d_rowidx[i], (size_t)kc * sizeof(int32_t)));
+    CK(cudaHostAlloc(&e->h_rowidx[i], (size_t)kc * sizeof(int32_t), cudaHostAllocDefault));
+  }
+  if (!e->d_bad_count) {
+    CK(cudaMalloc(&e->d_bad_count, 4 * sizeof(int32_t)));
+    CK(cudaMalloc(&e->d_bad_list, (size_t)dgrm_engine::kBadCap * sizeof(int64_t)));
+  }
+  e->have_ind = true;
+  return DGRM_OK;
+}
+
+int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
+  if (!e) return DGRM_E_INVALID;
+  if (!e->have_ind) return fail(e, DGRM_E_INVALID, "dgrm_begin: call dgrm_set_individuals first");
+  if (m_capacity <= 0) return fail(e, DGRM_E_INVALID, "dgrm_begin: m_capacity must be positive");
+  CK(cudaSetDevice(e->cfg.device));
+  if (m_capacity > e->m_cap) {
+    CK(cudaStreamSynchronize(e->stream));
+    release_stats(e);
+    CK(cudaMalloc(&e->d_freq, (size_t)m_capacity * 4 * sizeof(int32_t)));
+    CK(cudaMalloc(&e->d_nn, (size_t)m_capacity * sizeof(int32_t)));
+    CK(cudaMalloc(&e->d_p1, (size_t)m_capacity * sizeof(double)));
+    CK(cudaMalloc(&e->d_p2, (size_t)m_capacity * sizeof(double)));
+    CK(cudaMalloc(&e->d_sd, (size_t)m_capacity * sizeof(double)));
+    e->m_cap = m_capacity;
+  }
+  e->m = 0;
+  e->fill = 0;
+  e->chunks_done = 0;
+  e->finished = false;
+  CK(cudaMemsetAsync(e->d_bad_count, 0, 4 * sizeof(int32_t), e->stream));
+  CK(cudaMemsetAsync(e->d_diag, 0, (size_t)e->n_pad * sizeof(double), e->stream));
+  // S / N tiles are overwritten (not accumulated) by the first chunk; clear them so that an empty
+  // GRM (no SNP pushed) is still well defined.
+  if (e->ntiles > 0) {
+    CK(cudaMemsetAsync(e->d_S, 0, (size_t)e->ntiles * kTileElems * sizeof(double), e->stream));
+    if (e->d_N) CK(cudaMemsetAsync(e->d_N, 0, (size_t)e->ntiles * kTileElems * sizeof(int32_t), e->stream));
+  }
+  for (int k = 0; k < DGRM_K_NUM; ++k) {
+    for (auto& p : e->ev[k]) e->ev_pool.push_back(p);
+    e->ev[k].clear();
+    e->ms_acc[k] = 0;
+    e->launches[k] = 0;
+  }
+  e->begun = true;
+  return DGRM_OK;
+}
+
+int dgrm_push_bed_device(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64_t nrows, const uint8_t* row_keep,
+                         void* producer_stream) {
+  int rc = check_ready(e, false);
+  if (rc) return rc;
+  if (e->finished) return fail(e, DGRM_E_INVALID, "dgrm_push_bed_device after dgrm_finish");
+  if (!d_rows || nrows < 0 || pitch < e->b_fam) return fail(e, DGRM_E_INVALID, "dgrm_push_bed_device: bad rows/pitch");
+  CK(cudaSetDevice(e->cfg.device));
+  if (producer_stream) {
+    CK(cudaEventRecord(e->producer_ev, (cudaStream_t)producer_stream));
+    CK(cudaStreamWaitEvent(e->stream, e->producer_ev, 0));
+  }
+  // bound the host-side index list
+  for (int64_t r0 = 0; r0 < nrows; r0 += (1 << 20)) {
+    const int64_t cnt = std::min<int64_t>(nrows - r0, 1 << 20);
+    rc = push_device_rows(e, d_rows + r0 * pitch, pitch, cnt, row_keep ? row_keep + r0 : nullptr);
+    if (rc) return rc;
+  }
+  return DGRM_OK;
+}
+
+int dgrm_push_bed_host(dgrm_engine* e, const uint8_t* rows, int64_t pitch, int64_t nrows, const uint8_t* row_keep) {
+  int rc = check_ready(e, false);
+  if (rc) return rc;
+  if (e->finished) return fail(e, DGRM_E_INVALID, "dgrm_push_bed_host after dgrm_finish");
+  if (!rows || nrows < 0 || pitch < e->b_fam) return fail(e, DGRM_E_INVALID, "dgrm_push_bed_host: bad rows/pitch");
+  CK(cudaSetDevice(e->cfg.device));
+  for (int64_t r0 = 0; r0 < nrows; r0 += e->stage_rows) {
+    const int64_t cnt = std::min<int64_t>(nrows - r0, e->stage_rows);
+    const int s = e->stage_i;
+    e->stage_i ^= 1;
+    CK(cudaEventSynchronize(e->stage_free[s]));  // the gather that last read this slot is done
+    CK(cudaMemcpy2DAsync(e->d_stage[s], (size_t)e->stage_pitch, rows + r0 * pitch, (size_t)pitch, (size_t)e->b_fam,
+                         (size_t)cnt, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaEventRecord(e->stage_copied[s], e->copy_stream));
+    CK(cudaStreamWaitEvent(e->stream, e->stage_copied[s], 0));
+    rc = push_device_rows(e, e->d_stage[s], e->stage_pitch, cnt, row_keep ? row_keep + r0 : nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(e->stage_free[s], e->stream));
+  }
+  return DGRM_OK;
+}
+
+int dgrm_load_bed_file(dgrm_engine* e, const char* bed_path, int64_t m_file, const int64_t* snp_keep_idx,
+                       int64_t m_keep) {
+  int rc = check_ready(e, false);
+  if (rc) return rc;
+  if (!bed_path || m_file <= 0) return fail(e, DGRM_E_INVALID, "dgrm_load_bed_file: bad arguments");
+  FILE* f = fopen(bed_path, "rb");
+  if (!f) return fail(e, DGRM_E_IO, "Error: The file [ %s ] does not exist or cannot be opened.", bed_path);
+  unsigned char header[3];
+  if (fread(header, 1, 3, f) != 3) {
+    fclose(f);
+    return fail(e, DGRM_E_BADBED, "Error: The data file is not a valid binary BED > v1.0");
+  }
+  // genotype.cpp:581-605
+  if (header[0] != 0x6C || header[1] != 0x1B) {
+    fclose(f);
+    return fail(e, DGRM_E_BADBED, "Error: The data file is not a valid binary BED > v1.0");
+  }
+  if (header[2] == 0x0) {
+    fclose(f);
+    return fail(e, DGRM_E_BADBED,
+                "Error: The BED file is in Individual-major mode. This mode is not currently supported. Please, read "
+                "PLINK manual.");
+  }
+  if (header[2] != 0x1) {
+    fclose(f);
+    return fail(e, DGRM_E_BADBED,
+                "Error: The data file is not a valid binary BED.\nIt is not specified whether the file is in SNP-major "
+                "o Individual-major mode.");
+  }
+  std::vector<uint8_t> keep;
+  if (snp_keep_idx) {
+    keep.assign((size_t)m_file, 0);
+    int64_t prev = -1;
+    for (int64_t i = 0; i < m_keep; ++i) {
+      const int64_t s = snp_keep_idx[i];
+      if (s < 0 || s >= m_file || s <= prev) {
+        fclose(f);
+        return fail(e, DGRM_E_INVALID, "dgrm_load_bed_file: snp_keep_idx must be ascending positions in [0, m_file)");
+      }
+      keep[(size_t)s] = 1;
+      prev = s;
+    }
+  }
+  const int64_t slab = e->stage_rows;
+  uint8_t* buf[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; ++i)
+    if (cudaHostAlloc(&buf[i], (size_t)slab * e->b_fam, cudaHostAllocDefault) != cudaSuccess) {
+      if (buf[0]) cudaFreeHost(buf[0]);
+      fclose(f);
+      return fail(e, DGRM_E_NOMEM, "Error: There are not enough memory for reading the binary file.");
+    }
+  int which = 0;
+  rc = DGRM_OK;
+  for (int64_t r0 = 0; r0 < m_file && rc == DGRM_OK; r0 += slab, which ^= 1) {
+    const int64_t cnt = std::min<int64_t>(slab, m_file - r0);
+    // the previous push from this pinned buffer went through the same double-buffered stage: it is
+    // complete once the stage slot it used has been recycled, which push_bed_host waits for.
+    if (r0 >= 2 * slab) cudaStreamSynchronize(e->copy_stream);
+    const size_t got = fread(buf[which], (size_t)e->b_fam, (size_t)cnt, f);
+    if ((int64_t)got != cnt) {
+      rc = fail(e, DGRM_E_BADBED, "Error: An internal error has happened when reading the genotypes file.");
+      break;
+    }
+    rc = dgrm_push_bed_host(e, buf[which], e->b_fam, cnt, snp_keep_idx ? keep.data() + r0 : nullptr);
+  }
+  cudaStreamSynchronize(e->copy_stream);
+  cudaFreeHost(buf[0]);
+  cudaFreeHost(buf[1]);
+  fclose(f);
+  return rc;
+}
+
+int dgrm_finish(dgrm_engine* e) {
+  int rc = check_ready(e, false);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->cfg.device));
+  if (!e->finished) {
+    rc = process_chunk(e);
+    if (rc) return rc;
+    if (e->ntiles > 0 && e->m > 0) {
+      Prof pr(e, DGRM_K_FINAL);
+      fix_diag_kernel<<<(unsigned)((e->n + 255) / 256), 256, 0, e->stream>>>(e->d_S, e->d_index, e->ncp, (int)e->n,
+                                                                          e->d_diag);
+      CK(cudaGetLastError());
+    }
+    e->finished = true;
+  }
+  int32_t bad[4];
+  CK(cudaMemcpyAsync(bad, e->d_bad_count, sizeof bad, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaGetLastError());
+  if (bad[0] > 0)
+    return fail(e, DGRM_E_BADSNP,
+                "Error: There are SNPs with same genotype for all samples or insignificant variability. Please, filter "
+                "them before performing this analysis. (%d SNPs)",
+                bad[0]);
+  if (bad[1] > 0)
+    return fail(e, DGRM_E_NANSNP, "Error: %d SNPs have no non-missing genotype (allele frequency is 0/0).", bad[1]);
+  return DGRM_OK;
+}
+
+int dgrm_sync(dgrm_engine* e) {
+  if (!e) return DGRM_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->copy_stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return DGRM_OK;
+}
+
+int64_t dgrm_num_snps(const dgrm_engine* e) { return e ? e->m + e->fill : 0; }
+int64_t dgrm_num_individuals(const dgrm_engine* e) { return e ? e->n : 0; }
+
+int dgrm_snp_stats(dgrm_engine* e, int32_t* freq, int32_t* nn, double* p1, double* p2, double* sd) {
+  int rc = check_ready(e, false);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->stream));
+  const size_t m = (size_t)e->m;
+  if (m == 0) return DGRM_OK;
+  if (freq) CK(cudaMemcpy(freq, e->d_freq, m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (nn) CK(cudaMemcpy(nn, e->d_nn, m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (p1) CK(cudaMemcpy(p1, e->d_p1, m * sizeof(double), cudaMemcpyDeviceToHost));
+  if (p2) CK(cudaMemcpy(p2, e->d_p2, m * sizeof(double), cudaMemcpyDeviceToHost));
+  if (sd) CK(cudaMemcpy(sd, e->d_sd, m * sizeof(double), cudaMemcpyDeviceToHost));
+  return DGRM_OK;
+}
+
+int dgrm_bad_snps(dgrm_engine* e, int64_t* idx, int64_t cap, int64_t* count) {
+  int rc = check_ready(e, false);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->stream));
+  int32_t bad[4];
+  CK(cudaMemcpy(bad, e->d_bad_count, sizeof bad, cudaMemcpyDeviceToHost));
+  const int64_t have = std::min<int64_t>(bad[2], dgrm_engine::kBadCap);
+  if (count) *count = bad[2];
+  if (idx && cap > 0 && have > 0) {
+    std::vector<int64_t> tmp((size_t)have);
+    CK(cudaMemcpy(tmp.data(), e->d_bad_list, (size_t)have * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    for (auto& v : tmp)
+      if (v < 0) v = -v - 1;  // NaN SNPs are stored negative-coded
+    std::sort(tmp.begin(), tmp.end());
+    for (int64_t i = 0; i < std::min(cap, have); ++i) idx[i] = tmp[(size_t)i];
+  }
+  return DGRM_OK;
+}
+
+int dgrm_fetch_block_cyclic(dgrm_engine* e, int which, double* local, int64_t lld, int bs_r, int bs_c, int my_row,
+                            int my_col, int R, int C, char uplo) {
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  if (!local || which < 0 || which > 2 || bs_r < 1 || bs_c < 1 || R < 1 || C < 1 || my_row < 0 || my_row >= R ||
+      my_col < 0 || my_col >= C)
+    return fail(e, DGRM_E_INVALID, "dgrm_fetch_block_cyclic: bad arguments");
+  const int up = (uplo == 'L' || uplo == 'l') ? 0 : (uplo == 'U' || uplo == 'u') ? 1 : (uplo == 'B' || uplo == 'b') ? 2 : -1;
+  if (up < 0) return fail(e, DGRM_E_INVALID, "dgrm_fetch_block_cyclic: uplo must be L, U or B");
+  CK(cudaSetDevice(e->cfg.device));
+  CyclicGeom g;
+  g.bs_r = bs_r; g.bs_c = bs_c; g.my_row = my_row; g.my_col = my_col; g.R = R; g.C = C;
+  g.nloc_r = numroc((int)e->n, bs_r, my_row, R);
+  g.nloc_c = numroc((int)e->n, bs_c, my_col, C);
+  if (g.nloc_r == 0 || g.nloc_c == 0) return DGRM_OK;
+  if (lld < g.nloc_r) return fail(e, DGRM_E_INVALID, "dgrm_fetch_block_cyclic: lld %lld < local rows %d", (long long)lld, g.nloc_r);
+  const TileStore ts = tile_store(e);
+  const dim3 blk(128, 2);
+
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, local) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+                      attr.devicePointer != nullptr;
+  cudaGetLastError();
+  if (pinned) {
+    // zero-copy: the kernel stores straight into the caller's pinned Matrix::m over PCIe
+    Prof pr(e, DGRM_K_FETCH);
+    g.lld = lld;
+    const int PC = 4096;
+    for (int lc0 = 0; lc0 < g.nloc_c; lc0 += PC) {
+      const int lc1 = std::min(lc0 + PC, g.nloc_c);
+      const dim3 grid((g.nloc_r + 127) / 128, (lc1 - lc0 + 1) / 2);
+      fetch_block_cyclic_kernel<<<grid, blk, 0, e->stream>>>(ts, which, (double*)attr.devicePointer + (int64_t)lc0 * lld,
+                                                            g, lc0, lc1, up);
+      CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    return DGRM_OK;
+  }
+  // pageable destination: device panel -> pinned panel -> memcpy of exactly the requested rows
+  const int PC = (int)std::max<int64_t>(1, std::min<int64_t>(g.nloc_c, (64 << 20) / ((int64_t)g.nloc_r * 8)));
+  double* d_panel[2] = {nullptr, nullptr};
+  double* h_panel[2] = {nullptr, nullptr};
+  cudaEvent_t done[2];
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc(&d_panel[i], (size_t)PC * g.nloc_r * sizeof(double)));
+    CK(cudaHostAlloc(&h_panel[i], (size_t)PC * g.nloc_r * sizeof(double), cudaHostAllocDefault));
+    CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  }
+  g.lld = g.nloc_r;
+  auto drain = [&](int slot, int lc0, int lc1) -> int {
+    CK(cudaEventSynchronize(done[slot]));
+    for (int lc = lc0; lc < lc1; ++lc) {
+      const int gc = ((lc / bs_c) * C + my_col) * bs_c + lc % bs_c;
+      int lo = 0, hi = g.nloc_r;  // local row range to copy
+      if (up != 2) {
+        // first local row whose global index is >= gc (+1 for strict)
+        auto first_ge = [&](int target) {
+          int a = 0, b = g.nloc_r;
+          while (a < b) {
+            const int mid = (a + b) / 2;
+            const int gr = ((mid / bs_r) * R + my_row) * bs_r + mid % bs_r;
+            if (gr >= target) b = mid; else a = mid + 1;
+          }
+          return a;
+        };
+        if (up == 0) lo = first_ge(gc); else hi = first_ge(gc + 1);
+      }
+      if (hi > lo)
+        memcpy(local + (int64_t)lc * lld + lo, h_panel[slot] + (int64_t)(lc - lc0) * g.nloc_r + lo,
+               (size_t)(hi - lo) * sizeof(double));
+    }
+    return DGRM_OK;
+  };
+  int prev_slot = -1, prev0 = 0, prev1 = 0, slot = 0;
+  for (int lc0 = 0; lc0 < g.nloc_c; lc0 += PC, slot ^= 1) {
+    const int lc1 = std::min(lc0 + PC, g.nloc_c);
+    {
+      Prof pr(e, DGRM_K_FETCH);
+      CK(cudaMemsetAsync(d_panel[slot], 0, (size_t)(lc1 - lc0) * g.nloc_r * sizeof(double), e->stream));
+      const dim3 grid((g.nloc_r + 127) / 128, (lc1 - lc0 + 1) / 2);
+      fetch_block_cyclic_kernel<<<grid, blk, 0, e->stream>>>(ts, which, d_panel[slot], g, lc0, lc1, up);
+      CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(h_panel[slot], d_panel[slot], (size_t)(lc1 - lc0) * g.nloc_r * sizeof(double),
+                       cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaEventRecord(done[slot], e->stream));
+    if (prev_slot >= 0) {
+      rc = drain(prev_slot, prev0, prev1);
+      if (rc) return rc;
+    }
+    prev_slot = slot; prev0 = lc0; prev1 = lc1;
+  }
+  if (prev_slot >= 0) rc = drain(prev_slot, prev0, prev1);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(d_panel[i]);
+    cudaFreeHost(h_panel[i]);
+    cudaEventDestroy(done[i]);
+  }
+  return rc;
+}
+
+int dgrm_low_overlap_pairs(dgrm_engine* e, double min_overlap, int64_t* pairs, int64_t cap, int64_t* count) {
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  if (cap < 0 || (cap > 0 && !pairs) || !count) return fail(e, DGRM_E_INVALID, "dgrm_low_overlap_pairs: bad arguments");
+  CK(cudaSetDevice(e->cfg.device));
+  int64_t* d_pairs = nullptr;
+  unsigned long long* d_count = nullptr;
+  CK(cudaMalloc(&d_count, sizeof(unsigned long long)));
+  if (cap > 0) CK(cudaMalloc(&d_pairs, (size_t)cap * 2 * sizeof(int64_t)));
+  CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), e->stream));
+  const dim3 grid((unsigned)((e->n + 255) / 256), (unsigned)std::min<int64_t>(e->n, 32768));
+  low_overlap_kernel<<<grid, 256, 0, e->stream>>>(tile_store(e), min_overlap, d_pairs, cap, d_count);
+  CK(cudaGetLastError());
+  unsigned long long c = 0;
+  CK(cudaMemcpyAsync(&c, d_count, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  *count = (int64_t)c;
+  if (cap > 0 && c > 0)
+    CK(cudaMemcpy(pairs, d_pairs, (size_t)std::min<int64_t>(cap, (int64_t)c) * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  cudaFree(d_count);
+  if (d_pairs) cudaFree(d_pairs);
+  return DGRM_OK;
+}
+
+int dgrm_write_grm_dat(dgrm_engine* e, const char* path) {
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  if (e->cfg.world != 1) return fail(e, DGRM_E_INVALID, "dgrm_write_grm_dat needs the whole triangle (world == 1)");
+  if (!path) return fail(e, DGRM_E_INVALID, "dgrm_write_grm_dat: null path");
+  CK(cudaSetDevice(e->cfg.device));
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(e, DGRM_E_IO, "cannot open [ %s ] for writing", path);
+  // kernel.cpp:944-966
+  const unsigned char header[14] = {'G', 'R', 'M', 0, 0x5A, 0x99, 0x2, 0x1, (unsigned char)sizeof(double), 0x1, 0, 0, 0, 0};
+  if (fwrite(header, 1, 14, f) != 14) {
+    fclose(f);
+    return fail(e, DGRM_E_IO, "short write to [ %s ]", path);
+  }
+  const int n = (int)e->n;
+  const int64_t col_elems = (int64_t)n + 1;
+  const int PC = (int)std::max<int64_t>(1, std::min<int64_t>(n, (64 << 20) / (col_elems * 8)));
+  double* d_panel = nullptr;
+  double* h_panel = nullptr;
+  CK(cudaMalloc(&d_panel, (size_t)PC * col_elems * sizeof(double)));
+  CK(cudaHostAlloc(&h_panel, (size_t)PC * col_elems * sizeof(double), cudaHostAllocDefault));
+  const TileStore ts = tile_store(e);
+  rc = DGRM_OK;
+  for (int c0 = 0; c0 < n; c0 += PC) {
+    const int c1 = std::min(c0 + PC, n);
+    const dim3 grid((unsigned)((col_elems + 255) / 256), (unsigned)(c1 - c0));
+    pack_grm_kernel<<<grid, 256, 0, e->stream>>>(ts, d_panel, c0, c1);
+    cudaMemcpyAsync(h_panel, d_panel, (size_t)(c1 - c0) * col_elems * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
+      rc = fail(e, DGRM_E_CUDA, "pack_grm failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    const size_t cnt = (size_t)(c1 - c0) * col_elems;
+    if (fwrite(h_panel, sizeof(double), cnt, f) != cnt) {
+      rc = fail(e, DGRM_E_IO, "short write to [ %s ]", path);
+      break;
+    }
+  }
+  cudaFree(d_panel);
+  cudaFreeHost(h_panel);
+  if (fclose(f) != 0 && rc == DGRM_OK) rc = fail(e, DGRM_E_IO, "close failed on [ %s ]", path);
+  return rc;
+}
+
+int64_t dgrm_num_tiles(const dgrm_engine* e) { return e ? e->ntiles : 0; }
+
+int dgrm_tile_coords(const dgrm_engine* e, int32_t* tile_rc) {
+  if (!e || !tile_rc) return DGRM_E_INVALID;
+  memcpy(tile_rc, e->tile_rc.data(), e->tile_rc.size() * sizeof(int32_t));
+  return DGRM_OK;
+}
+
+int dgrm_fetch_tiles(dgrm_engine* e, int which, double* tiles) {
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  if (!tiles || which < 0 || which > 2) return fail(e, DGRM_E_INVALID, "dgrm_fetch_tiles: bad arguments");
+  if (e->ntiles == 0) return DGRM_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  const int64_t total = e->ntiles * kTileElems;
+  const int64_t slab = 8ll << 20;  // elements per pass
+  double* d_tmp = nullptr;
+  CK(cudaMalloc(&d_tmp, (size_t)std::min(total, slab) * sizeof(double)));
+  TileStore ts = tile_store(e);
+  for (int64_t o = 0; o < total; o += slab) {
+    const int64_t cnt = std::min(slab, total - o);
+    TileStore t2 = ts;
+    t2.S = ts.S + o;
+    t2.N = ts.N ? ts.N + o : nullptr;
+    {
+      Prof pr(e, DGRM_K_FETCH);
+      export_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(t2, which, cnt, d_tmp);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(tiles + o, d_tmp, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  cudaFree(d_tmp);
+  return DGRM_OK;
+}
+
+void* dgrm_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (bytes <= 0) return nullptr;
+  if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void dgrm_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int dgrm_kernel_times(dgrm_engine* e, double ms[DGRM_K_NUM], int64_t launches[DGRM_K_NUM]) {
+  if (!e) return DGRM_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->stream));
+  for (int k = 0; k < DGRM_K_NUM; ++k) {
+    for (auto& p : e->ev[k]) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) e->ms_acc[k] += t;
+      e->ev_pool.push_back(p);
+    }
+    e->ev[k].clear();
+    if (ms) ms[k] = e->ms_acc[k];
+    if (launches) launches[k] = e->launches[k];
+  }
+  cudaGetLastError();
+  return DGRM_OK;
+}
+
+}  // extern "C"

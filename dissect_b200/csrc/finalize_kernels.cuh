@@ -1,0 +1,120 @@
+// Kernels that read the tile store: exact-diagonal fix-up, A = S * (1/N) on the fly, block-cyclic
+// gather (Matrix::m layout, matrix.cpp:435-487), sanitizeKernel's low-overlap scan
+// (kernel.cpp:1993-2037) and the packed .grm.dat layout (matrix.cpp:2324-2334).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "syrk_tcgen05.cuh"
+
+namespace dgrm {
+
+struct TileStore {
+  const double* S;        // [tiles][256][128]
+  const int32_t* N;       // [tiles][256][128], NULL with flat normalisation
+  const int32_t* index;   // [nrb][ncp] -> storage index or -1 (not owned / above the diagonal)
+  int ncp;                // column panels
+  int n;                  // individuals
+  double flat_n;          // value of N under --grm-flat-norm
+};
+
+__device__ __forceinline__ int64_t tile_slot(const TileStore& ts, int r, int c) {
+  const int sidx = ts.index[(r >> 7) * ts.ncp + (c >> 8)];
+  if (sidx < 0) return -1;
+  return (int64_t)sidx * kTileElems + (int64_t)(c & 255) * kTileM + (r & 127);
+}
+
+// value of matrix `which` at lower-triangle coordinate (r >= c); false when the tile is not owned
+__device__ __forceinline__ bool tile_value(const TileStore& ts, int which, int r, int c, double* out) {
+  const int64_t slot = tile_slot(ts, r, c);
+  if (slot < 0) return false;
+  const double nval = ts.N ? (double)ts.N[slot] : ts.flat_n;
+  if (which == 2) { *out = nval; return true; }
+  const double s = ts.S[slot];
+  if (which == 1) { *out = s; return true; }
+  // matrix.cpp:4096: m[i] *= scale / m1->m[i] with scale = 1.  -> two roundings
+  *out = __dmul_rn(s, __ddiv_rn(1., nval));
+  return true;
+}
+
+// Overwrite the tensor-core diagonal of S with the exact fp64 sum of squares from bed_expand.
+__global__ void fix_diag_kernel(double* __restrict__ S, const int32_t* __restrict__ index, int ncp, int n,
+                                const double* __restrict__ diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int sidx = index[(i >> 7) * ncp + (i >> 8)];
+  if (sidx < 0) return;
+  S[(int64_t)sidx * kTileElems + (int64_t)(i & 255) * kTileM + (i & 127)] = diag[i];
+}
+
+struct CyclicGeom {
+  int bs_r, bs_c, my_row, my_col, R, C;
+  int nloc_r, nloc_c;  // numroc
+  int64_t lld;
+};
+
+__device__ __forceinline__ int local_to_global(int l, int bs, int me, int P) {
+  return ((l / bs) * P + me) * bs + (l % bs);
+}
+
+// dst[(lc - lc0) * lld + lr] for local columns [lc0, lc1): 2-D launch, x along local rows.
+__global__ void fetch_block_cyclic_kernel(const TileStore ts, int which, double* __restrict__ dst, CyclicGeom g,
+                                          int lc0, int lc1, int uplo /* 0 L, 1 U, 2 B */) {
+  const int lr = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lc = lc0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (lr >= g.nloc_r || lc >= lc1) return;
+  const int gr = local_to_global(lr, g.bs_r, g.my_row, g.R);
+  const int gc = local_to_global(lc, g.bs_c, g.my_col, g.C);
+  if (gr >= ts.n || gc >= ts.n) return;
+  const bool lower = gc <= gr;
+  if (uplo == 0 && !lower) return;
+  if (uplo == 1 && gc < gr) return;
+  double v;
+  if (!tile_value(ts, which, lower ? gr : gc, lower ? gc : gr, &v)) return;
+  dst[(int64_t)(lc - lc0) * g.lld + lr] = v;
+}
+
+// sanitizeKernel's scan: strictly-lower pairs with -0.1 < N < min_overlap - 0.1
+__global__ void low_overlap_kernel(const TileStore ts, double min_overlap, int64_t* __restrict__ pairs, int64_t cap,
+                                   unsigned long long* __restrict__ count) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= ts.n) return;
+  for (int c = blockIdx.y; c < r; c += gridDim.y) {
+    double nv;
+    if (!tile_value(ts, 2, r, c, &nv)) continue;
+    if (nv > -0.1 && nv < min_overlap - 0.1) {
+      const unsigned long long k = atomicAdd(count, 1ull);
+      if ((int64_t)k < cap) {
+        pairs[2 * k] = r;
+        pairs[2 * k + 1] = c;
+      }
+    }
+  }
+}
+
+// Packed (n+1) x n column-major array of packMatrices (matrix.cpp:2324-2334), columns [c0, c1):
+//   P[r][c] = N[r][c]   r = 0..c       (upper triangle of N incl. diagonal)
+//   P[r+1][c] = A[r][c] r = c..n-1     (lower triangle of A incl. diagonal)
+__global__ void pack_grm_kernel(const TileStore ts, double* __restrict__ dst, int c0, int c1) {
+  const int pr = blockIdx.x * blockDim.x + threadIdx.x;  // row of P, 0..n
+  const int c = c0 + blockIdx.y;
+  if (pr > ts.n || c >= c1) return;
+  double v = 0.;
+  if (pr <= c) tile_value(ts, 2, c, pr, &v);   // N[pr][c] = N[c][pr]
+  else tile_value(ts, 0, pr - 1, c, &v);       // A[pr-1][c]
+  dst[(int64_t)(c - c0) * (ts.n + 1) + pr] = v;
+}
+
+// tile export as doubles (multi-engine gather)
+__global__ void export_tiles_kernel(const TileStore ts, int which, int64_t total, double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double nval = ts.N ? (double)ts.N[i] : ts.flat_n;
+  double v;
+  if (which == 2) v = nval;
+  else if (which == 1) v = ts.S[i];
+  else v = (nval == 0.) ? 0. : __dmul_rn(ts.S[i], __ddiv_rn(1., nval));
+  dst[i] = v;
+}
+
+}  // namespace dgrm

@@ -1,0 +1,234 @@
+"""Python face of the C ABI (include/dgrm.h): one `GrmEngine` per GPU / per process.
+
+This is plumbing for tests, bench.py and the multi-GPU driver — all arithmetic happens in
+libdgrm.so's sm_100a kernels.  Method names follow the C entry points one to one.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+lib_path = _lib.LIB_PATH
+
+
+class DgrmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"dgrm error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def numroc(n, nb, iproc, nprocs):
+    """ScaLAPACK numroc_ with source process 0 (reference: matrix.cpp:1748-1749)."""
+    nblocks = n // nb
+    r = (nblocks // nprocs) * nb
+    extra = nblocks % nprocs
+    if iproc < extra:
+        r += nb
+    elif iproc == extra:
+        r += n % nb
+    return r
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (dgrm_host_alloc); freed with the object."""
+
+    def __init__(self, shape, dtype, order="C"):
+        self._lib = _lib.load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = self._lib.dgrm_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise MemoryError(f"dgrm_host_alloc({self.nbytes}) failed")
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape, order=order)
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                self.array = None
+                self._lib.dgrm_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class GrmEngine:
+    def __init__(self, device=0, rank=0, world=1, operand="fp16", count_method="mma", flat_norm=False,
+                 chunk_snps=8192, cta_group=2, profile=False):
+        self._lib = _lib.load()
+        cfg = _lib.Config()
+        self._lib.dgrm_default_config(C.byref(cfg))
+        cfg.device, cfg.rank, cfg.world = device, rank, world
+        cfg.operand = _lib.OPERANDS[operand]
+        cfg.count_method = _lib.COUNT_METHODS[count_method]
+        cfg.flat_norm = int(bool(flat_norm))
+        cfg.chunk_snps = chunk_snps
+        cfg.cta_group = cta_group
+        cfg.profile = int(bool(profile))
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self._lib.dgrm_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise DgrmError(rc, self._lib.dgrm_last_error(None).decode())
+        self._h = h
+        self._keep = []
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise DgrmError(rc, self._lib.dgrm_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dgrm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- C ABI, one to one ---------------------------------------------------------------------
+    def set_individuals(self, n_fam, keep_mask=None):
+        km = None
+        if keep_mask is not None:
+            km = np.ascontiguousarray(keep_mask, dtype=np.int32)
+            assert km.shape == (n_fam,)
+        self._ck(self._lib.dgrm_set_individuals(self._h, n_fam, km.ctypes.data if km is not None else None))
+
+    def begin(self, m_capacity):
+        self._ck(self._lib.dgrm_begin(self._h, int(m_capacity)))
+
+    def push_bed_host(self, rows, row_keep=None, pitch=None, nrows=None):
+        """rows: uint8 array [nrows, pitch] (C order) or a raw address with explicit pitch/nrows."""
+        rk = None
+        if row_keep is not None:
+            rk = np.ascontiguousarray(row_keep, dtype=np.uint8)
+        if isinstance(rows, np.ndarray):
+            assert rows.dtype == np.uint8 and rows.ndim == 2 and rows.strides[1] == 1
+            ptr, pitch, nrows = rows.ctypes.data, rows.strides[0], rows.shape[0]
+        else:
+            ptr = int(rows)
+        self._ck(self._lib.dgrm_push_bed_host(self._h, ptr, pitch, nrows, rk.ctypes.data if rk is not None else None))
+        self._keep.append((rows, rk))  # the copy is asynchronous: keep the sources alive
+
+    def push_bed_device(self, ptr, pitch, nrows, row_keep=None, stream=None):
+        rk = None
+        if row_keep is not None:
+            rk = np.ascontiguousarray(row_keep, dtype=np.uint8)
+        self._ck(self._lib.dgrm_push_bed_device(self._h, int(ptr), pitch, nrows,
+                                                rk.ctypes.data if rk is not None else None, stream))
+
+    def load_bed_file(self, path, m_file, snp_keep_idx=None):
+        idx = None
+        if snp_keep_idx is not None:
+            idx = np.ascontiguousarray(snp_keep_idx, dtype=np.int64)
+        self._ck(self._lib.dgrm_load_bed_file(self._h, str(path).encode(), m_file,
+                                              idx.ctypes.data if idx is not None else None,
+                                              len(idx) if idx is not None else 0))
+
+    def finish(self):
+        try:
+            self._ck(self._lib.dgrm_finish(self._h))
+        finally:
+            self._keep.clear()
+
+    def sync(self):
+        self._ck(self._lib.dgrm_sync(self._h))
+
+    @property
+    def num_snps(self):
+        return self._lib.dgrm_num_snps(self._h)
+
+    @property
+    def num_individuals(self):
+        return self._lib.dgrm_num_individuals(self._h)
+
+    def snp_stats(self):
+        m = self.num_snps
+        out = {
+            "freq": np.zeros((m, 4), np.int32), "nn": np.zeros(m, np.int32),
+            "p1": np.zeros(m), "p2": np.zeros(m), "sd": np.zeros(m),
+        }
+        self._ck(self._lib.dgrm_snp_stats(self._h, out["freq"].ctypes.data, out["nn"].ctypes.data,
+                                          out["p1"].ctypes.data, out["p2"].ctypes.data, out["sd"].ctypes.data))
+        return out
+
+    def bad_snps(self, cap=65536):
+        idx = np.zeros(cap, np.int64)
+        cnt = C.c_int64(0)
+        self._ck(self._lib.dgrm_bad_snps(self._h, idx.ctypes.data, cap, C.byref(cnt)))
+        return idx[: min(cap, cnt.value)].copy(), cnt.value
+
+    def fetch_block_cyclic(self, which="A", bs=(256, 256), grid=(1, 1), coords=(0, 0), uplo="L", out=None,
+                           fill=np.nan):
+        """Returns the caller-side local block (Fortran order, like Matrix::m)."""
+        n = self.num_individuals
+        nr = numroc(n, bs[0], coords[0], grid[0])
+        nc = numroc(n, bs[1], coords[1], grid[1])
+        if out is None:
+            out = np.full((nr, nc), fill, dtype=np.float64, order="F")
+        assert out.dtype == np.float64 and out.flags.f_contiguous and out.shape == (nr, nc)
+        self._ck(self._lib.dgrm_fetch_block_cyclic(self._h, _lib.FETCH[which], out.ctypes.data, max(nr, 1),
+                                                   bs[0], bs[1], coords[0], coords[1], grid[0], grid[1],
+                                                   uplo.encode()))
+        return out
+
+    def fetch_into(self, which, ptr, lld, bs=(256, 256), grid=(1, 1), coords=(0, 0), uplo="L"):
+        self._ck(self._lib.dgrm_fetch_block_cyclic(self._h, _lib.FETCH[which], int(ptr), lld, bs[0], bs[1],
+                                                   coords[0], coords[1], grid[0], grid[1], uplo.encode()))
+
+    def low_overlap_pairs(self, min_overlap=10.0, cap=1 << 20):
+        pairs = np.zeros((cap, 2), np.int64)
+        cnt = C.c_int64(0)
+        self._ck(self._lib.dgrm_low_overlap_pairs(self._h, float(min_overlap), pairs.ctypes.data, cap, C.byref(cnt)))
+        return pairs[: min(cap, cnt.value)].copy(), cnt.value
+
+    def write_grm_dat(self, path):
+        self._ck(self._lib.dgrm_write_grm_dat(self._h, str(path).encode()))
+
+    @property
+    def num_tiles(self):
+        return self._lib.dgrm_num_tiles(self._h)
+
+    def tile_coords(self):
+        rc = np.zeros((self.num_tiles, 2), np.int32)
+        if self.num_tiles:
+            self._ck(self._lib.dgrm_tile_coords(self._h, rc.ctypes.data))
+        return rc
+
+    def fetch_tiles(self, which="A"):
+        t = np.zeros((self.num_tiles, 256, 128), np.float64)  # [tile][col][row]
+        if self.num_tiles:
+            self._ck(self._lib.dgrm_fetch_tiles(self._h, _lib.FETCH[which], t.ctypes.data))
+        return t
+
+    def kernel_times(self):
+        ms = (C.c_double * _lib.K_NUM)()
+        ln = (C.c_int64 * _lib.K_NUM)()
+        self._ck(self._lib.dgrm_kernel_times(self._h, C.byref(ms), C.byref(ln)))
+        return {k: (ms[i], ln[i]) for i, k in enumerate(_lib.K_NAMES)}
+
+
+def assemble_from_tiles(n, tile_sets):
+    """Merge [(tile_coords, tiles)] from several engines into a dense lower-triangular n x n array
+    (NaN elsewhere).  Host-side helper for multi-engine gathers."""
+    out = np.full((n, n), np.nan)
+    for rc, tiles in tile_sets:
+        for (rb, cp), t in zip(rc, tiles):
+            r0, c0 = int(rb) * 128, int(cp) * 256
+            r1, c1 = min(r0 + 128, n), min(c0 + 256, n)
+            if r0 >= n or c0 >= n:
+                continue
+            out[r0:r1, c0:c1] = t[: c1 - c0, : r1 - r0].T
+    iu = np.triu_indices(n, 1)
+    out[iu] = np.nan
+    return out

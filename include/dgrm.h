@@ -1,0 +1,171 @@
+/*
+ * dgrm.h — C ABI of the B200-native GRM engine (libdgrm.so).
+ *
+ * This is the drop-in boundary for DISSECT's `--make-grm` hot path.  The reference has no
+ * FFI seam of its own; every entry point below names the reference code it
+ * replaces (file:line are relative to the reference tree).  Signatures carry only plain
+ * pointers and sizes.  All functions return DGRM_OK (0) or a negative DGRM_E_* code and
+ * never abort: the host adapter converts a non-zero status into `misc.error(...)`
+ * (misc.cpp:151-170) using dgrm_last_error().
+ *
+ * Threading: call from one host thread per engine (the reference makes every MPI/BLACS call
+ * from the rank's main thread).  The library never calls MPI.
+ * Ownership: the library only writes into caller-owned buffers (Matrix::m is allocated with
+ * new double[] and freed with delete[], matrix.cpp:1646, 99-106).
+ *
+ * There is no CPU fallback: every compute entry point fails with DGRM_E_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef DGRM_H
+#define DGRM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGRM_ABI_VERSION 1
+
+/* status codes */
+#define DGRM_OK            0
+#define DGRM_E_INVALID    -1  /* bad argument / call order                                   */
+#define DGRM_E_CUDA       -2  /* CUDA runtime/driver error, or no sm_100 device              */
+#define DGRM_E_NOMEM      -3  /* device or host allocation failed   (matrix.cpp:1662-1670)   */
+#define DGRM_E_BADBED     -4  /* bad magic / not SNP-major / short read (genotype.cpp:578-605, 693-696) */
+#define DGRM_E_BADSNP     -5  /* SNP with standardDev == 0          (genotype.cpp:924-939)   */
+#define DGRM_E_NANSNP     -6  /* SNP with no non-missing genotype (p1 = 0/0; the reference lets the NaN through, genotype.cpp:736) */
+#define DGRM_E_IO         -7  /* file could not be opened / written                          */
+
+/* operand format of the standardised genotypes fed to the tensor cores */
+#define DGRM_OPERAND_FP16    0  /* one pass, fp16 operands (default; |z| <= ~45 fits easily) */
+#define DGRM_OPERAND_BF16    1  /* one pass, bf16 operands                                   */
+#define DGRM_OPERAND_FP16X2  2  /* hi+lo fp16 split, three passes (hi.hi + lo.hi + hi.lo)    */
+
+/* how the per-pair non-missing count N (kernel.cpp:96-101) is formed */
+#define DGRM_COUNT_MMA   0  /* 0/1 e4m3 operands through tcgen05 kind::f8f6f4, exact in fp32  */
+#define DGRM_COUNT_POPC  1  /* AND + popcount over bit-packed non-missing masks               */
+
+/* which matrix dgrm_fetch_* returns */
+#define DGRM_FETCH_A  0  /* normalised GRM  A = S * (1/N)     (matrix.cpp:4096)               */
+#define DGRM_FETCH_S  1  /* unnormalised    S = Z^T Z         (kernel.cpp:94)                 */
+#define DGRM_FETCH_N  2  /* pair counts     N = M^T M         (kernel.cpp:100) or m if flat   */
+
+/* kernel classes reported by dgrm_kernel_times() */
+#define DGRM_K_COUNT    0  /* bed_count_stats                                                 */
+#define DGRM_K_EXPAND   1  /* bed_expand (+ diag partial reduce)                              */
+#define DGRM_K_SYRK     2  /* grm_syrk tcgen05, 16-bit operands                               */
+#define DGRM_K_PAIRCNT  3  /* pair count (fp8 tcgen05 or popcount)                            */
+#define DGRM_K_FINAL    4  /* diagonal fix-up                                                 */
+#define DGRM_K_FETCH    5  /* tile -> block-cyclic gather                                     */
+#define DGRM_K_NUM      6
+
+typedef struct dgrm_engine dgrm_engine;
+
+typedef struct dgrm_config {
+  int32_t device;        /* CUDA device ordinal                                              */
+  int32_t rank;          /* this engine's index in the tile-set partition                    */
+  int32_t world;         /* number of engines sharing the lower triangle (1 = all tiles)     */
+  int32_t operand;       /* DGRM_OPERAND_*                                                   */
+  int32_t count_method;  /* DGRM_COUNT_*                                                     */
+  int32_t flat_norm;     /* --grm-flat-norm: N := m, no pair count (kernel.cpp:102-109)      */
+  int32_t chunk_snps;    /* SNPs contracted per launch (fp32 in-chunk, fp64 across); mult. of 128 */
+  int32_t cta_group;     /* 1 = one-SM MMA 128x256 tiles, 2 = CTA-pair MMA 256x256 tiles     */
+  int32_t profile;       /* 1 = record CUDA events around every kernel launch                */
+  int32_t reserved[7];
+} dgrm_config;
+
+/* Fill *cfg with defaults (device 0, rank 0/1, fp16, MMA count, chunk 8192, cta_group 2). */
+int dgrm_default_config(dgrm_config *cfg);
+
+/* Engine life cycle.  Replaces nothing in the reference; owns device buffers and streams. */
+int dgrm_create(const dgrm_config *cfg, dgrm_engine **out);
+void dgrm_destroy(dgrm_engine *e);
+
+/* Text of the last error on this engine (or of the last failed dgrm_create when e == NULL).
+ * Stands in for the message DISSECT passes to misc.error (misc.cpp:151). */
+const char *dgrm_last_error(const dgrm_engine *e);
+
+int dgrm_abi_version(void);
+
+/* Cohort geometry.  n_fam = individuals in the .fam; keep_mask[n_fam] != 0 keeps individual f
+ * (individualBEDIdxsMaskToKeep, genotype.cpp:750); NULL keeps everyone. */
+int dgrm_set_individuals(dgrm_engine *e, int64_t n_fam, const int32_t *keep_mask);
+
+/* Start a GRM: clears S, N and the per-SNP statistics.  m_capacity >= number of SNPs that
+ * will be kept over all following pushes. */
+int dgrm_begin(dgrm_engine *e, int64_t m_capacity);
+
+/* Feed SNP-major .bed rows (header stripped): row r starts at rows + r*pitch and holds
+ * ceil(n_fam/4) bytes, individual f in byte f/4 bits 2(f%4)..2(f%4)+1 (genotype.cpp:662, 752, 784).
+ * row_keep[nrows] != 0 keeps a row (SNPsBEDIdxsToKeep, genotype.cpp:660-690); NULL keeps all.
+ * Replaces readBEDFile's decode loop + parseSNP/parseSNPbyte (genotype.cpp:639-787),
+ * normalizeGenotypes (genotype.cpp:888-961) and both pdsyrk_ calls (kernel.cpp:94,100) for
+ * these rows.  The host variant copies host->device itself (asynchronously when `rows` is
+ * pinned); the device variant reads rows already in HBM after `producer_stream` (a
+ * cudaStream_t, may be NULL) reaches the point of the call. */
+int dgrm_push_bed_host(dgrm_engine *e, const uint8_t *rows, int64_t pitch, int64_t nrows,
+                       const uint8_t *row_keep);
+int dgrm_push_bed_device(dgrm_engine *e, const uint8_t *d_rows, int64_t pitch, int64_t nrows,
+                         const uint8_t *row_keep, void *producer_stream);
+
+/* Whole-file convenience: validates the 3-byte header exactly as genotype.cpp:578-605 and
+ * streams the kept rows.  snp_keep_idx[m_keep] are ascending .bim positions, NULL = all
+ * m_file rows (SNPsBEDIdxsToKeep). */
+int dgrm_load_bed_file(dgrm_engine *e, const char *bed_path, int64_t m_file,
+                       const int64_t *snp_keep_idx, int64_t m_keep);
+
+/* Flush the last partial chunk, finish S and N.  Fails with DGRM_E_BADSNP / DGRM_E_NANSNP
+ * when a kept SNP is monomorphic / entirely missing (genotype.cpp:924-939); the offending
+ * SNP indices are then available from dgrm_bad_snps so the adapter can write <out>.badsnps. */
+int dgrm_finish(dgrm_engine *e);
+int dgrm_sync(dgrm_engine *e);
+
+int64_t dgrm_num_snps(const dgrm_engine *e);         /* SNPs pushed and kept so far          */
+int64_t dgrm_num_individuals(const dgrm_engine *e);  /* individuals kept                     */
+
+/* What `struct SNP` holds on the root rank after readBEDFile/gatherSNPData
+ * (genotype.h:65-69, genotype.cpp:735-738, 859-870): bit-exact counts, 0-ulp doubles.
+ * freq is [m][4] with freq[k][0] = missing, [1] = hom A1, [2] = het, [3] = hom A2.
+ * Any pointer may be NULL. */
+int dgrm_snp_stats(dgrm_engine *e, int32_t *freq, int32_t *n_non_missing, double *p1,
+                   double *p2, double *std_dev);
+int dgrm_bad_snps(dgrm_engine *e, int64_t *idx, int64_t cap, int64_t *count);
+
+/* Fill the caller's local piece of a 2-D block-cyclic n x n Matrix (matrix.cpp:435-487,
+ * 1748-1758; grid R x C row-major, source process (0,0)): global (gr,gc) owned by
+ * ((gr/bs_r)%R, (gc/bs_c)%C) lands at local[lc*lld + lr].  uplo 'L' writes only gc <= gr
+ * (what pdsyrk_('L',..) leaves defined, matrix.cpp:2679-2682), 'U' only gc >= gr, 'B' both.
+ * With world > 1 only entries of tiles this engine owns are written. */
+int dgrm_fetch_block_cyclic(dgrm_engine *e, int which, double *local, int64_t lld, int bs_r,
+                            int bs_c, int my_row, int my_col, int grid_rows, int grid_cols,
+                            char uplo);
+
+/* Pairs (i > j) whose shared non-missing count satisfies -0.1 < N_ij < min_overlap - 0.1,
+ * the scan sanitizeKernel performs (kernel.cpp:1993-2037, matrix.cpp:4334-4401).
+ * pairs is [cap][2] (row, col), *count receives the total found (may exceed cap). */
+int dgrm_low_overlap_pairs(dgrm_engine *e, double min_overlap, int64_t *pairs, int64_t cap,
+                           int64_t *count);
+
+/* Write <path> = the .grm.dat of Kernel::writeGRM (kernel.cpp:944-974): 14-byte header then
+ * the packed (n+1) x n column-major array of matrix.cpp:2324-2334.  world must be 1. */
+int dgrm_write_grm_dat(dgrm_engine *e, const char *path);
+
+/* Raw tile export for multi-engine runs: this engine's 128x256 tiles, column-major inside a
+ * tile.  tile_rc[ntiles][2] = (row block of 128, column panel of 256). */
+int64_t dgrm_num_tiles(const dgrm_engine *e);
+int dgrm_tile_coords(const dgrm_engine *e, int32_t *tile_rc);
+int dgrm_fetch_tiles(dgrm_engine *e, int which, double *tiles /* [ntiles][128*256] */);
+
+/* Pinned host memory helpers (Matrix::m replacement allocation for zero-staging fetches). */
+void *dgrm_host_alloc(int64_t bytes);
+void dgrm_host_free(void *p);
+
+/* Per-kernel-class device time (ms, CUDA events on the launching stream) and launch counts
+ * accumulated since dgrm_begin; requires cfg.profile = 1. */
+int dgrm_kernel_times(dgrm_engine *e, double ms[DGRM_K_NUM], int64_t launches[DGRM_K_NUM]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGRM_H */
