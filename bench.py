@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py — GRM build throughput (pair·SNP/s) of the B200-native `--make-grm` hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation
+
+A "step" is one complete GRM build (decode + per-SNP stats + standardise + Z'Z + pair counts) over the
+synthetic cohort named in `config.workload`.  `value` times K steps with the packed .bed rows already
+resident in HBM; `e2e` times the same build through the C ABI with HOST buffers: pinned .bed rows in,
+block-cyclic A and N (lower triangles) out into pinned Matrix::m-style arrays, every step.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# ---- workload family -----------------------------------------------------------------------------------
+# N = 1: BASELINE.json configs[1]  (20,000 individuals x 100,000 SNPs, 1% missing, MAF filter = extract list)
+# N > 1: same SNP set, individuals scaled by sqrt(N) so that the pair work per GPU stays fixed (weak scaling);
+#        N = 8 gives 56,568 individuals, between configs[1] and configs[2].
+BASE_N, BASE_M, MISSING, MAF_LO, MAF_HI, MAF_MIN, SEED = 20000, 100000, 0.01, 0.001, 0.5, 0.01, 2
+# bounded CPU sample of the same workload for the reference arm (about 10-30 s of host work)
+CPU_N, CPU_M = 4000, 16000
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "hbm_gbs": d["hbm_gbs"], "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, nm in enumerate(names):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def reference_step(workdir, threads):
+    """One step of the reference arm: the reference's own Genotype load + Kernel constructor
+    (oracle/_ref/grmtime, built from the unmodified sources) on the bounded CPU sample."""
+    from oracle import ref_runner
+    exe = os.path.join(ROOT, "oracle", "_ref", "grmtime")
+    cmd = [exe, "--make-grm", "--bfile", os.path.join(workdir, "cpu"), "--out", os.path.join(workdir, "cpu_out"),
+           "--extract", os.path.join(workdir, "cpu.extract")]
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OPENBLAS_NUM_THREADS=str(threads))
+    t0 = time.time()
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=3600)
+    wall = time.time() - t0
+    mt = re.search(r"GRMTIME n (\d+) m (\d+) threads (\d+) load_s ([\d.]+) compute_s ([\d.]+)", r.stdout)
+    if r.returncode != 0 or not mt:
+        raise RuntimeError("reference run failed: " + r.stdout[-2000:] + r.stderr[-2000:])
+    n, m = int(mt.group(1)), int(mt.group(2))
+    load_s, comp_s = float(mt.group(4)), float(mt.group(5))
+    del ref_runner
+    return {"n": n, "m": m, "load_s": load_s, "compute_s": comp_s, "wall_s": wall, "W": n * (n + 1) / 2 * m}
+
+
+def make_cpu_sample(workdir, m_file=CPU_M):
+    """Writes the bounded CPU sample (same distributions / filter as the GPU workload) as .bed/.bim/.fam."""
+    from dissect_b200 import bedio
+    pk, maf = bedio.synth_packed(CPU_N, m_file, SEED, maf_lo=MAF_LO, maf_hi=MAF_HI, missing=MISSING, return_maf=True)
+    bedio.write_bed(os.path.join(workdir, "cpu"), pk, CPU_N)
+    with open(os.path.join(workdir, "cpu.extract"), "w") as f:
+        for k in np.nonzero(maf >= MAF_MIN)[0]:
+            f.write(f"rs{k + 1}\n")
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def sample_desc(r, threads):
+    return (f"reference Genotype load + Kernel ctor (oracle/_ref/grmtime, unmodified reference sources, 1 MPI rank "
+            f"on a 1x1 BLACS shim, OpenBLAS dsyrk, {threads} threads) on n={r['n']} x m={r['m']} kept SNPs of the same "
+            f"synthetic family (1% missing, MAF>=0.01 extract list): load {r['load_s']:.2f}s + compute "
+            f"{r['compute_s']:.2f}s; the full config needs >= 42 GB and ~10 min on one rank")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    exe = os.path.join(ROOT, "oracle", "_ref", "grmtime")
+    threads = cpu_threads()
+    base = {"impl": "reference", "metric": "grm_pair_snp_per_s", "unit": "pair*SNP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    # the sample shrinks with K so that the whole --steps K --warmup W run stays within a few minutes
+    runs = args.steps + min(args.warmup, 1)
+    m_s = max(2000, min(CPU_M, int(CPU_M * 6 / max(runs, 1))))
+    if not os.path.exists(exe):
+        # the reference-built oracle travels prebuilt; without it fall back to the plain-C port
+        from oracle import c_oracle
+        from dissect_b200 import bedio
+        if not c_oracle.available():
+            base.update({"unavailable": "neither oracle/_ref/grmtime nor oracle/_ref/libgrm_oracle.so is built"})
+            print(json.dumps(base))
+            return
+        pk = bedio.synth_packed(CPU_N // 2, m_s // 4, SEED, maf_lo=0.05, maf_hi=MAF_HI, missing=MISSING)
+        res = []
+        for i in range(runs):
+            t0 = time.time()
+            c_oracle.grm(pk, CPU_N // 2)
+            if i >= runs - args.steps:
+                res.append({"n": CPU_N // 2, "m": m_s // 4, "load_s": 0.0, "compute_s": time.time() - t0,
+                            "W": (CPU_N // 2) * (CPU_N // 2 + 1) / 2 * (m_s // 4)})
+        kind = "port"
+    else:
+        kind = "reference"
+        with tempfile.TemporaryDirectory(prefix="dgrm_ref_") as wd:
+            make_cpu_sample(wd, m_s)
+            for _ in range(min(args.warmup, 1)):
+                reference_step(wd, threads)
+            res = [reference_step(wd, threads) for _ in range(args.steps)]
+    t = sum(r["load_s"] + r["compute_s"] for r in res)
+    W = sum(r["W"] for r in res)
+    val = W / t
+    base.update({
+        "value": val, "ms_per_step": 1e3 * t / len(res),
+        "config": {"workload": f"make-grm {res[-1]['n']}x{m_s if kind == 'reference' else res[-1]['m']} bounded CPU sample "
+                               "of configs[1] (20000x100000, 1% missing, MAF filter)",
+                   "parallelism": f"1 MPI rank, {threads} OpenMP/BLAS threads"},
+        "cpu_baseline": {"value": val, "unit": "pair*SNP/s", "cores": threads, "kind": kind,
+                         "sample": sample_desc(res[-1], threads) if kind == "reference" else
+                         f"plain-C restatement oracle/grm_oracle.c on n={res[-1]['n']} x m={res[-1]['m']}"},
+        "e2e": {"value": val, "unit": "pair*SNP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    })
+    print(json.dumps(base))
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from dissect_b200 import GrmEngine
+    from dissect_b200.engine import PinnedArray
+    from dissect_b200.synth import synth_packed_cuda
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the GRM engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    G = world
+    n = args.n if args.n else int(round(BASE_N * math.sqrt(G)))
+    m_file = args.m if args.m else BASE_M
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic cohort (same seed on every rank -> identical data; rank r keeps its row shard) ----------
+    pk_all, maf = synth_packed_cuda(n, m_file, SEED, maf_lo=MAF_LO, maf_hi=MAF_HI, missing=MISSING)
+    keep = (maf >= MAF_MIN).cpu().numpy().astype(np.uint8)          # "MAF filter" = --extract list
+    m_kept = int(keep.sum())
+    W = n * (n + 1) / 2 * m_kept
+    bpr = pk_all.shape[1]
+    chunk = args.chunk
+    # SNP rows are dealt to ranks in contiguous shards of every chunk; the packed chunk is all-gathered
+    # over NVLink (the path's one exchange step), then every rank expands it locally.
+    shard = (chunk + G - 1) // G
+    if G > 1:
+        mine = []
+        for c0 in range(0, m_file, chunk):
+            r0 = min(c0 + rank * shard, min(c0 + chunk, m_file))
+            r1 = min(r0 + shard, min(c0 + chunk, m_file))
+            mine.append((c0, r0, r1))
+        gather_buf = torch.zeros((G * shard, bpr), dtype=torch.uint8, device="cuda")
+        send_buf = torch.zeros((shard, bpr), dtype=torch.uint8, device="cuda")
+    host_pk = PinnedArray((m_file, bpr), np.uint8)
+    host_pk.array[:] = pk_all.cpu().numpy()
+
+    eng = GrmEngine(device=local, rank=rank, world=world, operand=args.operand, count_method=args.count,
+                    chunk_snps=chunk, cta_group=args.cg, profile=True)
+    eng.set_individuals(n)
+
+    def push_device_resident():
+        if G == 1:
+            eng.push_bed_device(pk_all.data_ptr(), pk_all.stride(0), m_file, row_keep=keep)
+            return
+        stream = torch.cuda.current_stream().cuda_stream
+        for (c0, r0, r1) in mine:
+            c1 = min(c0 + chunk, m_file)
+            send_buf.zero_()
+            if r1 > r0:
+                send_buf[: r1 - r0].copy_(pk_all[r0:r1])
+            dist.all_gather_into_tensor(gather_buf, send_buf)
+            # shards are padded to `shard` rows: rows beyond the chunk are dropped through row_keep
+            rk = np.zeros(G * shard, np.uint8)
+            for g in range(G):
+                a = c0 + g * shard
+                b = min(a + shard, c1)
+                if b > a:
+                    rk[g * shard: g * shard + (b - a)] = keep[a:b]
+            eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), G * shard, row_keep=rk, stream=stream)
+            eng.sync()  # gather_buf is reused by the next all-gather
+
+    def step_device():
+        eng.begin(m_kept)
+        push_device_resident()
+        eng.finish()
+
+    # ---- value: device-resident inputs ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    eng.kernel_times()  # reading resets the per-class counters: the timed region starts from zero
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_device()
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    kt = eng.kernel_times()
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    value = args.steps * W / dt
+
+    # ---- e2e: host buffers in, block-cyclic lower triangles of A and N out, every step -----------------
+    e2e = None
+    if G == 1 and not args.no_e2e:
+        A_host = PinnedArray((n, n), np.float64, order="F")
+        N_host = PinnedArray((n, n), np.float64, order="F")
+
+        def step_e2e():
+            eng.begin(m_kept)
+            eng.push_bed_host(host_pk.ptr, row_keep=keep, pitch=bpr, nrows=m_file)
+            eng.finish()
+            eng.fetch_into("A", A_host.ptr, n, bs=(256, 256), uplo="L")
+            eng.fetch_into("N", N_host.ptr, n, bs=(256, 256), uplo="L")
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(1, min(args.steps, 3))
+        for _ in range(ke):
+            step_e2e()
+        barrier()
+        dte = time.perf_counter() - t0
+        tri = n * (n + 1) // 2
+        e2e = {"value": ke * W / dte, "unit": "pair*SNP/s", "ms_per_step": 1e3 * dte / ke,
+               "h2d_bytes_per_step": int(m_file * bpr), "d2h_bytes_per_step": int(2 * tri * 8),
+               "result": "A and N lower triangles (fp64) into pinned block-cyclic Matrix::m buffers, bs 256, 1x1 grid",
+               "check_trace_A": float(np.trace(A_host.array[:2000, :2000]))}
+    elif G > 1 and not args.no_e2e:
+        # per-rank H2D of its row shards + all-gather + compute + D2H of the tiles this rank owns
+        ntl = eng.num_tiles
+        tiles_host = None
+
+        def step_e2e():
+            eng.begin(m_kept)
+            stream = torch.cuda.current_stream().cuda_stream
+            for (c0, r0, r1) in mine:
+                c1 = min(c0 + chunk, m_file)
+                send_buf.zero_()
+                if r1 > r0:
+                    send_buf[: r1 - r0].copy_(torch.from_numpy(host_pk.array[r0:r1]), non_blocking=True)
+                dist.all_gather_into_tensor(gather_buf, send_buf)
+                rk = np.zeros(G * shard, np.uint8)
+                for g in range(G):
+                    a = c0 + g * shard
+                    b = min(a + shard, c1)
+                    if b > a:
+                        rk[g * shard: g * shard + (b - a)] = keep[a:b]
+                eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), G * shard, row_keep=rk, stream=stream)
+                eng.sync()
+            eng.finish()
+            return eng.fetch_tiles("A"), eng.fetch_tiles("N")
+
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(1, min(args.steps, 2))
+        for _ in range(ke):
+            tiles_host = step_e2e()
+        barrier()
+        dte = time.perf_counter() - t0
+        t = torch.tensor([dte], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dte = float(t.item())
+        e2e = {"value": ke * W / dte, "unit": "pair*SNP/s", "ms_per_step": 1e3 * dte / ke,
+               "h2d_bytes_per_step": int(sum(r1 - r0 for (_, r0, r1) in mine) * bpr),
+               "d2h_bytes_per_step": int(2 * ntl * 128 * 256 * 8),
+               "result": "per rank: its packed row shards in, its owned 128x256 tiles of A and N (fp64) out"}
+        del tiles_host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    syrk_ms, syrk_launches = kt["syrk"]
+    launches = sum(v[1] for v in kt.values())
+    # algorithmic flops of the contraction: 2 per pair*SNP, lower triangle incl. diagonal;
+    # with G ranks each rank's launches cover 1/G of the triangle.
+    flops_total = 2.0 * W * args.steps / G
+    achieved = flops_total / (syrk_ms * 1e-3) / 1e12 if syrk_ms else None
+    peak = peaks["bf16_tflops_sustained"]
+    prof_traffic = None
+    pj = os.path.join(ROOT, "profiles", "syrk_traffic.json")
+    if os.path.exists(pj):
+        prof_traffic = json.load(open(pj)).get("dram_bytes_per_launch")
+    out = {
+        "metric": "grm_pair_snp_per_s", "value": value, "unit": "pair*SNP/s", "n_gpus": G, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"fp16": "f16 operands / f32 chunk accum / f64 across chunks; counts exact int32",
+                                       "bf16": "bf16 operands / f32 / f64; counts exact int32",
+                                       "fp16x2": "f16 hi+lo split (3 MMAs) / f32 / f64"}[args.operand],
+        "data": "synthetic",
+        "config": {
+            "workload": (f"make-grm {n} individuals x {m_file} SNPs ({m_kept} kept by the MAF>=0.01 extract list), "
+                         f"1% missing, seed {SEED}" + ("" if G == 1 else f"; weak scaling: n = 20000*sqrt({G})")),
+            "pair_snp_per_step": W, "chunk_snps": chunk, "cta_group": args.cg, "operand": args.operand,
+            "count_method": args.count,
+            "parallelism": "1 GPU" if G == 1 else f"{G} GPUs: lower-triangle tile sets, packed chunks all-gathered (NCCL)",
+            "l2": "inputs exceed L2 (packed rows + operand chunk + S/N tiles >> 126 MB)",
+        },
+        "pct_of_bf16_peak": {"burst": 100 * 2 * value / G / (peaks["bf16_tflops"] * 1e12),
+                             "sustained": 100 * 2 * value / G / (peaks["bf16_tflops_sustained"] * 1e12),
+                             "peaks": peaks["source"]},
+        "roofline": {"kernel": "grm_syrk_kernel (tcgen05 kind::f16)", "bound": "tensor", "achieved": achieved,
+                     "peak": peak, "peak_kind": f"bf16 sustained, {peaks['source']} (burst {peaks['bf16_tflops']})",
+                     "unit": "TFLOP/s", "frac": achieved / peak if achieved else None, "traffic": prof_traffic,
+                     "launches": syrk_launches, "avg_launch_ms": syrk_ms / max(syrk_launches, 1)},
+        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "e2e": e2e,
+    }
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------------
+    if G == 1 and not args.no_cpu:
+        try:
+            with tempfile.TemporaryDirectory(prefix="dgrm_cpu_") as wd:
+                make_cpu_sample(wd)
+                threads = cpu_threads()
+                r = reference_step(wd, threads)
+            v = r["W"] / (r["load_s"] + r["compute_s"])
+            out["cpu_baseline"] = {"value": v, "unit": "pair*SNP/s", "cores": threads, "kind": "reference",
+                                   "sample": sample_desc(r, threads)}
+        except Exception as ex:  # the baseline is reported, never required
+            out["cpu_baseline"] = {"value": None, "unit": "pair*SNP/s", "cores": cpu_threads(), "kind": "reference",
+                                   "sample": f"unavailable: {ex}"[:300]}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dgrm", choices=["dgrm", "reference"])
+    ap.add_argument("--n", type=int, default=0, help="override individuals (default 20000*sqrt(gpus))")
+    ap.add_argument("--m", type=int, default=0, help="override SNPs in the file (default 100000)")
+    ap.add_argument("--chunk", type=int, default=8192)
+    ap.add_argument("--cg", type=int, default=2)
+    ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16", "fp16x2"])
+    ap.add_argument("--count", default="mma", choices=["mma", "popc"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

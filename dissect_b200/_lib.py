@@ -5,8 +5,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdgrm.so")
 
-K_NUM = 6
-K_NAMES = ("count", "expand", "syrk", "paircnt", "final", "fetch")
+K_NUM = 7
+K_NAMES = ("count", "expand", "syrk", "paircnt", "final", "fetch", "gather")
 
 OPERANDS = {"fp16": 0, "bf16": 1, "fp16x2": 2}
 COUNT_METHODS = {"mma": 0, "popc": 1}
@@ -18,7 +18,7 @@ SYMBOLS = (
     "dgrm_set_individuals", "dgrm_begin", "dgrm_push_bed_host", "dgrm_push_bed_device",
     "dgrm_load_bed_file", "dgrm_finish", "dgrm_sync", "dgrm_num_snps", "dgrm_num_individuals",
     "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_low_overlap_pairs",
-    "dgrm_write_grm_dat", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles",
+    "dgrm_set_output_subset", "dgrm_write_grm_dat", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles",
     "dgrm_host_alloc", "dgrm_host_free", "dgrm_kernel_times",
 )
 
@@ -68,6 +68,7 @@ def load():
     lib.dgrm_bad_snps.argtypes = [vp, vp, i64, P(i64)]
     lib.dgrm_fetch_block_cyclic.argtypes = [vp, i32, vp, i64, i32, i32, i32, i32, i32, i32, C.c_char]
     lib.dgrm_low_overlap_pairs.argtypes = [vp, dbl, vp, i64, P(i64)]
+    lib.dgrm_set_output_subset.argtypes = [vp, vp, i64]
     lib.dgrm_write_grm_dat.argtypes = [vp, C.c_char_p]
     lib.dgrm_num_tiles.argtypes = [vp]
     lib.dgrm_num_tiles.restype = i64

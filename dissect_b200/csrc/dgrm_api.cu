@@ -61,6 +61,8 @@ struct dgrm_engine {
   double* d_S = nullptr;
   int32_t* d_N = nullptr;
   double* d_diag = nullptr;
+  int32_t* d_subset = nullptr;  // output subset (sanitizeKernel's filterIndividuals)
+  int64_t n_out = 0;
 
   // chunk state
   int kc_max = 0;
@@ -162,6 +164,8 @@ void release_geometry(dgrm_engine* e) {
   free_dev(e->d_S); e->d_S = nullptr;
   free_dev(e->d_N); e->d_N = nullptr;
   free_dev(e->d_diag); e->d_diag = nullptr;
+  free_dev(e->d_subset); e->d_subset = nullptr;
+  e->n_out = 0;
   free_dev(e->d_chunk); e->d_chunk = nullptr;
   free_dev(e->d_Z); e->d_Z = nullptr;
   free_dev(e->d_Q); e->d_Q = nullptr;
@@ -248,8 +252,9 @@ TileStore tile_store(const dgrm_engine* e) {
   ts.N = e->cfg.flat_norm ? nullptr : e->d_N;
   ts.index = e->d_index;
   ts.ncp = e->ncp;
-  ts.n = (int)e->n;
+  ts.n = (int)(e->d_subset ? e->n_out : e->n);
   ts.flat_n = (double)e->m;
+  ts.subset = e->d_subset;
   return ts;
 }
 
@@ -382,6 +387,7 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
       d_idx = e->d_rowidx[s];
     }
     {
+      Prof pr(e, DGRM_K_GATHER);
       const int nbytes = (int)(e->d_src_ind ? e->b_row : e->b_fam);
       const dim3 grid((unsigned)std::min<int64_t>((nbytes + 255) / 256, 64), (unsigned)take);
       bed_gather_kernel<<<grid, 256, 0, e->stream>>>(d_rows, pitch, d_idx, pos, take,
@@ -623,6 +629,12 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
   e->fill = 0;
   e->chunks_done = 0;
   e->finished = false;
+  if (e->d_subset) {
+    CK(cudaStreamSynchronize(e->stream));
+    free_dev(e->d_subset);
+    e->d_subset = nullptr;
+    e->n_out = 0;
+  }
   CK(cudaMemsetAsync(e->d_bad_count, 0, 4 * sizeof(int32_t), e->stream));
   CK(cudaMemsetAsync(e->d_diag, 0, (size_t)e->n_pad * sizeof(double), e->stream));
   // S / N tiles are overwritten (not accumulated) by the first chunk; clear them so that an empty
@@ -630,12 +642,6 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
   if (e->ntiles > 0) {
     CK(cudaMemsetAsync(e->d_S, 0, (size_t)e->ntiles * kTileElems * sizeof(double), e->stream));
     if (e->d_N) CK(cudaMemsetAsync(e->d_N, 0, (size_t)e->ntiles * kTileElems * sizeof(int32_t), e->stream));
-  }
-  for (int k = 0; k < DGRM_K_NUM; ++k) {
-    for (auto& p : e->ev[k]) e->ev_pool.push_back(p);
-    e->ev[k].clear();
-    e->ms_acc[k] = 0;
-    e->launches[k] = 0;
   }
   e->begun = true;
   return DGRM_OK;
@@ -842,8 +848,9 @@ int dgrm_fetch_block_cyclic(dgrm_engine* e, int which, double* local, int64_t ll
   CK(cudaSetDevice(e->cfg.device));
   CyclicGeom g;
   g.bs_r = bs_r; g.bs_c = bs_c; g.my_row = my_row; g.my_col = my_col; g.R = R; g.C = C;
-  g.nloc_r = numroc((int)e->n, bs_r, my_row, R);
-  g.nloc_c = numroc((int)e->n, bs_c, my_col, C);
+  const int n_vis = (int)(e->d_subset ? e->n_out : e->n);
+  g.nloc_r = numroc(n_vis, bs_r, my_row, R);
+  g.nloc_c = numroc(n_vis, bs_c, my_col, C);
   if (g.nloc_r == 0 || g.nloc_c == 0) return DGRM_OK;
   if (lld < g.nloc_r) return fail(e, DGRM_E_INVALID, "dgrm_fetch_block_cyclic: lld %lld < local rows %d", (long long)lld, g.nloc_r);
   const TileStore ts = tile_store(e);
@@ -941,7 +948,8 @@ int dgrm_low_overlap_pairs(dgrm_engine* e, double min_overlap, int64_t* pairs, i
   CK(cudaMalloc(&d_count, sizeof(unsigned long long)));
   if (cap > 0) CK(cudaMalloc(&d_pairs, (size_t)cap * 2 * sizeof(int64_t)));
   CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), e->stream));
-  const dim3 grid((unsigned)((e->n + 255) / 256), (unsigned)std::min<int64_t>(e->n, 32768));
+  const int64_t n_vis = e->d_subset ? e->n_out : e->n;
+  const dim3 grid((unsigned)((n_vis + 255) / 256), (unsigned)std::min<int64_t>(n_vis, 32768));
   low_overlap_kernel<<<grid, 256, 0, e->stream>>>(tile_store(e), min_overlap, d_pairs, cap, d_count);
   CK(cudaGetLastError());
   unsigned long long c = 0;
@@ -969,7 +977,7 @@ int dgrm_write_grm_dat(dgrm_engine* e, const char* path) {
     fclose(f);
     return fail(e, DGRM_E_IO, "short write to [ %s ]", path);
   }
-  const int n = (int)e->n;
+  const int n = (int)(e->d_subset ? e->n_out : e->n);
   const int64_t col_elems = (int64_t)n + 1;
   const int PC = (int)std::max<int64_t>(1, std::min<int64_t>(n, (64 << 20) / (col_elems * 8)));
   double* d_panel = nullptr;
@@ -997,6 +1005,29 @@ int dgrm_write_grm_dat(dgrm_engine* e, const char* path) {
   cudaFreeHost(h_panel);
   if (fclose(f) != 0 && rc == DGRM_OK) rc = fail(e, DGRM_E_IO, "close failed on [ %s ]", path);
   return rc;
+}
+
+int dgrm_set_output_subset(dgrm_engine* e, const int64_t* idx, int64_t count) {
+  int rc = check_ready(e, false);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->stream));
+  free_dev(e->d_subset);
+  e->d_subset = nullptr;
+  e->n_out = 0;
+  if (!idx || count <= 0) return DGRM_OK;
+  std::vector<int32_t> v((size_t)count);
+  int64_t prev = -1;
+  for (int64_t i = 0; i < count; ++i) {
+    if (idx[i] <= prev || idx[i] >= e->n)
+      return fail(e, DGRM_E_INVALID, "dgrm_set_output_subset: indices must be ascending and < %lld", (long long)e->n);
+    prev = idx[i];
+    v[(size_t)i] = (int32_t)idx[i];
+  }
+  CK(cudaMalloc(&e->d_subset, (size_t)count * sizeof(int32_t)));
+  CK(cudaMemcpy(e->d_subset, v.data(), (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice));
+  e->n_out = count;
+  return DGRM_OK;
 }
 
 int64_t dgrm_num_tiles(const dgrm_engine* e) { return e ? e->ntiles : 0; }
@@ -1062,6 +1093,8 @@ int dgrm_kernel_times(dgrm_engine* e, double ms[DGRM_K_NUM], int64_t launches[DG
     e->ev[k].clear();
     if (ms) ms[k] = e->ms_acc[k];
     if (launches) launches[k] = e->launches[k];
+    e->ms_acc[k] = 0;
+    e->launches[k] = 0;
   }
   cudaGetLastError();
   return DGRM_OK;

@@ -14,11 +14,13 @@ struct TileStore {
   const int32_t* N;       // [tiles][256][128], NULL with flat normalisation
   const int32_t* index;   // [nrb][ncp] -> storage index or -1 (not owned / above the diagonal)
   int ncp;                // column panels
-  int n;                  // individuals
+  int n;                  // individuals visible to fetch / pack (after an output subset)
   double flat_n;          // value of N under --grm-flat-norm
+  const int32_t* subset;  // visible index -> individual (ascending), NULL = identity
 };
 
 __device__ __forceinline__ int64_t tile_slot(const TileStore& ts, int r, int c) {
+  if (ts.subset) { r = ts.subset[r]; c = ts.subset[c]; }
   const int sidx = ts.index[(r >> 7) * ts.ncp + (c >> 8)];
   if (sidx < 0) return -1;
   return (int64_t)sidx * kTileElems + (int64_t)(c & 255) * kTileM + (r & 127);

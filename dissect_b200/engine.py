@@ -171,7 +171,7 @@ class GrmEngine:
     def fetch_block_cyclic(self, which="A", bs=(256, 256), grid=(1, 1), coords=(0, 0), uplo="L", out=None,
                            fill=np.nan):
         """Returns the caller-side local block (Fortran order, like Matrix::m)."""
-        n = self.num_individuals
+        n = getattr(self, "_n_out", None) or self.num_individuals
         nr = numroc(n, bs[0], coords[0], grid[0])
         nc = numroc(n, bs[1], coords[1], grid[1])
         if out is None:
@@ -191,6 +191,15 @@ class GrmEngine:
         cnt = C.c_int64(0)
         self._ck(self._lib.dgrm_low_overlap_pairs(self._h, float(min_overlap), pairs.ctypes.data, cap, C.byref(cnt)))
         return pairs[: min(cap, cnt.value)].copy(), cnt.value
+
+    def set_output_subset(self, idx=None):
+        if idx is None or len(idx) == 0:
+            self._ck(self._lib.dgrm_set_output_subset(self._h, None, 0))
+            self._n_out = None
+        else:
+            a = np.ascontiguousarray(idx, dtype=np.int64)
+            self._ck(self._lib.dgrm_set_output_subset(self._h, a.ctypes.data, len(a)))
+            self._n_out = len(a)
 
     def write_grm_dat(self, path):
         self._ck(self._lib.dgrm_write_grm_dat(self._h, str(path).encode()))

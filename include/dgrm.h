@@ -58,7 +58,8 @@ extern "C" {
 #define DGRM_K_PAIRCNT  3  /* pair count (fp8 tcgen05 or popcount)                            */
 #define DGRM_K_FINAL    4  /* diagonal fix-up                                                 */
 #define DGRM_K_FETCH    5  /* tile -> block-cyclic gather                                     */
-#define DGRM_K_NUM      6
+#define DGRM_K_GATHER   6  /* row / individual gather into the aligned chunk buffer           */
+#define DGRM_K_NUM      7
 
 typedef struct dgrm_engine dgrm_engine;
 
@@ -147,6 +148,12 @@ int dgrm_fetch_block_cyclic(dgrm_engine *e, int which, double *local, int64_t ll
 int dgrm_low_overlap_pairs(dgrm_engine *e, double min_overlap, int64_t *pairs, int64_t cap,
                            int64_t *count);
 
+/* Restrict every following fetch / write to the individuals idx[0..count) (ascending positions among
+ * the kept individuals), i.e. what Kernel::filterIndividuals leaves after sanitizeKernel removed
+ * individuals (kernel.cpp:2029-2033, 1378-1460): the matrices themselves are not recomputed.
+ * count == 0 or idx == NULL restores the full set. */
+int dgrm_set_output_subset(dgrm_engine *e, const int64_t *idx, int64_t count);
+
 /* Write <path> = the .grm.dat of Kernel::writeGRM (kernel.cpp:944-974): 14-byte header then
  * the packed (n+1) x n column-major array of matrix.cpp:2324-2334.  world must be 1. */
 int dgrm_write_grm_dat(dgrm_engine *e, const char *path);
@@ -161,8 +168,8 @@ int dgrm_fetch_tiles(dgrm_engine *e, int which, double *tiles /* [ntiles][128*25
 void *dgrm_host_alloc(int64_t bytes);
 void dgrm_host_free(void *p);
 
-/* Per-kernel-class device time (ms, CUDA events on the launching stream) and launch counts
- * accumulated since dgrm_begin; requires cfg.profile = 1. */
+/* Per-kernel-class device time (ms, CUDA events on the launching stream; needs cfg.profile = 1) and
+ * launch counts accumulated since the previous call (the call resets them). */
 int dgrm_kernel_times(dgrm_engine *e, double ms[DGRM_K_NUM], int64_t launches[DGRM_K_NUM]);
 
 #ifdef __cplusplus

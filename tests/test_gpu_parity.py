@@ -1,0 +1,348 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libdgrm.so via ctypes), against
+  * the golden fixtures the reference itself produced (tests/golden, oracle/make_golden.py),
+  * the oracle restatement on seeded inputs,
+  * size-independent properties (partition-sum invariance = the reference's test20, test.cpp:1677-1745;
+    symmetry of the count; chunk-size invariance of the exact quantities).
+Bars: allele counts, missingness, nNonMissing, N: bit-exact.  p1/p2/standardDev: 0 ulp.  A: the tolerance
+stated per operand format below, relative to the diagonal (mean diag(A) ~ 1)."""
+import os
+
+import numpy as np
+import pytest
+
+from dissect_b200 import DgrmError, GrmEngine, bedio
+from dissect_b200.engine import PinnedArray
+from oracle import grm_oracle as orc
+from tests.helpers import GOLDEN_GRM_CASES, kept_rows, load_case, lower_mask
+
+pytestmark = pytest.mark.gpu
+
+# max |A_gpu - A_ref| over the lower triangle (mean diag(A) ~ 1).  Operand rounding dominates and falls as
+# m^-1/2; measured on B200: fp16 1.9e-5 at m = 1e4, bf16 2.6e-4 at m = 3e3, split 2e-6.
+TOL_A = {"fp16": 3e-4, "bf16": 3e-3, "fp16x2": 5e-6}
+
+
+def tol_for(operand, m):
+    # scale the small-m bound by sqrt(1000/m), floor at the 1e4-SNP measurement
+    return TOL_A[operand] * max(0.25, min(2.0, (1000.0 / max(m, 1)) ** 0.5))
+
+
+def build(packed, n_fam, keep_mask=None, row_keep=None, **kw):
+    eng = GrmEngine(**kw)
+    eng.set_individuals(n_fam, keep_mask)
+    eng.begin(packed.shape[0])
+    eng.push_bed_host(np.ascontiguousarray(packed), row_keep=row_keep)
+    eng.finish()
+    return eng
+
+
+def fetch_all(eng):
+    n = eng.num_individuals
+    return {k: eng.fetch_block_cyclic(k, bs=(max(n, 1), max(n, 1))) for k in ("A", "S", "N")}
+
+
+def check_stats(st, ref):
+    assert np.array_equal(st["freq"], ref["freq"])
+    assert np.array_equal(st["nn"], ref["nn"])
+    for k in ("p1", "p2", "sd"):
+        assert np.array_equal(st[k].view(np.uint64), ref[k].view(np.uint64)), k
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("name", GOLDEN_GRM_CASES)
+def test_golden_reference_outputs(name, cg, tmp_path):
+    """Same inputs the reference binary consumed -> counts/N bit-exact, A within tolerance, .grm.dat layout."""
+    c = load_case(name)
+    eng = build(c["packed"], c["n_fam"], c["keep_mask"], c["snp_keep"], cta_group=cg, flat_norm=c["flat"],
+                chunk_snps=128 if name == "n258_m500_flat" else 8192)
+    check_stats(eng.snp_stats(), c["ref_stats"])
+    n = c["n"]
+    low = lower_mask(n)
+    got = fetch_all(eng)
+    assert np.array_equal(got["N"][low], c["ref_N"][low])
+    m = eng.num_snps
+    assert np.max(np.abs(got["A"][low] - c["ref_A"][low])) <= tol_for("fp16", m)
+    # exact fp64 diagonal of S (bed_expand) -> A_ii agrees far below the operand tolerance
+    assert np.max(np.abs(np.diag(got["A"]) - np.diag(c["ref_A"]))) <= 1e-12
+    # file writer: byte-identical header and N block, A block within tolerance
+    path = str(tmp_path / "out.grm.dat")
+    eng.write_grm_dat(path)
+    blob = open(path, "rb").read()
+    assert len(blob) == len(c["ref_dat"]) and blob[:14] == c["ref_dat"][:14]
+    A2, N2 = orc.unpack_grm_dat(blob, n)
+    assert np.array_equal(N2[low], c["ref_N"][low])
+    assert np.array_equal(A2[low], got["A"][low])
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 127, 128, 129, 255, 256, 257, 515])
+def test_counts_ragged_n(n):
+    """n mod 4 in {0,1,2,3}, n < 4, n around the 128 / 256 tile edges: padding bits never counted."""
+    m = 300
+    pk = bedio.synth_packed(n, m, 1000 + n, missing=0.1, ensure_poly=(n >= 2))
+    if n >= 2:
+        # set garbage in the padding bits of the last byte: must be ignored (genotype.cpp:733)
+        if n % 4:
+            pk[:, -1] |= np.uint8((0xFF << (2 * (n % 4))) & 0xFF)
+    codes = orc.decode_rows(pk, n)
+    ref = orc.snp_stats(codes)
+    eng = GrmEngine(chunk_snps=128)
+    eng.set_individuals(n)
+    eng.begin(m)
+    eng.push_bed_host(pk)
+    try:
+        eng.finish()
+    except DgrmError as ex:   # n = 1: every SNP is monomorphic or missing -> the reference's fatal errors
+        assert n < 2 and ex.code in (-5, -6)
+    st = eng.snp_stats()
+    assert np.array_equal(st["freq"], ref["freq"]) and np.array_equal(st["nn"], ref["nn"])
+    ok = ref["nn"] > 0
+    for k in ("p1", "p2", "sd"):
+        assert np.array_equal(st[k][ok].view(np.uint64), ref[k][ok].view(np.uint64)), k
+    eng.close()
+
+
+@pytest.mark.parametrize("operand,count,cg", [("fp16", "mma", 2), ("fp16", "mma", 1), ("bf16", "mma", 2),
+                                              ("fp16x2", "mma", 2), ("fp16", "popc", 1), ("fp16", "popc", 2)])
+def test_grm_vs_oracle_seeded(operand, count, cg):
+    n, m = 777, 3000
+    pk = bedio.synth_packed(n, m, 21, missing=0.02)
+    ref = orc.grm(orc.decode_rows(pk, n))
+    eng = build(pk, n, operand=operand, count_method=count, cta_group=cg, chunk_snps=1024)
+    check_stats(eng.snp_stats(), ref["stats"])
+    got = fetch_all(eng)
+    low = lower_mask(n)
+    assert np.array_equal(got["N"][low], ref["N"][low])
+    assert np.max(np.abs(got["A"][low] - ref["A"][low])) <= tol_for(operand, m)
+    assert np.max(np.abs(np.diag(got["S"]) - np.diag(ref["S"]))) <= 1e-9
+    eng.close()
+
+
+def test_config1_2000x10000():
+    """BASELINE.json configs[0]: 2,000 x 10,000, no missing — the reference's own CPU-runnable case."""
+    n, m = 2000, 10000
+    pk = bedio.synth_packed(n, m, 1, missing=0.0)
+    ref = orc.grm(orc.decode_rows(pk, n))
+    eng = build(pk, n)
+    check_stats(eng.snp_stats(), ref["stats"])
+    got = fetch_all(eng)
+    low = lower_mask(n)
+    assert np.array_equal(got["N"][low], ref["N"][low]) and np.all(got["N"][low] == m)
+    err = np.max(np.abs(got["A"][low] - ref["A"][low]))
+    assert err <= 5e-5, err      # measured 1.9e-5 (fp16 operands, m = 1e4)
+    eng.close()
+
+
+def test_partition_sum_invariance_and_chunking():
+    """The reference's test20 (test.cpp:1722-1729): a GRM from the merged file equals the sum over SNP
+    partitions: N exactly, S to accumulation order.  Here: one push vs. many ragged pushes, and chunk sizes."""
+    n, m = 300, 2500
+    pk = bedio.synth_packed(n, m, 33, missing=0.03)
+    a = build(pk, n, chunk_snps=8192)
+    b = GrmEngine(chunk_snps=256)
+    b.set_individuals(n)
+    b.begin(m)
+    cuts = [0, 1, 130, 131, 700, 1999, 2500]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        b.push_bed_host(np.ascontiguousarray(pk[lo:hi]))
+    b.finish()
+    ga, gb = fetch_all(a), fetch_all(b)
+    low = lower_mask(n)
+    assert np.array_equal(ga["N"][low], gb["N"][low])
+    check_stats(b.snp_stats(), a.snp_stats())
+    assert np.max(np.abs(ga["S"][low] - gb["S"][low])) <= 1e-3 * np.sqrt(m) / 50   # fp32 in-chunk accumulation order
+    assert np.array_equal(np.diag(ga["S"]) > 0, np.ones(n, bool))
+    a.close()
+    b.close()
+
+
+def test_keep_mask_and_extract_equal_physical_subset():
+    """--keep / --extract through masks == the same GRM built from a physically subsetted .bed."""
+    n_fam, m = 203, 600
+    pk = bedio.synth_packed(n_fam, m, 44, missing=0.02)
+    rng = np.random.default_rng(5)
+    keep = (rng.random(n_fam) < 0.8).astype(np.int32)
+    rows = (rng.random(m) < 0.7).astype(np.uint8)
+    codes = orc.decode_rows(pk[rows != 0], n_fam, keep)
+    ref = orc.grm(codes)
+    eng = build(pk, n_fam, keep, rows)
+    assert eng.num_individuals == int(keep.sum()) and eng.num_snps == int(rows.sum())
+    check_stats(eng.snp_stats(), ref["stats"])
+    got = fetch_all(eng)
+    low = lower_mask(int(keep.sum()))
+    assert np.array_equal(got["N"][low], ref["N"][low])
+    assert np.max(np.abs(got["A"][low] - ref["A"][low])) <= tol_for("fp16", int(rows.sum()))
+    eng.close()
+
+
+@pytest.mark.parametrize("bs,grid", [((3, 5), (2, 3)), ((16, 16), (2, 2)), ((256, 256), (1, 1)), ((7, 7), (3, 1))])
+def test_block_cyclic_fetch(bs, grid):
+    """Matrix::m layout (matrix.cpp:435-487, 1748-1758) incl. the odd tiny blocks of the reference's debug
+    runs (test.cpp:4444-4445); uplo 'L' leaves the upper triangle untouched, 'B' mirrors."""
+    n, m = 150, 400
+    pk = bedio.synth_packed(n, m, 55, missing=0.02)
+    eng = build(pk, n)
+    full = {k: eng.fetch_block_cyclic(k, bs=(n, n), uplo="B") for k in ("A", "N")}
+    assert np.allclose(full["A"], full["A"].T, equal_nan=False) and np.array_equal(full["N"], full["N"].T)
+    for pr in range(grid[0]):
+        for pc in range(grid[1]):
+            for which in ("A", "N"):
+                loc = eng.fetch_block_cyclic(which, bs=bs, grid=grid, coords=(pr, pc), uplo="L", fill=-7.0)
+                want = orc.block_cyclic_local(full[which], bs, grid, (pr, pc))
+                rows = [g for g in range(n) if (g // bs[0]) % grid[0] == pr]
+                cols = [g for g in range(n) if (g // bs[1]) % grid[1] == pc]
+                lowm = np.array([[gc <= gr for gc in cols] for gr in rows], bool).reshape(len(rows), len(cols))
+                assert np.array_equal(loc[lowm], want[lowm])
+                assert np.all(loc[~lowm] == -7.0)        # untouched, like pdsyrk_('L') leaves it
+    eng.close()
+
+
+def test_fetch_into_pinned_zero_copy():
+    n, m = 260, 500
+    pk = bedio.synth_packed(n, m, 66, missing=0.02)
+    eng = build(pk, n)
+    ref = eng.fetch_block_cyclic("A", bs=(n, n), uplo="L", fill=0.0)
+    pin = PinnedArray((n, n), np.float64, order="F")
+    pin.array[:] = 0.0
+    eng.fetch_into("A", pin.ptr, n, bs=(64, 64), uplo="L")
+    assert np.array_equal(pin.array, ref)
+    eng.close()
+
+
+def test_bad_snps_are_fatal_like_the_reference():
+    c = load_case("badsnp")
+    eng = GrmEngine()
+    eng.set_individuals(c["n_fam"])
+    eng.begin(c["m_file"])
+    eng.push_bed_host(c["packed"])
+    with pytest.raises(DgrmError) as ei:
+        eng.finish()
+    assert ei.value.code == -5 and "same genotype for all samples" in ei.value.msg
+    idx, cnt = eng.bad_snps()
+    assert [c["bim"][i] for i in idx] == open(os.path.join(c["dir"], "ref.badsnps")).read().split()
+    eng.close()
+
+
+def test_all_missing_snp_rejected():
+    n, m = 40, 10
+    pk = bedio.synth_packed(n, m, 77, missing=0.0)
+    pk[4, :] = 0x55          # every genotype missing -> p1 = 0/0 in the reference (genotype.cpp:736)
+    eng = GrmEngine()
+    eng.set_individuals(n)
+    eng.begin(m)
+    eng.push_bed_host(pk)
+    with pytest.raises(DgrmError) as ei:
+        eng.finish()
+    assert ei.value.code == -6
+    eng.close()
+
+
+def test_bed_file_header_checks(tmp_path):
+    n, m = 50, 64
+    pk = bedio.synth_packed(n, m, 88)
+    pre = str(tmp_path / "x")
+    bedio.write_bed(pre, pk, n)
+    eng = GrmEngine()
+    eng.set_individuals(n)
+    eng.begin(m)
+    eng.load_bed_file(pre + ".bed", m, snp_keep_idx=np.arange(0, m, 2))
+    eng.finish()
+    assert eng.num_snps == m // 2
+    ref = orc.grm(orc.decode_rows(pk[::2], n))
+    N = eng.fetch_block_cyclic("N", bs=(n, n))
+    assert np.array_equal(N[lower_mask(n)], ref["N"][lower_mask(n)])
+    for hdr, frag in ((b"\x00\x1b\x01", "not a valid binary BED"), (b"\x6c\x1b\x00", "Individual-major"),
+                      (b"\x6c\x1b\x07", "not specified whether")):
+        bad = str(tmp_path / "bad.bed")
+        with open(bad, "wb") as f:
+            f.write(hdr + pk.tobytes())
+        eng.begin(m)
+        with pytest.raises(DgrmError) as ei:
+            eng.load_bed_file(bad, m)
+        assert ei.value.code == -4 and frag in ei.value.msg
+    short = str(tmp_path / "short.bed")
+    with open(short, "wb") as f:
+        f.write(bedio.BED_MAGIC + pk.tobytes()[:-5])
+    eng.begin(m)
+    with pytest.raises(DgrmError) as ei:
+        eng.load_bed_file(short, m)
+    assert ei.value.code == -4
+    eng.close()
+
+
+def test_low_overlap_scan_and_output_subset():
+    """sanitizeKernel's scan (kernel.cpp:1993-2037) and filterIndividuals-style output subset."""
+    c = load_case("sanitize_remove")
+    eng = build(c["packed"], c["n_fam"])
+    pairs, cnt = eng.low_overlap_pairs(10.0)
+    codes = orc.decode_rows(c["packed"], c["n_fam"])
+    ref = orc.grm(codes)
+    want = orc.low_overlap_pairs(ref["N"], 10.0)
+    assert cnt == len(want) and sorted(map(tuple, pairs.tolist())) == want
+    kept_ids = [x[1] for x in c["ref_ids"]]
+    idx = [i for i, (fid, iid) in enumerate(c["fam"]) if iid in kept_ids]
+    eng.set_output_subset(idx)
+    k = len(idx)
+    A = eng.fetch_block_cyclic("A", bs=(k, k))
+    N = eng.fetch_block_cyclic("N", bs=(k, k))
+    low = lower_mask(k)
+    assert np.array_equal(N[low], c["ref_N"][low])
+    assert np.max(np.abs(A[low] - c["ref_A"][low])) <= 2e-3   # m = 60 SNPs only
+    eng.close()
+
+
+def test_two_engine_partition_covers_triangle_once():
+    """Multi-GPU tile partition emulated on one GPU: world = 3 engines, disjoint tile sets, union = triangle."""
+    from dissect_b200.engine import assemble_from_tiles
+    n, m = 700, 900
+    pk = bedio.synth_packed(n, m, 99, missing=0.02)
+    whole = build(pk, n)
+    ref = fetch_all(whole)
+    sets = {"A": [], "N": []}
+    seen = set()
+    for r in range(3):
+        e = build(pk, n, rank=r, world=3)
+        rc = e.tile_coords()
+        for t in map(tuple, rc.tolist()):
+            assert t not in seen
+            seen.add(t)
+        for k in sets:
+            sets[k].append((rc, e.fetch_tiles(k)))
+        e.close()
+    low = lower_mask(n)
+    for k in sets:
+        merged = assemble_from_tiles(n, sets[k])
+        assert np.array_equal(merged[low], ref[k][low]), k
+    whole.close()
+
+
+def test_config2_scale_properties():
+    """BASELINE.json configs[1] geometry at reduced m (20,000 individuals, 1% missing): properties that do not
+    need the oracle at full size — N symmetric-consistent with per-individual counts, trace(A) ~ n."""
+    import torch
+    from dissect_b200.synth import synth_packed_cuda
+    n, m = 20000, 4096
+    pk, maf = synth_packed_cuda(n, m, 2, maf_lo=0.001, maf_hi=0.5, missing=0.01)
+    keep = (maf >= 0.01).cpu().numpy().astype(np.uint8)
+    torch.cuda.synchronize()
+    eng = GrmEngine(chunk_snps=2048)
+    eng.set_individuals(n)
+    eng.begin(m)
+    eng.push_bed_device(pk.data_ptr(), pk.stride(0), m, row_keep=keep)
+    eng.finish()
+    st = eng.snp_stats()
+    mk = int(keep.sum())
+    assert st["freq"].shape[0] == mk and np.all(st["freq"].sum(axis=1) == n)
+    # N_ii = number of kept SNPs at which individual i is not missing = sum over SNPs of per-individual presence;
+    # sum_i N_ii must equal sum_k nNonMissing_k  (a checksum of checksums, exact)
+    Nfull = eng.fetch_block_cyclic("N", bs=(n, n), uplo="L", fill=0.0)
+    assert int(np.trace(Nfull)) == int(st["nn"].astype(np.int64).sum())
+    assert Nfull.max() <= mk and Nfull[np.tril_indices(n)].min() >= mk * 0.9
+    # column sums of the lower+upper N equal sum_k nn_k * present_ik  -> check one aggregate: sum of all N_ij
+    tot = 2 * np.tril(Nfull, -1).sum() + np.trace(Nfull)
+    assert int(tot) == int((st["nn"].astype(np.int64) ** 2).sum())
+    del Nfull
+    Afull = eng.fetch_block_cyclic("A", bs=(n, n), uplo="L", fill=0.0)
+    assert abs(np.trace(Afull) / n - 1.0) < 0.02
+    assert np.all(np.isfinite(Afull))
+    eng.close()
