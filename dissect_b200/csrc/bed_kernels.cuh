@@ -21,29 +21,36 @@ namespace dgrm {
 // src_ind == NULL: plain byte copy of nbytes per row.  Otherwise output individual i takes the 2-bit
 // field of .fam individual src_ind[i] (individualBEDIdxsMaskToKeep compaction, genotype.cpp:750-781).
 // ------------------------------------------------------------------------------------------------
+template <typename VecT>
 __global__ void bed_gather_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const int32_t* __restrict__ rows,
                                   int64_t row0, int nrows, uint8_t* __restrict__ dst, int64_t dst_pitch,
                                   int nbytes, const int32_t* __restrict__ src_ind, int n) {
+  constexpr int V = (int)sizeof(VecT);
   const int r = blockIdx.y;
   if (r >= nrows) return;
   const int64_t srow = rows ? (int64_t)rows[r] : row0 + r;
   const uint8_t* s = src + srow * src_pitch;
   uint8_t* d = dst + (int64_t)r * dst_pitch;
+  if (src_ind == nullptr) {
+    // plain row copy, VecT chosen by the host from the alignment of (src, src_pitch); dst rows are 128-aligned
+    const int nvec = nbytes / V;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nvec; b += gridDim.x * blockDim.x)
+      reinterpret_cast<VecT*>(d)[b] = __ldg(reinterpret_cast<const VecT*>(s) + b);
+    if (blockIdx.x == 0)
+      for (int b = nvec * V + threadIdx.x; b < nbytes; b += blockDim.x) d[b] = s[b];
+    return;
+  }
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbytes; b += gridDim.x * blockDim.x) {
-    if (src_ind == nullptr) {
-      d[b] = s[b];
-    } else {
-      uint32_t o = 0;
+    uint32_t o = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = 4 * b + j;
-        if (i < n) {
-          const int f = src_ind[i];
-          o |= (uint32_t)((s[f >> 2] >> (2 * (f & 3))) & 3) << (2 * j);
-        }
+    for (int j = 0; j < 4; ++j) {
+      const int i = 4 * b + j;
+      if (i < n) {
+        const int f = src_ind[i];
+        o |= (uint32_t)((s[f >> 2] >> (2 * (f & 3))) & 3) << (2 * j);
       }
-      d[b] = (uint8_t)o;
     }
+    d[b] = (uint8_t)o;
   }
 }
 

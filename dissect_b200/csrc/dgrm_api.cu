@@ -389,10 +389,19 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
     {
       Prof pr(e, DGRM_K_GATHER);
       const int nbytes = (int)(e->d_src_ind ? e->b_row : e->b_fam);
-      const dim3 grid((unsigned)std::min<int64_t>((nbytes + 255) / 256, 64), (unsigned)take);
-      bed_gather_kernel<<<grid, 256, 0, e->stream>>>(d_rows, pitch, d_idx, pos, take,
-                                                     e->d_chunk + (int64_t)e->fill * e->chunk_pitch, e->chunk_pitch,
-                                                     nbytes, e->d_src_ind, (int)e->n);
+      uint8_t* dst = e->d_chunk + (int64_t)e->fill * e->chunk_pitch;
+      const uint64_t align = (uint64_t)(uintptr_t)d_rows | (uint64_t)pitch;
+      const int vec = e->d_src_ind ? 1 : (align % 16 == 0 ? 16 : align % 8 == 0 ? 8 : align % 4 == 0 ? 4 : 1);
+      const int per_row = (nbytes / vec + 255) / 256;
+      const dim3 grid((unsigned)std::max(1, std::min(per_row, 64)), (unsigned)take);
+#define DGRM_GATHER(T)                                                                                            \
+  bed_gather_kernel<T><<<grid, 256, 0, e->stream>>>(d_rows, pitch, d_idx, pos, take, dst, e->chunk_pitch, nbytes, \
+                                                    e->d_src_ind, (int)e->n)
+      if (vec == 16) DGRM_GATHER(uint4);
+      else if (vec == 8) DGRM_GATHER(uint2);
+      else if (vec == 4) DGRM_GATHER(uint32_t);
+      else DGRM_GATHER(uint8_t);
+#undef DGRM_GATHER
       CK(cudaGetLastError());
       if (row_keep) CK(cudaEventRecord(e->rowidx_free[e->rowidx_i ^ 1], e->stream));
     }

@@ -1,0 +1,425 @@
+// Implementation of the host-side mirror (see host.h).  All GRM arithmetic happens in libdgrm.so.
+#include "host.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace dgrm_host {
+
+Communicator* communicator = new Communicator();
+Options options;
+Misc misc;
+
+void Misc::error(const std::string& e, int) const {
+  std::cerr << "\n**********************************\n" << e << "\n**********************************\n" << std::endl;
+  throw DissectError(e);
+}
+
+static void engine_check(dgrm_engine* e, int rc) {
+  if (rc != DGRM_OK) misc.error(dgrm_last_error(e), 0);
+}
+
+// ------------------------------------------------------------------------------------------ Options
+Options::Options()
+    : makeGRM(false), outFile("dissect"), flatGRMNormalization(false), minimumNumberOverlapingSNPs(10.),
+      maximumProportionOfElimitaedIndividuals(0.9), defaultBlockSize(256), device(0), operand(DGRM_OPERAND_FP16),
+      countMethod(DGRM_COUNT_MMA), chunkSNPs(8192), ctaGroup(2) {}
+
+void Options::parseOptions(int argc, char** argv) {
+  auto need = [&](int i) -> std::string {
+    if (i + 1 >= argc) misc.error(std::string("Error: The option ") + argv[i] + " needs an argument.", 0);
+    return argv[i + 1];
+  };
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "--make-grm") makeGRM = true;
+    else if (a == "--bfile") genotypeFile = need(i++);
+    else if (a == "--out") outFile = need(i++);
+    else if (a == "--extract") fileSNPsToKeep = need(i++);
+    else if (a == "--keep") fileIndividualsToKeep = need(i++);
+    else if (a == "--grm-flat-norm") flatGRMNormalization = true;
+    else if (a == "--min-overlap-snps") minimumNumberOverlapingSNPs = atof(need(i++).c_str());
+    else if (a == "--min-prop-grm-inds-kept") maximumProportionOfElimitaedIndividuals = atof(need(i++).c_str());
+    else if (a == "--default-block-size") {
+      defaultBlockSize = atoi(need(i++).c_str());
+      if (defaultBlockSize < 16 || defaultBlockSize > 4096)
+        misc.error("Error: --default-block-size is out of the range [16, 4096].", 0);
+    } else if (a == "--gpu-device") device = atoi(need(i++).c_str());
+    else if (a == "--gpu-operand") {
+      const std::string v = need(i++);
+      operand = v == "bf16" ? DGRM_OPERAND_BF16 : v == "fp16x2" ? DGRM_OPERAND_FP16X2 : DGRM_OPERAND_FP16;
+    } else if (a == "--gpu-count") countMethod = need(i++) == "popc" ? DGRM_COUNT_POPC : DGRM_COUNT_MMA;
+    else if (a == "--gpu-chunk-snps") chunkSNPs = atoi(need(i++).c_str());
+    else if (a == "--gpu-cta-group") ctaGroup = atoi(need(i++).c_str());
+    else misc.error("Error: Invalid option: " + a, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- Matrix
+static int numroc(int n, int nb, int iproc, int nprocs) {
+  const int nblocks = n / nb;
+  int r = (nblocks / nprocs) * nb;
+  const int extra = nblocks % nprocs;
+  if (iproc < extra) r += nb;
+  else if (iproc == extra) r += n % nb;
+  return r;
+}
+
+Matrix::Matrix(DistributionType dist)
+    : distribution(dist), m(NULL), nGlobRows(0), nGlobCols(0), nRows(0), nCols(0), nBlockRows(0), nBlockCols(0),
+      symmetric(false), uplo('B') {}
+
+Matrix::~Matrix() { delete[] m; }
+
+void Matrix::initParameters(int ngr, int ngc, int nbr, int nbc) {
+  delete[] m;
+  m = NULL;
+  nGlobRows = ngr; nGlobCols = ngc; nBlockRows = nbr; nBlockCols = nbc;
+  nRows = numroc(ngr, nbr, communicator->myRow, communicator->nProcRows);
+  nCols = numroc(ngc, nbc, communicator->myCol, communicator->nProcCols);
+  // the reference refuses local matrices beyond INT_MAX elements (matrix.cpp:1773-1779)
+  if ((double)nRows * (double)nCols > 2147483647.)
+    misc.error("Error: The local matrix is too large for this number of processes.", 0);
+  m = new (std::nothrow) double[(size_t)std::max(nRows, 1) * (size_t)std::max(nCols, 1)];
+  if (!m) misc.error("Error: Sorry, unable to allocate enough memory.", 0);
+}
+
+int Matrix::local2globalRow(int r) const {
+  return ((r / nBlockRows) * communicator->nProcRows + communicator->myRow) * nBlockRows + r % nBlockRows;
+}
+int Matrix::local2globalCol(int c) const {
+  return ((c / nBlockCols) * communicator->nProcCols + communicator->myCol) * nBlockCols + c % nBlockCols;
+}
+
+void Matrix::fillWithConstant(double v) {
+  for (size_t i = 0; i < (size_t)nRows * nCols; ++i) m[i] = v;
+}
+
+static void check_same_structure(const Matrix* a, const Matrix* b, const char* what) {
+  if (a->nGlobRows != b->nGlobRows || a->nGlobCols != b->nGlobCols || a->nRows != b->nRows || a->nCols != b->nCols ||
+      a->distribution != b->distribution || a->nBlockRows != b->nBlockRows || a->nBlockCols != b->nBlockCols)
+    misc.error(std::string("Error: An internal error was happened. Element wise ") + what +
+               " can not be performed on matrices with different structural properties.", 0);
+  if (a->symmetric != b->symmetric || a->uplo != b->uplo)
+    if ((a->symmetric && a->uplo != 'B') || (b->symmetric && b->uplo != 'B'))
+      misc.error(std::string("Error: An internal error was happened. Element wise ") + what +
+                 " can not be performed on matrices with different symmetry properties.", 0);
+}
+
+void Matrix::elementWiseDivision(Matrix* m1, double scale) {
+  check_same_structure(this, m1, "division");
+  // only the defined triangle is touched here (the reference sweeps the uninitialised half too)
+  for (int c = 0; c < nCols; ++c)
+    for (int r = 0; r < nRows; ++r) {
+      if (symmetric && uplo == 'L' && local2globalCol(c) > local2globalRow(r)) continue;
+      m[(size_t)c * nRows + r] *= scale / m1->m[(size_t)c * nRows + r];
+    }
+}
+
+void Matrix::elementWiseMultiplication(Matrix* m1, double scale) {
+  check_same_structure(this, m1, "multiplication");
+  for (int c = 0; c < nCols; ++c)
+    for (int r = 0; r < nRows; ++r) {
+      if (symmetric && uplo == 'L' && local2globalCol(c) > local2globalRow(r)) continue;
+      m[(size_t)c * nRows + r] *= scale * m1->m[(size_t)c * nRows + r];
+    }
+}
+
+// ----------------------------------------------------------------------------------------- Genotype
+static std::vector<std::vector<std::string> > read_table(const std::string& path, size_t min_cols) {
+  std::ifstream f(path.c_str());
+  if (!f) misc.error("Error: The file [ " + path + " ] does not exist or cannot be opened.", 0);
+  std::vector<std::vector<std::string> > rows;
+  std::string line;
+  while (std::getline(f, line)) {
+    std::istringstream ss(line);
+    std::vector<std::string> t;
+    std::string w;
+    while (ss >> w) t.push_back(w);
+    if (t.empty()) continue;
+    if (t.size() < min_cols) misc.error("Error: The file [ " + path + " ] has a line with too few columns.", 0);
+    rows.push_back(t);
+  }
+  return rows;
+}
+
+Genotype::Genotype(const std::string& fname) : nSNPs(0), nIndividuals(0), normalized(false), bedFile(fname + ".bed"), nBEDSNPs(0), nBEDIndividuals(0) {
+  std::set<std::string> keepSNPs, keepInds;
+  if (!options.fileSNPsToKeep.empty()) {
+    *misc.message << "Only SNPs specified in file [ " << options.fileSNPsToKeep << " ] will be kept." << std::endl;
+    for (auto& r : read_table(options.fileSNPsToKeep, 1)) keepSNPs.insert(r[0]);
+  }
+  if (!options.fileIndividualsToKeep.empty()) {
+    *misc.message << "Only individuals specified in file [ " << options.fileIndividualsToKeep << " ] will be kept." << std::endl;
+    for (auto& r : read_table(options.fileIndividualsToKeep, 2)) keepInds.insert(r[0] + "@" + r[1]);
+  }
+  readBIMFile(fname, keepSNPs);
+  readFAMFile(fname, keepInds);
+  if (nSNPs == 0 || nIndividuals == 0)
+    misc.error("Error: There are 0 SNPs and/or 0 individuals kept for the analysis. Aborting...", 0);
+}
+
+void Genotype::readBIMFile(const std::string& f, const std::set<std::string>& keepSNPs) {
+  *misc.message << "Reading SNPs data from file [ " << f << ".bim ] ..." << std::endl;
+  std::ifstream file((f + ".bim").c_str());
+  if (!file) misc.error("Error: The file [ " + f + ".bim ] does not exist or cannot be opened.", 0);
+  std::set<std::string> seen;
+  std::string line;
+  int ibed = 0;
+  while (std::getline(file, line)) {
+    std::istringstream ss(line);
+    std::string t[6];
+    ss >> t[0] >> t[1] >> t[2] >> t[3] >> t[4] >> t[5];
+    if (t[1].empty()) continue;
+    if (!keepSNPs.empty() && keepSNPs.find(t[1]) == keepSNPs.end()) { ++ibed; continue; }
+    SNPsBEDIdxsToKeep.push_back(ibed++);
+    SNP s;
+    s.chr = t[0]; s.name = t[1]; s.position = atoi(t[3].c_str()); s.allele1 = t[4]; s.allele2 = t[5];
+    s.nNonMissing = 0; s.frequencies[0] = s.frequencies[1] = s.frequencies[2] = s.frequencies[3] = 0;
+    s.p1 = s.p2 = s.standardDev = 0.;
+    if (!seen.insert(s.name).second)
+      misc.error("Error: The SNP with name: " + s.name + " appears more than one time in the genotypes BIM file.", 0);
+    SNPs.push_back(s);
+    SNPIds.push_back(s.name);
+  }
+  nBEDSNPs = ibed;
+  nSNPs = (int)SNPs.size();
+  if (keepSNPs.empty()) {
+    *misc.message << nSNPs << " SNPs found." << std::endl;
+    SNPsBEDIdxsToKeep.clear();
+  } else {
+    *misc.message << ibed << " SNPs found. " << nSNPs << " kept for the analysis." << std::endl;
+  }
+}
+
+void Genotype::readFAMFile(const std::string& f, const std::set<std::string>& keepInds) {
+  *misc.message << "Reading Individuals data from file [ " << f << ".fam ] ..." << std::endl;
+  std::ifstream file((f + ".fam").c_str());
+  if (!file) misc.error("Error: The file [ " + f + ".fam ] does not exist or cannot be opened.", 0);
+  std::set<std::string> seen;
+  std::string line;
+  while (std::getline(file, line)) {
+    std::istringstream ss(line);
+    Individual ind;
+    ss >> ind.familyID >> ind.individualID >> ind.paternalID >> ind.maternalID >> ind.sex;
+    if (ind.familyID.empty()) continue;
+    if ((ss >> ind.phenotype).fail())
+      misc.error("Error. The phenotype of the individual " + ind.familyID + " " + ind.individualID + " is not an integer.", 0);
+    const std::string key = ind.familyID + "@" + ind.individualID;
+    if (!keepInds.empty() && keepInds.find(key) == keepInds.end()) { individualBEDIdxsMaskToKeep.push_back(0); continue; }
+    individualBEDIdxsMaskToKeep.push_back(1);
+    if (!seen.insert(key).second)
+      misc.error("Error: The individual with family Id: " + ind.familyID + " and individual Id: " + ind.individualID +
+                 " appears more than one time in the genotypes FAM file.", 0);
+    individuals.push_back(ind);
+    individualIds.push_back(key);
+  }
+  nBEDIndividuals = (int)individualBEDIdxsMaskToKeep.size();
+  nIndividuals = (int)individuals.size();
+  if (keepInds.empty()) *misc.message << nIndividuals << " individuals found." << std::endl;
+  else *misc.message << nBEDIndividuals << " individuals found. " << nIndividuals << " kept for the analysis." << std::endl;
+}
+
+// ------------------------------------------------------------------------------------------- Kernel
+Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
+    : type(kernelGRM), name("default"), kernel(NULL), N(NULL), normalized(false), diagonalized(false), asymmetric(false),
+      nIndividuals(genotype->nIndividuals), eng_(NULL) {
+  for (int i = 0; i < genotype->nIndividuals; ++i) {
+    individuals.push_back(genotype->individuals[i]);
+    const std::string key = genotype->individualIds[i];
+    individualIds.push_back(key);
+    if (individualIdsIdx.count(key))
+      misc.error("Error: The individual with family Id: " + genotype->individuals[i].familyID + " and individual Id: " +
+                 genotype->individuals[i].individualID + " appears more than one time in the genotypes.", 0);
+    individualIdsIdx[key] = i;
+  }
+  randomVarNames = genotype->SNPIds;
+
+  *misc.message << "Starting GRM computation..." << std::endl;
+  dgrm_config cfg;
+  dgrm_default_config(&cfg);
+  cfg.device = options.device;
+  cfg.operand = options.operand;
+  cfg.count_method = options.countMethod;
+  cfg.flat_norm = options.flatGRMNormalization ? 1 : 0;
+  cfg.chunk_snps = options.chunkSNPs;
+  cfg.cta_group = options.ctaGroup;
+  if (dgrm_create(&cfg, &eng_) != DGRM_OK) misc.error(dgrm_last_error(NULL), 0);
+  engine_check(eng_, dgrm_set_individuals(eng_, genotype->nBEDIndividuals, genotype->individualBEDIdxsMaskToKeep.data()));
+  engine_check(eng_, dgrm_begin(eng_, genotype->nSNPs));
+  *misc.message << "Reading genotype data from file [ " << genotype->bedFile << " ] ..." << std::endl;
+  std::vector<int64_t> keepIdx(genotype->SNPsBEDIdxsToKeep.begin(), genotype->SNPsBEDIdxsToKeep.end());
+  engine_check(eng_, dgrm_load_bed_file(eng_, genotype->bedFile.c_str(), genotype->nBEDSNPs,
+                                        keepIdx.empty() ? NULL : keepIdx.data(), (int64_t)keepIdx.size()));
+  const int rc = dgrm_finish(eng_);
+  // per-SNP records, as gatherSNPData leaves them on the root (genotype.cpp:859-870)
+  {
+    const int m = genotype->nSNPs;
+    std::vector<int32_t> freq((size_t)m * 4), nn(m);
+    std::vector<double> p1(m), p2(m), sd(m);
+    engine_check(eng_, dgrm_snp_stats(eng_, freq.data(), nn.data(), p1.data(), p2.data(), sd.data()));
+    for (int k = 0; k < m; ++k) {
+      SNP& s = genotype->SNPs[k];
+      for (int c = 0; c < 4; ++c) s.frequencies[c] = freq[(size_t)k * 4 + c];
+      s.nNonMissing = nn[k]; s.p1 = p1[k]; s.p2 = p2[k]; s.standardDev = sd[k];
+    }
+  }
+  if (rc == DGRM_E_BADSNP) {
+    // genotype.cpp:924-939: list the offenders in <out>.badsnps, then fail
+    int64_t cnt = 0;
+    std::vector<int64_t> idx(65536);
+    dgrm_bad_snps(eng_, idx.data(), (int64_t)idx.size(), &cnt);
+    std::ofstream bad((options.outFile + ".badsnps").c_str());
+    for (int64_t i = 0; i < std::min<int64_t>(cnt, (int64_t)idx.size()); ++i) bad << genotype->SNPs[(size_t)idx[i]].name << std::endl;
+    *misc.message << "The SNPs are stored in the file [ " << options.outFile + ".badsnps" << " ]." << std::endl;
+  }
+  engine_check(eng_, rc);
+  genotype->normalized = true;  // the standardised values exist (on the GPU) from here on
+  if (!options.flatGRMNormalization)
+    *misc.message << "GRM will be normalized using the individuals shared non-missing SNPs." << std::endl;
+  else
+    *misc.message << "GRM will be normalized for all individuals by the total number of SNPs: " << double(genotype->nSNPs) << "." << std::endl;
+  normalized = normalizeGRM;
+  fetch();
+  *misc.message << "GRM computation finished." << std::endl;
+}
+
+Kernel::~Kernel() {
+  delete kernel;
+  delete N;
+  if (eng_) dgrm_destroy(eng_);
+}
+
+// (Re)fill kernel and N from the device tile store in this rank's block-cyclic layout.
+void Kernel::fetch() {
+  delete kernel; delete N;
+  kernel = new Matrix(cyclicDistribution);
+  N = new Matrix(cyclicDistribution);
+  const int bs = communicator->nDefaultBlockRows;
+  kernel->initParameters(nIndividuals, nIndividuals, bs, communicator->nDefaultBlockCols);
+  N->initParameters(nIndividuals, nIndividuals, bs, communicator->nDefaultBlockCols);
+  kernel->symmetric = N->symmetric = true;
+  kernel->uplo = N->uplo = 'L';  // matrix.cpp:2679-2680; kernel.cpp:105-108 for the flat case
+  engine_check(eng_, dgrm_fetch_block_cyclic(eng_, normalized ? DGRM_FETCH_A : DGRM_FETCH_S, kernel->m, std::max(kernel->nRows, 1),
+                                             kernel->nBlockRows, kernel->nBlockCols, communicator->myRow, communicator->myCol,
+                                             communicator->nProcRows, communicator->nProcCols, 'L'));
+  engine_check(eng_, dgrm_fetch_block_cyclic(eng_, DGRM_FETCH_N, N->m, std::max(N->nRows, 1), N->nBlockRows, N->nBlockCols,
+                                             communicator->myRow, communicator->myCol, communicator->nProcRows,
+                                             communicator->nProcCols, 'L'));
+}
+
+void Kernel::normalize() {
+  if (normalized) return;
+  if (diagonalized) misc.error("Error: Diagonalized Kernel cannot be normalized.", 0);
+  if (!N) misc.error("Error: An internal error was happened. GRM cannot be normalized because normalization matrix is not present.", 0);
+  if (N->uplo != kernel->uplo)
+    misc.error("Error: An internal error was happened when normalizing a GRM. GRM and normalization matrix should have same uplo properties.", 0);
+  kernel->elementWiseDivision(N);
+  normalized = true;
+}
+
+void Kernel::denormalize() {
+  if (!normalized) return;
+  if (diagonalized) misc.error("Error: Diagonalized Kernel cannot be unnormalized.", 0);
+  kernel->elementWiseMultiplication(N);
+  normalized = false;
+}
+
+// kernel.cpp:1861-1926, order-dependent greedy; pairs arrive as (row, col) then (col, row) per hit, hits in
+// column-major scan order of the lower triangle (matrix.cpp:4348-4377 on one rank).
+std::vector<std::string> Kernel::minimumIndividualsRemovePairs(const std::vector<int>& g1, const std::vector<int>& g2) {
+  std::vector<int> freq(nIndividuals, 0);
+  for (size_t i = 0; i < g1.size(); ++i)
+    if (g1[i] != g2[i]) { freq[g1[i]]++; freq[g2[i]]++; }
+  std::set<int> del;
+  for (size_t i = 0; i < g1.size(); ++i) {
+    if (g1[i] == g2[i]) continue;
+    if (freq[g1[i]] < freq[g2[i]]) {
+      if (del.find(g1[i]) == del.end()) del.insert(g2[i]);
+    } else {
+      if (del.find(g2[i]) == del.end()) del.insert(g1[i]);
+    }
+  }
+  std::vector<std::string> keep;
+  for (int i = 0; i < nIndividuals; ++i)
+    if (del.find(i) == del.end()) keep.push_back(individualIds[i]);
+  return keep;
+}
+
+bool Kernel::sanitizeKernel() {
+  if (!N) misc.error("Error: An internal error was happened. Kernel cannot be checked without the normalization matrix.", 0);
+  int64_t cnt = 0;
+  engine_check(eng_, dgrm_low_overlap_pairs(eng_, options.minimumNumberOverlapingSNPs, NULL, 0, &cnt));
+  std::vector<int64_t> pairs((size_t)std::max<int64_t>(cnt, 1) * 2);
+  if (cnt > 0) engine_check(eng_, dgrm_low_overlap_pairs(eng_, options.minimumNumberOverlapingSNPs, pairs.data(), cnt, &cnt));
+  std::vector<std::pair<int, int> > hits;  // (col, row) so that sorting gives the column-major scan order
+  for (int64_t i = 0; i < cnt; ++i) hits.push_back(std::make_pair((int)pairs[2 * i + 1], (int)pairs[2 * i]));
+  std::sort(hits.begin(), hits.end());
+  std::vector<int> i1, i2;
+  for (size_t i = 0; i < hits.size(); ++i) {
+    i1.push_back(hits[i].second); i2.push_back(hits[i].first);
+    i1.push_back(hits[i].first);  i2.push_back(hits[i].second);
+  }
+  const std::vector<std::string> keep = minimumIndividualsRemovePairs(i1, i2);
+  const double proportion = double(keep.size()) / double(nIndividuals);
+  if (proportion < options.maximumProportionOfElimitaedIndividuals) {
+    *misc.message << "More than 10% of the individuals have to be removed for not having an overlaping of at least "
+                  << int(options.minimumNumberOverlapingSNPs) << " SNPs on all pairs. Skipping this GRM." << std::endl;
+    return false;
+  }
+  if (keep.size() == 1) {
+    *misc.message << "Sorry, not enough individuals have an overlaping of at least " << int(options.minimumNumberOverlapingSNPs)
+                  << " SNPs. Skipping this GRM." << std::endl;
+    return false;
+  }
+  if ((int)keep.size() != nIndividuals) {
+    *misc.message << nIndividuals - keep.size() << " individuals will be removed since they do not have at least "
+                  << options.minimumNumberOverlapingSNPs << " overlapping non-missing SNPs." << std::endl;
+    filterIndividuals(keep);
+  }
+  return true;
+}
+
+// kernel.cpp:1378-1460: rows/columns of the already computed matrices are dropped; nothing is recomputed.
+void Kernel::filterIndividuals(const std::vector<std::string>& keepIds) {
+  std::set<std::string> keep(keepIds.begin(), keepIds.end());
+  std::vector<long long> base = subset_;
+  if (base.empty()) for (int i = 0; i < nIndividuals; ++i) base.push_back(i);
+  std::vector<long long> next;
+  std::vector<Individual> inds;
+  std::vector<std::string> ids;
+  for (int i = 0; i < nIndividuals; ++i)
+    if (keep.count(individualIds[i])) { next.push_back(base[i]); inds.push_back(individuals[i]); ids.push_back(individualIds[i]); }
+  subset_ = next;
+  individuals = inds;
+  individualIds = ids;
+  individualIdsIdx.clear();
+  for (size_t i = 0; i < ids.size(); ++i) individualIdsIdx[ids[i]] = (int)i;
+  nIndividuals = (int)ids.size();
+  std::vector<int64_t> idx(subset_.begin(), subset_.end());
+  engine_check(eng_, dgrm_set_output_subset(eng_, idx.data(), (int64_t)idx.size()));
+  fetch();
+}
+
+void Kernel::writeGRM(const std::string& f) {
+  if (asymmetric) misc.error("Error: An internal error was happened. This operation can not be performed on an asymmetric GRM", 0);
+  if (!normalized) misc.error("Error: An internal error was happened. GRM can only be stored in normalized form.", 0);
+  if (!N) misc.error("Error: An internal error was happened. GRM can only be stored when N information is stored.", 0);
+  *misc.message << "Writing GRM on [ " << f << ".grm.(ids/snps/dat) ]..." << std::endl;
+  if (communicator->mpiRoot) {
+    std::ofstream ids((f + ".grm.ids").c_str());
+    for (int i = 0; i < nIndividuals; ++i) ids << individuals[i].familyID << " " << individuals[i].individualID << std::endl;
+    std::ofstream snps((f + ".grm.snps").c_str());
+    for (size_t i = 0; i < randomVarNames.size(); ++i) snps << randomVarNames[i] << std::endl;
+  }
+  // packMatrices + writeMatrixMPI funnel every block through rank 0 in the reference (matrix.cpp:2308-2341);
+  // here the device packs the (n+1) x n array directly
+  engine_check(eng_, dgrm_write_grm_dat(eng_, (f + ".grm.dat").c_str()));
+  *misc.message << "GRM stored." << std::endl;
+}
+
+}  // namespace dgrm_host

@@ -1,0 +1,150 @@
+// Host-side mirror of the reference's interface for the `--make-grm` path, on top of the C ABI
+// (include/dgrm.h).  Same class names, member names and argument meaning as the reference so that the rest
+// of DISSECT (reml, multireml, gwas, pca) would use the result unchanged:
+//   Options      options.h:  the flag subset of SURVEY.md §2.1 (options.cpp:268-1183)
+//   Communicator communicator.h: process-grid description only (no MPI here; one engine per rank)
+//   Misc         misc.h: message stream + error() (misc.cpp:151-170)
+//   Matrix       matrix.h:79-963: cyclicDistribution local piece, numroc/local2global, symmetric/uplo
+//   Genotype     genotype.h:109-399: .bim/.fam/.bed metadata, --extract/--keep, per-SNP `SNP` records
+//   Kernel       kernel.h:49-379: kernel, N, ids, normalize/denormalize, sanitizeKernel, writeGRM
+// Differences are deliberate and listed in INTEGRATION.md: the genotype/missings fp64 matrices are never
+// materialised on the host (they live as 2-bit rows + tensor-core operands on the GPU).
+#ifndef DGRM_HOST_H
+#define DGRM_HOST_H
+
+#include <iostream>
+#include <map>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/dgrm.h"
+
+namespace dgrm_host {
+
+struct DissectError : std::runtime_error {
+  explicit DissectError(const std::string& m) : std::runtime_error(m) {}
+};
+
+struct Options {
+  bool makeGRM;
+  std::string genotypeFile;            // --bfile
+  std::string outFile;                 // --out            (default "dissect", options.cpp:60)
+  std::string fileSNPsToKeep;          // --extract
+  std::string fileIndividualsToKeep;   // --keep
+  bool flatGRMNormalization;           // --grm-flat-norm  (options.cpp:533-537)
+  double minimumNumberOverlapingSNPs;  // --min-overlap-snps (default 10, options.cpp:80)
+  double maximumProportionOfElimitaedIndividuals;  // --min-prop-grm-inds-kept (default 0.9, options.cpp:81)
+  int defaultBlockSize;                // --default-block-size (16..4096, default 256, options.cpp:244)
+  // engine knobs (no counterpart in the reference)
+  int device, operand, countMethod, chunkSNPs, ctaGroup;
+  Options();
+  void parseOptions(int argc, char** argv);
+};
+
+struct Communicator {
+  int nProcRows, nProcCols, myRow, myCol;  // BLACS grid coordinates (communicator.cpp:66-103)
+  int nDefaultBlockRows, nDefaultBlockCols;
+  bool mpiRoot;
+  Communicator() : nProcRows(1), nProcCols(1), myRow(0), myCol(0), nDefaultBlockRows(256), nDefaultBlockCols(256), mpiRoot(true) {}
+};
+
+struct Misc {
+  std::ostream* message;
+  Misc() : message(&std::cout) {}
+  // misc.cpp:151-170: prints and aborts the job; here it throws so callers (tests, the CLI) can decide
+  [[noreturn]] void error(const std::string& e, int) const;
+};
+
+extern Communicator* communicator;
+extern Options options;
+extern Misc misc;
+
+enum DistributionType { global, cyclicDistribution, diagonalDistribution };
+
+class Matrix {
+ public:
+  DistributionType distribution;
+  double* m;  // local column-major block, new double[nRows*nCols] (matrix.cpp:1646); owned, delete[]
+  int nGlobRows, nGlobCols, nRows, nCols, nBlockRows, nBlockCols;
+  bool symmetric;
+  char uplo;  // 'L', 'U' or 'B'
+  explicit Matrix(DistributionType dist = cyclicDistribution);
+  ~Matrix();
+  void initParameters(int ngr, int ngc, int nbr, int nbc);  // matrix.cpp:1700-1782 (numroc, allocation)
+  int local2globalRow(int r) const;                          // matrix.cpp:435-475
+  int local2globalCol(int c) const;
+  void fillWithConstant(double v);                           // matrix.cpp:125-137
+  void elementWiseDivision(Matrix* m1, double scale = 1.);   // matrix.cpp:4074-4099
+  void elementWiseMultiplication(Matrix* m1, double scale = 1.);
+ private:
+  Matrix(const Matrix&);
+  Matrix& operator=(const Matrix&);
+};
+
+struct SNP {  // genotype.h:56-72
+  std::string chr, name, allele1, allele2;
+  int position;
+  int nNonMissing;
+  int frequencies[4];
+  double p1, p2, standardDev;
+};
+
+struct Individual {  // genotype.h:85-95
+  std::string familyID, individualID, paternalID, maternalID, sex;
+  int phenotype;
+};
+
+class Genotype {
+ public:
+  int nSNPs, nIndividuals;
+  std::vector<SNP> SNPs;
+  std::vector<std::string> SNPIds;
+  std::vector<Individual> individuals;
+  std::vector<std::string> individualIds;
+  bool normalized;
+  // .bed selection exactly as readBIMFile/readFAMFile leave it (genotype.cpp:392-546)
+  std::string bedFile;
+  int nBEDSNPs, nBEDIndividuals;
+  std::vector<int> SNPsBEDIdxsToKeep;            // empty = all (genotype.cpp:452-456)
+  std::vector<int> individualBEDIdxsMaskToKeep;  // one flag per .fam line (genotype.cpp:750)
+  explicit Genotype(const std::string& fname);   // genotype.cpp:110 -> load :276 (metadata; rows stream later)
+ private:
+  void readBIMFile(const std::string& f, const std::set<std::string>& keepSNPs);
+  void readFAMFile(const std::string& f, const std::set<std::string>& keepIndividualIds);
+};
+
+enum KernelType { kernelGRM };
+
+class Kernel {
+ public:
+  KernelType type;
+  std::string name;
+  Matrix* kernel;  // A (normalized) or S (not), cyclicDistribution, symmetric, uplo 'L'
+  Matrix* N;       // pair counts (or m under --grm-flat-norm), same structure
+  bool normalized, diagonalized, asymmetric;
+  int nIndividuals;
+  std::vector<Individual> individuals;
+  std::vector<std::string> individualIds;
+  std::map<std::string, int> individualIdsIdx;
+  std::vector<std::string> randomVarNames;  // = genotype->SNPIds (kernel.cpp:85)
+  Kernel(Genotype* genotype, bool normalizeGRM = true);  // kernel.cpp:61-125, computed on the GPU
+  ~Kernel();
+  void normalize();      // kernel.cpp:382-414
+  void denormalize();    // kernel.cpp:416-448
+  bool sanitizeKernel(); // kernel.cpp:1993-2037
+  void writeGRM(const std::string& f);  // kernel.cpp:893-1009 (.grm.ids / .grm.snps / .grm.dat)
+  dgrm_engine* engine() { return eng_; }
+ private:
+  dgrm_engine* eng_;
+  std::vector<long long> subset_;  // individuals (positions) still in the kernel after sanitizeKernel
+  void fetch();
+  std::vector<std::string> minimumIndividualsRemovePairs(const std::vector<int>& i1, const std::vector<int>& i2);
+  void filterIndividuals(const std::vector<std::string>& keepIds);
+  Kernel(const Kernel&);
+  Kernel& operator=(const Kernel&);
+};
+
+}  // namespace dgrm_host
+#endif
