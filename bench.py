@@ -45,40 +45,59 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    """Samples SM clock, power and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
-        self.index = index
-        self.rows = []
-        self.proc = None
+        self.index, self.period = index, period
+        self.sm, self.power, self.reasons = [], [], 0
+        self.max_sm = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap ordinals; the boxes expose GPUs in order, so index == ordinal
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
 
     def run(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-        except Exception:
-            pass
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                self.reasons |= nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        reasons = []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for i, nm in enumerate(names):
-            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
-                reasons.append(nm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": len(self.sm)}
+        if self.sm:
+            s = sorted(self.sm)
+            out["sm_mhz"] = s[len(s) // 2]
+            out["sm_mhz_min"] = s[0]
+            out["power_w_max"] = max(self.power) if self.power else None
+        if self.ok:
+            nv = self.nv
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            out["reasons"] = [k for k, bit in names.items() if self.reasons & bit]
+        return out
 
 
 def reference_step(workdir, threads):
@@ -224,7 +243,7 @@ def run_gpu(args):
     host_pk.array[:] = pk_all.cpu().numpy()
 
     eng = GrmEngine(device=local, rank=rank, world=world, operand=args.operand, count_method=args.count,
-                    chunk_snps=chunk, cta_group=args.cg, profile=True)
+                    chunk_snps=chunk, cta_group=args.cg, profile=True, resident_chunks=args.resident)
     eng.set_individuals(n)
 
     def push_device_resident():
@@ -281,12 +300,15 @@ def run_gpu(args):
         A_host = PinnedArray((n, n), np.float64, order="F")
         N_host = PinnedArray((n, n), np.float64, order="F")
 
+        # the caller's Matrix::m buffers are bound once; every dgrm_finish streams the finished tile groups
+        # into them while later groups are still on the tensor cores
+        eng.bind_output("A", A_host.ptr, n, bs=(256, 256), uplo="L")
+        eng.bind_output("N", N_host.ptr, n, bs=(256, 256), uplo="L")
+
         def step_e2e():
             eng.begin(m_kept)
             eng.push_bed_host(host_pk.ptr, row_keep=keep, pitch=bpr, nrows=m_file)
             eng.finish()
-            eng.fetch_into("A", A_host.ptr, n, bs=(256, 256), uplo="L")
-            eng.fetch_into("N", N_host.ptr, n, bs=(256, 256), uplo="L")
 
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
@@ -302,6 +324,7 @@ def run_gpu(args):
                "h2d_bytes_per_step": int(m_file * bpr), "d2h_bytes_per_step": int(2 * tri * 8),
                "result": "A and N lower triangles (fp64) into pinned block-cyclic Matrix::m buffers, bs 256, 1x1 grid",
                "check_trace_A": float(np.trace(A_host.array[:2000, :2000]))}
+        eng.unbind_outputs()
     elif G > 1 and not args.no_e2e:
         # per-rank H2D of its row shards + all-gather + compute + D2H of the tiles this rank owns
         ntl = eng.num_tiles
@@ -409,7 +432,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dgrm", choices=["dgrm", "reference"])
     ap.add_argument("--n", type=int, default=0, help="override individuals (default 20000*sqrt(gpus))")
@@ -418,6 +441,7 @@ def main():
     ap.add_argument("--cg", type=int, default=2)
     ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16", "fp16x2"])
     ap.add_argument("--count", default="mma", choices=["mma", "popc"])
+    ap.add_argument("--resident", type=int, default=0, help="resident chunk slots (0 = auto, 1 = streaming)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

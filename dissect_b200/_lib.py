@@ -17,7 +17,7 @@ SYMBOLS = (
     "dgrm_default_config", "dgrm_create", "dgrm_destroy", "dgrm_last_error", "dgrm_abi_version",
     "dgrm_set_individuals", "dgrm_begin", "dgrm_push_bed_host", "dgrm_push_bed_device",
     "dgrm_load_bed_file", "dgrm_finish", "dgrm_sync", "dgrm_num_snps", "dgrm_num_individuals",
-    "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_low_overlap_pairs",
+    "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_bind_output", "dgrm_unbind_outputs", "dgrm_low_overlap_pairs",
     "dgrm_set_output_subset", "dgrm_write_grm_dat", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles",
     "dgrm_host_alloc", "dgrm_host_free", "dgrm_kernel_times",
 )
@@ -27,7 +27,8 @@ class Config(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("operand", C.c_int32),
         ("count_method", C.c_int32), ("flat_norm", C.c_int32), ("chunk_snps", C.c_int32),
-        ("cta_group", C.c_int32), ("profile", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("cta_group", C.c_int32), ("profile", C.c_int32), ("resident_chunks", C.c_int32), ("resident_mb", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -67,6 +68,8 @@ def load():
     lib.dgrm_snp_stats.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.dgrm_bad_snps.argtypes = [vp, vp, i64, P(i64)]
     lib.dgrm_fetch_block_cyclic.argtypes = [vp, i32, vp, i64, i32, i32, i32, i32, i32, i32, C.c_char]
+    lib.dgrm_bind_output.argtypes = [vp, i32, vp, i64, i32, i32, i32, i32, i32, i32, C.c_char]
+    lib.dgrm_unbind_outputs.argtypes = [vp]
     lib.dgrm_low_overlap_pairs.argtypes = [vp, dbl, vp, i64, P(i64)]
     lib.dgrm_set_output_subset.argtypes = [vp, vp, i64]
     lib.dgrm_write_grm_dat.argtypes = [vp, C.c_char_p]

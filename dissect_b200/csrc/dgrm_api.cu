@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -63,6 +64,27 @@ struct dgrm_engine {
   double* d_diag = nullptr;
   int32_t* d_subset = nullptr;  // output subset (sanitizeKernel's filterIndividuals)
   int64_t n_out = 0;
+
+  // output bindings (filled while dgrm_finish runs, tile group by tile group)
+  struct Binding {
+    int which = -1;
+    double* host = nullptr;     // caller pointer
+    double* dev = nullptr;      // device-visible alias when the buffer is pinned (zero-copy), else NULL
+    CyclicGeom g{};
+    int uplo = 0;
+  };
+  Binding bind[3];
+  int nbind = 0;
+  cudaStream_t out_stream = nullptr;
+  std::vector<cudaEvent_t> group_ev;
+
+  // resident operand slots: `slots` chunks of kc_max SNPs live side by side in Z / Q / MB
+  int slots = 0;
+  int chunks_in_super = 0;
+  int64_t supers_done = 0;
+  int slot_kpad[kMaxChunks] = {0};
+  int l2_policy = 1;  // see SyrkParams::l2_policy (DGRM_L2_POLICY overrides, for experiments)
+  int tile_major = 0; // DGRM_TILE_MAJOR=1: one launch walks all resident chunks per tile (experiment)
 
   // chunk state
   int kc_max = 0;
@@ -132,8 +154,9 @@ int fail(dgrm_engine* e, int code, const char* fmt, ...) {
 struct Prof {
   dgrm_engine* e;
   int k;
+  cudaStream_t st;
   EventPair p{nullptr, nullptr};
-  Prof(dgrm_engine* e_, int k_) : e(e_), k(k_) {
+  Prof(dgrm_engine* e_, int k_, cudaStream_t st_ = nullptr) : e(e_), k(k_), st(st_ ? st_ : e_->stream) {
     e->launches[k]++;
     if (!e->cfg.profile) return;
     if (!e->ev_pool.empty()) {
@@ -143,11 +166,11 @@ struct Prof {
       cudaEventCreate(&p.a);
       cudaEventCreate(&p.b);
     }
-    cudaEventRecord(p.a, e->stream);
+    cudaEventRecord(p.a, st);
   }
   ~Prof() {
     if (!e->cfg.profile) return;
-    cudaEventRecord(p.b, e->stream);
+    cudaEventRecord(p.b, st);
     e->ev[k].push_back(p);
   }
 };
@@ -267,7 +290,7 @@ int launch_syrk(dgrm_engine* e, const CUtensorMap& tmap, const SyrkParams& p) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  const int units = std::min<int>(p.num_work, CG == 2 ? e->sm_count / 2 : e->sm_count);
+  const int units = std::min<int>(p.work_end - p.work_begin, CG == 2 ? e->sm_count / 2 : e->sm_count);
   if (units <= 0) return DGRM_OK;
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(units * CG);
@@ -285,6 +308,9 @@ int launch_syrk(dgrm_engine* e, const CUtensorMap& tmap, const SyrkParams& p) {
   return DGRM_OK;
 }
 
+int flush_super(dgrm_engine* e, bool final);
+
+// One chunk of packed rows: per-SNP statistics, then expansion into resident operand slot `chunks_in_super`.
 int process_chunk(dgrm_engine* e) {
   const int kc = e->fill;
   if (kc == 0) return DGRM_OK;
@@ -293,6 +319,12 @@ int process_chunk(dgrm_engine* e) {
   const bool bf16 = e->cfg.operand == DGRM_OPERAND_BF16;
   const bool count_mma = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_MMA;
   const bool count_popc = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_POPC;
+  if (e->chunks_in_super == e->slots) {  // every resident slot is taken: contract them before reusing slot 0
+    const int rc = flush_super(e, false);
+    if (rc) return rc;
+  }
+  const int slot = e->chunks_in_super;
+  const int64_t col0 = (int64_t)slot * e->kc_max;
 
   {
     Prof pr(e, DGRM_K_COUNT);
@@ -305,9 +337,9 @@ int process_chunk(dgrm_engine* e) {
     Prof pr(e, DGRM_K_EXPAND);
     ExpandArgs a;
     a.chunk = e->d_chunk; a.pitch = e->chunk_pitch; a.kc = kc; a.n = (int)e->n; a.zt = e->d_zt;
-    a.Z = e->d_Z; a.z_pitch = e->z_pitch; a.lo_off = e->kc_max;
-    a.Q = count_mma ? e->d_Q : nullptr; a.q_pitch = e->q_pitch;
-    a.MB = count_popc ? e->d_MB : nullptr; a.mb_pitch = e->mb_pitch;
+    a.Z = e->d_Z + col0; a.z_pitch = e->z_pitch; a.lo_off = (int64_t)e->slots * e->kc_max;
+    a.Q = count_mma ? e->d_Q + col0 : nullptr; a.q_pitch = e->q_pitch;
+    a.MB = count_popc ? e->d_MB + col0 / 32 : nullptr; a.mb_pitch = e->mb_pitch;
     a.diag_part = e->d_diag_part; a.n_pad = (int)e->n_pad;
     const dim3 grid((unsigned)(e->n_pad / kExpI), (unsigned)(kc_pad / kExpK));
     const size_t smem = sizeof(ExpandSmem);
@@ -319,44 +351,118 @@ int process_chunk(dgrm_engine* e) {
                                                                                 (int)e->n_pad, e->d_diag);
     CK(cudaGetLastError());
   }
-  if (!e->work.empty()) {
-    SyrkParams p{};
-    p.work = e->d_work;
-    p.num_work = (int)e->work.size();
-    p.accumulate = e->chunks_done > 0;
-    {
-      Prof pr(e, DGRM_K_SYRK);
-      p.num_kblocks = kc_pad / 64;
-      p.npass = split ? 3 : 1;
-      p.a_off[0] = 0; p.a_off[1] = e->kc_max; p.a_off[2] = 0;
-      p.b_off[0] = 0; p.b_off[1] = 0; p.b_off[2] = e->kc_max;
-      p.out = e->d_S;
-      p.idesc = make_idesc(e->cfg.cta_group, bf16 ? 1 : 0);
-      const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, false, double>(e, e->tmap_z, p)
-                                           : launch_syrk<1, false, double>(e, e->tmap_z, p);
-      if (rc) return rc;
-    }
-    if (count_mma) {
-      Prof pr(e, DGRM_K_PAIRCNT);
-      p.num_kblocks = kc_pad / 128;
-      p.npass = 1;
-      p.a_off[0] = p.b_off[0] = 0;
-      p.out = e->d_N;
-      p.idesc = make_idesc(e->cfg.cta_group, 0 /* e4m3 */);
-      const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, true, int>(e, e->tmap_q, p)
-                                           : launch_syrk<1, true, int>(e, e->tmap_q, p);
-      if (rc) return rc;
-    } else if (count_popc) {
-      Prof pr(e, DGRM_K_PAIRCNT);
-      const int nw = (int)e->work_cg1.size();
-      pair_count_popc_kernel<<<std::min(nw, e->sm_count * 2), 256, 0, e->stream>>>(
-          e->d_MB, e->mb_pitch, kc_pad / 32, e->d_work_cg1, nw, e->d_N, e->chunks_done > 0);
-      CK(cudaGetLastError());
-    }
+  if (count_popc && !e->work_cg1.empty()) {
+    Prof pr(e, DGRM_K_PAIRCNT);
+    const int nw = (int)e->work_cg1.size();
+    pair_count_popc_kernel<<<std::min(nw, e->sm_count * 2), 256, 0, e->stream>>>(
+        e->d_MB + col0 / 32, e->mb_pitch, kc_pad / 32, e->d_work_cg1, nw, e->d_N, e->chunks_done > 0);
+    CK(cudaGetLastError());
   }
+  e->slot_kpad[slot] = kc_pad;
   e->m += kc;
   e->chunks_done++;
   e->fill = 0;
+  ++e->chunks_in_super;  // contracted lazily: by the next chunk that needs the slot, or by dgrm_finish
+  return DGRM_OK;
+}
+
+// stream the tiles of work[w0, w1) into every zero-copy binding (runs on out_stream after `after`)
+int emit_outputs(dgrm_engine* e, int w0, int w1, cudaEvent_t after) {
+  bool any = false;
+  for (int b = 0; b < e->nbind; ++b) any |= e->bind[b].dev != nullptr;
+  if (!any || w1 <= w0) return DGRM_OK;
+  CK(cudaStreamWaitEvent(e->out_stream, after, 0));
+  const int mul = e->cfg.cta_group == 2 ? 2 : 1;  // work_cg1 holds two 128-row tiles per supertile
+  const TileStore ts = tile_store(e);
+  for (int b = 0; b < e->nbind; ++b) {
+    const dgrm_engine::Binding& bd = e->bind[b];
+    if (!bd.dev) continue;
+    Prof pr(e, DGRM_K_FETCH, e->out_stream);
+    scatter_tiles_kernel<<<(unsigned)((w1 - w0) * mul), 256, 0, e->out_stream>>>(
+        ts, bd.which, e->d_diag, bd.dev, bd.g, bd.uplo, e->d_work_cg1, w0 * mul);
+    CK(cudaGetLastError());
+  }
+  return DGRM_OK;
+}
+
+// Contract the resident chunks: for every tile, every chunk in turn (fp32 in TMEM per chunk, fp64 / int32
+// read-modify-write of the tile across chunks, which stays in L2 because the same CTA revisits it).
+// `final`: the last contraction of this GRM; tiles then leave the device group by group while later
+// groups are still being computed.
+int flush_super(dgrm_engine* e, bool final) {
+  const int nch = e->chunks_in_super;
+  if (nch == 0) return DGRM_OK;
+  e->chunks_in_super = 0;
+  const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
+  const bool bf16 = e->cfg.operand == DGRM_OPERAND_BF16;
+  const bool count_mma = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_MMA;
+  const int nwork = (int)e->work.size();
+  if (nwork > 0) {
+    SyrkParams p{};
+    p.work = e->d_work;
+    p.l2_policy = e->l2_policy;
+    const int lo = e->slots * e->kc_max;
+    // tile groups: whole waves of the persistent grid, so that no launch has a ragged tail
+    const int units = e->cfg.cta_group == 2 ? e->sm_count / 2 : e->sm_count;
+    bool stream_out = false;
+    for (int b = 0; b < e->nbind; ++b) stream_out |= e->bind[b].dev != nullptr;
+    int group = nwork;
+    if (final && stream_out) {
+      const int waves = (nwork + units - 1) / units;
+      group = std::max(1, (waves + 7) / 8) * units;
+    }
+    // Within a tile group the chunks are contracted by one launch each (chunk-major inside the group): the
+    // launch boundary re-synchronises the persistent CTAs every few hundred microseconds, which is what keeps
+    // the A/B panels they share hot in L2.  (One tile-major launch over all chunks lets the CTAs drift apart
+    // and re-read every panel from HBM: measured 233 GB per launch instead of ~40 GB.)
+    const int per_launch = e->tile_major ? nch : 1;
+    size_t gi = 0;
+    for (int w0 = 0; w0 < nwork; w0 += group, ++gi) {
+      const int w1 = std::min(nwork, w0 + group);
+      p.work_begin = w0;
+      p.work_end = w1;
+      for (int j0 = 0; j0 < nch; j0 += per_launch) {
+        p.nchunks = per_launch;
+        for (int j = 0; j < per_launch; ++j) {
+          p.chunk_col[j] = (j0 + j) * e->kc_max;
+          p.chunk_kpad[j] = e->slot_kpad[j0 + j];
+        }
+        p.accumulate = e->supers_done > 0 || j0 > 0;
+        {
+          Prof pr(e, DGRM_K_SYRK);
+          p.npass = split ? 3 : 1;
+          p.a_off[0] = 0; p.a_off[1] = lo; p.a_off[2] = 0;
+          p.b_off[0] = 0; p.b_off[1] = 0; p.b_off[2] = lo;
+          p.out = e->d_S;
+          p.idesc = make_idesc(e->cfg.cta_group, bf16 ? 1 : 0);
+          const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, false, double>(e, e->tmap_z, p)
+                                               : launch_syrk<1, false, double>(e, e->tmap_z, p);
+          if (rc) return rc;
+        }
+        if (count_mma) {
+          Prof pr(e, DGRM_K_PAIRCNT);
+          p.npass = 1;
+          p.a_off[0] = p.b_off[0] = 0;
+          p.out = e->d_N;
+          p.idesc = make_idesc(e->cfg.cta_group, 0 /* e4m3 */);
+          const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, true, int>(e, e->tmap_q, p)
+                                               : launch_syrk<1, true, int>(e, e->tmap_q, p);
+          if (rc) return rc;
+        }
+      }
+      if (final && stream_out) {
+        while (e->group_ev.size() <= gi) {
+          cudaEvent_t ev;
+          CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+          e->group_ev.push_back(ev);
+        }
+        CK(cudaEventRecord(e->group_ev[gi], e->stream));
+        const int rc = emit_outputs(e, w0, w1, e->group_ev[gi]);
+        if (rc) return rc;
+      }
+    }
+  }
+  e->supers_done++;
   return DGRM_OK;
 }
 
@@ -415,6 +521,32 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
   return DGRM_OK;
 }
 
+// (Re)allocate the resident operand buffers for `slots` chunks of kc_max SNPs.
+int ensure_operands(dgrm_engine* e, int slots) {
+  if (slots == e->slots && e->d_Z) return DGRM_OK;
+  CK(cudaStreamSynchronize(e->stream));
+  free_dev(e->d_Z); e->d_Z = nullptr;
+  free_dev(e->d_Q); e->d_Q = nullptr;
+  free_dev(e->d_MB); e->d_MB = nullptr;
+  const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
+  const int64_t cols = (int64_t)slots * e->kc_max;
+  e->slots = slots;
+  e->z_pitch = cols * (split ? 2 : 1);
+  e->q_pitch = cols;
+  e->mb_pitch = cols / 32;
+  CK(cudaMalloc(&e->d_Z, (size_t)e->n_pad * e->z_pitch * sizeof(uint16_t)));
+  int rc = make_tmap(e, &e->tmap_z, e->d_Z, 2, e->z_pitch, e->n_pad, e->z_pitch * 2);
+  if (rc) return rc;
+  if (!e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_MMA) {
+    CK(cudaMalloc(&e->d_Q, (size_t)e->n_pad * e->q_pitch));
+    rc = make_tmap(e, &e->tmap_q, e->d_Q, 1, e->q_pitch, e->n_pad, e->q_pitch);
+    if (rc) return rc;
+  }
+  if (!e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_POPC)
+    CK(cudaMalloc(&e->d_MB, (size_t)e->n_pad * e->mb_pitch * sizeof(uint32_t)));
+  return DGRM_OK;
+}
+
 int check_ready(dgrm_engine* e, bool need_finished) {
   if (!e) return DGRM_E_INVALID;
   if (!e->have_ind) return fail(e, DGRM_E_INVALID, "dgrm_set_individuals has not been called");
@@ -452,6 +584,8 @@ int dgrm_default_config(dgrm_config* cfg) {
   cfg->chunk_snps = 8192;
   cfg->cta_group = 2;
   cfg->profile = 0;
+  cfg->resident_chunks = 0;  // auto
+  cfg->resident_mb = 16384;
   return DGRM_OK;
 }
 
@@ -467,6 +601,8 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
     return fail(nullptr, DGRM_E_INVALID, "dgrm_create: chunk_snps must be a multiple of 128 in [128, 32768]");
   if (cfg->cta_group != 1 && cfg->cta_group != 2)
     return fail(nullptr, DGRM_E_INVALID, "dgrm_create: cta_group must be 1 or 2");
+  if (cfg->resident_chunks < 0 || cfg->resident_chunks > kMaxChunks || cfg->resident_mb < 0)
+    return fail(nullptr, DGRM_E_INVALID, "dgrm_create: resident_chunks must be in [0, %d]", kMaxChunks);
   if (cfg->operand < 0 || cfg->operand > DGRM_OPERAND_FP16X2 || cfg->count_method < 0 ||
       cfg->count_method > DGRM_COUNT_POPC)
     return fail(nullptr, DGRM_E_INVALID, "dgrm_create: bad operand/count_method");
@@ -487,6 +623,8 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   e->cfg = *cfg;
   e->sm_count = prop.multiProcessorCount;
   e->kc_max = cfg->chunk_snps;
+  if (const char* pol = getenv("DGRM_L2_POLICY")) e->l2_policy = atoi(pol);
+  if (const char* tm = getenv("DGRM_TILE_MAJOR")) e->tile_major = atoi(tm);
 #define CKC(call)                                                                          \
   do {                                                                                     \
     cudaError_t _s = (call);                                                               \
@@ -499,6 +637,7 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   CKC(cudaSetDevice(cfg->device));
   CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     CKC(cudaEventCreateWithFlags(&e->stage_copied[i], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&e->stage_free[i], cudaEventDisableTiming));
@@ -544,6 +683,8 @@ void dgrm_destroy(dgrm_engine* e) {
   if (e->producer_ev) cudaEventDestroy(e->producer_ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->out_stream) cudaStreamDestroy(e->out_stream);
+  for (auto ev : e->group_ev) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -553,6 +694,7 @@ int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask
   CK(cudaSetDevice(e->cfg.device));
   CK(cudaStreamSynchronize(e->stream));
   release_geometry(e);
+  e->nbind = 0;
   e->begun = e->finished = false;
   std::vector<int32_t> src;
   bool identity = true;
@@ -573,11 +715,7 @@ int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask
   }
   build_tiles(e);
   CK(cudaGetLastError());
-  const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
   const int kc = e->kc_max;
-  e->z_pitch = (int64_t)kc * (split ? 2 : 1);
-  e->q_pitch = kc;
-  e->mb_pitch = kc / 32;
   if (e->ntiles > 0) {
     CK(cudaMalloc(&e->d_S, (size_t)e->ntiles * kTileElems * sizeof(double)));
     if (!e->cfg.flat_norm) CK(cudaMalloc(&e->d_N, (size_t)e->ntiles * kTileElems * sizeof(int32_t)));
@@ -585,24 +723,9 @@ int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask
   CK(cudaMalloc(&e->d_diag, (size_t)e->n_pad * sizeof(double)));
   CK(cudaMalloc(&e->d_chunk, (size_t)kc * e->chunk_pitch));
   CK(cudaMemset(e->d_chunk, 0x55, (size_t)kc * e->chunk_pitch));
-  CK(cudaMalloc(&e->d_Z, (size_t)e->n_pad * e->z_pitch * sizeof(uint16_t)));
-  CK(cudaMemset(e->d_Z, 0, (size_t)e->n_pad * e->z_pitch * sizeof(uint16_t)));
-  if (!e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_MMA) {
-    CK(cudaMalloc(&e->d_Q, (size_t)e->n_pad * e->q_pitch));
-    CK(cudaMemset(e->d_Q, 0, (size_t)e->n_pad * e->q_pitch));
-  }
-  if (!e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_POPC) {
-    CK(cudaMalloc(&e->d_MB, (size_t)e->n_pad * e->mb_pitch * sizeof(uint32_t)));
-    CK(cudaMemset(e->d_MB, 0, (size_t)e->n_pad * e->mb_pitch * sizeof(uint32_t)));
-  }
   CK(cudaMalloc(&e->d_zt, (size_t)kc * 4 * sizeof(double)));
   CK(cudaMalloc(&e->d_diag_part, (size_t)(kc / kExpK) * e->n_pad * sizeof(double)));
-  int rc = make_tmap(e, &e->tmap_z, e->d_Z, 2, e->z_pitch, e->n_pad, e->z_pitch * 2);
-  if (rc) return rc;
-  if (e->d_Q) {
-    rc = make_tmap(e, &e->tmap_q, e->d_Q, 1, e->q_pitch, e->n_pad, e->q_pitch);
-    if (rc) return rc;
-  }
+  e->slots = 0;  // operand slots are sized by dgrm_begin, once the SNP count is known
   // host staging: slabs of up to kc rows
   e->stage_rows = kc;
   e->stage_pitch = round_up(e->b_fam, 16);
@@ -634,9 +757,24 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
     CK(cudaMalloc(&e->d_sd, (size_t)m_capacity * sizeof(double)));
     e->m_cap = m_capacity;
   }
+  {
+    // resident operand slots: as many chunks as the SNP count needs, bounded by the memory budget
+    const int64_t need = (m_capacity + e->kc_max - 1) / e->kc_max;
+    const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
+    const double per_chunk = (double)e->n_pad * e->kc_max * ((split ? 4 : 2) + 1.0 + 1.0 / 8);
+    int64_t cap = e->cfg.resident_chunks > 0
+                      ? e->cfg.resident_chunks
+                      : (int64_t)std::max(1.0, std::floor((double)(e->cfg.resident_mb > 0 ? e->cfg.resident_mb : 16384) * 1048576.0 / per_chunk));
+    cap = std::min<int64_t>(cap, kMaxChunks);
+    const int slots = (int)std::max<int64_t>(1, std::min(need, cap));
+    const int rc = ensure_operands(e, slots);
+    if (rc) return rc;
+  }
   e->m = 0;
   e->fill = 0;
   e->chunks_done = 0;
+  e->chunks_in_super = 0;
+  e->supers_done = 0;
   e->finished = false;
   if (e->d_subset) {
     CK(cudaStreamSynchronize(e->stream));
@@ -646,12 +784,6 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
   }
   CK(cudaMemsetAsync(e->d_bad_count, 0, 4 * sizeof(int32_t), e->stream));
   CK(cudaMemsetAsync(e->d_diag, 0, (size_t)e->n_pad * sizeof(double), e->stream));
-  // S / N tiles are overwritten (not accumulated) by the first chunk; clear them so that an empty
-  // GRM (no SNP pushed) is still well defined.
-  if (e->ntiles > 0) {
-    CK(cudaMemsetAsync(e->d_S, 0, (size_t)e->ntiles * kTileElems * sizeof(double), e->stream));
-    if (e->d_N) CK(cudaMemsetAsync(e->d_N, 0, (size_t)e->ntiles * kTileElems * sizeof(int32_t), e->stream));
-  }
   e->begun = true;
   return DGRM_OK;
 }
@@ -777,6 +909,12 @@ int dgrm_finish(dgrm_engine* e) {
   if (!e->finished) {
     rc = process_chunk(e);
     if (rc) return rc;
+    rc = flush_super(e, true);
+    if (rc) return rc;
+    if (e->ntiles > 0 && e->chunks_done == 0) {  // no SNP at all: a well-defined empty GRM
+      CK(cudaMemsetAsync(e->d_S, 0, (size_t)e->ntiles * kTileElems * sizeof(double), e->stream));
+      if (e->d_N) CK(cudaMemsetAsync(e->d_N, 0, (size_t)e->ntiles * kTileElems * sizeof(int32_t), e->stream));
+    }
     if (e->ntiles > 0 && e->m > 0) {
       Prof pr(e, DGRM_K_FINAL);
       fix_diag_kernel<<<(unsigned)((e->n + 255) / 256), 256, 0, e->stream>>>(e->d_S, e->d_index, e->ncp, (int)e->n,
@@ -784,6 +922,16 @@ int dgrm_finish(dgrm_engine* e) {
       CK(cudaGetLastError());
     }
     e->finished = true;
+    CK(cudaStreamSynchronize(e->out_stream));
+    // bindings that could not stream (pageable memory, or nothing was contracted): fill them now
+    for (int b = 0; b < e->nbind; ++b) {
+      const dgrm_engine::Binding& bd = e->bind[b];
+      if (bd.dev && e->chunks_done > 0 && !e->work.empty()) continue;
+      const char up = bd.uplo == 0 ? 'L' : bd.uplo == 1 ? 'U' : 'B';
+      rc = dgrm_fetch_block_cyclic(e, bd.which, bd.host, bd.g.lld, bd.g.bs_r, bd.g.bs_c, bd.g.my_row, bd.g.my_col, bd.g.R,
+                                   bd.g.C, up);
+      if (rc) return rc;
+    }
   }
   int32_t bad[4];
   CK(cudaMemcpyAsync(bad, e->d_bad_count, sizeof bad, cudaMemcpyDeviceToHost, e->stream));
@@ -804,6 +952,45 @@ int dgrm_sync(dgrm_engine* e) {
   CK(cudaSetDevice(e->cfg.device));
   CK(cudaStreamSynchronize(e->copy_stream));
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->out_stream));
+  return DGRM_OK;
+}
+
+int dgrm_bind_output(dgrm_engine* e, int which, double* local, int64_t lld, int bs_r, int bs_c, int my_row, int my_col,
+                     int R, int C, char uplo) {
+  if (!e) return DGRM_E_INVALID;
+  if (!e->have_ind) return fail(e, DGRM_E_INVALID, "dgrm_bind_output: call dgrm_set_individuals first");
+  if (!local || which < 0 || which > 2 || bs_r < 1 || bs_c < 1 || R < 1 || C < 1 || my_row < 0 || my_row >= R ||
+      my_col < 0 || my_col >= C)
+    return fail(e, DGRM_E_INVALID, "dgrm_bind_output: bad arguments");
+  const int up = (uplo == 'L' || uplo == 'l') ? 0 : (uplo == 'U' || uplo == 'u') ? 1 : (uplo == 'B' || uplo == 'b') ? 2 : -1;
+  if (up < 0) return fail(e, DGRM_E_INVALID, "dgrm_bind_output: uplo must be L, U or B");
+  CK(cudaSetDevice(e->cfg.device));
+  int slot = e->nbind;
+  for (int b = 0; b < e->nbind; ++b)
+    if (e->bind[b].which == which) slot = b;
+  if (slot >= 3) return fail(e, DGRM_E_INVALID, "dgrm_bind_output: at most three bindings");
+  dgrm_engine::Binding& bd = e->bind[slot];
+  bd.which = which;
+  bd.host = local;
+  bd.uplo = up;
+  bd.g.bs_r = bs_r; bd.g.bs_c = bs_c; bd.g.my_row = my_row; bd.g.my_col = my_col; bd.g.R = R; bd.g.C = C;
+  bd.g.nloc_r = numroc((int)e->n, bs_r, my_row, R);
+  bd.g.nloc_c = numroc((int)e->n, bs_c, my_col, C);
+  bd.g.lld = lld;
+  if (lld < std::max(bd.g.nloc_r, 1)) return fail(e, DGRM_E_INVALID, "dgrm_bind_output: lld < local rows");
+  cudaPointerAttributes attr;
+  bd.dev = nullptr;
+  if (cudaPointerGetAttributes(&attr, local) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+    bd.dev = (double*)attr.devicePointer;
+  cudaGetLastError();
+  if (slot == e->nbind) e->nbind++;
+  return DGRM_OK;
+}
+
+int dgrm_unbind_outputs(dgrm_engine* e) {
+  if (!e) return DGRM_E_INVALID;
+  e->nbind = 0;
   return DGRM_OK;
 }
 
@@ -1093,6 +1280,7 @@ int dgrm_kernel_times(dgrm_engine* e, double ms[DGRM_K_NUM], int64_t launches[DG
   if (!e) return DGRM_E_INVALID;
   CK(cudaSetDevice(e->cfg.device));
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->out_stream));
   for (int k = 0; k < DGRM_K_NUM; ++k) {
     for (auto& p : e->ev[k]) {
       float t = 0.f;

@@ -3,10 +3,13 @@
 // Replaces pdsyrk_('L','T', n, k=m, 1.0, G, 0.0, C) (matrix.cpp:2677-2683), which the reference
 // reaches twice from Kernel::Kernel (kernel.cpp:94 for S = Z^T Z, kernel.cpp:100 for N = M^T M).
 //
-// One launch contracts one SNP chunk.  The operand is the K-major matrix X[n_pad][K] written by
-// bed_expand (row = individual, 128-byte-swizzle friendly row pitch).  Output tiles are 128 rows x
-// 256 columns, stored column-major inside a tile (what DISSECT's Matrix uses locally,
-// matrix.cpp:1748-1758), only for column panels that intersect the lower triangle.
+// One launch contracts every resident SNP chunk for a range of output tiles, tile-major and chunk-inner:
+// a CTA (pair) keeps its tile while it walks the chunks, accumulating each chunk in fp32 in TMEM and
+// folding it into the fp64 (int32) tile, which therefore stays in L2 between chunks.  The operand is
+// the K-major matrix X[n_pad][chunks * Kc] written by bed_expand (row = individual, 128-byte-swizzle
+// friendly row pitch).  Output tiles are 128 rows x 256 columns, stored column-major inside a tile
+// (what DISSECT's Matrix uses locally, matrix.cpp:1748-1758), only for column panels that intersect
+// the lower triangle.
 //
 // Structure (persistent, warp specialised):
 //   warp 0   TMA producer  : cp.async.bulk.tensor 2-D boxes of 128 rows x 128 B -> swizzled smem ring
@@ -22,16 +25,22 @@
 
 namespace dgrm {
 
+constexpr int kMaxChunks = 32;  // SNP chunks resident at once (one fp32 TMEM accumulation each)
+
 struct SyrkParams {
   const int4* work;   // {first A row, first B row, storage index (rank 0), storage index (rank 1)}
-  int num_work;
-  int num_kblocks;    // 128-byte k-blocks per pass
+  int work_begin;     // this launch covers work[work_begin, work_end)
+  int work_end;
+  int nchunks;                  // resident chunks contracted per tile, in order (tile-major, chunk-inner)
+  int chunk_col[kMaxChunks];    // element column of chunk j in the operand
+  int chunk_kpad[kMaxChunks];   // SNP columns of chunk j, padded to 128
   int npass;          // 1, or 3 for the hi/lo split
   int a_off[3];       // per-pass element column offset of the A operand
   int b_off[3];       // per-pass element column offset of the B operand
   void* out;          // tile storage, [storage index][256 cols][128 rows]
-  int accumulate;     // 0: overwrite (first chunk), 1: add to what is there
+  int accumulate;     // chunk 0 of this launch: 0 = overwrite, 1 = add to what is there (later chunks always add)
   uint32_t idesc;     // tcgen05 instruction descriptor
+  int l2_policy;      // 0: no preference; 1: keep output tiles (evict_last); 2: 1 + operand panels evict_first
 };
 
 constexpr int kTileM = 128;
@@ -105,37 +114,41 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int kb_total = p.npass * p.num_kblocks;
-
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = unit; w < p.num_work; w += nunits) {
+      // operand panels are shared by the CTAs of a wave and then dead: let them go first so that the fp64
+      // tiles (evict_last below) survive in L2 from one chunk to the next
+      const uint64_t pol = p.l2_policy == 2 ? ptx::policy_evict_first() : ptx::policy_evict_normal();
+      for (int w = p.work_begin + unit; w < p.work_end; w += nunits) {
         const int4 t = p.work[w];
         const int a_row = t.x + (CG == 2 ? (int)rank * 128 : 0);
         const int b_row = t.y + (CG == 2 ? (int)rank * 128 : 0);
+        for (int j = 0; j < p.nchunks; ++j) {
+        const int num_kblocks = p.chunk_kpad[j] / kKElems;
         for (int pass = 0; pass < p.npass; ++pass) {
-          const int a_col0 = p.a_off[pass];
-          const int b_col0 = p.b_off[pass];
-          for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          const int a_col0 = p.a_off[pass] + p.chunk_col[j];
+          const int b_col0 = p.b_off[pass] + p.chunk_col[j];
+          for (int kb = 0; kb < num_kblocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
             if constexpr (CG == 1) {
               ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              ptx::tma_load_2d(sa, &tmap, &full_bar[stage], a_col0 + kb * kKElems, a_row);
-              ptx::tma_load_2d(sb, &tmap, &full_bar[stage], b_col0 + kb * kKElems, b_row);
-              ptx::tma_load_2d(sb + 128 * 128, &tmap, &full_bar[stage], b_col0 + kb * kKElems, b_row + 128);
+              ptx::tma_load_2d(sa, &tmap, &full_bar[stage], a_col0 + kb * kKElems, a_row, pol);
+              ptx::tma_load_2d(sb, &tmap, &full_bar[stage], b_col0 + kb * kKElems, b_row, pol);
+              ptx::tma_load_2d(sb + 128 * 128, &tmap, &full_bar[stage], b_col0 + kb * kKElems, b_row + 128, pol);
             } else {
-              ptx::tma_load_2d_2sm(sa, &tmap, &full_bar[stage], a_col0 + kb * kKElems, a_row);
-              ptx::tma_load_2d_2sm(sb, &tmap, &full_bar[stage], b_col0 + kb * kKElems, b_row);
+              ptx::tma_load_2d_2sm(sa, &tmap, &full_bar[stage], a_col0 + kb * kKElems, a_row, pol);
+              ptx::tma_load_2d_2sm(sb, &tmap, &full_bar[stage], b_col0 + kb * kKElems, b_row, pol);
               if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
               else ptx::mbar_arrive_cluster(&full_bar[stage], 0);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
+        }
         }
       }
     }
@@ -145,7 +158,9 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = unit; w < p.num_work; w += nunits, ++it) {
+      for (int w = p.work_begin + unit; w < p.work_end; w += nunits) {
+      for (int j = 0; j < p.nchunks; ++j, ++it) {
+        const int kb_total = p.npass * (p.chunk_kpad[j] / kKElems);
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         ptx::mbar_wait(&tempty_bar[as], aphase ^ 1u);
@@ -170,6 +185,7 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
+      }
       if constexpr (CG == 2) {
         // keep the leader's barriers alive until the peer's last tmem-empty arrivals landed
         if (it > 0) {
@@ -183,13 +199,19 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
     const int q = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
     OutT* out = reinterpret_cast<OutT*>(p.out);
+    // several resident chunks: the tile is revisited one chunk later by the same threads -> keep it in L2;
+    // a single chunk per launch: the tile is dead until the next launch -> stream it
+    const uint64_t pol_rmw = p.l2_policy == 0 ? ptx::policy_evict_normal()
+                             : p.nchunks > 1 ? ptx::policy_evict_last() : ptx::policy_evict_first();
     int it = 0;
-    for (int w = unit; w < p.num_work; w += nunits, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+    for (int w = p.work_begin + unit; w < p.work_end; w += nunits) {
       const int4 t = p.work[w];
       const int sidx = (rank == 0) ? t.z : t.w;
       OutT* tile = out + (size_t)sidx * kTileElems + row;
+    for (int j = 0; j < p.nchunks; ++j, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const bool accumulate = p.accumulate || j > 0;
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kTileN);
@@ -205,17 +227,19 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
           else ptx::mbar_arrive_cluster(&tempty_bar[as], 0);
         }
         OutT* po = tile + (size_t)(cc * 32) * kTileM;
-        if (p.accumulate) {
+        const uint64_t pol_st = (p.l2_policy != 0 && j == p.nchunks - 1) ? ptx::policy_evict_first() : pol_rmw;  // last visit
+        if (accumulate) {
           OutT old[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) old[j] = __ldcs(po + j * kTileM);
+          for (int q2 = 0; q2 < 32; ++q2) old[q2] = ptx::ld_hint<OutT>(po + q2 * kTileM, pol_rmw);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) __stcs(po + j * kTileM, old[j] + acc_convert<OutT>(v[j]));
+          for (int q2 = 0; q2 < 32; ++q2) ptx::st_hint(po + q2 * kTileM, old[q2] + acc_convert<OutT>(v[q2]), pol_st);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) __stcs(po + j * kTileM, acc_convert<OutT>(v[j]));
+          for (int q2 = 0; q2 < 32; ++q2) ptx::st_hint(po + q2 * kTileM, acc_convert<OutT>(v[q2]), pol_st);
         }
       }
+    }
     }
   }
 

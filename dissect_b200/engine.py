@@ -55,7 +55,7 @@ class PinnedArray:
 
 class GrmEngine:
     def __init__(self, device=0, rank=0, world=1, operand="fp16", count_method="mma", flat_norm=False,
-                 chunk_snps=8192, cta_group=2, profile=False):
+                 chunk_snps=8192, cta_group=2, profile=False, resident_chunks=0, resident_mb=16384):
         self._lib = _lib.load()
         cfg = _lib.Config()
         self._lib.dgrm_default_config(C.byref(cfg))
@@ -66,6 +66,8 @@ class GrmEngine:
         cfg.chunk_snps = chunk_snps
         cfg.cta_group = cta_group
         cfg.profile = int(bool(profile))
+        cfg.resident_chunks = resident_chunks
+        cfg.resident_mb = resident_mb
         self.cfg = cfg
         h = C.c_void_p()
         rc = self._lib.dgrm_create(C.byref(cfg), C.byref(h))
@@ -185,6 +187,13 @@ class GrmEngine:
     def fetch_into(self, which, ptr, lld, bs=(256, 256), grid=(1, 1), coords=(0, 0), uplo="L"):
         self._ck(self._lib.dgrm_fetch_block_cyclic(self._h, _lib.FETCH[which], int(ptr), lld, bs[0], bs[1],
                                                    coords[0], coords[1], grid[0], grid[1], uplo.encode()))
+
+    def bind_output(self, which, ptr, lld, bs=(256, 256), grid=(1, 1), coords=(0, 0), uplo="L"):
+        self._ck(self._lib.dgrm_bind_output(self._h, _lib.FETCH[which], int(ptr), lld, bs[0], bs[1], coords[0],
+                                            coords[1], grid[0], grid[1], uplo.encode()))
+
+    def unbind_outputs(self):
+        self._ck(self._lib.dgrm_unbind_outputs(self._h))
 
     def low_overlap_pairs(self, min_overlap=10.0, cap=1 << 20):
         pairs = np.zeros((cap, 2), np.int64)

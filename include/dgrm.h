@@ -73,7 +73,9 @@ typedef struct dgrm_config {
   int32_t chunk_snps;    /* SNPs contracted per launch (fp32 in-chunk, fp64 across); mult. of 128 */
   int32_t cta_group;     /* 1 = one-SM MMA 128x256 tiles, 2 = CTA-pair MMA 256x256 tiles     */
   int32_t profile;       /* 1 = record CUDA events around every kernel launch                */
-  int32_t reserved[7];
+  int32_t resident_chunks; /* SNP chunks whose operands stay resident and are contracted tile-major (0 = auto) */
+  int32_t resident_mb;   /* memory budget (MiB) for resident operands when resident_chunks == 0     */
+  int32_t reserved[5];
 } dgrm_config;
 
 /* Fill *cfg with defaults (device 0, rank 0/1, fp16, MMA count, chunk 8192, cta_group 2). */
@@ -141,6 +143,17 @@ int dgrm_bad_snps(dgrm_engine *e, int64_t *idx, int64_t cap, int64_t *count);
 int dgrm_fetch_block_cyclic(dgrm_engine *e, int which, double *local, int64_t lld, int bs_r,
                             int bs_c, int my_row, int my_col, int grid_rows, int grid_cols,
                             char uplo);
+
+/* Bind a caller-owned local block-cyclic buffer (same arguments as dgrm_fetch_block_cyclic) that
+ * dgrm_finish fills with matrix `which`.  When the buffer is pinned (dgrm_host_alloc) the tiles are
+ * stored into it group by group while later tile groups are still being contracted, so the
+ * device->host traffic overlaps the tensor-core work; pageable buffers are filled at the end of
+ * dgrm_finish.  One binding per `which`; bindings survive dgrm_begin and are dropped by
+ * dgrm_set_individuals / dgrm_unbind_outputs.  Replaces the result hand-over of Kernel::Kernel
+ * (kernel.cpp:94-116: kernel->m and N->m are the outputs). */
+int dgrm_bind_output(dgrm_engine *e, int which, double *local, int64_t lld, int bs_r, int bs_c,
+                     int my_row, int my_col, int grid_rows, int grid_cols, char uplo);
+int dgrm_unbind_outputs(dgrm_engine *e);
 
 /* Pairs (i > j) whose shared non-missing count satisfies -0.1 < N_ij < min_overlap - 0.1,
  * the scan sanitizeKernel performs (kernel.cpp:1993-2037, matrix.cpp:4334-4401).

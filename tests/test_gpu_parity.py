@@ -209,6 +209,53 @@ def test_fetch_into_pinned_zero_copy():
     eng.close()
 
 
+@pytest.mark.parametrize("resident", [1, 2, 0])
+def test_resident_modes_agree(resident):
+    """Streaming (one resident chunk, many contractions), partial residency and full residency accumulate the
+    same chunks in the same order: S bit-identical, N exact."""
+    n, m = 520, 1500
+    pk = bedio.synth_packed(n, m, 123, missing=0.02)
+    base = build(pk, n, chunk_snps=256, resident_chunks=1)
+    eng = build(pk, n, chunk_snps=256, resident_chunks=resident)
+    a, b = fetch_all(base), fetch_all(eng)
+    low = lower_mask(n)
+    assert np.array_equal(a["N"][low], b["N"][low])
+    assert np.array_equal(a["S"][low], b["S"][low])
+    base.close()
+    eng.close()
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("uplo,bs,grid,coords", [("L", (256, 256), (1, 1), (0, 0)), ("B", (64, 32), (2, 2), (1, 0)),
+                                                 ("U", (100, 100), (1, 2), (0, 1))])
+def test_bound_outputs_equal_fetch(pinned, uplo, bs, grid, coords):
+    """dgrm_bind_output (tile groups streamed during dgrm_finish) == dgrm_fetch_block_cyclic afterwards."""
+    from dissect_b200.engine import numroc
+    n, m = 700, 900
+    pk = bedio.synth_packed(n, m, 321, missing=0.02)
+    eng = GrmEngine(chunk_snps=256)
+    eng.set_individuals(n)
+    nr, nc = numroc(n, bs[0], coords[0], grid[0]), numroc(n, bs[1], coords[1], grid[1])
+    outs = {}
+    for which in ("A", "N"):
+        if pinned:
+            pa = PinnedArray((nr, nc), np.float64, order="F")
+            pa.array[:] = -3.0
+            outs[which] = (pa, pa.array, pa.ptr)
+        else:
+            arr = np.full((nr, nc), -3.0, order="F")
+            outs[which] = (arr, arr, arr.ctypes.data)
+        eng.bind_output(which, outs[which][2], max(nr, 1), bs=bs, grid=grid, coords=coords, uplo=uplo)
+    for rep in range(2):     # bindings survive dgrm_begin
+        eng.begin(m)
+        eng.push_bed_host(pk)
+        eng.finish()
+    for which in ("A", "N"):
+        want = eng.fetch_block_cyclic(which, bs=bs, grid=grid, coords=coords, uplo=uplo, fill=-3.0)
+        assert np.array_equal(outs[which][1], want), which
+    eng.close()
+
+
 def test_bad_snps_are_fatal_like_the_reference():
     c = load_case("badsnp")
     eng = GrmEngine()

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--missing", type=float, default=0.02)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--flat", action="store_true")
+    ap.add_argument("--resident", type=int, default=0)
     ap.add_argument("--tolA", type=float, default=None)
     args = ap.parse_args()
     n, m = args.n, args.m
@@ -44,7 +45,7 @@ def main():
     ref = orc.grm(codes, flat_norm=args.flat)
     t_ref = time.time() - t0
     eng = GrmEngine(operand=args.operand, count_method=args.count, chunk_snps=args.chunk, cta_group=args.cg,
-                    flat_norm=args.flat, profile=True)
+                    flat_norm=args.flat, profile=True, resident_chunks=args.resident)
     eng.set_individuals(n)
     eng.begin(m)
     t0 = time.time()

@@ -13,6 +13,9 @@ CASES = [
     ["--n", "777", "--m", "3000", "--cg", "2", "--operand", "fp16x2", "--chunk", "1024"],
     ["--n", "777", "--m", "3000", "--cg", "1", "--count", "popc", "--chunk", "1024"],
     ["--n", "500", "--m", "2000", "--cg", "2", "--flat"],
+    ["--n", "600", "--m", "3000", "--cg", "2", "--chunk", "256", "--resident", "1"],
+    ["--n", "600", "--m", "3000", "--cg", "2", "--chunk", "256", "--resident", "4"],
+    ["--n", "600", "--m", "3000", "--cg", "1", "--chunk", "256", "--resident", "5", "--operand", "fp16x2"],
     ["--n", "2000", "--m", "10000", "--cg", "1"],
     ["--n", "2000", "--m", "10000", "--cg", "2"],
     ["--n", "2000", "--m", "10000", "--cg", "2", "--chunk", "2048"],
