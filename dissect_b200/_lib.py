@@ -5,8 +5,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdgrm.so")
 
-K_NUM = 7
-K_NAMES = ("count", "expand", "syrk", "paircnt", "final", "fetch", "gather")
+K_NUM = 8
+K_NAMES = ("count", "expand", "syrk", "paircnt", "final", "fetch", "gather", "d2h")
 
 OPERANDS = {"fp16": 0, "bf16": 1, "fp16x2": 2}
 COUNT_METHODS = {"mma": 0, "popc": 1}

@@ -75,8 +75,16 @@ struct dgrm_engine {
   };
   Binding bind[3];
   int nbind = 0;
-  cudaStream_t out_stream = nullptr;
+  cudaStream_t out_stream = nullptr;   // packs finished row groups into staging
+  cudaStream_t d2h_stream = nullptr;   // copy engine: staging -> caller buffer
   std::vector<cudaEvent_t> group_ev;
+  double* d_out_stage[2] = {nullptr, nullptr};
+  size_t out_stage_bytes = 0;
+  cudaEvent_t stage_packed[2] = {nullptr, nullptr}, stage_copied_out[2] = {nullptr, nullptr};
+  int out_stage_i = 0;
+  std::vector<int> rg_end;    // per raster row group: end index in `work` of its last owned supertile
+  std::vector<int> rg_row1;   // per raster row group: one past its last global row
+  int rg_emitted = 0;
 
   // resident operand slots: `slots` chunks of kc_max SNPs live side by side in Z / Q / MB
   int slots = 0;
@@ -238,9 +246,12 @@ void build_tiles(dgrm_engine* e) {
   e->work_cg1.clear();
   e->tile_rc.clear();
   std::vector<int32_t> index((size_t)e->nrb * e->ncp, -1);
+  e->rg_end.clear();
+  e->rg_row1.clear();
   int64_t s = 0, ls = 0;
   for (int g = 0; g < T; g += GR) {
     const int imax = std::min(g + GR, T) - 1;
+    if (g > 0) e->rg_end.push_back((int)(e->cfg.cta_group == 2 ? e->work.size() : e->work_cg1.size()));
     for (int J = 0; J <= imax; ++J) {
       for (int I = std::max(g, J); I <= imax; ++I, ++s) {
         if ((int)(s % e->cfg.world) != e->cfg.rank) continue;
@@ -257,6 +268,8 @@ void build_tiles(dgrm_engine* e) {
     }
   }
   if (e->cfg.cta_group == 1) e->work = e->work_cg1;
+  e->rg_end.push_back((int)e->work.size());
+  for (int g = 0; g < T; g += GR) e->rg_row1.push_back(std::min(g + GR, T) * 256);
   e->ntiles = 2 * ls;
   // upload
   cudaMalloc(&e->d_index, index.size() * sizeof(int32_t));
@@ -366,21 +379,81 @@ int process_chunk(dgrm_engine* e) {
   return DGRM_OK;
 }
 
-// stream the tiles of work[w0, w1) into every zero-copy binding (runs on out_stream after `after`)
-int emit_outputs(dgrm_engine* e, int w0, int w1, cudaEvent_t after) {
+bool binding_streams(const dgrm_engine::Binding& bd) { return bd.dev != nullptr && bd.uplo == 0; }
+
+// first local index whose global index is >= target (block-cyclic, monotone)
+int first_local_ge(int target, int nloc, int bs, int me, int P) {
+  int a = 0, b = nloc;
+  while (a < b) {
+    const int mid = (a + b) / 2;
+    const int gidx = ((mid / bs) * P + me) * bs + mid % bs;
+    if (gidx >= target) b = mid; else a = mid + 1;
+  }
+  return a;
+}
+
+// Every raster row group whose tiles are all contracted once work[0, w_done) is done leaves the device:
+// pack kernel (out_stream) -> device staging -> copy engine (d2h_stream) -> the caller's bound buffers.
+int emit_outputs(dgrm_engine* e, int w_done, cudaEvent_t after) {
   bool any = false;
-  for (int b = 0; b < e->nbind; ++b) any |= e->bind[b].dev != nullptr;
-  if (!any || w1 <= w0) return DGRM_OK;
-  CK(cudaStreamWaitEvent(e->out_stream, after, 0));
-  const int mul = e->cfg.cta_group == 2 ? 2 : 1;  // work_cg1 holds two 128-row tiles per supertile
+  for (int b = 0; b < e->nbind; ++b) any |= binding_streams(e->bind[b]);
+  if (!any) return DGRM_OK;
+  bool waited = false;
   const TileStore ts = tile_store(e);
-  for (int b = 0; b < e->nbind; ++b) {
-    const dgrm_engine::Binding& bd = e->bind[b];
-    if (!bd.dev) continue;
-    Prof pr(e, DGRM_K_FETCH, e->out_stream);
-    scatter_tiles_kernel<<<(unsigned)((w1 - w0) * mul), 256, 0, e->out_stream>>>(
-        ts, bd.which, e->d_diag, bd.dev, bd.g, bd.uplo, e->d_work_cg1, w0 * mul);
-    CK(cudaGetLastError());
+  while (e->rg_emitted < (int)e->rg_end.size() && e->rg_end[e->rg_emitted] <= w_done) {
+    const int rg = e->rg_emitted++;
+    const int row0 = rg == 0 ? 0 : e->rg_row1[rg - 1];
+    const int row1 = std::min<int>(e->rg_row1[rg], (int)e->n);
+    if (row0 >= row1) continue;
+    if (!waited) {
+      CK(cudaStreamWaitEvent(e->out_stream, after, 0));
+      waited = true;
+    }
+    for (int b = 0; b < e->nbind; ++b) {
+      const dgrm_engine::Binding& bd = e->bind[b];
+      if (!binding_streams(bd)) continue;
+      const CyclicGeom& g = bd.g;
+      const int lr0 = first_local_ge(row0, g.nloc_r, g.bs_r, g.my_row, g.R);
+      const int lr1 = first_local_ge(row1, g.nloc_r, g.bs_r, g.my_row, g.R);
+      const int lc1 = first_local_ge(row1, g.nloc_c, g.bs_c, g.my_col, g.C);
+      if (lr1 <= lr0 || lc1 <= 0) continue;
+      const size_t bytes = (size_t)(lr1 - lr0) * lc1 * sizeof(double);
+      if (bytes > e->out_stage_bytes) return fail(e, DGRM_E_INVALID, "internal: output staging too small");
+      const int sl = e->out_stage_i;
+      e->out_stage_i ^= 1;
+      CK(cudaStreamWaitEvent(e->out_stream, e->stage_copied_out[sl], 0));  // staging slot free again
+      {
+        Prof pr(e, DGRM_K_FETCH, e->out_stream);
+        const dim3 blk(128, 2);
+        const dim3 grid((unsigned)((lr1 - lr0 + 127) / 128), (unsigned)((lc1 + 1) / 2));
+        pack_rows_kernel<<<grid, blk, 0, e->out_stream>>>(ts, bd.which, e->d_diag, e->d_out_stage[sl], g, lr0, lr1, lc1);
+        CK(cudaGetLastError());
+      }
+      CK(cudaEventRecord(e->stage_packed[sl], e->out_stream));
+      CK(cudaStreamWaitEvent(e->d2h_stream, e->stage_packed[sl], 0));
+      {
+        // copy engine: everything left of the diagonal block in one strided copy, the diagonal block itself as
+        // 256-column strips that start at their own diagonal (so almost nothing above the diagonal is moved)
+        Prof pr(e, DGRM_K_D2H, e->d2h_stream);
+        const int h = lr1 - lr0;
+        auto copy_rect = [&](int lra, int lrb, int lca, int lcb) -> cudaError_t {
+          if (lrb <= lra || lcb <= lca) return cudaSuccess;
+          return cudaMemcpy2DAsync(bd.host + (int64_t)lca * g.lld + lra, (size_t)g.lld * sizeof(double),
+                                   e->d_out_stage[sl] + (int64_t)lca * h + (lra - lr0), (size_t)h * sizeof(double),
+                                   (size_t)(lrb - lra) * sizeof(double), (size_t)(lcb - lca), cudaMemcpyDeviceToHost,
+                                   e->d2h_stream);
+        };
+        const int lc0d = first_local_ge(row0, g.nloc_c, g.bs_c, g.my_col, g.C);
+        CK(copy_rect(lr0, lr1, 0, lc0d));
+        for (int g0 = row0; g0 < row1; g0 += 256) {
+          const int lca = first_local_ge(g0, g.nloc_c, g.bs_c, g.my_col, g.C);
+          const int lcb = first_local_ge(std::min(g0 + 256, row1), g.nloc_c, g.bs_c, g.my_col, g.C);
+          const int lra = first_local_ge(g0, g.nloc_r, g.bs_r, g.my_row, g.R);
+          CK(copy_rect(lra, lr1, lca, lcb));
+        }
+      }
+      CK(cudaEventRecord(e->stage_copied_out[sl], e->d2h_stream));
+    }
   }
   return DGRM_OK;
 }
@@ -405,20 +478,52 @@ int flush_super(dgrm_engine* e, bool final) {
     // tile groups: whole waves of the persistent grid, so that no launch has a ragged tail
     const int units = e->cfg.cta_group == 2 ? e->sm_count / 2 : e->sm_count;
     bool stream_out = false;
-    for (int b = 0; b < e->nbind; ++b) stream_out |= e->bind[b].dev != nullptr;
-    int group = nwork;
+    for (int b = 0; b < e->nbind; ++b) stream_out |= binding_streams(e->bind[b]);
     if (final && stream_out) {
-      const int waves = (nwork + units - 1) / units;
-      group = std::max(1, (waves + 7) / 8) * units;
+      // staging: the largest row-group rectangle of any streaming binding, two slots
+      size_t need = 0;
+      for (int b = 0; b < e->nbind; ++b) {
+        const dgrm_engine::Binding& bd = e->bind[b];
+        if (!binding_streams(bd)) continue;
+        for (size_t rg = 0; rg < e->rg_row1.size(); ++rg) {
+          const int row0 = rg == 0 ? 0 : e->rg_row1[rg - 1], row1 = std::min<int>(e->rg_row1[rg], (int)e->n);
+          if (row0 >= row1) continue;
+          const int lr0 = first_local_ge(row0, bd.g.nloc_r, bd.g.bs_r, bd.g.my_row, bd.g.R);
+          const int lr1 = first_local_ge(row1, bd.g.nloc_r, bd.g.bs_r, bd.g.my_row, bd.g.R);
+          const int lc1 = first_local_ge(row1, bd.g.nloc_c, bd.g.bs_c, bd.g.my_col, bd.g.C);
+          need = std::max(need, (size_t)std::max(lr1 - lr0, 0) * (size_t)std::max(lc1, 0) * sizeof(double));
+        }
+      }
+      if (need > e->out_stage_bytes) {
+        CK(cudaStreamSynchronize(e->d2h_stream));
+        CK(cudaStreamSynchronize(e->out_stream));
+        for (int i = 0; i < 2; ++i) {
+          free_dev(e->d_out_stage[i]);
+          e->d_out_stage[i] = nullptr;
+          CK(cudaMalloc(&e->d_out_stage[i], need));
+        }
+        e->out_stage_bytes = need;
+      }
+      e->rg_emitted = 0;
     }
+    // Tile groups.  Streaming outputs: one group per raster row group, its end rounded up to whole waves of
+    // the persistent grid (no ragged tail, and the row group is final as soon as its launches are done).
+    std::vector<int> group_end;
+    if (final && stream_out) {
+      for (size_t rg = 0; rg < e->rg_end.size(); ++rg) {
+        const int end = std::min(nwork, (e->rg_end[rg] + units - 1) / units * units);
+        if (end > (group_end.empty() ? 0 : group_end.back())) group_end.push_back(end);
+      }
+    }
+    if (group_end.empty() || group_end.back() != nwork) group_end.push_back(nwork);
     // Within a tile group the chunks are contracted by one launch each (chunk-major inside the group): the
     // launch boundary re-synchronises the persistent CTAs every few hundred microseconds, which is what keeps
     // the A/B panels they share hot in L2.  (One tile-major launch over all chunks lets the CTAs drift apart
     // and re-read every panel from HBM: measured 233 GB per launch instead of ~40 GB.)
     const int per_launch = e->tile_major ? nch : 1;
-    size_t gi = 0;
-    for (int w0 = 0; w0 < nwork; w0 += group, ++gi) {
-      const int w1 = std::min(nwork, w0 + group);
+    int w0 = 0;
+    for (size_t gi = 0; gi < group_end.size(); w0 = group_end[gi], ++gi) {
+      const int w1 = group_end[gi];
       p.work_begin = w0;
       p.work_end = w1;
       for (int j0 = 0; j0 < nch; j0 += per_launch) {
@@ -457,7 +562,7 @@ int flush_super(dgrm_engine* e, bool final) {
           e->group_ev.push_back(ev);
         }
         CK(cudaEventRecord(e->group_ev[gi], e->stream));
-        const int rc = emit_outputs(e, w0, w1, e->group_ev[gi]);
+        const int rc = emit_outputs(e, w1, e->group_ev[gi]);
         if (rc) return rc;
       }
     }
@@ -638,6 +743,11 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CKC(cudaEventCreateWithFlags(&e->stage_packed[i], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&e->stage_copied_out[i], cudaEventDisableTiming));
+  }
   for (int i = 0; i < 2; ++i) {
     CKC(cudaEventCreateWithFlags(&e->stage_copied[i], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&e->stage_free[i], cudaEventDisableTiming));
@@ -653,6 +763,10 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
     return DGRM_E_CUDA;
   }
   e->encode = (EncodeTiledFn)fn;
+  // The output kernels run on their own stream while grm_syrk CTAs (198 KB of smem each) occupy every SM: they can
+  // only be co-scheduled onto those SMs when they ask for the same L1/shared-memory split.
+  CKC(cudaFuncSetAttribute(pack_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared));
   CKC(cudaFuncSetAttribute(bed_expand_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(ExpandSmem)));
   CKC(cudaFuncSetAttribute(bed_expand_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -684,7 +798,13 @@ void dgrm_destroy(dgrm_engine* e) {
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->out_stream) cudaStreamDestroy(e->out_stream);
+  if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
   for (auto ev : e->group_ev) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; ++i) {
+    free_dev(e->d_out_stage[i]);
+    if (e->stage_packed[i]) cudaEventDestroy(e->stage_packed[i]);
+    if (e->stage_copied_out[i]) cudaEventDestroy(e->stage_copied_out[i]);
+  }
   delete e;
 }
 
@@ -923,10 +1043,11 @@ int dgrm_finish(dgrm_engine* e) {
     }
     e->finished = true;
     CK(cudaStreamSynchronize(e->out_stream));
-    // bindings that could not stream (pageable memory, or nothing was contracted): fill them now
+    CK(cudaStreamSynchronize(e->d2h_stream));
+    // bindings that could not stream (pageable memory, uplo U/B, or nothing was contracted): fill them now
     for (int b = 0; b < e->nbind; ++b) {
       const dgrm_engine::Binding& bd = e->bind[b];
-      if (bd.dev && e->chunks_done > 0 && !e->work.empty()) continue;
+      if (binding_streams(bd) && e->chunks_done > 0 && !e->work.empty()) continue;
       const char up = bd.uplo == 0 ? 'L' : bd.uplo == 1 ? 'U' : 'B';
       rc = dgrm_fetch_block_cyclic(e, bd.which, bd.host, bd.g.lld, bd.g.bs_r, bd.g.bs_c, bd.g.my_row, bd.g.my_col, bd.g.R,
                                    bd.g.C, up);
@@ -953,6 +1074,7 @@ int dgrm_sync(dgrm_engine* e) {
   CK(cudaStreamSynchronize(e->copy_stream));
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaStreamSynchronize(e->out_stream));
+  CK(cudaStreamSynchronize(e->d2h_stream));
   return DGRM_OK;
 }
 
@@ -1281,6 +1403,7 @@ int dgrm_kernel_times(dgrm_engine* e, double ms[DGRM_K_NUM], int64_t launches[DG
   CK(cudaSetDevice(e->cfg.device));
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaStreamSynchronize(e->out_stream));
+  CK(cudaStreamSynchronize(e->d2h_stream));
   for (int k = 0; k < DGRM_K_NUM; ++k) {
     for (auto& p : e->ev[k]) {
       float t = 0.f;

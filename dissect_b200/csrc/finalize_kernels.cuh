@@ -76,45 +76,33 @@ __global__ void fetch_block_cyclic_kernel(const TileStore ts, int which, double*
   dst[(int64_t)(lc - lc0) * g.lld + lr] = v;
 }
 
-// Tile-driven counterpart of fetch_block_cyclic_kernel: one block per 128x256 tile of `work` (a finished
-// tile group), every lower-triangle element is stored into the caller's local block if this process owns it.
-// `diag` supplies the exact fp64 diagonal of S (the tile store is only patched after the last group).
-__device__ __forceinline__ void store_block_cyclic(double* __restrict__ dst, const CyclicGeom& g, int gr, int gc,
-                                                   double v) {
-  const int br = gr / g.bs_r, bc = gc / g.bs_c;
-  if (br % g.R != g.my_row || bc % g.C != g.my_col) return;
-  const int lr = (br / g.R) * g.bs_r + gr % g.bs_r;
-  const int lc = (bc / g.C) * g.bs_c + gc % g.bs_c;
-  dst[(int64_t)lc * g.lld + lr] = v;
-}
-
-__global__ void __launch_bounds__(256)
-scatter_tiles_kernel(const TileStore ts, int which, const double* __restrict__ diag, double* __restrict__ dst,
-                     const CyclicGeom g, int uplo /* 0 L, 1 U, 2 B */, const int4* __restrict__ work, int t0) {
-  const int4 t = work[t0 + blockIdx.x];
-  const int64_t base = (int64_t)t.z * kTileElems;
-  const int r = threadIdx.x & 127;
-  const int gr = t.x + r;
-  if (gr >= ts.n) return;
-  for (int c = threadIdx.x >> 7; c < kTileN; c += 2) {
-    const int gc = t.y + c;
-    if (gc > gr || gc >= ts.n) break;
-    const int64_t slot = base + (int64_t)c * kTileM + r;
-    const double nval = ts.N ? (double)ts.N[slot] : ts.flat_n;
-    double v;
-    if (which == 2) {
-      v = nval;
-    } else {
-      const double sv = (gr == gc) ? diag[gr] : ts.S[slot];
-      v = (which == 1) ? sv : __dmul_rn(sv, __ddiv_rn(1., nval));
-    }
-    if (gr == gc) {
-      store_block_cyclic(dst, g, gr, gc, v);
-    } else {
-      if (uplo != 1) store_block_cyclic(dst, g, gr, gc, v);
-      if (uplo != 0) store_block_cyclic(dst, g, gc, gr, v);
+// Streaming output: local rows [lr0, lr1) x local columns [0, lc1) of the caller's block-cyclic matrix, packed
+// column-major into a device staging buffer (pitch lr1 - lr0) that the copy engine then moves to the host while
+// the tensor cores work on later tile groups.  The rectangle belongs to one finished raster row group; entries
+// above the diagonal (inside its diagonal block) get the symmetric value, tiles this engine does not own get 0.
+// `diag` supplies the exact fp64 diagonal of S (the tile store itself is patched after the last group).
+__global__ void pack_rows_kernel(const TileStore ts, int which, const double* __restrict__ diag,
+                                 double* __restrict__ stage, const CyclicGeom g, int lr0, int lr1, int lc1) {
+  const int lr = lr0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int lc = blockIdx.y * blockDim.y + threadIdx.y;
+  if (lr >= lr1 || lc >= lc1) return;
+  const int gr = local_to_global(lr, g.bs_r, g.my_row, g.R);
+  const int gc = local_to_global(lc, g.bs_c, g.my_col, g.C);
+  double v = 0.;
+  if (gr < ts.n && gc < ts.n) {
+    const int r = gr >= gc ? gr : gc, c = gr >= gc ? gc : gr;
+    const int64_t slot = tile_slot(ts, r, c);
+    if (slot >= 0) {
+      const double nval = ts.N ? (double)ts.N[slot] : ts.flat_n;
+      if (which == 2) {
+        v = nval;
+      } else {
+        const double sv = (r == c) ? diag[r] : ts.S[slot];
+        v = (which == 1) ? sv : __dmul_rn(sv, __ddiv_rn(1., nval));
+      }
     }
   }
+  stage[(int64_t)lc * (lr1 - lr0) + (lr - lr0)] = v;
 }
 
 // sanitizeKernel's scan: strictly-lower pairs with -0.1 < N < min_overlap - 0.1

@@ -59,7 +59,8 @@ extern "C" {
 #define DGRM_K_FINAL    4  /* diagonal fix-up                                                 */
 #define DGRM_K_FETCH    5  /* tile -> block-cyclic gather                                     */
 #define DGRM_K_GATHER   6  /* row / individual gather into the aligned chunk buffer           */
-#define DGRM_K_NUM      7
+#define DGRM_K_D2H      7  /* copy-engine transfers of streamed (bound) outputs, not a kernel  */
+#define DGRM_K_NUM      8
 
 typedef struct dgrm_engine dgrm_engine;
 
@@ -147,8 +148,10 @@ int dgrm_fetch_block_cyclic(dgrm_engine *e, int which, double *local, int64_t ll
 /* Bind a caller-owned local block-cyclic buffer (same arguments as dgrm_fetch_block_cyclic) that
  * dgrm_finish fills with matrix `which`.  When the buffer is pinned (dgrm_host_alloc) the tiles are
  * stored into it group by group while later tile groups are still being contracted, so the
- * device->host traffic overlaps the tensor-core work; pageable buffers are filled at the end of
- * dgrm_finish.  One binding per `which`; bindings survive dgrm_begin and are dropped by
+ * device->host traffic (copy engine) overlaps the tensor-core work; this streaming applies to pinned
+ * uplo 'L' bindings and may additionally deposit the symmetric value above the diagonal inside the
+ * 256-row diagonal blocks (the reference leaves that half uninitialised, matrix.cpp:1646, 2682).
+ * Pageable buffers and uplo 'U'/'B' are filled at the end of dgrm_finish.  One binding per `which`; bindings survive dgrm_begin and are dropped by
  * dgrm_set_individuals / dgrm_unbind_outputs.  Replaces the result hand-over of Kernel::Kernel
  * (kernel.cpp:94-116: kernel->m and N->m are the outputs). */
 int dgrm_bind_output(dgrm_engine *e, int which, double *local, int64_t lld, int bs_r, int bs_c,

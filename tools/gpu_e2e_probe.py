@@ -52,7 +52,8 @@ def main():
         best = min(ts, key=lambda x: x[3])
         kt = eng.kernel_times()
         print(f"{label:28s} push {best[0]*1e3:7.2f}  finish {best[1]*1e3:7.2f}  fetch {best[2]*1e3:7.2f}  total "
-              f"{best[3]*1e3:7.2f} ms   fetch-class ms/rep {kt['fetch'][0]/a.reps:.2f} launches {kt['fetch'][1]}")
+              f"{best[3]*1e3:7.2f} ms   fetch-class ms/rep {kt['fetch'][0]/a.reps:.2f} launches {kt['fetch'][1]}  "
+              f"d2h ms/rep {kt['d2h'][0]/a.reps:.2f} copies {kt['d2h'][1]}")
 
     run("compute only (H2D in)", False, False)
     run("bound outputs (streamed)", True, False)
