@@ -321,6 +321,8 @@ int launch_syrk(dgrm_engine* e, const CUtensorMap& tmap, const SyrkParams& p) {
   return DGRM_OK;
 }
 
+constexpr int kCountMerge = 4;  // resident chunks per pair-count accumulation (4 * 8192 SNPs << 2^24)
+
 int flush_super(dgrm_engine* e, bool final);
 
 // One chunk of packed rows: per-SNP statistics, then expansion into resident operand slot `chunks_in_super`.
@@ -544,7 +546,24 @@ int flush_super(dgrm_engine* e, bool final) {
                                                : launch_syrk<1, false, double>(e, e->tmap_z, p);
           if (rc) return rc;
         }
-        if (count_mma) {
+        // pair count: 0/1 products accumulate exactly in fp32 up to 2^24, so up to four resident chunks
+        // (32768 SNPs) share one TMEM accumulation and one int32 read-modify-write of the tile
+        if (count_mma && per_launch == 1 && (j0 % kCountMerge == 0)) {
+          Prof pr(e, DGRM_K_PAIRCNT);
+          const int j1 = std::min(nch, j0 + kCountMerge);
+          int kpad = 0;
+          for (int j = j0; j < j1; ++j) kpad += e->slot_kpad[j];   // slots are adjacent; only the last can be short
+          p.nchunks = 1;
+          p.chunk_col[0] = j0 * e->kc_max;
+          p.chunk_kpad[0] = kpad;
+          p.npass = 1;
+          p.a_off[0] = p.b_off[0] = 0;
+          p.out = e->d_N;
+          p.idesc = make_idesc(e->cfg.cta_group, 0 /* e4m3 */);
+          const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, true, int>(e, e->tmap_q, p)
+                                               : launch_syrk<1, true, int>(e, e->tmap_q, p);
+          if (rc) return rc;
+        } else if (count_mma && per_launch != 1) {
           Prof pr(e, DGRM_K_PAIRCNT);
           p.npass = 1;
           p.a_off[0] = p.b_off[0] = 0;
@@ -915,10 +934,10 @@ int dgrm_push_bed_device(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, i
   if (e->finished) return fail(e, DGRM_E_INVALID, "dgrm_push_bed_device after dgrm_finish");
   if (!d_rows || nrows < 0 || pitch < e->b_fam) return fail(e, DGRM_E_INVALID, "dgrm_push_bed_device: bad rows/pitch");
   CK(cudaSetDevice(e->cfg.device));
-  if (producer_stream) {
-    CK(cudaEventRecord(e->producer_ev, (cudaStream_t)producer_stream));
-    CK(cudaStreamWaitEvent(e->stream, e->producer_ev, 0));
-  }
+  // order after the producer; NULL is the legacy default stream (what torch uses unless told otherwise), which the
+  // engine's non-blocking streams do not synchronise with implicitly
+  CK(cudaEventRecord(e->producer_ev, (cudaStream_t)producer_stream));
+  CK(cudaStreamWaitEvent(e->stream, e->producer_ev, 0));
   // bound the host-side index list
   for (int64_t r0 = 0; r0 < nrows; r0 += (1 << 20)) {
     const int64_t cnt = std::min<int64_t>(nrows - r0, 1 << 20);
@@ -1363,24 +1382,36 @@ int dgrm_fetch_tiles(dgrm_engine* e, int which, double* tiles) {
   if (e->ntiles == 0) return DGRM_OK;
   CK(cudaSetDevice(e->cfg.device));
   const int64_t total = e->ntiles * kTileElems;
-  const int64_t slab = 8ll << 20;  // elements per pass
-  double* d_tmp = nullptr;
-  CK(cudaMalloc(&d_tmp, (size_t)std::min(total, slab) * sizeof(double)));
+  const int64_t slab = 32ll << 20;  // elements per pass (256 MB), two staging buffers
+  double* d_tmp[2] = {nullptr, nullptr};
+  cudaEvent_t done[2];
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc(&d_tmp[i], (size_t)std::min(total, slab) * sizeof(double)));
+    CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  }
   TileStore ts = tile_store(e);
-  for (int64_t o = 0; o < total; o += slab) {
+  int sl = 0;
+  for (int64_t o = 0; o < total; o += slab, sl ^= 1) {
     const int64_t cnt = std::min(slab, total - o);
     TileStore t2 = ts;
     t2.S = ts.S + o;
     t2.N = ts.N ? ts.N + o : nullptr;
+    CK(cudaStreamWaitEvent(e->stream, done[sl], 0));
     {
       Prof pr(e, DGRM_K_FETCH);
-      export_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(t2, which, cnt, d_tmp);
+      export_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(t2, which, cnt, d_tmp[sl]);
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(tiles + o, d_tmp, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventRecord(e->stage_packed[sl], e->stream));
+    CK(cudaStreamWaitEvent(e->d2h_stream, e->stage_packed[sl], 0));
+    CK(cudaMemcpyAsync(tiles + o, d_tmp[sl], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, e->d2h_stream));
+    CK(cudaEventRecord(done[sl], e->d2h_stream));
   }
-  cudaFree(d_tmp);
+  CK(cudaStreamSynchronize(e->d2h_stream));
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(d_tmp[i]);
+    cudaEventDestroy(done[i]);
+  }
   return DGRM_OK;
 }
 

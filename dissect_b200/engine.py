@@ -223,8 +223,13 @@ class GrmEngine:
             self._ck(self._lib.dgrm_tile_coords(self._h, rc.ctypes.data))
         return rc
 
-    def fetch_tiles(self, which="A"):
-        t = np.zeros((self.num_tiles, 256, 128), np.float64)  # [tile][col][row]
+    def fetch_tiles(self, which="A", out_ptr=None):
+        """This engine's tiles as doubles, [tile][col][row]; out_ptr: caller buffer (e.g. pinned) to fill instead."""
+        if out_ptr is not None:
+            if self.num_tiles:
+                self._ck(self._lib.dgrm_fetch_tiles(self._h, _lib.FETCH[which], int(out_ptr)))
+            return None
+        t = np.zeros((self.num_tiles, 256, 128), np.float64)
         if self.num_tiles:
             self._ck(self._lib.dgrm_fetch_tiles(self._h, _lib.FETCH[which], t.ctypes.data))
         return t

@@ -106,8 +106,8 @@ int dgrm_begin(dgrm_engine *e, int64_t m_capacity);
  * Replaces readBEDFile's decode loop + parseSNP/parseSNPbyte (genotype.cpp:639-787),
  * normalizeGenotypes (genotype.cpp:888-961) and both pdsyrk_ calls (kernel.cpp:94,100) for
  * these rows.  The host variant copies host->device itself (asynchronously when `rows` is
- * pinned); the device variant reads rows already in HBM after `producer_stream` (a
- * cudaStream_t, may be NULL) reaches the point of the call. */
+ * pinned); the device variant reads rows already in HBM once `producer_stream` (a
+ * cudaStream_t; NULL = the legacy default stream) reaches the point of the call. */
 int dgrm_push_bed_host(dgrm_engine *e, const uint8_t *rows, int64_t pitch, int64_t nrows,
                        const uint8_t *row_keep);
 int dgrm_push_bed_device(dgrm_engine *e, const uint8_t *d_rows, int64_t pitch, int64_t nrows,
