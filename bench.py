@@ -239,8 +239,8 @@ def run_gpu(args):
             mine.append((c0, r0, r1))
         # rows are exchanged with a 16-byte aligned pitch so that the engine's row gather can use 128-bit copies
         bpr_pad = (bpr + 15) // 16 * 16
-        gather_buf = torch.zeros((G * shard, bpr_pad), dtype=torch.uint8, device="cuda")
-        send_buf = torch.zeros((shard, bpr_pad), dtype=torch.uint8, device="cuda")
+        gather_bufs = [torch.zeros((G * shard, bpr_pad), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        send_bufs = [torch.zeros((shard, bpr_pad), dtype=torch.uint8, device="cuda") for _ in range(2)]
     host_pk = PinnedArray((m_file, bpr), np.uint8)
     host_pk.array[:] = pk_all.cpu().numpy()
 
@@ -253,8 +253,9 @@ def run_gpu(args):
             eng.push_bed_device(pk_all.data_ptr(), pk_all.stride(0), m_file, row_keep=keep)
             return
         stream = torch.cuda.current_stream().cuda_stream
-        for (c0, r0, r1) in mine:
+        for ci, (c0, r0, r1) in enumerate(mine):
             c1 = min(c0 + chunk, m_file)
+            gather_buf, send_buf = gather_bufs[ci & 1], send_bufs[ci & 1]
             if r1 > r0:
                 send_buf[: r1 - r0, :bpr].copy_(pk_all[r0:r1])
             dist.all_gather_into_tensor(gather_buf, send_buf)
@@ -266,7 +267,8 @@ def run_gpu(args):
                 if b > a:
                     rk[g * shard: g * shard + (b - a)] = keep[a:b]
             eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), G * shard, row_keep=rk, stream=stream)
-            eng.sync()  # gather_buf is reused by the next all-gather
+            # two exchange buffers: the all-gather of chunk c+2 into this one is ordered after the engine read it
+            eng.release_inputs(stream)
 
     def step_device():
         eng.begin(m_kept)
@@ -335,8 +337,9 @@ def run_gpu(args):
         def step_e2e():
             eng.begin(m_kept)
             stream = torch.cuda.current_stream().cuda_stream
-            for (c0, r0, r1) in mine:
+            for ci, (c0, r0, r1) in enumerate(mine):
                 c1 = min(c0 + chunk, m_file)
+                gather_buf, send_buf = gather_bufs[ci & 1], send_bufs[ci & 1]
                 if r1 > r0:
                     send_buf[: r1 - r0, :bpr].copy_(torch.from_numpy(host_pk.array[r0:r1]), non_blocking=True)
                 dist.all_gather_into_tensor(gather_buf, send_buf)
@@ -347,7 +350,7 @@ def run_gpu(args):
                     if b > a:
                         rk[g * shard: g * shard + (b - a)] = keep[a:b]
                 eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), G * shard, row_keep=rk, stream=stream)
-                eng.sync()
+                eng.release_inputs(stream)
             eng.finish()
             eng.fetch_tiles("A", out_ptr=tiles_A.ptr)
             eng.fetch_tiles("N", out_ptr=tiles_N.ptr)
@@ -438,7 +441,7 @@ def main():
     ap.add_argument("--impl", default="dgrm", choices=["dgrm", "reference"])
     ap.add_argument("--n", type=int, default=0, help="override individuals (default 20000*sqrt(gpus))")
     ap.add_argument("--m", type=int, default=0, help="override SNPs in the file (default 100000)")
-    ap.add_argument("--chunk", type=int, default=8192)
+    ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--cg", type=int, default=2)
     ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16", "fp16x2"])
     ap.add_argument("--count", default="mma", choices=["mma", "popc"])

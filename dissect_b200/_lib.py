@@ -15,7 +15,7 @@ FETCH = {"A": 0, "S": 1, "N": 2}
 # every symbol include/dgrm.h declares
 SYMBOLS = (
     "dgrm_default_config", "dgrm_create", "dgrm_destroy", "dgrm_last_error", "dgrm_abi_version",
-    "dgrm_set_individuals", "dgrm_begin", "dgrm_push_bed_host", "dgrm_push_bed_device",
+    "dgrm_set_individuals", "dgrm_begin", "dgrm_push_bed_host", "dgrm_push_bed_device", "dgrm_release_inputs",
     "dgrm_load_bed_file", "dgrm_finish", "dgrm_sync", "dgrm_num_snps", "dgrm_num_individuals",
     "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_bind_output", "dgrm_unbind_outputs", "dgrm_low_overlap_pairs",
     "dgrm_set_output_subset", "dgrm_write_grm_dat", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles",
@@ -58,6 +58,7 @@ def load():
     lib.dgrm_begin.argtypes = [vp, i64]
     lib.dgrm_push_bed_host.argtypes = [vp, vp, i64, i64, vp]
     lib.dgrm_push_bed_device.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.dgrm_release_inputs.argtypes = [vp, vp]
     lib.dgrm_load_bed_file.argtypes = [vp, C.c_char_p, i64, vp, i64]
     lib.dgrm_finish.argtypes = [vp]
     lib.dgrm_sync.argtypes = [vp]

@@ -78,13 +78,23 @@ struct dgrm_engine {
   cudaStream_t out_stream = nullptr;   // packs finished row groups into staging
   cudaStream_t d2h_stream = nullptr;   // copy engine: staging -> caller buffer
   std::vector<cudaEvent_t> group_ev;
-  double* d_out_stage[2] = {nullptr, nullptr};
+  static constexpr int kOutSlots = 3;
+  void* d_out_stage[kOutSlots] = {nullptr, nullptr, nullptr};
+  void* h_out_stage[kOutSlots] = {nullptr, nullptr, nullptr};  // pinned; staged jobs are finished by host threads
   size_t out_stage_bytes = 0;
-  cudaEvent_t stage_packed[2] = {nullptr, nullptr}, stage_copied_out[2] = {nullptr, nullptr};
-  int out_stage_i = 0;
+  cudaEvent_t stage_packed[kOutSlots] = {nullptr, nullptr, nullptr}, stage_copied_out[kOutSlots] = {nullptr, nullptr, nullptr};
+  struct OutJob {
+    int b;                  // binding
+    int row0, row1;         // global rows of the raster row group
+    int lr0, lr1, lc1;      // local rectangle rows [lr0, lr1) x cols [0, lc1)
+    int ev;                 // tile-group event after which the rectangle is final
+    bool direct;            // copy engine writes straight into the caller's (pinned) buffer
+    bool as_int;            // pair counts cross PCIe as int32 and are widened by the host
+  };
+  std::vector<OutJob> jobs;
+  size_t jobs_issued = 0, jobs_done = 0;
   std::vector<int> rg_end;    // per raster row group: end index in `work` of its last owned supertile
   std::vector<int> rg_row1;   // per raster row group: one past its last global row
-  int rg_emitted = 0;
 
   // resident operand slots: `slots` chunks of kc_max SNPs live side by side in Z / Q / MB
   int slots = 0;
@@ -321,7 +331,7 @@ int launch_syrk(dgrm_engine* e, const CUtensorMap& tmap, const SyrkParams& p) {
   return DGRM_OK;
 }
 
-constexpr int kCountMerge = 4;  // resident chunks per pair-count accumulation (4 * 8192 SNPs << 2^24)
+constexpr int kCountMergeSnps = 32768;  // SNPs per pair-count accumulation (exact in fp32: << 2^24)
 
 int flush_super(dgrm_engine* e, bool final);
 
@@ -381,7 +391,7 @@ int process_chunk(dgrm_engine* e) {
   return DGRM_OK;
 }
 
-bool binding_streams(const dgrm_engine::Binding& bd) { return bd.dev != nullptr && bd.uplo == 0; }
+bool binding_streams(const dgrm_engine::Binding& bd) { return bd.uplo == 0; }
 
 // first local index whose global index is >= target (block-cyclic, monotone)
 int first_local_ge(int target, int nloc, int bs, int me, int P) {
@@ -394,68 +404,96 @@ int first_local_ge(int target, int nloc, int bs, int me, int P) {
   return a;
 }
 
-// Every raster row group whose tiles are all contracted once work[0, w_done) is done leaves the device:
-// pack kernel (out_stream) -> device staging -> copy engine (d2h_stream) -> the caller's bound buffers.
-int emit_outputs(dgrm_engine* e, int w_done, cudaEvent_t after) {
-  bool any = false;
-  for (int b = 0; b < e->nbind; ++b) any |= binding_streams(e->bind[b]);
-  if (!any) return DGRM_OK;
-  bool waited = false;
+// Issue output job k: pack kernel (out_stream) -> device staging -> copy engine (d2h_stream) -> either the
+// caller's pinned buffer (direct) or the library's pinned host staging (finished by finish_job).
+int issue_job(dgrm_engine* e, size_t k) {
+  const dgrm_engine::OutJob& j = e->jobs[k];
+  const dgrm_engine::Binding& bd = e->bind[j.b];
+  const CyclicGeom& g = bd.g;
+  const int sl = (int)(k % dgrm_engine::kOutSlots);
   const TileStore ts = tile_store(e);
-  while (e->rg_emitted < (int)e->rg_end.size() && e->rg_end[e->rg_emitted] <= w_done) {
-    const int rg = e->rg_emitted++;
-    const int row0 = rg == 0 ? 0 : e->rg_row1[rg - 1];
-    const int row1 = std::min<int>(e->rg_row1[rg], (int)e->n);
-    if (row0 >= row1) continue;
-    if (!waited) {
-      CK(cudaStreamWaitEvent(e->out_stream, after, 0));
-      waited = true;
+  CK(cudaStreamWaitEvent(e->out_stream, e->group_ev[(size_t)j.ev], 0));
+  {
+    Prof pr(e, DGRM_K_FETCH, e->out_stream);
+    const dim3 blk(128, 2);
+    const dim3 grid((unsigned)((j.lr1 - j.lr0 + 127) / 128), (unsigned)((j.lc1 + 1) / 2));
+    if (j.as_int)
+      pack_rows_kernel<int><<<grid, blk, 0, e->out_stream>>>(ts, bd.which, e->d_diag, (int*)e->d_out_stage[sl], g, j.lr0,
+                                                            j.lr1, j.lc1);
+    else
+      pack_rows_kernel<double><<<grid, blk, 0, e->out_stream>>>(ts, bd.which, e->d_diag, (double*)e->d_out_stage[sl], g,
+                                                               j.lr0, j.lr1, j.lc1);
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(e->stage_packed[sl], e->out_stream));
+  CK(cudaStreamWaitEvent(e->d2h_stream, e->stage_packed[sl], 0));
+  {
+    // copy engine: everything left of the diagonal block in one strided copy, the diagonal block itself as
+    // 256-column strips that start at their own diagonal (so almost nothing above the diagonal is moved)
+    Prof pr(e, DGRM_K_D2H, e->d2h_stream);
+    const int h = j.lr1 - j.lr0;
+    const size_t es = j.as_int ? sizeof(int32_t) : sizeof(double);
+    auto copy_rect = [&](int lra, int lrb, int lca, int lcb) -> cudaError_t {
+      if (lrb <= lra || lcb <= lca) return cudaSuccess;
+      const char* src = (const char*)e->d_out_stage[sl] + ((int64_t)lca * h + (lra - j.lr0)) * es;
+      if (j.direct)
+        return cudaMemcpy2DAsync(bd.host + (int64_t)lca * g.lld + lra, (size_t)g.lld * sizeof(double), src, (size_t)h * es,
+                                 (size_t)(lrb - lra) * es, (size_t)(lcb - lca), cudaMemcpyDeviceToHost, e->d2h_stream);
+      char* dst = (char*)e->h_out_stage[sl] + ((int64_t)lca * h + (lra - j.lr0)) * es;
+      return cudaMemcpy2DAsync(dst, (size_t)h * es, src, (size_t)h * es, (size_t)(lrb - lra) * es, (size_t)(lcb - lca),
+                               cudaMemcpyDeviceToHost, e->d2h_stream);
+    };
+    const int lc0d = first_local_ge(j.row0, g.nloc_c, g.bs_c, g.my_col, g.C);
+    CK(copy_rect(j.lr0, j.lr1, 0, lc0d));
+    for (int g0 = j.row0; g0 < j.row1; g0 += 256) {
+      const int lca = first_local_ge(g0, g.nloc_c, g.bs_c, g.my_col, g.C);
+      const int lcb = first_local_ge(std::min(g0 + 256, j.row1), g.nloc_c, g.bs_c, g.my_col, g.C);
+      const int lra = first_local_ge(g0, g.nloc_r, g.bs_r, g.my_row, g.R);
+      CK(copy_rect(lra, j.lr1, lca, lcb));
     }
-    for (int b = 0; b < e->nbind; ++b) {
-      const dgrm_engine::Binding& bd = e->bind[b];
-      if (!binding_streams(bd)) continue;
-      const CyclicGeom& g = bd.g;
-      const int lr0 = first_local_ge(row0, g.nloc_r, g.bs_r, g.my_row, g.R);
-      const int lr1 = first_local_ge(row1, g.nloc_r, g.bs_r, g.my_row, g.R);
-      const int lc1 = first_local_ge(row1, g.nloc_c, g.bs_c, g.my_col, g.C);
-      if (lr1 <= lr0 || lc1 <= 0) continue;
-      const size_t bytes = (size_t)(lr1 - lr0) * lc1 * sizeof(double);
-      if (bytes > e->out_stage_bytes) return fail(e, DGRM_E_INVALID, "internal: output staging too small");
-      const int sl = e->out_stage_i;
-      e->out_stage_i ^= 1;
-      CK(cudaStreamWaitEvent(e->out_stream, e->stage_copied_out[sl], 0));  // staging slot free again
-      {
-        Prof pr(e, DGRM_K_FETCH, e->out_stream);
-        const dim3 blk(128, 2);
-        const dim3 grid((unsigned)((lr1 - lr0 + 127) / 128), (unsigned)((lc1 + 1) / 2));
-        pack_rows_kernel<<<grid, blk, 0, e->out_stream>>>(ts, bd.which, e->d_diag, e->d_out_stage[sl], g, lr0, lr1, lc1);
-        CK(cudaGetLastError());
-      }
-      CK(cudaEventRecord(e->stage_packed[sl], e->out_stream));
-      CK(cudaStreamWaitEvent(e->d2h_stream, e->stage_packed[sl], 0));
-      {
-        // copy engine: everything left of the diagonal block in one strided copy, the diagonal block itself as
-        // 256-column strips that start at their own diagonal (so almost nothing above the diagonal is moved)
-        Prof pr(e, DGRM_K_D2H, e->d2h_stream);
-        const int h = lr1 - lr0;
-        auto copy_rect = [&](int lra, int lrb, int lca, int lcb) -> cudaError_t {
-          if (lrb <= lra || lcb <= lca) return cudaSuccess;
-          return cudaMemcpy2DAsync(bd.host + (int64_t)lca * g.lld + lra, (size_t)g.lld * sizeof(double),
-                                   e->d_out_stage[sl] + (int64_t)lca * h + (lra - lr0), (size_t)h * sizeof(double),
-                                   (size_t)(lrb - lra) * sizeof(double), (size_t)(lcb - lca), cudaMemcpyDeviceToHost,
-                                   e->d2h_stream);
-        };
-        const int lc0d = first_local_ge(row0, g.nloc_c, g.bs_c, g.my_col, g.C);
-        CK(copy_rect(lr0, lr1, 0, lc0d));
-        for (int g0 = row0; g0 < row1; g0 += 256) {
-          const int lca = first_local_ge(g0, g.nloc_c, g.bs_c, g.my_col, g.C);
-          const int lcb = first_local_ge(std::min(g0 + 256, row1), g.nloc_c, g.bs_c, g.my_col, g.C);
-          const int lra = first_local_ge(g0, g.nloc_r, g.bs_r, g.my_row, g.R);
-          CK(copy_rect(lra, lr1, lca, lcb));
-        }
-      }
-      CK(cudaEventRecord(e->stage_copied_out[sl], e->d2h_stream));
+  }
+  CK(cudaEventRecord(e->stage_copied_out[sl], e->d2h_stream));
+  return DGRM_OK;
+}
+
+// Wait for job k's transfer; staged jobs are then moved (and pair counts widened to double) into the caller's
+// buffer by host threads, exactly the rows on or below the diagonal of every column.
+int finish_job(dgrm_engine* e, size_t k) {
+  const dgrm_engine::OutJob& j = e->jobs[k];
+  const int sl = (int)(k % dgrm_engine::kOutSlots);
+  CK(cudaEventSynchronize(e->stage_copied_out[sl]));
+  if (j.direct) return DGRM_OK;
+  const dgrm_engine::Binding& bd = e->bind[j.b];
+  const CyclicGeom g = bd.g;
+  const int h = j.lr1 - j.lr0;
+  const void* hs = e->h_out_stage[sl];
+  double* host = bd.host;
+  const bool as_int = j.as_int;
+  const int lr0 = j.lr0, lr1 = j.lr1;
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int lc = 0; lc < j.lc1; ++lc) {
+    const int gc = ((lc / g.bs_c) * g.C + g.my_col) * g.bs_c + lc % g.bs_c;
+    const int lra = std::max(lr0, first_local_ge(gc, g.nloc_r, g.bs_r, g.my_row, g.R));
+    if (lra >= lr1) continue;
+    double* dst = host + (int64_t)lc * g.lld + lra;
+    const int cnt = lr1 - lra;
+    if (as_int) {
+      const int32_t* src = (const int32_t*)hs + (int64_t)lc * h + (lra - lr0);
+      for (int i = 0; i < cnt; ++i) dst[i] = (double)src[i];
+    } else {
+      memcpy(dst, (const double*)hs + (int64_t)lc * h + (lra - lr0), (size_t)cnt * sizeof(double));
     }
+  }
+  return DGRM_OK;
+}
+
+// issue every job that is final after tile group `gi` for which a staging slot is free
+int issue_ready_jobs(dgrm_engine* e, int gi) {
+  while (e->jobs_issued < e->jobs.size() && e->jobs[e->jobs_issued].ev <= gi &&
+         e->jobs_issued - e->jobs_done < (size_t)dgrm_engine::kOutSlots) {
+    const int rc = issue_job(e, e->jobs_issued);
+    if (rc) return rc;
+    e->jobs_issued++;
   }
   return DGRM_OK;
 }
@@ -481,43 +519,55 @@ int flush_super(dgrm_engine* e, bool final) {
     const int units = e->cfg.cta_group == 2 ? e->sm_count / 2 : e->sm_count;
     bool stream_out = false;
     for (int b = 0; b < e->nbind; ++b) stream_out |= binding_streams(e->bind[b]);
+    // Tile groups.  Streaming outputs: one group per raster row group, its end rounded up to whole waves of
+    // the persistent grid (no ragged tail, and the row group is final as soon as its launches are done).
+    std::vector<int> group_end;
+    std::vector<int> rg_group(e->rg_end.size(), 0);
     if (final && stream_out) {
-      // staging: the largest row-group rectangle of any streaming binding, two slots
+      for (size_t rg = 0; rg < e->rg_end.size(); ++rg) {
+        const int end = std::min(nwork, (e->rg_end[rg] + units - 1) / units * units);
+        if (end > (group_end.empty() ? 0 : group_end.back())) group_end.push_back(end);
+        rg_group[rg] = (int)group_end.size() - 1;
+      }
+    }
+    if (group_end.empty() || group_end.back() != nwork) group_end.push_back(nwork);
+    if (final && stream_out) {
+      // output jobs: one per (raster row group, streaming binding), in the order the row groups finish
+      e->jobs.clear();
+      e->jobs_issued = e->jobs_done = 0;
       size_t need = 0;
-      for (int b = 0; b < e->nbind; ++b) {
-        const dgrm_engine::Binding& bd = e->bind[b];
-        if (!binding_streams(bd)) continue;
-        for (size_t rg = 0; rg < e->rg_row1.size(); ++rg) {
-          const int row0 = rg == 0 ? 0 : e->rg_row1[rg - 1], row1 = std::min<int>(e->rg_row1[rg], (int)e->n);
-          if (row0 >= row1) continue;
-          const int lr0 = first_local_ge(row0, bd.g.nloc_r, bd.g.bs_r, bd.g.my_row, bd.g.R);
-          const int lr1 = first_local_ge(row1, bd.g.nloc_r, bd.g.bs_r, bd.g.my_row, bd.g.R);
-          const int lc1 = first_local_ge(row1, bd.g.nloc_c, bd.g.bs_c, bd.g.my_col, bd.g.C);
-          need = std::max(need, (size_t)std::max(lr1 - lr0, 0) * (size_t)std::max(lc1, 0) * sizeof(double));
+      for (size_t rg = 0; rg < e->rg_row1.size(); ++rg) {
+        const int row0 = rg == 0 ? 0 : e->rg_row1[rg - 1], row1 = std::min<int>(e->rg_row1[rg], (int)e->n);
+        if (row0 >= row1) continue;
+        for (int b = 0; b < e->nbind; ++b) {
+          const dgrm_engine::Binding& bd = e->bind[b];
+          if (!binding_streams(bd)) continue;
+          dgrm_engine::OutJob j;
+          j.b = b; j.row0 = row0; j.row1 = row1; j.ev = rg_group[rg];
+          j.lr0 = first_local_ge(row0, bd.g.nloc_r, bd.g.bs_r, bd.g.my_row, bd.g.R);
+          j.lr1 = first_local_ge(row1, bd.g.nloc_r, bd.g.bs_r, bd.g.my_row, bd.g.R);
+          j.lc1 = first_local_ge(row1, bd.g.nloc_c, bd.g.bs_c, bd.g.my_col, bd.g.C);
+          if (j.lr1 <= j.lr0 || j.lc1 <= 0) continue;
+          j.as_int = bd.which == DGRM_FETCH_N && !e->cfg.flat_norm;
+          j.direct = bd.dev != nullptr && !j.as_int;
+          need = std::max(need, (size_t)(j.lr1 - j.lr0) * (size_t)j.lc1 * sizeof(double));
+          e->jobs.push_back(j);
         }
       }
       if (need > e->out_stage_bytes) {
         CK(cudaStreamSynchronize(e->d2h_stream));
         CK(cudaStreamSynchronize(e->out_stream));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < dgrm_engine::kOutSlots; ++i) {
           free_dev(e->d_out_stage[i]);
           e->d_out_stage[i] = nullptr;
+          if (e->h_out_stage[i]) cudaFreeHost(e->h_out_stage[i]);
+          e->h_out_stage[i] = nullptr;
           CK(cudaMalloc(&e->d_out_stage[i], need));
+          CK(cudaHostAlloc(&e->h_out_stage[i], need, cudaHostAllocDefault));
         }
         e->out_stage_bytes = need;
       }
-      e->rg_emitted = 0;
     }
-    // Tile groups.  Streaming outputs: one group per raster row group, its end rounded up to whole waves of
-    // the persistent grid (no ragged tail, and the row group is final as soon as its launches are done).
-    std::vector<int> group_end;
-    if (final && stream_out) {
-      for (size_t rg = 0; rg < e->rg_end.size(); ++rg) {
-        const int end = std::min(nwork, (e->rg_end[rg] + units - 1) / units * units);
-        if (end > (group_end.empty() ? 0 : group_end.back())) group_end.push_back(end);
-      }
-    }
-    if (group_end.empty() || group_end.back() != nwork) group_end.push_back(nwork);
     // Within a tile group the chunks are contracted by one launch each (chunk-major inside the group): the
     // launch boundary re-synchronises the persistent CTAs every few hundred microseconds, which is what keeps
     // the A/B panels they share hot in L2.  (One tile-major launch over all chunks lets the CTAs drift apart
@@ -546,11 +596,12 @@ int flush_super(dgrm_engine* e, bool final) {
                                                : launch_syrk<1, false, double>(e, e->tmap_z, p);
           if (rc) return rc;
         }
-        // pair count: 0/1 products accumulate exactly in fp32 up to 2^24, so up to four resident chunks
-        // (32768 SNPs) share one TMEM accumulation and one int32 read-modify-write of the tile
-        if (count_mma && per_launch == 1 && (j0 % kCountMerge == 0)) {
+        // pair count: 0/1 products accumulate exactly in fp32 up to 2^24, so resident chunks are merged up to
+        // 32768 SNPs per TMEM accumulation (one int32 read-modify-write of the tile per merged group)
+        const int merge = std::max(1, kCountMergeSnps / e->kc_max);
+        if (count_mma && per_launch == 1 && (j0 % merge == 0)) {
           Prof pr(e, DGRM_K_PAIRCNT);
-          const int j1 = std::min(nch, j0 + kCountMerge);
+          const int j1 = std::min(nch, j0 + merge);
           int kpad = 0;
           for (int j = j0; j < j1; ++j) kpad += e->slot_kpad[j];   // slots are adjacent; only the last can be short
           p.nchunks = 1;
@@ -581,8 +632,18 @@ int flush_super(dgrm_engine* e, bool final) {
           e->group_ev.push_back(ev);
         }
         CK(cudaEventRecord(e->group_ev[gi], e->stream));
-        const int rc = emit_outputs(e, w1, e->group_ev[gi]);
+        const int rc = issue_ready_jobs(e, (int)gi);
         if (rc) return rc;
+      }
+    }
+    if (final && stream_out) {
+      // everything is queued on the compute stream: now feed the copy engine and finish the staged jobs
+      while (e->jobs_done < e->jobs.size()) {
+        int rc = issue_ready_jobs(e, (int)group_end.size());
+        if (rc) return rc;
+        rc = finish_job(e, e->jobs_done);
+        if (rc) return rc;
+        e->jobs_done++;
       }
     }
   }
@@ -705,7 +766,7 @@ int dgrm_default_config(dgrm_config* cfg) {
   cfg->operand = DGRM_OPERAND_FP16;
   cfg->count_method = DGRM_COUNT_MMA;
   cfg->flat_norm = 0;
-  cfg->chunk_snps = 8192;
+  cfg->chunk_snps = 16384;
   cfg->cta_group = 2;
   cfg->profile = 0;
   cfg->resident_chunks = 0;  // auto
@@ -763,7 +824,7 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   CKC(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < dgrm_engine::kOutSlots; ++i) {
     CKC(cudaEventCreateWithFlags(&e->stage_packed[i], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&e->stage_copied_out[i], cudaEventDisableTiming));
   }
@@ -784,7 +845,9 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   e->encode = (EncodeTiledFn)fn;
   // The output kernels run on their own stream while grm_syrk CTAs (198 KB of smem each) occupy every SM: they can
   // only be co-scheduled onto those SMs when they ask for the same L1/shared-memory split.
-  CKC(cudaFuncSetAttribute(pack_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+  CKC(cudaFuncSetAttribute(pack_rows_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared));
+  CKC(cudaFuncSetAttribute(pack_rows_kernel<int>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)cudaSharedmemCarveoutMaxShared));
   CKC(cudaFuncSetAttribute(bed_expand_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(ExpandSmem)));
@@ -819,8 +882,9 @@ void dgrm_destroy(dgrm_engine* e) {
   if (e->out_stream) cudaStreamDestroy(e->out_stream);
   if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
   for (auto ev : e->group_ev) cudaEventDestroy(ev);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < dgrm_engine::kOutSlots; ++i) {
     free_dev(e->d_out_stage[i]);
+    if (e->h_out_stage[i]) cudaFreeHost(e->h_out_stage[i]);
     if (e->stage_packed[i]) cudaEventDestroy(e->stage_packed[i]);
     if (e->stage_copied_out[i]) cudaEventDestroy(e->stage_copied_out[i]);
   }
@@ -944,6 +1008,15 @@ int dgrm_push_bed_device(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, i
     rc = push_device_rows(e, d_rows + r0 * pitch, pitch, cnt, row_keep ? row_keep + r0 : nullptr);
     if (rc) return rc;
   }
+  return DGRM_OK;
+}
+
+int dgrm_release_inputs(dgrm_engine* e, void* consumer_stream) {
+  if (!e) return DGRM_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  // the row gather into the chunk buffer is the only reader of caller memory and runs on e->stream
+  CK(cudaEventRecord(e->producer_ev, e->stream));
+  CK(cudaStreamWaitEvent((cudaStream_t)consumer_stream, e->producer_ev, 0));
   return DGRM_OK;
 }
 

@@ -81,8 +81,9 @@ __global__ void fetch_block_cyclic_kernel(const TileStore ts, int which, double*
 // the tensor cores work on later tile groups.  The rectangle belongs to one finished raster row group; entries
 // above the diagonal (inside its diagonal block) get the symmetric value, tiles this engine does not own get 0.
 // `diag` supplies the exact fp64 diagonal of S (the tile store itself is patched after the last group).
+template <typename T>
 __global__ void pack_rows_kernel(const TileStore ts, int which, const double* __restrict__ diag,
-                                 double* __restrict__ stage, const CyclicGeom g, int lr0, int lr1, int lc1) {
+                                 T* __restrict__ stage, const CyclicGeom g, int lr0, int lr1, int lc1) {
   const int lr = lr0 + blockIdx.x * blockDim.x + threadIdx.x;
   const int lc = blockIdx.y * blockDim.y + threadIdx.y;
   if (lr >= lr1 || lc >= lc1) return;
@@ -102,7 +103,7 @@ __global__ void pack_rows_kernel(const TileStore ts, int which, const double* __
       }
     }
   }
-  stage[(int64_t)lc * (lr1 - lr0) + (lr - lr0)] = v;
+  stage[(int64_t)lc * (lr1 - lr0) + (lr - lr0)] = (T)v;   // T = int only for the (exact, integer) pair counts
 }
 
 // sanitizeKernel's scan: strictly-lower pairs with -0.1 < N < min_overlap - 0.1

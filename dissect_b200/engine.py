@@ -55,7 +55,7 @@ class PinnedArray:
 
 class GrmEngine:
     def __init__(self, device=0, rank=0, world=1, operand="fp16", count_method="mma", flat_norm=False,
-                 chunk_snps=8192, cta_group=2, profile=False, resident_chunks=0, resident_mb=16384):
+                 chunk_snps=16384, cta_group=2, profile=False, resident_chunks=0, resident_mb=16384):
         self._lib = _lib.load()
         cfg = _lib.Config()
         self._lib.dgrm_default_config(C.byref(cfg))
@@ -128,6 +128,10 @@ class GrmEngine:
             rk = np.ascontiguousarray(row_keep, dtype=np.uint8)
         self._ck(self._lib.dgrm_push_bed_device(self._h, int(ptr), pitch, nrows,
                                                 rk.ctypes.data if rk is not None else None, stream))
+
+    def release_inputs(self, stream=None):
+        """`stream` waits until the engine has read every buffer pushed so far (no host synchronisation)."""
+        self._ck(self._lib.dgrm_release_inputs(self._h, stream))
 
     def load_bed_file(self, path, m_file, snp_keep_idx=None):
         idx = None

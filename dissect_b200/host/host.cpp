@@ -27,7 +27,7 @@ static void engine_check(dgrm_engine* e, int rc) {
 Options::Options()
     : makeGRM(false), outFile("dissect"), flatGRMNormalization(false), minimumNumberOverlapingSNPs(10.),
       maximumProportionOfElimitaedIndividuals(0.9), defaultBlockSize(256), device(0), operand(DGRM_OPERAND_FP16),
-      countMethod(DGRM_COUNT_MMA), chunkSNPs(8192), ctaGroup(2) {}
+      countMethod(DGRM_COUNT_MMA), chunkSNPs(16384), ctaGroup(2) {}
 
 void Options::parseOptions(int argc, char** argv) {
   auto need = [&](int i) -> std::string {

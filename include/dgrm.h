@@ -79,7 +79,7 @@ typedef struct dgrm_config {
   int32_t reserved[5];
 } dgrm_config;
 
-/* Fill *cfg with defaults (device 0, rank 0/1, fp16, MMA count, chunk 8192, cta_group 2). */
+/* Fill *cfg with defaults (device 0, rank 0/1, fp16, MMA count, chunk 16384, cta_group 2). */
 int dgrm_default_config(dgrm_config *cfg);
 
 /* Engine life cycle.  Replaces nothing in the reference; owns device buffers and streams. */
@@ -112,6 +112,11 @@ int dgrm_push_bed_host(dgrm_engine *e, const uint8_t *rows, int64_t pitch, int64
                        const uint8_t *row_keep);
 int dgrm_push_bed_device(dgrm_engine *e, const uint8_t *d_rows, int64_t pitch, int64_t nrows,
                          const uint8_t *row_keep, void *producer_stream);
+
+/* Make `consumer_stream` (a cudaStream_t; NULL = legacy default stream) wait until the engine has read every
+ * buffer handed to dgrm_push_bed_device so far, so that the caller may overwrite those buffers (e.g. with the
+ * next NCCL all-gather) without a host synchronisation. */
+int dgrm_release_inputs(dgrm_engine *e, void *consumer_stream);
 
 /* Whole-file convenience: validates the 3-byte header exactly as genotype.cpp:578-605 and
  * streams the kept rows.  snp_keep_idx[m_keep] are ascending .bim positions, NULL = all

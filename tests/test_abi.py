@@ -36,7 +36,7 @@ def test_no_cpu_fallback():
     lib = _lib.load()
     cfg = _lib.Config()
     assert lib.dgrm_default_config(C.byref(cfg)) == 0
-    assert (cfg.chunk_snps, cfg.cta_group, cfg.world) == (8192, 2, 1)
+    assert (cfg.chunk_snps, cfg.cta_group, cfg.world) == (16384, 2, 1)
     h = C.c_void_p()
     rc = lib.dgrm_create(C.byref(cfg), C.byref(h))
     assert rc == -2 and not h.value
@@ -50,7 +50,7 @@ def test_bad_config_rejected_before_touching_the_gpu():
     h = C.c_void_p()
     cfg.chunk_snps = 100
     assert lib.dgrm_create(C.byref(cfg), C.byref(h)) == -1
-    cfg.chunk_snps = 8192
+    cfg.chunk_snps = 16384
     cfg.rank, cfg.world = 3, 2
     assert lib.dgrm_create(C.byref(cfg), C.byref(h)) == -1
     assert lib.dgrm_set_individuals(None, 10, None) == -1
