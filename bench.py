@@ -444,7 +444,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--cg", type=int, default=2)
     ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16", "fp16x2"])
-    ap.add_argument("--count", default="mma", choices=["mma", "popc"])
+    ap.add_argument("--count", default="fp4", choices=["mma", "popc", "fp4"])
     ap.add_argument("--resident", type=int, default=0, help="resident chunk slots (0 = auto, 1 = streaming)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -9,7 +9,7 @@ K_NUM = 8
 K_NAMES = ("count", "expand", "syrk", "paircnt", "final", "fetch", "gather", "d2h")
 
 OPERANDS = {"fp16": 0, "bf16": 1, "fp16x2": 2}
-COUNT_METHODS = {"mma": 0, "popc": 1}
+COUNT_METHODS = {"mma": 0, "popc": 1, "fp4": 2}
 FETCH = {"A": 0, "S": 1, "N": 2}
 
 # every symbol include/dgrm.h declares

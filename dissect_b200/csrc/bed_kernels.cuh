@@ -146,6 +146,7 @@ bed_count_stats_kernel(const uint8_t* __restrict__ chunk, int64_t pitch, int nro
 //   Z  [n_pad][z_pitch] 16-bit, K-major: Z[i][k] = round16(zt[k][pattern(k,i)])         (hi part)
 //      with SPLIT also Z[i][lo_off + k] = round16(zt - hi)                                 (lo part)
 //   Q  [n_pad][q_pitch] e4m3 0/1, K-major: Q[i][k] = (pattern != 01)                      (missings)
+//   Q4 [n_pad][q4_pitch] e2m1 0/1, two SNPs per byte (same nibble order for both MMA operands)   (fp4 count)
 //   MB [n_pad][mb_pitch] bit k of row i = (pattern != 01)                                  (popcount path)
 //   diag_part[ktile][i] = sum over the tile's SNPs of zt^2 in fp64 (exact diagonal of S)
 // Block = 128 SNPs x 128 individuals, 256 threads; lanes run along individuals so every smem access
@@ -155,6 +156,7 @@ constexpr int kExpK = 128;          // SNPs per block
 constexpr int kExpI = 128;          // individuals per block
 constexpr int kExpZPitch = 272;     // bytes per staged Z row (256 + 16 pad)
 constexpr int kExpQPitch = 136;     // bytes per staged Q row (128 + 8 pad)
+constexpr int kExpQ4Pitch = 68;     // bytes per staged Q4 row (64 + 4 pad)
 
 struct ExpandSmem {
   uint8_t pk[kExpK][32];            // packed genotypes: row = SNP, 32 bytes = 128 individuals
@@ -165,6 +167,7 @@ struct ExpandSmem {
   uint8_t outz[kExpI * kExpZPitch];
   uint8_t outq[kExpI * kExpQPitch];
   uint32_t outm[kExpI][4];          // 128 mask bits per individual
+  uint8_t outq4[kExpI * kExpQ4Pitch];  // e2m1 0/1, two SNPs per byte
 };
 
 template <bool BF16>
@@ -195,6 +198,8 @@ struct ExpandArgs {
   int64_t lo_off;    // element offset of the lo part (SPLIT)
   uint8_t* Q;        // may be NULL (flat norm / popcount)
   int64_t q_pitch;
+  uint8_t* Q4;       // e2m1 0/1 operand (two SNPs per byte), may be NULL
+  int64_t q4_pitch;  // bytes
   uint32_t* MB;      // may be NULL
   int64_t mb_pitch;  // 32-bit words
   double* diag_part; // [ktiles][n_pad]
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
     for (int j = 0; j < 8; ++j) {
       const int kg = kh + 2 * j;
       uint32_t h[4];
-      uint32_t ql = 0, qh = 0, mb = 0;
+      uint32_t ql = 0, qh = 0, mb = 0, q4 = 0;
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const int k = kg * 8 + t;
@@ -258,6 +263,7 @@ __global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
           const uint32_t present = (code != 1u);
           if (t < 4) ql |= (present * 0x38u) << (8 * t); else qh |= (present * 0x38u) << (8 * (t - 4));
           mb |= present << t;
+          q4 |= (present * 0x2u) << (4 * t);   // e2m1 1.0 = 0b0010
           dsum = __dadd_rn(dsum, sm.lut_sq[k][code]);
         }
       }
@@ -265,6 +271,7 @@ __global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
       if (part == 0) {
         *reinterpret_cast<uint2*>(&sm.outq[il * kExpQPitch + kg * 8]) = make_uint2(ql, qh);
         reinterpret_cast<uint8_t*>(&sm.outm[il][0])[kg] = (uint8_t)mb;
+        *reinterpret_cast<uint32_t*>(&sm.outq4[il * kExpQ4Pitch + kg * 4]) = q4;
       }
     }
     if (part == 0) sm.dpart[kh][il] = dsum;
@@ -286,6 +293,14 @@ __global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
             const int r = ps * 16 + (tid >> 4);
             const uint2 v = *reinterpret_cast<const uint2*>(&sm.outq[r * kExpQPitch + c * 8]);
             *reinterpret_cast<uint2*>(a.Q + (int64_t)(i0 + r) * a.q_pitch + k0 + c * 8) = v;
+          }
+        }
+        if (a.Q4) {
+#pragma unroll
+          for (int ps = 0; ps < kExpI / 16; ++ps) {
+            const int r = ps * 16 + (tid >> 4);
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(&sm.outq4[r * kExpQ4Pitch + c * 4]);
+            *reinterpret_cast<uint32_t*>(a.Q4 + (int64_t)(i0 + r) * a.q4_pitch + (k0 >> 1) + c * 4) = v;
           }
         }
         if (a.MB && tid < kExpI) {

@@ -112,11 +112,13 @@ struct dgrm_engine {
   int64_t z_pitch = 0;
   uint8_t* d_Q = nullptr;
   int64_t q_pitch = 0;
+  uint8_t* d_Q4 = nullptr;
+  int64_t q4_pitch = 0;
   uint32_t* d_MB = nullptr;
   int64_t mb_pitch = 0;
   double* d_zt = nullptr;
   double* d_diag_part = nullptr;
-  CUtensorMap tmap_z, tmap_q;
+  CUtensorMap tmap_z, tmap_q, tmap_q4;
   int64_t chunks_done = 0;
 
   // per-SNP statistics
@@ -210,6 +212,7 @@ void release_geometry(dgrm_engine* e) {
   free_dev(e->d_chunk); e->d_chunk = nullptr;
   free_dev(e->d_Z); e->d_Z = nullptr;
   free_dev(e->d_Q); e->d_Q = nullptr;
+  free_dev(e->d_Q4); e->d_Q4 = nullptr;
   free_dev(e->d_MB); e->d_MB = nullptr;
   free_dev(e->d_zt); e->d_zt = nullptr;
   free_dev(e->d_diag_part); e->d_diag_part = nullptr;
@@ -304,10 +307,10 @@ TileStore tile_store(const dgrm_engine* e) {
   return ts;
 }
 
-template <int CG, bool KIND8, typename OutT>
+template <int CG, int KIND, typename OutT>
 int launch_syrk(dgrm_engine* e, const CUtensorMap& tmap, const SyrkParams& p) {
   using Cfg = SyrkCfg<CG>;
-  auto kern = grm_syrk_kernel<CG, KIND8, OutT>;
+  auto kern = grm_syrk_kernel<CG, KIND, OutT>;
   static bool attr_done = false;
   if (!attr_done) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -339,10 +342,11 @@ int flush_super(dgrm_engine* e, bool final);
 int process_chunk(dgrm_engine* e) {
   const int kc = e->fill;
   if (kc == 0) return DGRM_OK;
-  const int kc_pad = (int)round_up(kc, 128);
+  const int kc_pad = (int)round_up(kc, 256);  // whole 128-byte k-blocks for every operand width (fp4: 256 SNPs)
   const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
   const bool bf16 = e->cfg.operand == DGRM_OPERAND_BF16;
   const bool count_mma = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_MMA;
+  const bool count_fp4 = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_FP4;
   const bool count_popc = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_POPC;
   if (e->chunks_in_super == e->slots) {  // every resident slot is taken: contract them before reusing slot 0
     const int rc = flush_super(e, false);
@@ -364,6 +368,7 @@ int process_chunk(dgrm_engine* e) {
     a.chunk = e->d_chunk; a.pitch = e->chunk_pitch; a.kc = kc; a.n = (int)e->n; a.zt = e->d_zt;
     a.Z = e->d_Z + col0; a.z_pitch = e->z_pitch; a.lo_off = (int64_t)e->slots * e->kc_max;
     a.Q = count_mma ? e->d_Q + col0 : nullptr; a.q_pitch = e->q_pitch;
+    a.Q4 = count_fp4 ? e->d_Q4 + col0 / 2 : nullptr; a.q4_pitch = e->q4_pitch;
     a.MB = count_popc ? e->d_MB + col0 / 32 : nullptr; a.mb_pitch = e->mb_pitch;
     a.diag_part = e->d_diag_part; a.n_pad = (int)e->n_pad;
     const dim3 grid((unsigned)(e->n_pad / kExpI), (unsigned)(kc_pad / kExpK));
@@ -508,7 +513,8 @@ int flush_super(dgrm_engine* e, bool final) {
   e->chunks_in_super = 0;
   const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
   const bool bf16 = e->cfg.operand == DGRM_OPERAND_BF16;
-  const bool count_mma = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_MMA;
+  const bool count_fp4 = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_FP4;
+  const bool count_mma = !e->cfg.flat_norm && (e->cfg.count_method == DGRM_COUNT_MMA || count_fp4);
   const int nwork = (int)e->work.size();
   if (nwork > 0) {
     SyrkParams p{};
@@ -592,8 +598,8 @@ int flush_super(dgrm_engine* e, bool final) {
           p.b_off[0] = 0; p.b_off[1] = 0; p.b_off[2] = lo;
           p.out = e->d_S;
           p.idesc = make_idesc(e->cfg.cta_group, bf16 ? 1 : 0);
-          const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, false, double>(e, e->tmap_z, p)
-                                               : launch_syrk<1, false, double>(e, e->tmap_z, p);
+          const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, 0, double>(e, e->tmap_z, p)
+                                               : launch_syrk<1, 0, double>(e, e->tmap_z, p);
           if (rc) return rc;
         }
         // pair count: 0/1 products accumulate exactly in fp32 up to 2^24, so resident chunks are merged up to
@@ -605,14 +611,21 @@ int flush_super(dgrm_engine* e, bool final) {
           int kpad = 0;
           for (int j = j0; j < j1; ++j) kpad += e->slot_kpad[j];   // slots are adjacent; only the last can be short
           p.nchunks = 1;
-          p.chunk_col[0] = j0 * e->kc_max;
-          p.chunk_kpad[0] = kpad;
           p.npass = 1;
           p.a_off[0] = p.b_off[0] = 0;
           p.out = e->d_N;
-          p.idesc = make_idesc(e->cfg.cta_group, 0 /* e4m3 */);
-          const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, true, int>(e, e->tmap_q, p)
-                                               : launch_syrk<1, true, int>(e, e->tmap_q, p);
+          int rc;
+          if (count_fp4) {  // operand addressed in bytes: two SNPs per byte
+            p.chunk_col[0] = j0 * e->kc_max / 2;
+            p.chunk_kpad[0] = kpad / 2;
+            p.idesc = make_idesc_mxf4(e->cfg.cta_group);
+            rc = e->cfg.cta_group == 2 ? launch_syrk<2, 2, int>(e, e->tmap_q4, p) : launch_syrk<1, 2, int>(e, e->tmap_q4, p);
+          } else {
+            p.chunk_col[0] = j0 * e->kc_max;
+            p.chunk_kpad[0] = kpad;
+            p.idesc = make_idesc(e->cfg.cta_group, 0 /* e4m3 */);
+            rc = e->cfg.cta_group == 2 ? launch_syrk<2, 1, int>(e, e->tmap_q, p) : launch_syrk<1, 1, int>(e, e->tmap_q, p);
+          }
           if (rc) return rc;
         } else if (count_mma && per_launch != 1) {
           Prof pr(e, DGRM_K_PAIRCNT);
@@ -620,8 +633,8 @@ int flush_super(dgrm_engine* e, bool final) {
           p.a_off[0] = p.b_off[0] = 0;
           p.out = e->d_N;
           p.idesc = make_idesc(e->cfg.cta_group, 0 /* e4m3 */);
-          const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, true, int>(e, e->tmap_q, p)
-                                               : launch_syrk<1, true, int>(e, e->tmap_q, p);
+          const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, 1, int>(e, e->tmap_q, p)
+                                               : launch_syrk<1, 1, int>(e, e->tmap_q, p);
           if (rc) return rc;
         }
       }
@@ -712,6 +725,7 @@ int ensure_operands(dgrm_engine* e, int slots) {
   CK(cudaStreamSynchronize(e->stream));
   free_dev(e->d_Z); e->d_Z = nullptr;
   free_dev(e->d_Q); e->d_Q = nullptr;
+  free_dev(e->d_Q4); e->d_Q4 = nullptr;
   free_dev(e->d_MB); e->d_MB = nullptr;
   const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
   const int64_t cols = (int64_t)slots * e->kc_max;
@@ -725,6 +739,12 @@ int ensure_operands(dgrm_engine* e, int slots) {
   if (!e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_MMA) {
     CK(cudaMalloc(&e->d_Q, (size_t)e->n_pad * e->q_pitch));
     rc = make_tmap(e, &e->tmap_q, e->d_Q, 1, e->q_pitch, e->n_pad, e->q_pitch);
+    if (rc) return rc;
+  }
+  if (!e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_FP4) {
+    e->q4_pitch = cols / 2;
+    CK(cudaMalloc(&e->d_Q4, (size_t)e->n_pad * e->q4_pitch));
+    rc = make_tmap(e, &e->tmap_q4, e->d_Q4, 1, e->q4_pitch, e->n_pad, e->q4_pitch);
     if (rc) return rc;
   }
   if (!e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_POPC)
@@ -764,7 +784,7 @@ int dgrm_default_config(dgrm_config* cfg) {
   cfg->rank = 0;
   cfg->world = 1;
   cfg->operand = DGRM_OPERAND_FP16;
-  cfg->count_method = DGRM_COUNT_MMA;
+  cfg->count_method = DGRM_COUNT_FP4;
   cfg->flat_norm = 0;
   cfg->chunk_snps = 16384;
   cfg->cta_group = 2;
@@ -782,14 +802,14 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   *out = nullptr;
   if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world)
     return fail(nullptr, DGRM_E_INVALID, "dgrm_create: bad rank/world %d/%d", cfg->rank, cfg->world);
-  if (cfg->chunk_snps < 128 || cfg->chunk_snps % 128 != 0 || cfg->chunk_snps > 32768)
-    return fail(nullptr, DGRM_E_INVALID, "dgrm_create: chunk_snps must be a multiple of 128 in [128, 32768]");
+  if (cfg->chunk_snps < 256 || cfg->chunk_snps % 256 != 0 || cfg->chunk_snps > 32768)
+    return fail(nullptr, DGRM_E_INVALID, "dgrm_create: chunk_snps must be a multiple of 256 in [256, 32768]");
   if (cfg->cta_group != 1 && cfg->cta_group != 2)
     return fail(nullptr, DGRM_E_INVALID, "dgrm_create: cta_group must be 1 or 2");
   if (cfg->resident_chunks < 0 || cfg->resident_chunks > kMaxChunks || cfg->resident_mb < 0)
     return fail(nullptr, DGRM_E_INVALID, "dgrm_create: resident_chunks must be in [0, %d]", kMaxChunks);
   if (cfg->operand < 0 || cfg->operand > DGRM_OPERAND_FP16X2 || cfg->count_method < 0 ||
-      cfg->count_method > DGRM_COUNT_POPC)
+      cfg->count_method > DGRM_COUNT_FP4)
     return fail(nullptr, DGRM_E_INVALID, "dgrm_create: bad operand/count_method");
   int ndev = 0;
   cudaError_t st = cudaGetDeviceCount(&ndev);

@@ -225,6 +225,36 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
   }
 }
 
+// Block-scaled FP4 (e2m1, UE8M0 scale per 32 elements): D[tmem] (+)= (A * SFA) * (B * SFB)^T, K = 64 per instruction.
+template <int CG>
+__device__ __forceinline__ void umma_mxf4(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t sfa_tmem, uint32_t sfb_tmem, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+        : "memory");
+  }
+}
+
+// 32 lanes x 32 columns: every thread of the warp stores 32 consecutive 32-bit columns of its lane.
+__device__ __forceinline__ void tmem_st_32x32_splat(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Signal `bar` when every tcgen05.mma issued so far by this thread has completed.
 // CG == 2: the arrive is multicast to the barrier at the same offset in both CTAs of the pair.
 template <int CG>

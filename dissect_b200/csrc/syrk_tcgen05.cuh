@@ -70,12 +70,16 @@ __device__ __forceinline__ int acc_convert<int>(uint32_t bits) {
   return __float2int_rn(__uint_as_float(bits));
 }
 
-template <int CG, bool KIND8, typename OutT>
+// KIND: 0 = kind::f16 (fp16/bf16 operands), 1 = kind::f8f6f4 (e4m3 0/1 operands), 2 = kind::mxf4 block-scaled (e2m1 0/1
+// operands, all scale factors 1.0); kinds 1 and 2 address the operand in bytes (128 per k-block).
+template <int CG, int KIND, typename OutT>
 __global__ void __launch_bounds__(256, 1)
 grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
   using Cfg = SyrkCfg<CG>;
   constexpr int kStages = Cfg::kStages;
-  constexpr int kKElems = KIND8 ? 128 : 64;  // elements per 128-byte k-block
+  constexpr int kKElems = KIND == 0 ? 64 : 128;  // operand-map elements per 128-byte k-block
+  constexpr int kAccStages = KIND == 2 ? 1 : 2;   // mxf4 keeps TMEM columns for its scale factors: one accumulator
+  constexpr uint32_t kSfaCol = 256, kSfbCol = 320;  // 64 columns each, every byte = UE8M0 1.0
 
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms are 1024 B: align the ring by hand (same offset in both CTAs of a pair).
@@ -113,6 +117,18 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
   if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if constexpr (KIND == 2) {
+    // scale factors: 1.0 (0x7F) in every byte of the SFA / SFB column ranges, whatever sub-layout the MMA reads
+    if (warp >= 4) {
+      const uint32_t lane_base = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < 128; c += 32) ptx::tmem_st_32x32_splat(lane_base + kSfaCol + c, 0x7F7F7F7Fu);
+      ptx::tmem_st_wait();
+    }
+    ptx::tcgen05_fence_before();
+    if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+    ptx::tcgen05_fence_after();
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
@@ -161,8 +177,8 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
       for (int w = p.work_begin + unit; w < p.work_end; w += nunits) {
       for (int j = 0; j < p.nchunks; ++j, ++it) {
         const int kb_total = p.npass * (p.chunk_kpad[j] / kKElems);
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        const int as = it % kAccStages;
+        const uint32_t aphase = (uint32_t)(it / kAccStages) & 1u;
         ptx::mbar_wait(&tempty_bar[as], aphase ^ 1u);
         ptx::tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kTileN);
@@ -176,7 +192,11 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
             for (int k = 0; k < 4; ++k) {  // 4 x (UMMA_K * element size = 32 B) per 128-byte k-block
               const uint64_t adesc = ptx::make_smem_desc_kmajor_sw128(a_addr + k * 32);
               const uint64_t bdesc = ptx::make_smem_desc_kmajor_sw128(b_addr + k * 32);
-              ptx::umma<CG, KIND8>(d_tmem, adesc, bdesc, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if constexpr (KIND == 2)
+                ptx::umma_mxf4<CG>(d_tmem, adesc, bdesc, p.idesc, tmem_base + kSfaCol, tmem_base + kSfbCol,
+                                   (kb > 0 || k > 0) ? 1u : 0u);
+              else
+                ptx::umma<CG, KIND == 1>(d_tmem, adesc, bdesc, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit<CG>(&empty_bar[stage]);                      // smem slot reusable
             if (kb == kb_total - 1) ptx::umma_commit<CG>(&tfull_bar[as]);  // accumulator complete
@@ -190,7 +210,7 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
         // keep the leader's barriers alive until the peer's last tmem-empty arrivals landed
         if (it > 0) {
           const int last = it - 1;
-          ptx::mbar_wait(&tempty_bar[last & 1], (uint32_t)(last >> 1) & 1u);
+          ptx::mbar_wait(&tempty_bar[last % kAccStages], (uint32_t)(last / kAccStages) & 1u);
         }
       }
     }
@@ -209,8 +229,8 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
       const int sidx = (rank == 0) ? t.z : t.w;
       OutT* tile = out + (size_t)sidx * kTileElems + row;
     for (int j = 0; j < p.nchunks; ++j, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const int as = it % kAccStages;
+      const uint32_t aphase = (uint32_t)(it / kAccStages) & 1u;
       const bool accumulate = p.accumulate || j > 0;
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tcgen05_fence_after();
@@ -246,6 +266,17 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
   ptx::tcgen05_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, 512);
+}
+
+// Block-scaled descriptor for kind::mxf4: e2m1 operands (format 1), UE8M0 scales, K = 64, scale-factor ids 0.
+inline uint32_t make_idesc_mxf4(int cg) {
+  uint32_t d = 0;
+  d |= 1u << 7;                               // A format: E2M1
+  d |= 1u << 10;                              // B format: E2M1
+  d |= (uint32_t)(256 >> 3) << 17;            // N >> 3
+  d |= 1u << 23;                              // scale format: UE8M0
+  d |= (uint32_t)((128 * cg) >> 4) << 24;     // M >> 4
+  return d;
 }
 
 // tcgen05 instruction descriptor: fp32 accumulate, both operands K-major, N = 256, M = 128 * CG.

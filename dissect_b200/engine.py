@@ -54,7 +54,7 @@ class PinnedArray:
 
 
 class GrmEngine:
-    def __init__(self, device=0, rank=0, world=1, operand="fp16", count_method="mma", flat_norm=False,
+    def __init__(self, device=0, rank=0, world=1, operand="fp16", count_method="fp4", flat_norm=False,
                  chunk_snps=16384, cta_group=2, profile=False, resident_chunks=0, resident_mb=16384):
         self._lib = _lib.load()
         cfg = _lib.Config()

@@ -27,7 +27,7 @@ static void engine_check(dgrm_engine* e, int rc) {
 Options::Options()
     : makeGRM(false), outFile("dissect"), flatGRMNormalization(false), minimumNumberOverlapingSNPs(10.),
       maximumProportionOfElimitaedIndividuals(0.9), defaultBlockSize(256), device(0), operand(DGRM_OPERAND_FP16),
-      countMethod(DGRM_COUNT_MMA), chunkSNPs(16384), ctaGroup(2) {}
+      countMethod(DGRM_COUNT_FP4), chunkSNPs(16384), ctaGroup(2) {}
 
 void Options::parseOptions(int argc, char** argv) {
   auto need = [&](int i) -> std::string {
@@ -52,7 +52,10 @@ void Options::parseOptions(int argc, char** argv) {
     else if (a == "--gpu-operand") {
       const std::string v = need(i++);
       operand = v == "bf16" ? DGRM_OPERAND_BF16 : v == "fp16x2" ? DGRM_OPERAND_FP16X2 : DGRM_OPERAND_FP16;
-    } else if (a == "--gpu-count") countMethod = need(i++) == "popc" ? DGRM_COUNT_POPC : DGRM_COUNT_MMA;
+    } else if (a == "--gpu-count") {
+      const std::string v = need(i++);
+      countMethod = v == "popc" ? DGRM_COUNT_POPC : v == "fp8" ? DGRM_COUNT_MMA : DGRM_COUNT_FP4;
+    }
     else if (a == "--gpu-chunk-snps") chunkSNPs = atoi(need(i++).c_str());
     else if (a == "--gpu-cta-group") ctaGroup = atoi(need(i++).c_str());
     else misc.error("Error: Invalid option: " + a, 0);
@@ -288,6 +291,124 @@ Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
   *misc.message << "GRM computation finished." << std::endl;
 }
 
+Kernel::Kernel()
+    : type(kernelGRM), name("default"), kernel(NULL), N(NULL), normalized(false), diagonalized(false), asymmetric(false),
+      nIndividuals(0), eng_(NULL) {}
+
+// readGRM (kernel.cpp:1023-1196): <f>.grm.ids / .grm.snps / .grm.dat -> kernel (lower) and N (lower; the file holds
+// N's upper triangle, matrix.cpp:2324-2334).  Single host rank (1 x 1 grid) only.
+Kernel::Kernel(const std::string& f)
+    : type(kernelGRM), name(f), kernel(NULL), N(NULL), normalized(true), diagonalized(false), asymmetric(false),
+      nIndividuals(0), eng_(NULL) {
+  if (communicator->nProcRows != 1 || communicator->nProcCols != 1)
+    misc.error("Error: reading a GRM file is implemented for a 1x1 process grid in this adapter.", 0);
+  *misc.message << "Reading GRM from [ " << f << ".grm.(ids/snps/dat) ]..." << std::endl;
+  for (auto& r : read_table(f + ".grm.ids", 2)) {
+    Individual ind;
+    ind.familyID = r[0]; ind.individualID = r[1]; ind.phenotype = 0;
+    const std::string key = r[0] + "@" + r[1];
+    if (individualIdsIdx.count(key))
+      misc.error("Error: The individual with family Id: " + r[0] + " and individual Id: " + r[1] + " appears more than one time in file [ " + f + ".grm.ids ].", 0);
+    individualIdsIdx[key] = (int)individuals.size();
+    individuals.push_back(ind);
+    individualIds.push_back(key);
+  }
+  nIndividuals = (int)individuals.size();
+  for (auto& r : read_table(f + ".grm.snps", 1)) randomVarNames.push_back(r[0]);
+  std::ifstream dat((f + ".grm.dat").c_str(), std::ios::binary);
+  if (!dat) misc.error("Error: The file [ " + f + ".grm.dat ] does not exist or cannot be opened.", 0);
+  unsigned char header[14];
+  dat.read((char*)header, 14);
+  // kernel.cpp:1066-1138: magic 'G','R','M',0,0x5A,0x99, version 2, doubles, sizeof(double), 1 = normalized
+  if (!dat || header[0] != 'G' || header[1] != 'R' || header[2] != 'M' || header[4] != 0x5A || header[5] != 0x99 ||
+      header[7] != 0x1 || header[8] != sizeof(double))
+    misc.error("Error: The file [ " + f + ".grm.dat ] is not a valid GRM file.", 0);
+  if (header[9] != 0x1) misc.error("Error: Only normalized, non-diagonalized GRM files are supported by this adapter.", 0);
+  const int n = nIndividuals;
+  std::vector<double> col((size_t)n + 1);
+  kernel = new Matrix(cyclicDistribution);
+  N = new Matrix(cyclicDistribution);
+  kernel->initParameters(n, n, communicator->nDefaultBlockRows, communicator->nDefaultBlockCols);
+  N->initParameters(n, n, communicator->nDefaultBlockRows, communicator->nDefaultBlockCols);
+  kernel->symmetric = N->symmetric = true;
+  kernel->uplo = N->uplo = 'L';
+  for (int c = 0; c < n; ++c) {
+    dat.read((char*)col.data(), (std::streamsize)((size_t)(n + 1) * sizeof(double)));
+    if (!dat) misc.error("Error: An error was happened when reading a matrix. Could the file be corrupt?", 0);
+    for (int r = 0; r <= c; ++r) N->m[(size_t)r * n + c] = col[(size_t)r];          // N[r][c] -> lower (c, r)
+    for (int r = c; r < n; ++r) kernel->m[(size_t)c * n + r] = col[(size_t)r + 1];  // A[r][c]
+  }
+  *misc.message << "GRM loaded." << std::endl;
+}
+
+static void add_lower(Matrix* a, const Matrix* b, double sa, double sb) {
+  check_same_structure(a, b, "addition");
+  for (int c = 0; c < a->nCols; ++c)
+    for (int r = 0; r < a->nRows; ++r) {
+      if (a->local2globalCol(c) > a->local2globalRow(r)) continue;
+      double& x = a->m[(size_t)c * a->nRows + r];
+      x = sa * x + sb * b->m[(size_t)c * a->nRows + r];
+    }
+}
+
+static Matrix* clone_matrix(const Matrix* src) {
+  Matrix* m = new Matrix(src->distribution);
+  m->initParameters(src->nGlobRows, src->nGlobCols, src->nBlockRows, src->nBlockCols);
+  m->symmetric = src->symmetric;
+  m->uplo = src->uplo;
+  memcpy(m->m, src->m, (size_t)src->nRows * src->nCols * sizeof(double));
+  return m;
+}
+
+void Kernel::addKernels(double s1, Kernel* grm1, double s2, Kernel* grm2) {
+  if (grm1 == this || grm2 == this)
+    misc.error("Error: An internal error was happened when adding two GRMs. GRMs to add must be different instances than the resulting GRM.", 0);
+  if ((s1 != 1. && s1 != -1.) || (s2 != 1. && s2 != -1.))
+    misc.error("Error: An internal error was happened. Scaling factor when adding or substracting GRMs can only be 1 or -1.", 0);
+  if (!grm1->N || !grm2->N) misc.error("Error: An internal error was happened. GRMs can not be added without the N matrix.", 0);
+  if (grm1->individualIds != grm2->individualIds || grm1->nIndividuals != grm2->nIndividuals)
+    misc.error("Error: An internal error was happened. GRMs with different individuals can not be added.", 0);
+  // SNP bookkeeping (kernel.cpp:1819-1856)
+  std::vector<std::string> result;
+  std::set<std::string> set1(grm1->randomVarNames.begin(), grm1->randomVarNames.end());
+  std::set<std::string> set2(grm2->randomVarNames.begin(), grm2->randomVarNames.end());
+  if (s1 == s2) {
+    for (auto& x : grm1->randomVarNames)
+      if (set2.count(x)) misc.error("Error: Invalid operation. Two GRMs cannot be added together if the SNPs used for computing them intersect.", 0);
+    result = grm2->randomVarNames;
+    result.insert(result.end(), grm1->randomVarNames.begin(), grm1->randomVarNames.end());
+  } else {
+    const std::vector<std::string>& big = (s1 == 1.) ? grm1->randomVarNames : grm2->randomVarNames;
+    const std::set<std::string>& bigset = (s1 == 1.) ? set1 : set2;
+    const std::vector<std::string>& small = (s1 == 1.) ? grm2->randomVarNames : grm1->randomVarNames;
+    const std::set<std::string>& smallset = (s1 == 1.) ? set2 : set1;
+    for (auto& x : small)
+      if (!bigset.count(x)) misc.error("Error: Invalid operation. Two GRMs cannot be substracted if all the SNPs of one are not contained into the other.", 0);
+    for (auto& x : big)
+      if (!smallset.count(x)) result.push_back(x);
+  }
+  // arithmetic on the unnormalised pair: S = A o N (denormalize), S = s1 S1 + s2 S2, N = s1 N1 + s2 N2, re-divide
+  const bool n1 = grm1->normalized, n2 = grm2->normalized;
+  grm1->denormalize();
+  grm2->denormalize();
+  delete kernel; delete N;
+  kernel = clone_matrix(grm1->kernel);
+  N = clone_matrix(grm1->N);
+  add_lower(kernel, grm2->kernel, s1, s2);
+  add_lower(N, grm2->N, s1, s2);
+  if (n1) grm1->normalize();
+  if (n2) grm2->normalize();
+  type = kernelGRM;
+  individuals = grm1->individuals;
+  individualIds = grm1->individualIds;
+  individualIdsIdx = grm1->individualIdsIdx;
+  nIndividuals = grm1->nIndividuals;
+  normalized = false;
+  if (n1) normalize();
+  randomVarNames = result;
+  name = grm1->name + " " + grm2->name;
+}
+
 Kernel::~Kernel() {
   delete kernel;
   delete N;
@@ -351,6 +472,7 @@ std::vector<std::string> Kernel::minimumIndividualsRemovePairs(const std::vector
 }
 
 bool Kernel::sanitizeKernel() {
+  if (!eng_) misc.error("Error: sanitizeKernel on a host-only GRM is not implemented in this adapter.", 0);
   if (!N) misc.error("Error: An internal error was happened. Kernel cannot be checked without the normalization matrix.", 0);
   int64_t cnt = 0;
   engine_check(eng_, dgrm_low_overlap_pairs(eng_, options.minimumNumberOverlapingSNPs, NULL, 0, &cnt));
@@ -416,9 +538,26 @@ void Kernel::writeGRM(const std::string& f) {
     std::ofstream snps((f + ".grm.snps").c_str());
     for (size_t i = 0; i < randomVarNames.size(); ++i) snps << randomVarNames[i] << std::endl;
   }
-  // packMatrices + writeMatrixMPI funnel every block through rank 0 in the reference (matrix.cpp:2308-2341);
-  // here the device packs the (n+1) x n array directly
-  engine_check(eng_, dgrm_write_grm_dat(eng_, (f + ".grm.dat").c_str()));
+  if (eng_) {
+    // packMatrices + writeMatrixMPI funnel every block through rank 0 in the reference (matrix.cpp:2308-2341);
+    // here the device packs the (n+1) x n array directly
+    engine_check(eng_, dgrm_write_grm_dat(eng_, (f + ".grm.dat").c_str()));
+  } else {
+    // host-only kernel (read from file / addKernels result): kernel.cpp:944-974 + matrix.cpp:2324-2334 on one rank
+    if (communicator->nProcRows != 1 || communicator->nProcCols != 1)
+      misc.error("Error: writing a host-side GRM is implemented for a 1x1 process grid in this adapter.", 0);
+    std::ofstream dat((f + ".grm.dat").c_str(), std::ios::binary);
+    const unsigned char header[14] = {'G', 'R', 'M', 0, 0x5A, 0x99, 0x2, 0x1, (unsigned char)sizeof(double), 0x1, 0, 0, 0, 0};
+    dat.write((const char*)header, 14);
+    const int n = nIndividuals;
+    std::vector<double> col((size_t)n + 1);
+    for (int c = 0; c < n; ++c) {
+      for (int r = 0; r <= c; ++r) col[(size_t)r] = N->m[(size_t)r * n + c];
+      for (int r = c; r < n; ++r) col[(size_t)r + 1] = kernel->m[(size_t)c * n + r];
+      dat.write((const char*)col.data(), (std::streamsize)((size_t)(n + 1) * sizeof(double)));
+    }
+    if (!dat) misc.error("Error: An error was happened when writing a matrix. Is there enough space in the hard disk?", 0);
+  }
   *misc.message << "GRM stored." << std::endl;
 }
 

@@ -130,7 +130,12 @@ class Kernel {
   std::map<std::string, int> individualIdsIdx;
   std::vector<std::string> randomVarNames;  // = genotype->SNPIds (kernel.cpp:85)
   Kernel(Genotype* genotype, bool normalizeGRM = true);  // kernel.cpp:61-125, computed on the GPU
+  explicit Kernel(const std::string& f);                 // kernel.cpp:127-... -> readGRM :1023-1196 (host only)
+  Kernel();                                              // empty, for addKernels results
   ~Kernel();
+  // kernel.cpp:1705-1859 (addGRMs): this = s1*grm1 + s2*grm2 on the unnormalised (S, N) pair, s = +1 or -1.
+  // Regional / LOCO algebra: global - regional is exact in N and exact to rounding in S (singlereml.cpp:293-298).
+  void addKernels(double scalingFactor1, Kernel* grm1, double scalingFactor2, Kernel* grm2);
   void normalize();      // kernel.cpp:382-414
   void denormalize();    // kernel.cpp:416-448
   bool sanitizeKernel(); // kernel.cpp:1993-2037

@@ -45,6 +45,7 @@ extern "C" {
 /* how the per-pair non-missing count N (kernel.cpp:96-101) is formed */
 #define DGRM_COUNT_MMA   0  /* 0/1 e4m3 operands through tcgen05 kind::f8f6f4, exact in fp32  */
 #define DGRM_COUNT_POPC  1  /* AND + popcount over bit-packed non-missing masks               */
+#define DGRM_COUNT_FP4   2  /* 0/1 e2m1 operands through block-scaled tcgen05 kind::mxf4 (all scales 1.0), exact in fp32 */
 
 /* which matrix dgrm_fetch_* returns */
 #define DGRM_FETCH_A  0  /* normalised GRM  A = S * (1/N)     (matrix.cpp:4096)               */
@@ -71,7 +72,7 @@ typedef struct dgrm_config {
   int32_t operand;       /* DGRM_OPERAND_*                                                   */
   int32_t count_method;  /* DGRM_COUNT_*                                                     */
   int32_t flat_norm;     /* --grm-flat-norm: N := m, no pair count (kernel.cpp:102-109)      */
-  int32_t chunk_snps;    /* SNPs contracted per launch (fp32 in-chunk, fp64 across); mult. of 128 */
+  int32_t chunk_snps;    /* SNPs contracted per launch (fp32 in-chunk, fp64 across); mult. of 256 */
   int32_t cta_group;     /* 1 = one-SM MMA 128x256 tiles, 2 = CTA-pair MMA 256x256 tiles     */
   int32_t profile;       /* 1 = record CUDA events around every kernel launch                */
   int32_t resident_chunks; /* SNP chunks whose operands stay resident and are contracted tile-major (0 = auto) */
@@ -79,7 +80,7 @@ typedef struct dgrm_config {
   int32_t reserved[5];
 } dgrm_config;
 
-/* Fill *cfg with defaults (device 0, rank 0/1, fp16, MMA count, chunk 16384, cta_group 2). */
+/* Fill *cfg with defaults (device 0, rank 0/1, fp16 operands, fp4 pair count, chunk 16384, cta_group 2). */
 int dgrm_default_config(dgrm_config *cfg);
 
 /* Engine life cycle.  Replaces nothing in the reference; owns device buffers and streams. */

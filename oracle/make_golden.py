@@ -120,6 +120,31 @@ def main():
         print("sanitize_reject: grm written?", os.path.exists(out + ".grm.dat"))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+    # partition fixtures (the reference's test20 / test57 invariants): GRMs of SNP subsets a, b and of all SNPs
+    tmp = tempfile.mkdtemp(prefix="golden_")
+    try:
+        n, m = 48, 160
+        pk = bedio.synth_packed(n, m, 109, maf_lo=0.1, missing=0.03)
+        bf = os.path.join(tmp, "p")
+        bedio.write_bed(bf, pk, n)
+        dst = os.path.join(GOLD, "parts")
+        os.makedirs(dst, exist_ok=True)
+        for name, rng in (("a", range(0, 70)), ("b", range(70, 160)), ("all", range(0, 160))):
+            ext = os.path.join(tmp, name + ".extract")
+            with open(ext, "w") as f:
+                f.write("".join(f"rs{k + 1}\n" for k in rng))
+            rc, log = ref_runner.run_make_grm(bf, os.path.join(tmp, name), extract=ext)
+            if rc != 0:
+                raise SystemExit("parts case failed\n" + log[-3000:])
+            for e in (".grm.dat", ".grm.ids", ".grm.snps"):
+                shutil.copy(os.path.join(tmp, name + e), os.path.join(dst, name + e))
+        for e in (".bed", ".bim", ".fam"):
+            shutil.copy(bf + e, os.path.join(dst, "in" + e))
+        with open(os.path.join(dst, "case.txt"), "w") as f:
+            f.write(f"n_fam {n}\nm {m}\nsplit 70\n")
+        print("parts: ok")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
     # error-path fixture: a monomorphic SNP makes the reference abort and write <out>.badsnps
     tmp = tempfile.mkdtemp(prefix="golden_")
     try:

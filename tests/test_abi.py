@@ -48,7 +48,7 @@ def test_bad_config_rejected_before_touching_the_gpu():
     cfg = _lib.Config()
     lib.dgrm_default_config(C.byref(cfg))
     h = C.c_void_p()
-    cfg.chunk_snps = 100
+    cfg.chunk_snps = 128          # must be a multiple of 256
     assert lib.dgrm_create(C.byref(cfg), C.byref(h)) == -1
     cfg.chunk_snps = 16384
     cfg.rank, cfg.world = 3, 2

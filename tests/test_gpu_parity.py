@@ -54,7 +54,7 @@ def test_golden_reference_outputs(name, cg, tmp_path):
     """Same inputs the reference binary consumed -> counts/N bit-exact, A within tolerance, .grm.dat layout."""
     c = load_case(name)
     eng = build(c["packed"], c["n_fam"], c["keep_mask"], c["snp_keep"], cta_group=cg, flat_norm=c["flat"],
-                chunk_snps=128 if name == "n258_m500_flat" else 8192)
+                chunk_snps=256 if name == "n258_m500_flat" else 8192)
     check_stats(eng.snp_stats(), c["ref_stats"])
     n = c["n"]
     low = lower_mask(n)
@@ -86,7 +86,7 @@ def test_counts_ragged_n(n):
             pk[:, -1] |= np.uint8((0xFF << (2 * (n % 4))) & 0xFF)
     codes = orc.decode_rows(pk, n)
     ref = orc.snp_stats(codes)
-    eng = GrmEngine(chunk_snps=128)
+    eng = GrmEngine(chunk_snps=256)
     eng.set_individuals(n)
     eng.begin(m)
     eng.push_bed_host(pk)
@@ -102,8 +102,9 @@ def test_counts_ragged_n(n):
     eng.close()
 
 
-@pytest.mark.parametrize("operand,count,cg", [("fp16", "mma", 2), ("fp16", "mma", 1), ("bf16", "mma", 2),
-                                              ("fp16x2", "mma", 2), ("fp16", "popc", 1), ("fp16", "popc", 2)])
+@pytest.mark.parametrize("operand,count,cg", [("fp16", "fp4", 2), ("fp16", "fp4", 1), ("fp16", "mma", 2),
+                                              ("fp16", "mma", 1), ("bf16", "fp4", 2), ("fp16x2", "mma", 2),
+                                              ("fp16", "popc", 1), ("fp16", "popc", 2)])
 def test_grm_vs_oracle_seeded(operand, count, cg):
     n, m = 777, 3000
     pk = bedio.synth_packed(n, m, 21, missing=0.02)

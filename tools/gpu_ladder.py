@@ -16,6 +16,9 @@ CASES = [
     ["--n", "600", "--m", "3000", "--cg", "2", "--chunk", "256", "--resident", "1"],
     ["--n", "600", "--m", "3000", "--cg", "2", "--chunk", "256", "--resident", "4"],
     ["--n", "600", "--m", "3000", "--cg", "1", "--chunk", "256", "--resident", "5", "--operand", "fp16x2"],
+    ["--n", "300", "--m", "1000", "--cg", "1", "--count", "fp4"],
+    ["--n", "300", "--m", "1000", "--cg", "2", "--count", "fp4"],
+    ["--n", "777", "--m", "3000", "--cg", "2", "--count", "fp4", "--chunk", "1024", "--missing", "0.2"],
     ["--n", "2000", "--m", "10000", "--cg", "1"],
     ["--n", "2000", "--m", "10000", "--cg", "2"],
     ["--n", "2000", "--m", "10000", "--cg", "2", "--chunk", "2048"],
