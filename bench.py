@@ -162,7 +162,7 @@ def run_reference(args):
         from dissect_b200 import bedio
         if not c_oracle.available():
             base.update({"unavailable": "neither oracle/_ref/grmtime nor oracle/_ref/libgrm_oracle.so is built"})
-            print(json.dumps(base))
+            emit(base)
             return
         pk = bedio.synth_packed(CPU_N // 2, m_s // 4, SEED, maf_lo=0.05, maf_hi=MAF_HI, missing=MISSING)
         res = []
@@ -194,12 +194,13 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "pair*SNP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
-    print(json.dumps(base))
+    emit(base)
 
 
 def run_gpu(args):
     import torch
     import torch.distributed as dist
+    from cuda.bindings import runtime as cudart
     from dissect_b200 import GrmEngine
     from dissect_b200.engine import PinnedArray
     from dissect_b200.synth import synth_packed_cuda
@@ -334,14 +335,21 @@ def run_gpu(args):
         tiles_A = PinnedArray((max(ntl, 1), 256, 128), np.float64)
         tiles_N = PinnedArray((max(ntl, 1), 256, 128), np.float64)
 
+        dbg = os.environ.get("DGRM_BENCH_DEBUG") and rank == 0
+        eng.bind_tiles("A", tiles_A.ptr)      # finished tile groups stream out while later groups are contracted
+        eng.bind_tiles("N", tiles_N.ptr)
+
         def step_e2e():
+            t_a = time.perf_counter()
             eng.begin(m_kept)
             stream = torch.cuda.current_stream().cuda_stream
             for ci, (c0, r0, r1) in enumerate(mine):
                 c1 = min(c0 + chunk, m_file)
                 gather_buf, send_buf = gather_bufs[ci & 1], send_bufs[ci & 1]
                 if r1 > r0:
-                    send_buf[: r1 - r0, :bpr].copy_(torch.from_numpy(host_pk.array[r0:r1]), non_blocking=True)
+                    # this rank's shard of the chunk: pinned host rows -> device (row pitch padded to 16 bytes)
+                    cudart.cudaMemcpy2DAsync(send_buf.data_ptr(), bpr_pad, host_pk.ptr + r0 * bpr, bpr, bpr, r1 - r0,
+                                             cudart.cudaMemcpyKind.cudaMemcpyHostToDevice, stream)
                 dist.all_gather_into_tensor(gather_buf, send_buf)
                 rk = np.zeros(G * shard, np.uint8)
                 for g in range(G):
@@ -351,9 +359,12 @@ def run_gpu(args):
                         rk[g * shard: g * shard + (b - a)] = keep[a:b]
                 eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), G * shard, row_keep=rk, stream=stream)
                 eng.release_inputs(stream)
+            t_b = time.perf_counter()
             eng.finish()
-            eng.fetch_tiles("A", out_ptr=tiles_A.ptr)
-            eng.fetch_tiles("N", out_ptr=tiles_N.ptr)
+            t_c = time.perf_counter()
+            if dbg:
+                print(f"[e2e rank0] push {1e3*(t_b-t_a):.1f} ms, finish (compute + streamed tiles) {1e3*(t_c-t_b):.1f} ms",
+                      file=sys.stderr)
 
         step_e2e()
         barrier()
@@ -369,10 +380,15 @@ def run_gpu(args):
         e2e = {"value": ke * W / dte, "unit": "pair*SNP/s", "ms_per_step": 1e3 * dte / ke,
                "h2d_bytes_per_step": int(sum(r1 - r0 for (_, r0, r1) in mine) * bpr),
                "d2h_bytes_per_step": int(2 * ntl * 128 * 256 * 8),
-               "result": "per rank: its packed row shards in, its owned 128x256 tiles of A and N (fp64) out (pinned)"}
+               "result": "per rank: its packed row shards in, its owned 128x256 tiles of A and N (fp64) streamed out "
+                         "into bound pinned buffers",
+               "check_tile_sum_A": float(tiles_A.array[0, 0, 0])}
+        eng.unbind_outputs()
 
     if rank != 0:
+        eng.close()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -428,12 +444,31 @@ def run_gpu(args):
         except Exception as ex:  # the baseline is reported, never required
             out["cpu_baseline"] = {"value": None, "unit": "pair*SNP/s", "cores": cpu_threads(), "kind": "reference",
                                    "sample": f"unavailable: {ex}"[:300]}
-    print(json.dumps(out))
+    emit(out)
+    eng.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line, written with a single syscall to the process's original stdout.  Everything else that
+    writes to fd 1 (NCCL prints its version there) has been pointed at stderr by main()."""
+    line = (json.dumps(obj) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    off = 0
+    while off < len(line):
+        off += os.write(fd, line[off:])
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)          # C-level chatter (NCCL, drivers) goes to stderr; stdout carries only the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

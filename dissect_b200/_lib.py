@@ -17,7 +17,7 @@ SYMBOLS = (
     "dgrm_default_config", "dgrm_create", "dgrm_destroy", "dgrm_last_error", "dgrm_abi_version",
     "dgrm_set_individuals", "dgrm_begin", "dgrm_push_bed_host", "dgrm_push_bed_device", "dgrm_release_inputs",
     "dgrm_load_bed_file", "dgrm_finish", "dgrm_sync", "dgrm_num_snps", "dgrm_num_individuals",
-    "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_bind_output", "dgrm_unbind_outputs", "dgrm_low_overlap_pairs",
+    "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_bind_output", "dgrm_unbind_outputs", "dgrm_bind_tiles", "dgrm_low_overlap_pairs",
     "dgrm_set_output_subset", "dgrm_write_grm_dat", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles",
     "dgrm_host_alloc", "dgrm_host_free", "dgrm_kernel_times",
 )
@@ -71,6 +71,7 @@ def load():
     lib.dgrm_fetch_block_cyclic.argtypes = [vp, i32, vp, i64, i32, i32, i32, i32, i32, i32, C.c_char]
     lib.dgrm_bind_output.argtypes = [vp, i32, vp, i64, i32, i32, i32, i32, i32, i32, C.c_char]
     lib.dgrm_unbind_outputs.argtypes = [vp]
+    lib.dgrm_bind_tiles.argtypes = [vp, i32, vp]
     lib.dgrm_low_overlap_pairs.argtypes = [vp, dbl, vp, i64, P(i64)]
     lib.dgrm_set_output_subset.argtypes = [vp, vp, i64]
     lib.dgrm_write_grm_dat.argtypes = [vp, C.c_char_p]

@@ -58,6 +58,7 @@ struct dgrm_engine {
   int4* d_work = nullptr;
   int4* d_work_cg1 = nullptr;
   int32_t* d_index = nullptr;
+  int2* d_tile_rc = nullptr;   // per storage tile: first global row / column
   int64_t ntiles = 0;
   double* d_S = nullptr;
   int32_t* d_N = nullptr;
@@ -75,6 +76,13 @@ struct dgrm_engine {
   };
   Binding bind[3];
   int nbind = 0;
+  struct TileBinding {
+    int which = -1;
+    double* host = nullptr;
+    bool pinned = false;
+  };
+  TileBinding tbind[3];
+  int ntbind = 0;
   cudaStream_t out_stream = nullptr;   // packs finished row groups into staging
   cudaStream_t d2h_stream = nullptr;   // copy engine: staging -> caller buffer
   std::vector<cudaEvent_t> group_ev;
@@ -90,6 +98,8 @@ struct dgrm_engine {
     int ev;                 // tile-group event after which the rectangle is final
     bool direct;            // copy engine writes straight into the caller's (pinned) buffer
     bool as_int;            // pair counts cross PCIe as int32 and are widened by the host
+    bool tiles;             // tile-range job (dgrm_bind_tiles): b indexes tbind, elements [t0, t1) of the tile store
+    int64_t t0, t1;
   };
   std::vector<OutJob> jobs;
   size_t jobs_issued = 0, jobs_done = 0;
@@ -204,6 +214,7 @@ void release_geometry(dgrm_engine* e) {
   free_dev(e->d_work); e->d_work = nullptr;
   free_dev(e->d_work_cg1); e->d_work_cg1 = nullptr;
   free_dev(e->d_index); e->d_index = nullptr;
+  free_dev(e->d_tile_rc); e->d_tile_rc = nullptr;
   free_dev(e->d_S); e->d_S = nullptr;
   free_dev(e->d_N); e->d_N = nullptr;
   free_dev(e->d_diag); e->d_diag = nullptr;
@@ -287,6 +298,12 @@ void build_tiles(dgrm_engine* e) {
   // upload
   cudaMalloc(&e->d_index, index.size() * sizeof(int32_t));
   cudaMemcpy(e->d_index, index.data(), index.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (!e->work_cg1.empty()) {
+    std::vector<int2> rc(e->work_cg1.size());
+    for (size_t t = 0; t < e->work_cg1.size(); ++t) rc[(size_t)e->work_cg1[t].z] = make_int2(e->work_cg1[t].x, e->work_cg1[t].y);
+    cudaMalloc(&e->d_tile_rc, rc.size() * sizeof(int2));
+    cudaMemcpy(e->d_tile_rc, rc.data(), rc.size() * sizeof(int2), cudaMemcpyHostToDevice);
+  }
   if (!e->work.empty()) {
     cudaMalloc(&e->d_work, e->work.size() * sizeof(int4));
     cudaMemcpy(e->d_work, e->work.data(), e->work.size() * sizeof(int4), cudaMemcpyHostToDevice);
@@ -413,6 +430,30 @@ int first_local_ge(int target, int nloc, int bs, int me, int P) {
 // caller's pinned buffer (direct) or the library's pinned host staging (finished by finish_job).
 int issue_job(dgrm_engine* e, size_t k) {
   const dgrm_engine::OutJob& j = e->jobs[k];
+  if (j.tiles) {
+    const dgrm_engine::TileBinding& tb = e->tbind[j.b];
+    const int sl = (int)(k % dgrm_engine::kOutSlots);
+    const int64_t cnt = j.t1 - j.t0;
+    TileStore ts = tile_store(e);
+    ts.S = ts.S + j.t0;
+    ts.N = ts.N ? ts.N + j.t0 : nullptr;
+    CK(cudaStreamWaitEvent(e->out_stream, e->group_ev[(size_t)j.ev], 0));
+    {
+      Prof pr(e, DGRM_K_FETCH, e->out_stream);
+      export_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, e->out_stream>>>(
+          ts, tb.which, cnt, (double*)e->d_out_stage[sl], e->d_tile_rc, j.t0 / kTileElems, e->d_diag);
+      CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(e->stage_packed[sl], e->out_stream));
+    CK(cudaStreamWaitEvent(e->d2h_stream, e->stage_packed[sl], 0));
+    {
+      Prof pr(e, DGRM_K_D2H, e->d2h_stream);
+      void* dst = j.direct ? (void*)(tb.host + j.t0) : e->h_out_stage[sl];
+      CK(cudaMemcpyAsync(dst, e->d_out_stage[sl], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, e->d2h_stream));
+    }
+    CK(cudaEventRecord(e->stage_copied_out[sl], e->d2h_stream));
+    return DGRM_OK;
+  }
   const dgrm_engine::Binding& bd = e->bind[j.b];
   const CyclicGeom& g = bd.g;
   const int sl = (int)(k % dgrm_engine::kOutSlots);
@@ -468,6 +509,15 @@ int finish_job(dgrm_engine* e, size_t k) {
   const int sl = (int)(k % dgrm_engine::kOutSlots);
   CK(cudaEventSynchronize(e->stage_copied_out[sl]));
   if (j.direct) return DGRM_OK;
+  if (j.tiles) {
+    const double* src = (const double*)e->h_out_stage[sl];
+    double* dst = e->tbind[j.b].host + j.t0;
+    const int64_t cnt = j.t1 - j.t0;
+#pragma omp parallel for schedule(static)
+    for (int64_t o = 0; o < cnt; o += 1 << 16)
+      memcpy(dst + o, src + o, (size_t)std::min<int64_t>(1 << 16, cnt - o) * sizeof(double));
+    return DGRM_OK;
+  }
   const dgrm_engine::Binding& bd = e->bind[j.b];
   const CyclicGeom g = bd.g;
   const int h = j.lr1 - j.lr0;
@@ -523,7 +573,7 @@ int flush_super(dgrm_engine* e, bool final) {
     const int lo = e->slots * e->kc_max;
     // tile groups: whole waves of the persistent grid, so that no launch has a ragged tail
     const int units = e->cfg.cta_group == 2 ? e->sm_count / 2 : e->sm_count;
-    bool stream_out = false;
+    bool stream_out = e->ntbind > 0;
     for (int b = 0; b < e->nbind; ++b) stream_out |= binding_streams(e->bind[b]);
     // Tile groups.  Streaming outputs: one group per raster row group, its end rounded up to whole waves of
     // the persistent grid (no ragged tail, and the row group is final as soon as its launches are done).
@@ -556,9 +606,35 @@ int flush_super(dgrm_engine* e, bool final) {
           if (j.lr1 <= j.lr0 || j.lc1 <= 0) continue;
           j.as_int = bd.which == DGRM_FETCH_N && !e->cfg.flat_norm;
           j.direct = bd.dev != nullptr && !j.as_int;
+          j.tiles = false;
+          j.t0 = j.t1 = 0;
           need = std::max(need, (size_t)(j.lr1 - j.lr0) * (size_t)j.lc1 * sizeof(double));
           e->jobs.push_back(j);
         }
+      }
+      // tile bindings: one job per tile group (the group's tiles are contiguous in the store)
+      if (e->ntbind > 0) {
+        const int64_t per_work = (e->cfg.cta_group == 2 ? 2 : 1) * (int64_t)kTileElems;
+        std::vector<dgrm_engine::OutJob> tj;
+        int w0g = 0;
+        for (size_t gi = 0; gi < group_end.size(); w0g = group_end[gi], ++gi) {
+          for (int b = 0; b < e->ntbind; ++b) {
+            dgrm_engine::OutJob j{};
+            j.b = b; j.ev = (int)gi; j.tiles = true; j.as_int = false; j.direct = e->tbind[b].pinned;
+            j.t0 = (int64_t)w0g * per_work;
+            j.t1 = (int64_t)group_end[gi] * per_work;
+            need = std::max(need, (size_t)(j.t1 - j.t0) * sizeof(double));
+            tj.push_back(j);
+          }
+        }
+        // merge with the rectangle jobs, ordered by the group that completes them
+        std::vector<dgrm_engine::OutJob> all;
+        size_t a = 0, b2 = 0;
+        while (a < e->jobs.size() || b2 < tj.size()) {
+          if (b2 >= tj.size() || (a < e->jobs.size() && e->jobs[a].ev <= tj[b2].ev)) all.push_back(e->jobs[a++]);
+          else all.push_back(tj[b2++]);
+        }
+        e->jobs.swap(all);
       }
       if (need > e->out_stage_bytes) {
         CK(cudaStreamSynchronize(e->d2h_stream));
@@ -918,6 +994,7 @@ int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask
   CK(cudaStreamSynchronize(e->stream));
   release_geometry(e);
   e->nbind = 0;
+  e->ntbind = 0;
   e->begun = e->finished = false;
   std::vector<int32_t> src;
   bool identity = true;
@@ -1156,6 +1233,11 @@ int dgrm_finish(dgrm_engine* e) {
     e->finished = true;
     CK(cudaStreamSynchronize(e->out_stream));
     CK(cudaStreamSynchronize(e->d2h_stream));
+    if (e->chunks_done == 0 || e->work.empty())
+      for (int b = 0; b < e->ntbind; ++b) {
+        rc = dgrm_fetch_tiles(e, e->tbind[b].which, e->tbind[b].host);
+        if (rc) return rc;
+      }
     // bindings that could not stream (pageable memory, uplo U/B, or nothing was contracted): fill them now
     for (int b = 0; b < e->nbind; ++b) {
       const dgrm_engine::Binding& bd = e->bind[b];
@@ -1225,6 +1307,25 @@ int dgrm_bind_output(dgrm_engine* e, int which, double* local, int64_t lld, int 
 int dgrm_unbind_outputs(dgrm_engine* e) {
   if (!e) return DGRM_E_INVALID;
   e->nbind = 0;
+  e->ntbind = 0;
+  return DGRM_OK;
+}
+
+int dgrm_bind_tiles(dgrm_engine* e, int which, double* tiles) {
+  if (!e) return DGRM_E_INVALID;
+  if (!e->have_ind) return fail(e, DGRM_E_INVALID, "dgrm_bind_tiles: call dgrm_set_individuals first");
+  if (!tiles || which < 0 || which > 2) return fail(e, DGRM_E_INVALID, "dgrm_bind_tiles: bad arguments");
+  CK(cudaSetDevice(e->cfg.device));
+  int slot = e->ntbind;
+  for (int b = 0; b < e->ntbind; ++b)
+    if (e->tbind[b].which == which) slot = b;
+  if (slot >= 3) return fail(e, DGRM_E_INVALID, "dgrm_bind_tiles: at most three bindings");
+  e->tbind[slot].which = which;
+  e->tbind[slot].host = tiles;
+  cudaPointerAttributes attr;
+  e->tbind[slot].pinned = cudaPointerGetAttributes(&attr, tiles) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (slot == e->ntbind) e->ntbind++;
   return DGRM_OK;
 }
 
@@ -1492,7 +1593,8 @@ int dgrm_fetch_tiles(dgrm_engine* e, int which, double* tiles) {
     CK(cudaStreamWaitEvent(e->stream, done[sl], 0));
     {
       Prof pr(e, DGRM_K_FETCH);
-      export_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(t2, which, cnt, d_tmp[sl]);
+      export_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(t2, which, cnt, d_tmp[sl], e->d_tile_rc,
+                                                                               o / kTileElems, e->d_diag);
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->stage_packed[sl], e->stream));

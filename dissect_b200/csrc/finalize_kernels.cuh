@@ -137,15 +137,25 @@ __global__ void pack_grm_kernel(const TileStore ts, double* __restrict__ dst, in
   dst[(int64_t)(c - c0) * (ts.n + 1) + pr] = v;
 }
 
-// tile export as doubles (multi-engine gather)
-__global__ void export_tiles_kernel(const TileStore ts, int which, int64_t total, double* __restrict__ dst) {
+// tile export as doubles (multi-engine gather).  ts.S / ts.N already point at the first exported element;
+// tile_rc[t] = (first global row, first global column) of storage tile tile0 + t lets the exact fp64 diagonal
+// override the tensor-core one (the tile store itself is only patched after the last tile group).
+__global__ void export_tiles_kernel(const TileStore ts, int which, int64_t total, double* __restrict__ dst,
+                                    const int2* __restrict__ tile_rc, int64_t tile0, const double* __restrict__ diag) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const double nval = ts.N ? (double)ts.N[i] : ts.flat_n;
   double v;
-  if (which == 2) v = nval;
-  else if (which == 1) v = ts.S[i];
-  else v = (nval == 0.) ? 0. : __dmul_rn(ts.S[i], __ddiv_rn(1., nval));
+  if (which == 2) {
+    v = nval;
+  } else {
+    double sv = ts.S[i];
+    const int2 rc = tile_rc[tile0 + i / kTileElems];
+    const int e = (int)(i % kTileElems);
+    const int gr = rc.x + (e & 127), gc = rc.y + (e >> 7);
+    if (gr == gc && gr < ts.n) sv = diag[gr];
+    v = (which == 1) ? sv : ((nval == 0.) ? 0. : __dmul_rn(sv, __ddiv_rn(1., nval)));
+  }
   dst[i] = v;
 }
 

@@ -196,6 +196,10 @@ class GrmEngine:
         self._ck(self._lib.dgrm_bind_output(self._h, _lib.FETCH[which], int(ptr), lld, bs[0], bs[1], coords[0],
                                             coords[1], grid[0], grid[1], uplo.encode()))
 
+    def bind_tiles(self, which, ptr):
+        """dgrm_finish streams this engine's tiles of `which` ([num_tiles][256][128] doubles) into `ptr`."""
+        self._ck(self._lib.dgrm_bind_tiles(self._h, _lib.FETCH[which], int(ptr)))
+
     def unbind_outputs(self):
         self._ck(self._lib.dgrm_unbind_outputs(self._h))
 

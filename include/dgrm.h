@@ -164,6 +164,11 @@ int dgrm_bind_output(dgrm_engine *e, int which, double *local, int64_t lld, int 
                      int my_row, int my_col, int grid_rows, int grid_cols, char uplo);
 int dgrm_unbind_outputs(dgrm_engine *e);
 
+/* Multi-engine counterpart of dgrm_bind_output: bind a caller buffer [dgrm_num_tiles][256][128] that dgrm_finish
+ * fills with this engine's tiles of matrix `which` (same layout as dgrm_fetch_tiles), tile group by tile group
+ * while later groups are still being contracted.  One binding per `which`; dropped by dgrm_unbind_outputs. */
+int dgrm_bind_tiles(dgrm_engine *e, int which, double *tiles);
+
 /* Pairs (i > j) whose shared non-missing count satisfies -0.1 < N_ij < min_overlap - 0.1,
  * the scan sanitizeKernel performs (kernel.cpp:1993-2037, matrix.cpp:4334-4401).
  * pairs is [cap][2] (row, col), *count receives the total found (may exceed cap). */

@@ -268,6 +268,35 @@ def test_bound_outputs_equal_fetch(pinned, uplo, bs, grid, coords):
     eng.close()
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_bound_tiles_equal_fetch_tiles(pinned):
+    """dgrm_bind_tiles (tile groups streamed during dgrm_finish) == dgrm_fetch_tiles afterwards, on a partial
+    (rank 1 of 2) tile set."""
+    n, m = 1100, 800
+    pk = bedio.synth_packed(n, m, 654, missing=0.02)
+    eng = GrmEngine(chunk_snps=256, rank=1, world=2)
+    eng.set_individuals(n)
+    nt = eng.num_tiles
+    bufs = {}
+    for which in ("A", "N", "S"):
+        if pinned:
+            pa = PinnedArray((nt, 256, 128), np.float64)
+            pa.array[:] = -1.0
+            bufs[which] = (pa, pa.array, pa.ptr)
+        else:
+            arr = np.full((nt, 256, 128), -1.0)
+            bufs[which] = (arr, arr, arr.ctypes.data)
+        eng.bind_tiles(which, bufs[which][2])
+    eng.begin(m)
+    eng.push_bed_host(pk)
+    eng.finish()
+    for which in ("A", "N", "S"):
+        want = eng.fetch_tiles(which)
+        got = bufs[which][1]
+        assert np.array_equal(got, want), which     # incl. the exact fp64 diagonal
+    eng.close()
+
+
 def test_bad_snps_are_fatal_like_the_reference():
     c = load_case("badsnp")
     eng = GrmEngine()
