@@ -242,11 +242,14 @@ def run_gpu(args):
         bpr_pad = (bpr + 15) // 16 * 16
         gather_bufs = [torch.zeros((G * shard, bpr_pad), dtype=torch.uint8, device="cuda") for _ in range(2)]
         send_bufs = [torch.zeros((shard, bpr_pad), dtype=torch.uint8, device="cuda") for _ in range(2)]
-    host_pk = PinnedArray((m_file, bpr), np.uint8)
-    host_pk.array[:] = pk_all.cpu().numpy()
+    host_pk = None
+    if not args.no_e2e:   # the e2e leg starts from pinned host rows
+        host_pk = PinnedArray((m_file, bpr), np.uint8)
+        host_pk.array[:] = pk_all.cpu().numpy()
 
     eng = GrmEngine(device=local, rank=rank, world=world, operand=args.operand, count_method=args.count,
-                    chunk_snps=chunk, cta_group=args.cg, profile=True, resident_chunks=args.resident)
+                    chunk_snps=chunk, cta_group=args.cg, profile=True, resident_chunks=args.resident,
+                    resident_mb=args.resident_mb)
     eng.set_individuals(n)
 
     def push_device_resident():
@@ -285,11 +288,17 @@ def run_gpu(args):
     sampler.start()
     time.sleep(0.3)
     barrier()
+    # device clock: events on this rank's current stream; every dgrm_finish returns only when the engine's own
+    # streams are idle, so the closing event cannot be recorded before the last GRM is complete
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    ev0.record()
     for _ in range(args.steps):
         step_device()
+    ev1.record()
     barrier()
-    dt = time.perf_counter() - t0
+    wall_dt = time.perf_counter() - t0
+    dt = ev0.elapsed_time(ev1) * 1e-3
     clocks = sampler.stop()
     kt = eng.kernel_times()
     if world > 1:
@@ -317,12 +326,14 @@ def run_gpu(args):
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
         barrier()
-        t0 = time.perf_counter()
         ke = max(1, min(args.steps, 3))
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ee0.record()
         for _ in range(ke):
             step_e2e()
+        ee1.record()
         barrier()
-        dte = time.perf_counter() - t0
+        dte = ee0.elapsed_time(ee1) * 1e-3
         tri = n * (n + 1) // 2
         e2e = {"value": ke * W / dte, "unit": "pair*SNP/s", "ms_per_step": 1e3 * dte / ke,
                "h2d_bytes_per_step": int(m_file * bpr), "d2h_bytes_per_step": int(2 * tri * 8),
@@ -368,12 +379,14 @@ def run_gpu(args):
 
         step_e2e()
         barrier()
-        t0 = time.perf_counter()
         ke = max(1, min(args.steps, 2))
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ee0.record()
         for _ in range(ke):
             step_e2e()
+        ee1.record()
         barrier()
-        dte = time.perf_counter() - t0
+        dte = ee0.elapsed_time(ee1) * 1e-3
         t = torch.tensor([dte], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dte = float(t.item())
@@ -406,7 +419,9 @@ def run_gpu(args):
         prof_traffic = json.load(open(pj)).get("dram_bytes_per_launch")
     out = {
         "metric": "grm_pair_snp_per_s", "value": value, "unit": "pair*SNP/s", "n_gpus": G, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "wall_ms_per_step": 1e3 * wall_dt / args.steps,
+        "timing": "CUDA events on the rank's stream around the K steps (each step ends in dgrm_finish, which drains the "
+                  "engine's streams), max over ranks", "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"fp16": "f16 operands / f32 chunk accum / f64 across chunks; counts exact int32",
                                        "bf16": "bf16 operands / f32 / f64; counts exact int32",
                                        "fp16x2": "f16 hi+lo split (3 MMAs) / f32 / f64"}[args.operand],
@@ -481,6 +496,7 @@ def main():
     ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16", "fp16x2"])
     ap.add_argument("--count", default="fp4", choices=["mma", "popc", "fp4"])
     ap.add_argument("--resident", type=int, default=0, help="resident chunk slots (0 = auto, 1 = streaming)")
+    ap.add_argument("--resident-mb", type=int, default=16384, help="memory budget for resident operands (MiB)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

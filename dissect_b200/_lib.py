@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdgrm.so")
+LIB_PATH = os.environ.get("DGRM_LIB") or os.path.join(_HERE, "libdgrm.so")   # DGRM_LIB: experiment builds
 
 K_NUM = 8
 K_NAMES = ("count", "expand", "syrk", "paircnt", "final", "fetch", "gather", "d2h")

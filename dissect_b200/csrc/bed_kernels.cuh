@@ -157,6 +157,7 @@ constexpr int kExpI = 128;          // individuals per block
 constexpr int kExpZPitch = 272;     // bytes per staged Z row (256 + 16 pad)
 constexpr int kExpQPitch = 136;     // bytes per staged Q row (128 + 8 pad)
 constexpr int kExpQ4Pitch = 68;     // bytes per staged Q4 row (64 + 4 pad)
+constexpr int kExpMPitch = 20;      // bytes per staged mask row (16 + 4 pad)
 
 struct ExpandSmem {
   uint8_t pk[kExpK][32];            // packed genotypes: row = SNP, 32 bytes = 128 individuals
@@ -165,9 +166,7 @@ struct ExpandSmem {
   double lut_sq[kExpK][4];
   double dpart[2][kExpI];
   uint8_t outz[kExpI * kExpZPitch];
-  uint8_t outq[kExpI * kExpQPitch];
-  uint32_t outm[kExpI][4];          // 128 mask bits per individual
-  uint8_t outq4[kExpI * kExpQ4Pitch];  // e2m1 0/1, two SNPs per byte
+  uint8_t outq[kExpI * kExpQPitch]; // count operand staging: e4m3 bytes, e2m1 nibbles or mask bits (one kind per launch)
 };
 
 template <bool BF16>
@@ -196,17 +195,18 @@ struct ExpandArgs {
   uint16_t* Z;
   int64_t z_pitch;   // elements
   int64_t lo_off;    // element offset of the lo part (SPLIT)
-  uint8_t* Q;        // may be NULL (flat norm / popcount)
+  uint8_t* Q;        // e4m3 0/1 operand (QK 1)
   int64_t q_pitch;
-  uint8_t* Q4;       // e2m1 0/1 operand (two SNPs per byte), may be NULL
+  uint8_t* Q4;       // e2m1 0/1 operand, two SNPs per byte (QK 2)
   int64_t q4_pitch;  // bytes
-  uint32_t* MB;      // may be NULL
+  uint32_t* MB;      // non-missing bit masks (QK 3)
   int64_t mb_pitch;  // 32-bit words
   double* diag_part; // [ktiles][n_pad]
   int n_pad;
 };
 
-template <bool BF16, bool SPLIT>
+// QK: which count operand this launch writes (0 none, 1 e4m3 bytes, 2 e2m1 nibbles, 3 bit masks)
+template <bool BF16, bool SPLIT, int QK>
 __global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
   extern __shared__ __align__(16) uint8_t expand_smem_raw[];
   ExpandSmem& sm = *reinterpret_cast<ExpandSmem*>(expand_smem_raw);
@@ -214,13 +214,25 @@ __global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
   const int i0 = blockIdx.x * kExpI;
   const int k0 = blockIdx.y * kExpK;
 
-  // packed tile: 128 rows x 32 bytes = 256 uint4... one 16-byte piece per thread
+  // packed tile: 128 rows x 32 bytes, one 16-byte piece per thread; rows past the chunk and individuals past n
+  // become "missing" (01) here, so the hot loop below needs no bounds logic at all
   {
     const int r = tid >> 1, h = tid & 1;
-    uint4 v = make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);  // all missing
+    uint4 v = make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);
     if (k0 + r < a.kc) {
       const int64_t off = (int64_t)(k0 + r) * a.pitch + (i0 >> 2) + h * 16;
       if ((i0 >> 2) + h * 16 < a.pitch) v = __ldg(reinterpret_cast<const uint4*>(a.chunk + off));
+    }
+    if (i0 + kExpI > a.n) {  // block-uniform: only the last block of individuals
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int valid = a.n - (i0 + (h * 4 + q) * 16);  // individuals of this 32-bit word that exist
+        valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
+        const uint32_t keep = valid == 16 ? 0xFFFFFFFFu : ((1u << (2 * valid)) - 1u);
+        w[q] = (w[q] & keep) | (0x55555555u & ~keep);
+      }
+      v = make_uint4(w[0], w[1], w[2], w[3]);
     }
     *reinterpret_cast<uint4*>(&sm.pk[r][h * 16]) = v;
   }
@@ -242,36 +254,54 @@ __global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
 
   const int il = tid & (kExpI - 1);
   const int kh = tid >> 7;
-  const bool live = (i0 + il) < a.n;
-  const int bsel = il >> 2;
   const int bshift = 2 * (il & 3);
+  const uint8_t* pkcol = &sm.pk[0][il >> 2];
   double dsum = 0.;
 #pragma unroll 1
   for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+    const uint16_t* lut = part == 0 ? &sm.lut_hi[0][0] : &sm.lut_lo[0][0];
 #pragma unroll 2
     for (int j = 0; j < 8; ++j) {
       const int kg = kh + 2 * j;
+      const uint8_t* pkc = pkcol + kg * 8 * 32;
+      const uint16_t* lh = lut + kg * 8 * 4;
+      const double* lq = &sm.lut_sq[kg * 8][0];
       uint32_t h[4];
-      uint32_t ql = 0, qh = 0, mb = 0, q4 = 0;
+      uint32_t c16 = 0;  // the 8 two-bit patterns of this individual, SNP t at bits 2t
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
-        const int k = kg * 8 + t;
-        const uint32_t code = live ? ((sm.pk[k][bsel] >> bshift) & 3u) : 1u;
-        const uint32_t v = part == 0 ? sm.lut_hi[k][code] : sm.lut_lo[k][code];
-        if (t & 1) h[t >> 1] |= v << 16; else h[t >> 1] = v;
+        const uint32_t code = ((uint32_t)pkc[t * 32] >> bshift) & 3u;
+        const uint32_t v = lh[t * 4 + code];
+        if (t & 1) h[t >> 1] = v * 65536u + h[t >> 1]; else h[t >> 1] = v;
         if (part == 0) {
-          const uint32_t present = (code != 1u);
-          if (t < 4) ql |= (present * 0x38u) << (8 * t); else qh |= (present * 0x38u) << (8 * (t - 4));
-          mb |= present << t;
-          q4 |= (present * 0x2u) << (4 * t);   // e2m1 1.0 = 0b0010
-          dsum = __dadd_rn(dsum, sm.lut_sq[k][code]);
+          c16 = code * (1u << (2 * t)) + c16;
+          dsum = __dadd_rn(dsum, lq[t * 4 + code]);
         }
       }
       *reinterpret_cast<uint4*>(&sm.outz[il * kExpZPitch + kg * 16]) = make_uint4(h[0], h[1], h[2], h[3]);
-      if (part == 0) {
-        *reinterpret_cast<uint2*>(&sm.outq[il * kExpQPitch + kg * 8]) = make_uint2(ql, qh);
-        reinterpret_cast<uint8_t*>(&sm.outm[il][0])[kg] = (uint8_t)mb;
-        *reinterpret_cast<uint32_t*>(&sm.outq4[il * kExpQ4Pitch + kg * 4]) = q4;
+      if (part == 0 && QK != 0) {
+        // present <=> pattern != 01 <=> hi bit set or lo bit clear; one flag per SNP at bit 2t
+        const uint32_t lo = c16 & 0x5555u, hi = (c16 >> 1) & 0x5555u;
+        uint32_t x = (hi | (lo ^ 0x5555u)) & 0x5555u;
+        if constexpr (QK == 2) {
+          // spread flag t from bit 2t to bit 4t + 1 (e2m1 1.0 = 0b0010 in nibble t)
+          x = (x & 0xFFu) | ((x & 0xFF00u) << 8);           // SNPs 4..7 to the upper half-word
+          x = (x & 0x000F000Fu) | ((x & 0x00F000F0u) << 4);  // pairs to separate bytes
+          x = (x & 0x01010101u) | ((x & 0x04040404u) << 2);  // each flag to the base of its nibble
+          *reinterpret_cast<uint32_t*>(&sm.outq[il * kExpQ4Pitch + kg * 4]) = x << 1;
+        } else {
+          // compress the flags to 8 adjacent bits
+          x = (x | (x >> 1)) & 0x3333u;
+          x = (x | (x >> 2)) & 0x0F0Fu;
+          x = (x | (x >> 4)) & 0x00FFu;
+          if constexpr (QK == 3) {
+            sm.outq[il * kExpMPitch + kg] = (uint8_t)x;
+          } else {  // e4m3 1.0 = 0x38, one byte per SNP
+            const uint32_t ql = (((x & 0xFu) * 0x00204081u) & 0x01010101u) * 0x38u;
+            const uint32_t qh = (((x >> 4) * 0x00204081u) & 0x01010101u) * 0x38u;
+            *reinterpret_cast<uint2*>(&sm.outq[il * kExpQPitch + kg * 8]) = make_uint2(ql, qh);
+          }
+        }
       }
     }
     if (part == 0) sm.dpart[kh][il] = dsum;
@@ -287,7 +317,7 @@ __global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
         *reinterpret_cast<uint4*>(zbase + (int64_t)(i0 + r) * a.z_pitch + c * 8) = v;
       }
       if (part == 0) {
-        if (a.Q) {
+        if constexpr (QK == 1) {
 #pragma unroll
           for (int ps = 0; ps < kExpI / 16; ++ps) {
             const int r = ps * 16 + (tid >> 4);
@@ -295,17 +325,20 @@ __global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
             *reinterpret_cast<uint2*>(a.Q + (int64_t)(i0 + r) * a.q_pitch + k0 + c * 8) = v;
           }
         }
-        if (a.Q4) {
+        if constexpr (QK == 2) {
 #pragma unroll
           for (int ps = 0; ps < kExpI / 16; ++ps) {
             const int r = ps * 16 + (tid >> 4);
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(&sm.outq4[r * kExpQ4Pitch + c * 4]);
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(&sm.outq[r * kExpQ4Pitch + c * 4]);
             *reinterpret_cast<uint32_t*>(a.Q4 + (int64_t)(i0 + r) * a.q4_pitch + (k0 >> 1) + c * 4) = v;
           }
         }
-        if (a.MB && tid < kExpI) {
-          const uint4 v = *reinterpret_cast<const uint4*>(&sm.outm[tid][0]);
-          *reinterpret_cast<uint4*>(a.MB + (int64_t)(i0 + tid) * a.mb_pitch + (k0 >> 5)) = v;
+        if constexpr (QK == 3) {
+          if (tid < kExpI) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.outq[tid * kExpMPitch]);
+            *reinterpret_cast<uint4*>(a.MB + (int64_t)(i0 + tid) * a.mb_pitch + (k0 >> 5)) =
+                make_uint4(src[0], src[1], src[2], src[3]);
+          }
         }
         if (tid < kExpI)
           a.diag_part[(int64_t)blockIdx.y * a.n_pad + i0 + tid] = __dadd_rn(sm.dpart[0][tid], sm.dpart[1][tid]);

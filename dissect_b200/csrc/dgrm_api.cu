@@ -5,12 +5,17 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "../../include/dgrm.h"
 #include "bed_kernels.cuh"
@@ -109,10 +114,10 @@ struct dgrm_engine {
   // resident operand slots: `slots` chunks of kc_max SNPs live side by side in Z / Q / MB
   int slots = 0;
   int chunks_in_super = 0;
+  int launched_s = 0, launched_n = 0;  // resident chunks of this super already contracted into S / N
   int64_t supers_done = 0;
   int slot_kpad[kMaxChunks] = {0};
-  int l2_policy = 1;  // see SyrkParams::l2_policy (DGRM_L2_POLICY overrides, for experiments)
-  int tile_major = 0; // DGRM_TILE_MAJOR=1: one launch walks all resident chunks per tile (experiment)
+  int l2_policy = 3;  // see SyrkParams::l2_policy (DGRM_L2_POLICY overrides, for experiments)
 
   // chunk state
   int kc_max = 0;
@@ -151,6 +156,11 @@ struct dgrm_engine {
   cudaEvent_t rowidx_free[2] = {nullptr, nullptr};
   int rowidx_i = 0;
   cudaEvent_t producer_ev = nullptr;
+  // `prep` decodes (gather, count, expand) while `stream` contracts the chunks that are already resident
+  cudaStream_t prep = nullptr;
+  cudaEvent_t prep_ev = nullptr, mma_ev = nullptr;
+  double out_wait_ms = 0, out_host_ms = 0;  // DGRM_TRACE_OUT: host time waiting for / finishing output jobs
+  int overlap = 1;  // DGRM_OVERLAP=0: contract only in dgrm_finish (experiments)
 
   bool have_ind = false, begun = false, finished = false;
 
@@ -353,7 +363,8 @@ int launch_syrk(dgrm_engine* e, const CUtensorMap& tmap, const SyrkParams& p) {
 
 constexpr int kCountMergeSnps = 32768;  // SNPs per pair-count accumulation (exact in fp32: << 2^24)
 
-int flush_super(dgrm_engine* e, bool final);
+int flush_super(dgrm_engine* e, bool final, bool wrap = false);
+bool streaming_bound(const dgrm_engine* e);
 
 // One chunk of packed rows: per-SNP statistics, then expansion into resident operand slot `chunks_in_super`.
 int process_chunk(dgrm_engine* e) {
@@ -366,21 +377,21 @@ int process_chunk(dgrm_engine* e) {
   const bool count_fp4 = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_FP4;
   const bool count_popc = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_POPC;
   if (e->chunks_in_super == e->slots) {  // every resident slot is taken: contract them before reusing slot 0
-    const int rc = flush_super(e, false);
+    const int rc = flush_super(e, false, true);
     if (rc) return rc;
   }
   const int slot = e->chunks_in_super;
   const int64_t col0 = (int64_t)slot * e->kc_max;
 
   {
-    Prof pr(e, DGRM_K_COUNT);
+    Prof pr(e, DGRM_K_COUNT, e->prep);
     SnpStatsOut so{e->d_freq, e->d_nn, e->d_p1, e->d_p2, e->d_sd, e->d_bad_count, e->d_bad_list, dgrm_engine::kBadCap};
     const int blocks = (kc * 32 + 255) / 256;
-    bed_count_stats_kernel<<<blocks, 256, 0, e->stream>>>(e->d_chunk, e->chunk_pitch, kc, (int)e->n, e->m, so, e->d_zt);
+    bed_count_stats_kernel<<<blocks, 256, 0, e->prep>>>(e->d_chunk, e->chunk_pitch, kc, (int)e->n, e->m, so, e->d_zt);
     CK(cudaGetLastError());
   }
   {
-    Prof pr(e, DGRM_K_EXPAND);
+    Prof pr(e, DGRM_K_EXPAND, e->prep);
     ExpandArgs a;
     a.chunk = e->d_chunk; a.pitch = e->chunk_pitch; a.kc = kc; a.n = (int)e->n; a.zt = e->d_zt;
     a.Z = e->d_Z + col0; a.z_pitch = e->z_pitch; a.lo_off = (int64_t)e->slots * e->kc_max;
@@ -390,30 +401,42 @@ int process_chunk(dgrm_engine* e) {
     a.diag_part = e->d_diag_part; a.n_pad = (int)e->n_pad;
     const dim3 grid((unsigned)(e->n_pad / kExpI), (unsigned)(kc_pad / kExpK));
     const size_t smem = sizeof(ExpandSmem);
-    if (bf16) bed_expand_kernel<true, false><<<grid, 256, smem, e->stream>>>(a);
-    else if (split) bed_expand_kernel<false, true><<<grid, 256, smem, e->stream>>>(a);
-    else bed_expand_kernel<false, false><<<grid, 256, smem, e->stream>>>(a);
+    const int qk = count_mma ? 1 : count_fp4 ? 2 : count_popc ? 3 : 0;
+#define DGRM_EXPAND(B, S, K) bed_expand_kernel<B, S, K><<<grid, 256, smem, e->prep>>>(a)
+#define DGRM_EXPAND_Q(B, S)                                              \
+  do {                                                                   \
+    if (qk == 0) DGRM_EXPAND(B, S, 0); else if (qk == 1) DGRM_EXPAND(B, S, 1); \
+    else if (qk == 2) DGRM_EXPAND(B, S, 2); else DGRM_EXPAND(B, S, 3);   \
+  } while (0)
+    if (bf16) DGRM_EXPAND_Q(true, false);
+    else if (split) DGRM_EXPAND_Q(false, true);
+    else DGRM_EXPAND_Q(false, false);
+#undef DGRM_EXPAND_Q
+#undef DGRM_EXPAND
     CK(cudaGetLastError());
-    diag_reduce_kernel<<<(unsigned)((e->n_pad + 255) / 256), 256, 0, e->stream>>>(e->d_diag_part, kc_pad / kExpK,
-                                                                                (int)e->n_pad, e->d_diag);
-    CK(cudaGetLastError());
-  }
-  if (count_popc && !e->work_cg1.empty()) {
-    Prof pr(e, DGRM_K_PAIRCNT);
-    const int nw = (int)e->work_cg1.size();
-    pair_count_popc_kernel<<<std::min(nw, e->sm_count * 2), 256, 0, e->stream>>>(
-        e->d_MB + col0 / 32, e->mb_pitch, kc_pad / 32, e->d_work_cg1, nw, e->d_N, e->chunks_done > 0);
+    diag_reduce_kernel<<<(unsigned)((e->n_pad + 255) / 256), 256, 0, e->prep>>>(e->d_diag_part, kc_pad / kExpK,
+                                                                              (int)e->n_pad, e->d_diag);
     CK(cudaGetLastError());
   }
   e->slot_kpad[slot] = kc_pad;
   e->m += kc;
   e->chunks_done++;
   e->fill = 0;
-  ++e->chunks_in_super;  // contracted lazily: by the next chunk that needs the slot, or by dgrm_finish
+  ++e->chunks_in_super;
+  // Without streaming output bindings the chunk is contracted right away on the MMA stream, so that the decode of
+  // the next chunk (prep stream) overlaps it; with them the contraction waits for dgrm_finish, which walks the
+  // tiles group by group so that finished groups leave the device early.
+  if (e->overlap && !streaming_bound(e)) return flush_super(e, false);
   return DGRM_OK;
 }
 
 bool binding_streams(const dgrm_engine::Binding& bd) { return bd.uplo == 0; }
+
+bool streaming_bound(const dgrm_engine* e) {
+  bool s = e->ntbind > 0;
+  for (int b = 0; b < e->nbind; ++b) s |= binding_streams(e->bind[b]);
+  return s;
+}
 
 // first local index whose global index is >= target (block-cyclic, monotone)
 int first_local_ge(int target, int nloc, int bs, int me, int P) {
@@ -502,12 +525,39 @@ int issue_job(dgrm_engine* e, size_t k) {
   return DGRM_OK;
 }
 
+// int32 pair counts -> the caller's fp64 matrix.  The destination is written once and not read again by this
+// library: non-temporal stores skip the read-for-ownership of every line (a third of the host memory traffic).
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void widen_i32_stream(double* dst, const int32_t* src, int cnt) {
+  int i = 0;
+  for (; i < cnt && ((uintptr_t)(dst + i) & 31); ++i) dst[i] = (double)src[i];
+  for (; i + 4 <= cnt; i += 4)
+    _mm256_stream_pd(dst + i, _mm256_cvtepi32_pd(_mm_loadu_si128((const __m128i*)(src + i))));
+  for (; i < cnt; ++i) dst[i] = (double)src[i];
+}
+#endif
+
+void widen_i32(double* dst, const int32_t* src, int cnt, bool stream) {
+#if defined(__x86_64__)
+  if (stream) return widen_i32_stream(dst, src, cnt);
+#endif
+  for (int i = 0; i < cnt; ++i) dst[i] = (double)src[i];
+}
+
 // Wait for job k's transfer; staged jobs are then moved (and pair counts widened to double) into the caller's
 // buffer by host threads, exactly the rows on or below the diagonal of every column.
 int finish_job(dgrm_engine* e, size_t k) {
   const dgrm_engine::OutJob& j = e->jobs[k];
   const int sl = (int)(k % dgrm_engine::kOutSlots);
+  const auto tw0 = std::chrono::steady_clock::now();
   CK(cudaEventSynchronize(e->stage_copied_out[sl]));
+  const auto tw1 = std::chrono::steady_clock::now();
+  e->out_wait_ms += std::chrono::duration<double, std::milli>(tw1 - tw0).count();
+  struct Acc {
+    dgrm_engine* e;
+    std::chrono::steady_clock::time_point t;
+    ~Acc() { e->out_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); }
+  } acc{e, tw1};
   if (j.direct) return DGRM_OK;
   if (j.tiles) {
     const double* src = (const double*)e->h_out_stage[sl];
@@ -525,7 +575,14 @@ int finish_job(dgrm_engine* e, size_t k) {
   double* host = bd.host;
   const bool as_int = j.as_int;
   const int lr0 = j.lr0, lr1 = j.lr1;
-#pragma omp parallel for schedule(dynamic, 16)
+#if defined(__x86_64__)
+  static const bool nt = __builtin_cpu_supports("avx2") && !getenv("DGRM_NO_NT");
+#else
+  static const bool nt = false;
+#endif
+#pragma omp parallel
+  {
+#pragma omp for schedule(dynamic, 16) nowait
   for (int lc = 0; lc < j.lc1; ++lc) {
     const int gc = ((lc / g.bs_c) * g.C + g.my_col) * g.bs_c + lc % g.bs_c;
     const int lra = std::max(lr0, first_local_ge(gc, g.nloc_r, g.bs_r, g.my_row, g.R));
@@ -533,11 +590,14 @@ int finish_job(dgrm_engine* e, size_t k) {
     double* dst = host + (int64_t)lc * g.lld + lra;
     const int cnt = lr1 - lra;
     if (as_int) {
-      const int32_t* src = (const int32_t*)hs + (int64_t)lc * h + (lra - lr0);
-      for (int i = 0; i < cnt; ++i) dst[i] = (double)src[i];
+      widen_i32(dst, (const int32_t*)hs + (int64_t)lc * h + (lra - lr0), cnt, nt);
     } else {
       memcpy(dst, (const double*)hs + (int64_t)lc * h + (lra - lr0), (size_t)cnt * sizeof(double));
     }
+  }
+#if defined(__x86_64__)
+  _mm_sfence();
+#endif
   }
   return DGRM_OK;
 }
@@ -553,28 +613,37 @@ int issue_ready_jobs(dgrm_engine* e, int gi) {
   return DGRM_OK;
 }
 
-// Contract the resident chunks: for every tile, every chunk in turn (fp32 in TMEM per chunk, fp64 / int32
-// read-modify-write of the tile across chunks, which stays in L2 because the same CTA revisits it).
-// `final`: the last contraction of this GRM; tiles then leave the device group by group while later
-// groups are still being computed.
-int flush_super(dgrm_engine* e, bool final) {
+// Contract resident chunks that have not been contracted yet (fp32 in TMEM per chunk, fp64 / int32
+// read-modify-write of the tile across chunks).  S: chunks [launched_s, nch); N: merged groups from launched_n up to
+// the last complete group (every chunk when `final` or `wrap`).
+// `wrap`: every slot is taken and slot 0 is about to be overwritten.
+// `final`: the last contraction of this GRM; with streaming bindings tiles then leave the device group by
+// group while later groups are still being computed.
+int flush_super(dgrm_engine* e, bool final, bool wrap) {
   const int nch = e->chunks_in_super;
   if (nch == 0) return DGRM_OK;
-  e->chunks_in_super = 0;
   const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
   const bool bf16 = e->cfg.operand == DGRM_OPERAND_BF16;
   const bool count_fp4 = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_FP4;
   const bool count_mma = !e->cfg.flat_norm && (e->cfg.count_method == DGRM_COUNT_MMA || count_fp4);
+  const bool count_popc = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_POPC;
+  // pair count: 0/1 products accumulate exactly in fp32 up to 2^24, so resident chunks are merged up to
+  // 32768 SNPs per TMEM accumulation (one int32 read-modify-write of the tile per merged group)
+  const int merge = count_mma ? std::max(1, kCountMergeSnps / e->kc_max) : 1;
+  const int ls = e->launched_s, ln = e->launched_n;
+  const int n_to = (final || wrap) ? nch : nch / merge * merge;
   const int nwork = (int)e->work.size();
-  if (nwork > 0) {
+  // the operands of every chunk expanded so far must be complete before the MMA stream reads them
+  CK(cudaEventRecord(e->prep_ev, e->prep));
+  CK(cudaStreamWaitEvent(e->stream, e->prep_ev, 0));
+  const bool stream_out = streaming_bound(e);
+  if (nwork > 0 && (ls < nch || ln < n_to || (final && stream_out))) {
     SyrkParams p{};
     p.work = e->d_work;
     p.l2_policy = e->l2_policy;
     const int lo = e->slots * e->kc_max;
     // tile groups: whole waves of the persistent grid, so that no launch has a ragged tail
     const int units = e->cfg.cta_group == 2 ? e->sm_count / 2 : e->sm_count;
-    bool stream_out = e->ntbind > 0;
-    for (int b = 0; b < e->nbind; ++b) stream_out |= binding_streams(e->bind[b]);
     // Tile groups.  Streaming outputs: one group per raster row group, its end rounded up to whole waves of
     // the persistent grid (no ragged tail, and the row group is final as soon as its launches are done).
     std::vector<int> group_end;
@@ -654,21 +723,18 @@ int flush_super(dgrm_engine* e, bool final) {
     // launch boundary re-synchronises the persistent CTAs every few hundred microseconds, which is what keeps
     // the A/B panels they share hot in L2.  (One tile-major launch over all chunks lets the CTAs drift apart
     // and re-read every panel from HBM: measured 233 GB per launch instead of ~40 GB.)
-    const int per_launch = e->tile_major ? nch : 1;
     int w0 = 0;
     for (size_t gi = 0; gi < group_end.size(); w0 = group_end[gi], ++gi) {
       const int w1 = group_end[gi];
       p.work_begin = w0;
       p.work_end = w1;
-      for (int j0 = 0; j0 < nch; j0 += per_launch) {
-        p.nchunks = per_launch;
-        for (int j = 0; j < per_launch; ++j) {
-          p.chunk_col[j] = (j0 + j) * e->kc_max;
-          p.chunk_kpad[j] = e->slot_kpad[j0 + j];
-        }
-        p.accumulate = e->supers_done > 0 || j0 > 0;
-        {
+      for (int j0 = std::min(ls, ln); j0 < nch; ++j0) {
+        if (j0 >= ls) {
           Prof pr(e, DGRM_K_SYRK);
+          p.nchunks = 1;
+          p.chunk_col[0] = j0 * e->kc_max;
+          p.chunk_kpad[0] = e->slot_kpad[j0];
+          p.accumulate = e->supers_done > 0 || j0 > 0;
           p.npass = split ? 3 : 1;
           p.a_off[0] = 0; p.a_off[1] = lo; p.a_off[2] = 0;
           p.b_off[0] = 0; p.b_off[1] = 0; p.b_off[2] = lo;
@@ -678,18 +744,23 @@ int flush_super(dgrm_engine* e, bool final) {
                                                : launch_syrk<1, 0, double>(e, e->tmap_z, p);
           if (rc) return rc;
         }
-        // pair count: 0/1 products accumulate exactly in fp32 up to 2^24, so resident chunks are merged up to
-        // 32768 SNPs per TMEM accumulation (one int32 read-modify-write of the tile per merged group)
-        const int merge = std::max(1, kCountMergeSnps / e->kc_max);
-        if (count_mma && per_launch == 1 && (j0 % merge == 0)) {
-          Prof pr(e, DGRM_K_PAIRCNT);
-          const int j1 = std::min(nch, j0 + merge);
+        if (j0 < ln || j0 >= n_to || j0 % merge != 0) continue;
+        Prof pr(e, DGRM_K_PAIRCNT);
+        if (count_popc) {
+          const int nw1 = w1 * e->cfg.cta_group, nw0 = w0 * e->cfg.cta_group;  // 128-row tiles of this group
+          pair_count_popc_kernel<<<std::min(nw1 - nw0, e->sm_count * 2), 256, 0, e->stream>>>(
+              e->d_MB + (int64_t)j0 * e->kc_max / 32, e->mb_pitch, e->slot_kpad[j0] / 32, e->d_work_cg1 + nw0, nw1 - nw0,
+              e->d_N, e->supers_done > 0 || j0 > 0);
+          CK(cudaGetLastError());
+        } else if (count_mma) {
+          const int j1 = std::min(n_to, j0 + merge);
           int kpad = 0;
           for (int j = j0; j < j1; ++j) kpad += e->slot_kpad[j];   // slots are adjacent; only the last can be short
           p.nchunks = 1;
           p.npass = 1;
           p.a_off[0] = p.b_off[0] = 0;
           p.out = e->d_N;
+          p.accumulate = e->supers_done > 0 || j0 > 0;
           int rc;
           if (count_fp4) {  // operand addressed in bytes: two SNPs per byte
             p.chunk_col[0] = j0 * e->kc_max / 2;
@@ -702,15 +773,6 @@ int flush_super(dgrm_engine* e, bool final) {
             p.idesc = make_idesc(e->cfg.cta_group, 0 /* e4m3 */);
             rc = e->cfg.cta_group == 2 ? launch_syrk<2, 1, int>(e, e->tmap_q, p) : launch_syrk<1, 1, int>(e, e->tmap_q, p);
           }
-          if (rc) return rc;
-        } else if (count_mma && per_launch != 1) {
-          Prof pr(e, DGRM_K_PAIRCNT);
-          p.npass = 1;
-          p.a_off[0] = p.b_off[0] = 0;
-          p.out = e->d_N;
-          p.idesc = make_idesc(e->cfg.cta_group, 0 /* e4m3 */);
-          const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, 1, int>(e, e->tmap_q, p)
-                                               : launch_syrk<1, 1, int>(e, e->tmap_q, p);
           if (rc) return rc;
         }
       }
@@ -727,6 +789,7 @@ int flush_super(dgrm_engine* e, bool final) {
     }
     if (final && stream_out) {
       // everything is queued on the compute stream: now feed the copy engine and finish the staged jobs
+      e->out_wait_ms = e->out_host_ms = 0;
       while (e->jobs_done < e->jobs.size()) {
         int rc = issue_ready_jobs(e, (int)group_end.size());
         if (rc) return rc;
@@ -734,9 +797,21 @@ int flush_super(dgrm_engine* e, bool final) {
         if (rc) return rc;
         e->jobs_done++;
       }
+      if (getenv("DGRM_TRACE_OUT"))
+        fprintf(stderr, "[dgrm] %zu output jobs: waited %.2f ms for the copy engine, %.2f ms in host conversion\n",
+                e->jobs.size(), e->out_wait_ms, e->out_host_ms);
     }
   }
-  e->supers_done++;
+  e->launched_s = nch;
+  e->launched_n = n_to;
+  if (final || wrap) {
+    // the next chunk overwrites slot 0: the decode stream has to wait for the contractions queued so far
+    CK(cudaEventRecord(e->mma_ev, e->stream));
+    CK(cudaStreamWaitEvent(e->prep, e->mma_ev, 0));
+    e->chunks_in_super = 0;
+    e->launched_s = e->launched_n = 0;
+    e->supers_done++;
+  }
   return DGRM_OK;
 }
 
@@ -763,11 +838,11 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
       CK(cudaEventSynchronize(e->rowidx_free[s]));
       memcpy(e->h_rowidx[s], idx.data() + pos, (size_t)take * sizeof(int32_t));
       CK(cudaMemcpyAsync(e->d_rowidx[s], e->h_rowidx[s], (size_t)take * sizeof(int32_t), cudaMemcpyHostToDevice,
-                         e->stream));
+                         e->prep));
       d_idx = e->d_rowidx[s];
     }
     {
-      Prof pr(e, DGRM_K_GATHER);
+      Prof pr(e, DGRM_K_GATHER, e->prep);
       const int nbytes = (int)(e->d_src_ind ? e->b_row : e->b_fam);
       uint8_t* dst = e->d_chunk + (int64_t)e->fill * e->chunk_pitch;
       const uint64_t align = (uint64_t)(uintptr_t)d_rows | (uint64_t)pitch;
@@ -775,15 +850,15 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
       const int per_row = (nbytes / vec + 255) / 256;
       const dim3 grid((unsigned)std::max(1, std::min(per_row, 64)), (unsigned)take);
 #define DGRM_GATHER(T)                                                                                            \
-  bed_gather_kernel<T><<<grid, 256, 0, e->stream>>>(d_rows, pitch, d_idx, pos, take, dst, e->chunk_pitch, nbytes, \
-                                                    e->d_src_ind, (int)e->n)
+  bed_gather_kernel<T><<<grid, 256, 0, e->prep>>>(d_rows, pitch, d_idx, pos, take, dst, e->chunk_pitch, nbytes, \
+                                                  e->d_src_ind, (int)e->n)
       if (vec == 16) DGRM_GATHER(uint4);
       else if (vec == 8) DGRM_GATHER(uint2);
       else if (vec == 4) DGRM_GATHER(uint32_t);
       else DGRM_GATHER(uint8_t);
 #undef DGRM_GATHER
       CK(cudaGetLastError());
-      if (row_keep) CK(cudaEventRecord(e->rowidx_free[e->rowidx_i ^ 1], e->stream));
+      if (row_keep) CK(cudaEventRecord(e->rowidx_free[e->rowidx_i ^ 1], e->prep));
     }
     e->fill += take;
     pos += take;
@@ -798,6 +873,7 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
 // (Re)allocate the resident operand buffers for `slots` chunks of kc_max SNPs.
 int ensure_operands(dgrm_engine* e, int slots) {
   if (slots == e->slots && e->d_Z) return DGRM_OK;
+  CK(cudaStreamSynchronize(e->prep));
   CK(cudaStreamSynchronize(e->stream));
   free_dev(e->d_Z); e->d_Z = nullptr;
   free_dev(e->d_Q); e->d_Q = nullptr;
@@ -905,7 +981,7 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   e->sm_count = prop.multiProcessorCount;
   e->kc_max = cfg->chunk_snps;
   if (const char* pol = getenv("DGRM_L2_POLICY")) e->l2_policy = atoi(pol);
-  if (const char* tm = getenv("DGRM_TILE_MAJOR")) e->tile_major = atoi(tm);
+  if (const char* ov = getenv("DGRM_OVERLAP")) e->overlap = atoi(ov);
 #define CKC(call)                                                                          \
   do {                                                                                     \
     cudaError_t _s = (call);                                                               \
@@ -917,6 +993,7 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   } while (0)
   CKC(cudaSetDevice(cfg->device));
   CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&e->prep, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
@@ -930,6 +1007,8 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
     CKC(cudaEventCreateWithFlags(&e->rowidx_free[i], cudaEventDisableTiming));
   }
   CKC(cudaEventCreateWithFlags(&e->producer_ev, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&e->prep_ev, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&e->mma_ev, cudaEventDisableTiming));
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   CKC(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -945,12 +1024,12 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
                            (int)cudaSharedmemCarveoutMaxShared));
   CKC(cudaFuncSetAttribute(pack_rows_kernel<int>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)cudaSharedmemCarveoutMaxShared));
-  CKC(cudaFuncSetAttribute(bed_expand_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sizeof(ExpandSmem)));
-  CKC(cudaFuncSetAttribute(bed_expand_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sizeof(ExpandSmem)));
-  CKC(cudaFuncSetAttribute(bed_expand_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sizeof(ExpandSmem)));
+#define DGRM_EXPAND_ATTR(B, S, K)                                                                          \
+  CKC(cudaFuncSetAttribute(bed_expand_kernel<B, S, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem)))
+  DGRM_EXPAND_ATTR(false, false, 0); DGRM_EXPAND_ATTR(false, false, 1); DGRM_EXPAND_ATTR(false, false, 2); DGRM_EXPAND_ATTR(false, false, 3);
+  DGRM_EXPAND_ATTR(true, false, 0); DGRM_EXPAND_ATTR(true, false, 1); DGRM_EXPAND_ATTR(true, false, 2); DGRM_EXPAND_ATTR(true, false, 3);
+  DGRM_EXPAND_ATTR(false, true, 0); DGRM_EXPAND_ATTR(false, true, 1); DGRM_EXPAND_ATTR(false, true, 2); DGRM_EXPAND_ATTR(false, true, 3);
+#undef DGRM_EXPAND_ATTR
 #undef CKC
   *out = e;
   return DGRM_OK;
@@ -973,6 +1052,9 @@ void dgrm_destroy(dgrm_engine* e) {
     if (e->rowidx_free[i]) cudaEventDestroy(e->rowidx_free[i]);
   }
   if (e->producer_ev) cudaEventDestroy(e->producer_ev);
+  if (e->prep_ev) cudaEventDestroy(e->prep_ev);
+  if (e->mma_ev) cudaEventDestroy(e->mma_ev);
+  if (e->prep) cudaStreamDestroy(e->prep);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->out_stream) cudaStreamDestroy(e->out_stream);
@@ -991,6 +1073,7 @@ int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask
   if (!e) return DGRM_E_INVALID;
   if (n_fam <= 0 || n_fam > (1 << 30)) return fail(e, DGRM_E_INVALID, "dgrm_set_individuals: bad n_fam");
   CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->prep));
   CK(cudaStreamSynchronize(e->stream));
   release_geometry(e);
   e->nbind = 0;
@@ -1048,6 +1131,7 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
   if (m_capacity <= 0) return fail(e, DGRM_E_INVALID, "dgrm_begin: m_capacity must be positive");
   CK(cudaSetDevice(e->cfg.device));
   if (m_capacity > e->m_cap) {
+    CK(cudaStreamSynchronize(e->prep));
     CK(cudaStreamSynchronize(e->stream));
     release_stats(e);
     CK(cudaMalloc(&e->d_freq, (size_t)m_capacity * 4 * sizeof(int32_t)));
@@ -1074,6 +1158,7 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
   e->fill = 0;
   e->chunks_done = 0;
   e->chunks_in_super = 0;
+  e->launched_s = e->launched_n = 0;
   e->supers_done = 0;
   e->finished = false;
   if (e->d_subset) {
@@ -1082,8 +1167,11 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
     e->d_subset = nullptr;
     e->n_out = 0;
   }
-  CK(cudaMemsetAsync(e->d_bad_count, 0, 4 * sizeof(int32_t), e->stream));
-  CK(cudaMemsetAsync(e->d_diag, 0, (size_t)e->n_pad * sizeof(double), e->stream));
+  // a GRM that was abandoned before dgrm_finish may still have contractions in flight
+  CK(cudaEventRecord(e->mma_ev, e->stream));
+  CK(cudaStreamWaitEvent(e->prep, e->mma_ev, 0));
+  CK(cudaMemsetAsync(e->d_bad_count, 0, 4 * sizeof(int32_t), e->prep));
+  CK(cudaMemsetAsync(e->d_diag, 0, (size_t)e->n_pad * sizeof(double), e->prep));
   e->begun = true;
   return DGRM_OK;
 }
@@ -1098,7 +1186,7 @@ int dgrm_push_bed_device(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, i
   // order after the producer; NULL is the legacy default stream (what torch uses unless told otherwise), which the
   // engine's non-blocking streams do not synchronise with implicitly
   CK(cudaEventRecord(e->producer_ev, (cudaStream_t)producer_stream));
-  CK(cudaStreamWaitEvent(e->stream, e->producer_ev, 0));
+  CK(cudaStreamWaitEvent(e->prep, e->producer_ev, 0));
   // bound the host-side index list
   for (int64_t r0 = 0; r0 < nrows; r0 += (1 << 20)) {
     const int64_t cnt = std::min<int64_t>(nrows - r0, 1 << 20);
@@ -1111,8 +1199,8 @@ int dgrm_push_bed_device(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, i
 int dgrm_release_inputs(dgrm_engine* e, void* consumer_stream) {
   if (!e) return DGRM_E_INVALID;
   CK(cudaSetDevice(e->cfg.device));
-  // the row gather into the chunk buffer is the only reader of caller memory and runs on e->stream
-  CK(cudaEventRecord(e->producer_ev, e->stream));
+  // the row gather into the chunk buffer is the only reader of caller memory and runs on the decode stream
+  CK(cudaEventRecord(e->producer_ev, e->prep));
   CK(cudaStreamWaitEvent((cudaStream_t)consumer_stream, e->producer_ev, 0));
   return DGRM_OK;
 }
@@ -1131,10 +1219,10 @@ int dgrm_push_bed_host(dgrm_engine* e, const uint8_t* rows, int64_t pitch, int64
     CK(cudaMemcpy2DAsync(e->d_stage[s], (size_t)e->stage_pitch, rows + r0 * pitch, (size_t)pitch, (size_t)e->b_fam,
                          (size_t)cnt, cudaMemcpyHostToDevice, e->copy_stream));
     CK(cudaEventRecord(e->stage_copied[s], e->copy_stream));
-    CK(cudaStreamWaitEvent(e->stream, e->stage_copied[s], 0));
+    CK(cudaStreamWaitEvent(e->prep, e->stage_copied[s], 0));
     rc = push_device_rows(e, e->d_stage[s], e->stage_pitch, cnt, row_keep ? row_keep + r0 : nullptr);
     if (rc) return rc;
-    CK(cudaEventRecord(e->stage_free[s], e->stream));
+    CK(cudaEventRecord(e->stage_free[s], e->prep));
   }
   return DGRM_OK;
 }
@@ -1220,6 +1308,8 @@ int dgrm_finish(dgrm_engine* e) {
     if (rc) return rc;
     rc = flush_super(e, true);
     if (rc) return rc;
+    CK(cudaEventRecord(e->prep_ev, e->prep));  // statistics, bad-SNP list and the exact diagonal live on the decode stream
+    CK(cudaStreamWaitEvent(e->stream, e->prep_ev, 0));
     if (e->ntiles > 0 && e->chunks_done == 0) {  // no SNP at all: a well-defined empty GRM
       CK(cudaMemsetAsync(e->d_S, 0, (size_t)e->ntiles * kTileElems * sizeof(double), e->stream));
       if (e->d_N) CK(cudaMemsetAsync(e->d_N, 0, (size_t)e->ntiles * kTileElems * sizeof(int32_t), e->stream));
@@ -1266,6 +1356,7 @@ int dgrm_sync(dgrm_engine* e) {
   if (!e) return DGRM_E_INVALID;
   CK(cudaSetDevice(e->cfg.device));
   CK(cudaStreamSynchronize(e->copy_stream));
+  CK(cudaStreamSynchronize(e->prep));
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaStreamSynchronize(e->out_stream));
   CK(cudaStreamSynchronize(e->d2h_stream));
@@ -1336,6 +1427,7 @@ int dgrm_snp_stats(dgrm_engine* e, int32_t* freq, int32_t* nn, double* p1, doubl
   int rc = check_ready(e, false);
   if (rc) return rc;
   CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->prep));
   CK(cudaStreamSynchronize(e->stream));
   const size_t m = (size_t)e->m;
   if (m == 0) return DGRM_OK;
@@ -1351,6 +1443,7 @@ int dgrm_bad_snps(dgrm_engine* e, int64_t* idx, int64_t cap, int64_t* count) {
   int rc = check_ready(e, false);
   if (rc) return rc;
   CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->prep));
   CK(cudaStreamSynchronize(e->stream));
   int32_t bad[4];
   CK(cudaMemcpy(bad, e->d_bad_count, sizeof bad, cudaMemcpyDeviceToHost));
@@ -1627,6 +1720,7 @@ void dgrm_host_free(void* p) {
 int dgrm_kernel_times(dgrm_engine* e, double ms[DGRM_K_NUM], int64_t launches[DGRM_K_NUM]) {
   if (!e) return DGRM_E_INVALID;
   CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->prep));
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaStreamSynchronize(e->out_stream));
   CK(cudaStreamSynchronize(e->d2h_stream));

@@ -40,7 +40,8 @@ struct SyrkParams {
   void* out;          // tile storage, [storage index][256 cols][128 rows]
   int accumulate;     // chunk 0 of this launch: 0 = overwrite, 1 = add to what is there (later chunks always add)
   uint32_t idesc;     // tcgen05 instruction descriptor
-  int l2_policy;      // 0: no preference; 1: keep output tiles (evict_last); 2: 1 + operand panels evict_first
+  int l2_policy;      // 0: no preference; 1: output tiles evict_last when revisited in-launch; 2: 1 + operands evict_first;
+                      // 3: 1 + A panels (reused by the next waves of the raster row group) evict_last
 };
 
 constexpr int kTileM = 128;
@@ -49,7 +50,10 @@ constexpr int kTileElems = kTileM * kTileN;
 
 template <int CG>
 struct SyrkCfg {
-  static constexpr int kStages = (CG == 1) ? 4 : 6;
+#ifndef DGRM_CG2_STAGES
+#define DGRM_CG2_STAGES 4
+#endif
+  static constexpr int kStages = (CG == 1) ? 4 : DGRM_CG2_STAGES;
   static constexpr int kABytes = 128 * 128;                    // 128 rows x 128 B
   static constexpr int kBRows = (CG == 1) ? 256 : 128;         // CG 2: each CTA stages half of B
   static constexpr int kBBytes = kBRows * 128;
@@ -138,6 +142,7 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
       // operand panels are shared by the CTAs of a wave and then dead: let them go first so that the fp64
       // tiles (evict_last below) survive in L2 from one chunk to the next
       const uint64_t pol = p.l2_policy == 2 ? ptx::policy_evict_first() : ptx::policy_evict_normal();
+      const uint64_t pol_a = p.l2_policy == 3 ? ptx::policy_evict_last() : pol;
       for (int w = p.work_begin + unit; w < p.work_end; w += nunits) {
         const int4 t = p.work[w];
         const int a_row = t.x + (CG == 2 ? (int)rank * 128 : 0);
@@ -153,11 +158,11 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
             uint8_t* sb = sa + Cfg::kABytes;
             if constexpr (CG == 1) {
               ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              ptx::tma_load_2d(sa, &tmap, &full_bar[stage], a_col0 + kb * kKElems, a_row, pol);
+              ptx::tma_load_2d(sa, &tmap, &full_bar[stage], a_col0 + kb * kKElems, a_row, pol_a);
               ptx::tma_load_2d(sb, &tmap, &full_bar[stage], b_col0 + kb * kKElems, b_row, pol);
               ptx::tma_load_2d(sb + 128 * 128, &tmap, &full_bar[stage], b_col0 + kb * kKElems, b_row + 128, pol);
             } else {
-              ptx::tma_load_2d_2sm(sa, &tmap, &full_bar[stage], a_col0 + kb * kKElems, a_row, pol);
+              ptx::tma_load_2d_2sm(sa, &tmap, &full_bar[stage], a_col0 + kb * kKElems, a_row, pol_a);
               ptx::tma_load_2d_2sm(sb, &tmap, &full_bar[stage], b_col0 + kb * kKElems, b_row, pol);
               if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
               else ptx::mbar_arrive_cluster(&full_bar[stage], 0);
