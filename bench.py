@@ -489,8 +489,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dgrm", choices=["dgrm", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="override individuals (default 20000*sqrt(gpus))")
-    ap.add_argument("--m", type=int, default=0, help="override SNPs in the file (default 100000)")
+    ap.add_argument("--n", "--individuals", dest="n", type=int, default=0, help="override individuals (default 20000*sqrt(gpus))")
+    ap.add_argument("--m", "--snps", dest="m", type=int, default=0, help="override SNPs in the file (default 100000)")
     ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--cg", type=int, default=2)
     ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16", "fp16x2"])

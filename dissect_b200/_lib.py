@@ -28,7 +28,7 @@ class Config(C.Structure):
         ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("operand", C.c_int32),
         ("count_method", C.c_int32), ("flat_norm", C.c_int32), ("chunk_snps", C.c_int32),
         ("cta_group", C.c_int32), ("profile", C.c_int32), ("resident_chunks", C.c_int32), ("resident_mb", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("reserve_sms", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 

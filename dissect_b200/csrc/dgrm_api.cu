@@ -159,7 +159,10 @@ struct dgrm_engine {
   // `prep` decodes (gather, count, expand) while `stream` contracts the chunks that are already resident
   cudaStream_t prep = nullptr;
   cudaEvent_t prep_ev = nullptr, mma_ev = nullptr;
+  cudaEvent_t slot_ev[kMaxChunks] = {nullptr};  // recorded on `stream` once every contraction that reads the slot is queued
+  int slots_evented = 0;
   double out_wait_ms = 0, out_host_ms = 0;  // DGRM_TRACE_OUT: host time waiting for / finishing output jobs
+  int reserve_sms = 0;
   int overlap = 1;  // DGRM_OVERLAP=0: contract only in dgrm_finish (experiments)
 
   bool have_ind = false, begun = false, finished = false;
@@ -270,7 +273,10 @@ int make_tmap(dgrm_engine* e, CUtensorMap* map, void* base, int elem_bytes, int6
 }
 
 // Lower-triangle supertiles (256x256) in an L2-friendly raster: groups of 8 supertile rows, swept
-// column by column, dealt round-robin to the engines of the partition.
+// column by column.  Engine r of a partition of G owns the contiguous raster segment [r*K/G, (r+1)*K/G) of the
+// K supertiles: equal work (every tile costs the same), and its concurrent CTAs share A/B panels exactly as on
+// one GPU (dealing tiles round-robin gave each engine one row of every column: 1 + 74 panels per k-block
+// instead of 8 + 9, and the contraction ran 20 % slower at 8 GPUs).
 void build_tiles(dgrm_engine* e) {
   const int T = (int)(e->n_pad / 256);
   const int GR = 8;
@@ -283,12 +289,14 @@ void build_tiles(dgrm_engine* e) {
   e->rg_end.clear();
   e->rg_row1.clear();
   int64_t s = 0, ls = 0;
+  const int64_t total = (int64_t)T * (T + 1) / 2;
+  const int64_t own0 = total * e->cfg.rank / e->cfg.world, own1 = total * (e->cfg.rank + 1) / e->cfg.world;
   for (int g = 0; g < T; g += GR) {
     const int imax = std::min(g + GR, T) - 1;
     if (g > 0) e->rg_end.push_back((int)(e->cfg.cta_group == 2 ? e->work.size() : e->work_cg1.size()));
     for (int J = 0; J <= imax; ++J) {
       for (int I = std::max(g, J); I <= imax; ++I, ++s) {
-        if ((int)(s % e->cfg.world) != e->cfg.rank) continue;
+        if (s < own0 || s >= own1) continue;
         const int s0 = (int)(2 * ls), s1 = (int)(2 * ls + 1);
         index[(size_t)(2 * I) * e->ncp + J] = s0;
         index[(size_t)(2 * I + 1) * e->ncp + J] = s1;
@@ -343,7 +351,7 @@ int launch_syrk(dgrm_engine* e, const CUtensorMap& tmap, const SyrkParams& p) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  const int units = std::min<int>(p.work_end - p.work_begin, CG == 2 ? e->sm_count / 2 : e->sm_count);
+  const int units = std::min<int>(p.work_end - p.work_begin, (e->sm_count - e->reserve_sms) / CG);
   if (units <= 0) return DGRM_OK;
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(units * CG);
@@ -382,6 +390,7 @@ int process_chunk(dgrm_engine* e) {
   }
   const int slot = e->chunks_in_super;
   const int64_t col0 = (int64_t)slot * e->kc_max;
+  if (e->supers_done > 0) CK(cudaStreamWaitEvent(e->prep, e->slot_ev[slot], 0));  // the slot's previous chunk is contracted
 
   {
     Prof pr(e, DGRM_K_COUNT, e->prep);
@@ -643,7 +652,7 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
     p.l2_policy = e->l2_policy;
     const int lo = e->slots * e->kc_max;
     // tile groups: whole waves of the persistent grid, so that no launch has a ragged tail
-    const int units = e->cfg.cta_group == 2 ? e->sm_count / 2 : e->sm_count;
+    const int units = (e->sm_count - e->reserve_sms) / e->cfg.cta_group;
     // Tile groups.  Streaming outputs: one group per raster row group, its end rounded up to whole waves of
     // the persistent grid (no ragged tail, and the row group is final as soon as its launches are done).
     std::vector<int> group_end;
@@ -804,12 +813,18 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
   }
   e->launched_s = nch;
   e->launched_n = n_to;
+  // slots whose contractions are all queued can be overwritten once the MMA stream gets here: process_chunk makes
+  // the decode stream wait for the slot's own event only, so the decode of the next super overlaps the rest of this one
+  const int done = e->cfg.flat_norm ? nch : std::min(nch, n_to);
+  for (; e->slots_evented < done; ++e->slots_evented) {
+    cudaEvent_t& ev = e->slot_ev[e->slots_evented];
+    if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, e->stream));
+  }
   if (final || wrap) {
-    // the next chunk overwrites slot 0: the decode stream has to wait for the contractions queued so far
-    CK(cudaEventRecord(e->mma_ev, e->stream));
-    CK(cudaStreamWaitEvent(e->prep, e->mma_ev, 0));
     e->chunks_in_super = 0;
     e->launched_s = e->launched_n = 0;
+    e->slots_evented = 0;
     e->supers_done++;
   }
   return DGRM_OK;
@@ -943,6 +958,7 @@ int dgrm_default_config(dgrm_config* cfg) {
   cfg->profile = 0;
   cfg->resident_chunks = 0;  // auto
   cfg->resident_mb = 16384;
+  cfg->reserve_sms = -1;
   return DGRM_OK;
 }
 
@@ -982,6 +998,9 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   e->kc_max = cfg->chunk_snps;
   if (const char* pol = getenv("DGRM_L2_POLICY")) e->l2_policy = atoi(pol);
   if (const char* ov = getenv("DGRM_OVERLAP")) e->overlap = atoi(ov);
+  e->reserve_sms = cfg->reserve_sms > 0 ? cfg->reserve_sms : 0;
+  if (const char* rs = getenv("DGRM_RESERVE_SMS")) e->reserve_sms = atoi(rs);
+  e->reserve_sms = std::max(0, std::min(e->reserve_sms, e->sm_count - 2));
 #define CKC(call)                                                                          \
   do {                                                                                     \
     cudaError_t _s = (call);                                                               \
@@ -1054,6 +1073,7 @@ void dgrm_destroy(dgrm_engine* e) {
   if (e->producer_ev) cudaEventDestroy(e->producer_ev);
   if (e->prep_ev) cudaEventDestroy(e->prep_ev);
   if (e->mma_ev) cudaEventDestroy(e->mma_ev);
+  for (auto ev : e->slot_ev) if (ev) cudaEventDestroy(ev);
   if (e->prep) cudaStreamDestroy(e->prep);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -1159,6 +1179,7 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
   e->chunks_done = 0;
   e->chunks_in_super = 0;
   e->launched_s = e->launched_n = 0;
+  e->slots_evented = 0;
   e->supers_done = 0;
   e->finished = false;
   if (e->d_subset) {
@@ -1724,6 +1745,28 @@ int dgrm_kernel_times(dgrm_engine* e, double ms[DGRM_K_NUM], int64_t launches[DG
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaStreamSynchronize(e->out_stream));
   CK(cudaStreamSynchronize(e->d2h_stream));
+  if (getenv("DGRM_TRACE")) {  // launch timeline of everything recorded since the last call (stderr; experiments)
+    static const char* names[DGRM_K_NUM] = {"count", "expand", "syrk", "paircnt", "final", "fetch", "gather", "d2h"};
+    cudaEvent_t base = nullptr;
+    float best = 0.f;
+    for (int k = 0; k < DGRM_K_NUM; ++k)
+      for (auto& p : e->ev[k]) {
+        float t = 0.f;
+        if (!base) { base = p.a; continue; }
+        if (cudaEventElapsedTime(&t, base, p.a) == cudaSuccess && t < best) { base = p.a; best = 0.f; }
+      }
+    struct Row { float t0, dt; int k; };
+    std::vector<Row> rows;
+    for (int k = 0; k < DGRM_K_NUM; ++k)
+      for (auto& p : e->ev[k]) {
+        Row r{0.f, 0.f, k};
+        cudaEventElapsedTime(&r.t0, base, p.a);
+        cudaEventElapsedTime(&r.dt, p.a, p.b);
+        rows.push_back(r);
+      }
+    std::sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.t0 < b.t0; });
+    for (auto& r : rows) fprintf(stderr, "[dgrm trace r%d] %9.3f ms  +%8.3f  %s\n", e->cfg.rank, r.t0, r.dt, names[r.k]);
+  }
   for (int k = 0; k < DGRM_K_NUM; ++k) {
     for (auto& p : e->ev[k]) {
       float t = 0.f;

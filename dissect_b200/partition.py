@@ -16,11 +16,15 @@ def supertile_order(n_pad, group_rows=8):
 
 
 def tiles_of_rank(n, rank, world):
-    """(row block of 128, column panel of 256) pairs owned by `rank` (round-robin over the raster)."""
+    """(row block of 128, column panel of 256) pairs owned by `rank`: the contiguous raster segment
+    [rank*K/world, (rank+1)*K/world) of the K supertiles."""
     n_pad = (n + 255) // 256 * 256
     tiles = []
-    for s, (I, J) in enumerate(supertile_order(n_pad)):
-        if s % world == rank:
+    order = supertile_order(n_pad)
+    total = len(order)
+    s0, s1 = total * rank // world, total * (rank + 1) // world
+    for s, (I, J) in enumerate(order):
+        if s0 <= s < s1:
             tiles.append((2 * I, J))
             tiles.append((2 * I + 1, J))
     return tiles

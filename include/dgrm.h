@@ -77,7 +77,10 @@ typedef struct dgrm_config {
   int32_t profile;       /* 1 = record CUDA events around every kernel launch                */
   int32_t resident_chunks; /* SNP chunks whose operands stay resident and are contracted tile-major (0 = auto) */
   int32_t resident_mb;   /* memory budget (MiB) for resident operands when resident_chunks == 0     */
-  int32_t reserved[5];
+  int32_t reserve_sms;   /* SMs the persistent contraction leaves free for the caller's own kernels (e.g. NCCL
+                            all-gather CTAs, which cannot co-reside with it); -1 or 0 = none.  Measured at 2 GPUs:
+                            no net gain (the contraction loses what the exchange wins), so the default is 0 */
+  int32_t reserved[4];
 } dgrm_config;
 
 /* Fill *cfg with defaults (device 0, rank 0/1, fp16 operands, fp4 pair count, chunk 16384, cta_group 2). */
