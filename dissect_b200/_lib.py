@@ -20,7 +20,11 @@ SYMBOLS = (
     "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_bind_output", "dgrm_unbind_outputs", "dgrm_bind_tiles", "dgrm_low_overlap_pairs",
     "dgrm_set_output_subset", "dgrm_write_grm_dat", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles",
     "dgrm_host_alloc", "dgrm_host_free", "dgrm_kernel_times",
+    "dgrm_store_bed_file", "dgrm_store_bed_host", "dgrm_store_clear", "dgrm_stored_snps", "dgrm_push_stored",
+    "dgrm_fetch_standardised", "dgrm_save", "dgrm_set_view",
 )
+SAVE = {"copy": 0, "add": 1, "drop": 2}
+VIEW = {"current": 0, "saved": 1, "saved-current": 2, "saved+current": 3}
 
 
 class Config(C.Structure):
@@ -84,6 +88,15 @@ def load():
     lib.dgrm_host_free.argtypes = [vp]
     lib.dgrm_host_free.restype = None
     lib.dgrm_kernel_times.argtypes = [vp, P(dbl * K_NUM), P(i64 * K_NUM)]
+    lib.dgrm_store_bed_file.argtypes = [vp, C.c_char_p, i64]
+    lib.dgrm_store_bed_host.argtypes = [vp, vp, i64, i64]
+    lib.dgrm_store_clear.argtypes = [vp]
+    lib.dgrm_stored_snps.argtypes = [vp]
+    lib.dgrm_stored_snps.restype = i64
+    lib.dgrm_push_stored.argtypes = [vp, i64, i64, vp]
+    lib.dgrm_fetch_standardised.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, i32]
+    lib.dgrm_save.argtypes = [vp, i32]
+    lib.dgrm_set_view.argtypes = [vp, i32]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:

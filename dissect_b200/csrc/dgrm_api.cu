@@ -167,6 +167,22 @@ struct dgrm_engine {
 
   bool have_ind = false, begun = false, finished = false;
 
+  // resident packed cohort (dgrm_store_*): SNP-major rows of ceil(n_fam/4) bytes at pitch bed_pitch
+  uint8_t* d_bed = nullptr;
+  int64_t bed_pitch = 0, bed_rows = 0, bed_cap = 0, bed_nfam = 0;
+  cudaEvent_t bed_ev = nullptr;           // last upload into the store
+  std::vector<int32_t> grm_rows;          // stored row of every SNP of the current GRM, in GRM order
+  bool grm_from_store = true;             // false once a SNP of the current GRM came from somewhere else
+  int32_t* d_grm_rows = nullptr;
+  int64_t d_grm_rows_cap = 0;
+
+  // saved (S, N) store and the view every reader sees (dgrm_save / dgrm_set_view)
+  double* d_S2 = nullptr;
+  int32_t* d_N2 = nullptr;
+  int64_t m2 = 0;
+  bool saved = false, saved_flat = false;
+  int view = DGRM_VIEW_CURRENT;
+
   // profiling
   std::vector<EventPair> ev[DGRM_K_NUM];
   std::vector<EventPair> ev_pool;
@@ -233,6 +249,10 @@ void release_geometry(dgrm_engine* e) {
   free_dev(e->d_diag); e->d_diag = nullptr;
   free_dev(e->d_subset); e->d_subset = nullptr;
   e->n_out = 0;
+  free_dev(e->d_S2); e->d_S2 = nullptr;
+  free_dev(e->d_N2); e->d_N2 = nullptr;
+  e->saved = false;
+  e->view = DGRM_VIEW_CURRENT;
   free_dev(e->d_chunk); e->d_chunk = nullptr;
   free_dev(e->d_Z); e->d_Z = nullptr;
   free_dev(e->d_Q); e->d_Q = nullptr;
@@ -339,6 +359,10 @@ TileStore tile_store(const dgrm_engine* e) {
   ts.n = (int)(e->d_subset ? e->n_out : e->n);
   ts.flat_n = (double)e->m;
   ts.subset = e->d_subset;
+  ts.S2 = e->d_S2;
+  ts.N2 = e->saved_flat ? nullptr : e->d_N2;
+  ts.flat_n2 = (double)e->m2;
+  ts.view = e->saved ? e->view : DGRM_VIEW_CURRENT;
   return ts;
 }
 
@@ -469,6 +493,8 @@ int issue_job(dgrm_engine* e, size_t k) {
     TileStore ts = tile_store(e);
     ts.S = ts.S + j.t0;
     ts.N = ts.N ? ts.N + j.t0 : nullptr;
+    ts.S2 = ts.S2 ? ts.S2 + j.t0 : nullptr;
+    ts.N2 = ts.N2 ? ts.N2 + j.t0 : nullptr;
     CK(cudaStreamWaitEvent(e->out_stream, e->group_ev[(size_t)j.ev], 0));
     {
       Prof pr(e, DGRM_K_FETCH, e->out_stream);
@@ -919,6 +945,37 @@ int ensure_operands(dgrm_engine* e, int slots) {
   return DGRM_OK;
 }
 
+// Open a PLINK .bed and validate its 3-byte header with the reference's checks and messages
+// (genotype.cpp:578-605).
+int open_bed(dgrm_engine* e, const char* bed_path, FILE** out) {
+  FILE* f = fopen(bed_path, "rb");
+  if (!f) return fail(e, DGRM_E_IO, "Error: The file [ %s ] does not exist or cannot be opened.", bed_path);
+  unsigned char header[3];
+  if (fread(header, 1, 3, f) != 3) {
+    fclose(f);
+    return fail(e, DGRM_E_BADBED, "Error: The data file is not a valid binary BED > v1.0");
+  }
+  // genotype.cpp:581-605
+  if (header[0] != 0x6C || header[1] != 0x1B) {
+    fclose(f);
+    return fail(e, DGRM_E_BADBED, "Error: The data file is not a valid binary BED > v1.0");
+  }
+  if (header[2] == 0x0) {
+    fclose(f);
+    return fail(e, DGRM_E_BADBED,
+                "Error: The BED file is in Individual-major mode. This mode is not currently supported. Please, read "
+                "PLINK manual.");
+  }
+  if (header[2] != 0x1) {
+    fclose(f);
+    return fail(e, DGRM_E_BADBED,
+                "Error: The data file is not a valid binary BED.\nIt is not specified whether the file is in SNP-major "
+                "o Individual-major mode.");
+  }
+  *out = f;
+  return DGRM_OK;
+}
+
 int check_ready(dgrm_engine* e, bool need_finished) {
   if (!e) return DGRM_E_INVALID;
   if (!e->have_ind) return fail(e, DGRM_E_INVALID, "dgrm_set_individuals has not been called");
@@ -1026,6 +1083,7 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
     CKC(cudaEventCreateWithFlags(&e->rowidx_free[i], cudaEventDisableTiming));
   }
   CKC(cudaEventCreateWithFlags(&e->producer_ev, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&e->bed_ev, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&e->prep_ev, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&e->mma_ev, cudaEventDisableTiming));
   void* fn = nullptr;
@@ -1071,6 +1129,9 @@ void dgrm_destroy(dgrm_engine* e) {
     if (e->rowidx_free[i]) cudaEventDestroy(e->rowidx_free[i]);
   }
   if (e->producer_ev) cudaEventDestroy(e->producer_ev);
+  if (e->bed_ev) cudaEventDestroy(e->bed_ev);
+  free_dev(e->d_bed);
+  free_dev(e->d_grm_rows);
   if (e->prep_ev) cudaEventDestroy(e->prep_ev);
   if (e->mma_ev) cudaEventDestroy(e->mma_ev);
   for (auto ev : e->slot_ev) if (ev) cudaEventDestroy(ev);
@@ -1096,6 +1157,10 @@ int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask
   CK(cudaStreamSynchronize(e->prep));
   CK(cudaStreamSynchronize(e->stream));
   release_geometry(e);
+  if (e->d_bed && e->bed_nfam != n_fam) {  // the resident rows belong to another .fam
+    free_dev(e->d_bed); e->d_bed = nullptr;
+    e->bed_rows = e->bed_cap = 0;
+  }
   e->nbind = 0;
   e->ntbind = 0;
   e->begun = e->finished = false;
@@ -1182,6 +1247,8 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
   e->slots_evented = 0;
   e->supers_done = 0;
   e->finished = false;
+  e->grm_rows.clear();
+  e->grm_from_store = true;
   if (e->d_subset) {
     CK(cudaStreamSynchronize(e->stream));
     free_dev(e->d_subset);
@@ -1204,6 +1271,7 @@ int dgrm_push_bed_device(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, i
   if (e->finished) return fail(e, DGRM_E_INVALID, "dgrm_push_bed_device after dgrm_finish");
   if (!d_rows || nrows < 0 || pitch < e->b_fam) return fail(e, DGRM_E_INVALID, "dgrm_push_bed_device: bad rows/pitch");
   CK(cudaSetDevice(e->cfg.device));
+  e->grm_from_store = false;
   // order after the producer; NULL is the legacy default stream (what torch uses unless told otherwise), which the
   // engine's non-blocking streams do not synchronise with implicitly
   CK(cudaEventRecord(e->producer_ev, (cudaStream_t)producer_stream));
@@ -1232,6 +1300,7 @@ int dgrm_push_bed_host(dgrm_engine* e, const uint8_t* rows, int64_t pitch, int64
   if (e->finished) return fail(e, DGRM_E_INVALID, "dgrm_push_bed_host after dgrm_finish");
   if (!rows || nrows < 0 || pitch < e->b_fam) return fail(e, DGRM_E_INVALID, "dgrm_push_bed_host: bad rows/pitch");
   CK(cudaSetDevice(e->cfg.device));
+  e->grm_from_store = false;
   for (int64_t r0 = 0; r0 < nrows; r0 += e->stage_rows) {
     const int64_t cnt = std::min<int64_t>(nrows - r0, e->stage_rows);
     const int s = e->stage_i;
@@ -1253,30 +1322,9 @@ int dgrm_load_bed_file(dgrm_engine* e, const char* bed_path, int64_t m_file, con
   int rc = check_ready(e, false);
   if (rc) return rc;
   if (!bed_path || m_file <= 0) return fail(e, DGRM_E_INVALID, "dgrm_load_bed_file: bad arguments");
-  FILE* f = fopen(bed_path, "rb");
-  if (!f) return fail(e, DGRM_E_IO, "Error: The file [ %s ] does not exist or cannot be opened.", bed_path);
-  unsigned char header[3];
-  if (fread(header, 1, 3, f) != 3) {
-    fclose(f);
-    return fail(e, DGRM_E_BADBED, "Error: The data file is not a valid binary BED > v1.0");
-  }
-  // genotype.cpp:581-605
-  if (header[0] != 0x6C || header[1] != 0x1B) {
-    fclose(f);
-    return fail(e, DGRM_E_BADBED, "Error: The data file is not a valid binary BED > v1.0");
-  }
-  if (header[2] == 0x0) {
-    fclose(f);
-    return fail(e, DGRM_E_BADBED,
-                "Error: The BED file is in Individual-major mode. This mode is not currently supported. Please, read "
-                "PLINK manual.");
-  }
-  if (header[2] != 0x1) {
-    fclose(f);
-    return fail(e, DGRM_E_BADBED,
-                "Error: The data file is not a valid binary BED.\nIt is not specified whether the file is in SNP-major "
-                "o Individual-major mode.");
-  }
+  FILE* f = nullptr;
+  rc = open_bed(e, bed_path, &f);
+  if (rc) return rc;
   std::vector<uint8_t> keep;
   if (snp_keep_idx) {
     keep.assign((size_t)m_file, 0);
@@ -1704,6 +1752,8 @@ int dgrm_fetch_tiles(dgrm_engine* e, int which, double* tiles) {
     TileStore t2 = ts;
     t2.S = ts.S + o;
     t2.N = ts.N ? ts.N + o : nullptr;
+    t2.S2 = ts.S2 ? ts.S2 + o : nullptr;
+    t2.N2 = ts.N2 ? ts.N2 + o : nullptr;
     CK(cudaStreamWaitEvent(e->stream, done[sl], 0));
     {
       Prof pr(e, DGRM_K_FETCH);
@@ -1723,6 +1773,263 @@ int dgrm_fetch_tiles(dgrm_engine* e, int which, double* tiles) {
   }
   return DGRM_OK;
 }
+
+// ---- resident cohort -------------------------------------------------------------------------------------
+
+static int store_reserve(dgrm_engine* e, int64_t rows_total) {
+  if (rows_total <= e->bed_cap) return DGRM_OK;
+  const int64_t pitch = round_up(e->b_fam, 16);
+  const int64_t cap = std::max<int64_t>(rows_total, e->bed_cap + e->bed_cap / 2);
+  uint8_t* nb = nullptr;
+  CK(cudaMalloc(&nb, (size_t)cap * pitch));
+  if (e->d_bed && e->bed_rows > 0) {
+    CK(cudaStreamSynchronize(e->copy_stream));
+    CK(cudaStreamSynchronize(e->prep));
+    CK(cudaMemcpy(nb, e->d_bed, (size_t)e->bed_rows * pitch, cudaMemcpyDeviceToDevice));
+  }
+  free_dev(e->d_bed);
+  e->d_bed = nb;
+  e->bed_cap = cap;
+  e->bed_pitch = pitch;
+  e->bed_nfam = e->n_fam;
+  return DGRM_OK;
+}
+
+int dgrm_store_clear(dgrm_engine* e) {
+  if (!e) return DGRM_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->copy_stream));
+  CK(cudaStreamSynchronize(e->prep));
+  free_dev(e->d_bed);
+  e->d_bed = nullptr;
+  e->bed_rows = e->bed_cap = 0;
+  return DGRM_OK;
+}
+
+int64_t dgrm_stored_snps(const dgrm_engine* e) { return e ? e->bed_rows : 0; }
+
+int dgrm_store_bed_host(dgrm_engine* e, const uint8_t* rows, int64_t pitch, int64_t nrows) {
+  if (!e) return DGRM_E_INVALID;
+  if (!e->have_ind) return fail(e, DGRM_E_INVALID, "dgrm_store_bed_host: call dgrm_set_individuals first");
+  if (!rows || nrows < 0 || pitch < e->b_fam) return fail(e, DGRM_E_INVALID, "dgrm_store_bed_host: bad rows/pitch");
+  if (e->bed_rows + nrows > INT32_MAX) return fail(e, DGRM_E_INVALID, "dgrm_store_bed_host: too many rows");
+  CK(cudaSetDevice(e->cfg.device));
+  const int rc = store_reserve(e, e->bed_rows + nrows);
+  if (rc) return rc;
+  if (nrows > 0) {
+    CK(cudaMemcpy2DAsync(e->d_bed + e->bed_rows * e->bed_pitch, (size_t)e->bed_pitch, rows, (size_t)pitch,
+                         (size_t)e->b_fam, (size_t)nrows, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaEventRecord(e->bed_ev, e->copy_stream));
+    // pageable sources are staged by the runtime: the call may return before the DMA has read a pinned one
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, rows) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) CK(cudaStreamSynchronize(e->copy_stream));
+  }
+  e->bed_rows += nrows;
+  return DGRM_OK;
+}
+
+int dgrm_store_bed_file(dgrm_engine* e, const char* bed_path, int64_t m_file) {
+  if (!e) return DGRM_E_INVALID;
+  if (!e->have_ind) return fail(e, DGRM_E_INVALID, "dgrm_store_bed_file: call dgrm_set_individuals first");
+  if (!bed_path || m_file <= 0) return fail(e, DGRM_E_INVALID, "dgrm_store_bed_file: bad arguments");
+  FILE* f = nullptr;
+  int rc = open_bed(e, bed_path, &f);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->cfg.device));
+  rc = store_reserve(e, e->bed_rows + m_file);
+  const int64_t slab = std::max<int64_t>(1, (64 << 20) / e->b_fam);
+  uint8_t* buf[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2 && rc == DGRM_OK; ++i)
+    if (cudaHostAlloc(&buf[i], (size_t)slab * e->b_fam, cudaHostAllocDefault) != cudaSuccess)
+      rc = fail(e, DGRM_E_NOMEM, "Error: There are not enough memory for reading the binary file.");
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2 && rc == DGRM_OK; ++i) cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+  int which = 0;
+  for (int64_t r0 = 0; r0 < m_file && rc == DGRM_OK; r0 += slab, which ^= 1) {
+    const int64_t cnt = std::min<int64_t>(slab, m_file - r0);
+    cudaEventSynchronize(done[which]);  // the copy that last read this buffer
+    const size_t got = fread(buf[which], (size_t)e->b_fam, (size_t)cnt, f);
+    if ((int64_t)got != cnt) {
+      rc = fail(e, DGRM_E_BADBED, "Error: An internal error has happened when reading the genotypes file.");
+      break;
+    }
+    if (cudaMemcpy2DAsync(e->d_bed + e->bed_rows * e->bed_pitch, (size_t)e->bed_pitch, buf[which], (size_t)e->b_fam,
+                          (size_t)e->b_fam, (size_t)cnt, cudaMemcpyHostToDevice, e->copy_stream) != cudaSuccess) {
+      rc = fail(e, DGRM_E_CUDA, "dgrm_store_bed_file: host to device copy failed");
+      break;
+    }
+    cudaEventRecord(done[which], e->copy_stream);
+    e->bed_rows += cnt;
+  }
+  cudaEventRecord(e->bed_ev, e->copy_stream);
+  cudaStreamSynchronize(e->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (buf[i]) cudaFreeHost(buf[i]);
+    if (done[i]) cudaEventDestroy(done[i]);
+  }
+  fclose(f);
+  return rc;
+}
+
+int dgrm_push_stored(dgrm_engine* e, int64_t first, int64_t nrows, const uint8_t* row_keep) {
+  int rc = check_ready(e, false);
+  if (rc) return rc;
+  if (e->finished) return fail(e, DGRM_E_INVALID, "dgrm_push_stored after dgrm_finish");
+  if (!e->d_bed || first < 0 || nrows < 0 || first + nrows > e->bed_rows)
+    return fail(e, DGRM_E_INVALID, "dgrm_push_stored: rows [%lld, %lld) are not in the resident store (%lld rows)",
+                (long long)first, (long long)(first + nrows), (long long)e->bed_rows);
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamWaitEvent(e->prep, e->bed_ev, 0));
+  for (int64_t r = 0; r < nrows; ++r)
+    if (!row_keep || row_keep[r]) e->grm_rows.push_back((int32_t)(first + r));
+  for (int64_t r0 = 0; r0 < nrows; r0 += (1 << 20)) {
+    const int64_t cnt = std::min<int64_t>(nrows - r0, 1 << 20);
+    rc = push_device_rows(e, e->d_bed + (first + r0) * e->bed_pitch, e->bed_pitch, cnt, row_keep ? row_keep + r0 : nullptr);
+    if (rc) return rc;
+  }
+  return DGRM_OK;
+}
+
+int dgrm_fetch_standardised(dgrm_engine* e, double* local, int64_t lld, int bs_r, int bs_c, int my_row, int my_col,
+                            int R, int C) {
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  if (!local || bs_r < 1 || bs_c < 1 || R < 1 || C < 1 || my_row < 0 || my_row >= R || my_col < 0 || my_col >= C)
+    return fail(e, DGRM_E_INVALID, "dgrm_fetch_standardised: bad arguments");
+  if (!e->grm_from_store || !e->d_bed || (int64_t)e->grm_rows.size() != e->m)
+    return fail(e, DGRM_E_INVALID,
+                "dgrm_fetch_standardised: the genotypes of this GRM are not resident (use dgrm_store_bed_* + dgrm_push_stored)");
+  CK(cudaSetDevice(e->cfg.device));
+  CyclicGeom g;
+  g.bs_r = bs_r; g.bs_c = bs_c; g.my_row = my_row; g.my_col = my_col; g.R = R; g.C = C;
+  g.nloc_r = numroc((int)e->m, bs_r, my_row, R);
+  g.nloc_c = numroc((int)e->n, bs_c, my_col, C);
+  if (g.nloc_r == 0 || g.nloc_c == 0) return DGRM_OK;
+  if (lld < g.nloc_r) return fail(e, DGRM_E_INVALID, "dgrm_fetch_standardised: lld %lld < local rows %d", (long long)lld, g.nloc_r);
+  if (e->m > e->d_grm_rows_cap) {
+    free_dev(e->d_grm_rows);
+    e->d_grm_rows = nullptr;
+    CK(cudaMalloc(&e->d_grm_rows, (size_t)e->m * sizeof(int32_t)));
+    e->d_grm_rows_cap = e->m;
+  }
+  CK(cudaMemcpyAsync(e->d_grm_rows, e->grm_rows.data(), (size_t)e->m * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  StandardisedArgs a;
+  a.bed = e->d_bed; a.pitch = e->bed_pitch; a.rows = e->d_grm_rows; a.src_ind = e->d_src_ind;
+  a.p2 = e->d_p2; a.sd = e->d_sd; a.m = (int)e->m; a.n = (int)e->n;
+  const dim3 blk(128, 2);
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, local) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+                      attr.devicePointer != nullptr;
+  cudaGetLastError();
+  // columns go through a device panel and the copy engine; a pinned destination receives them directly
+  const int PC = (int)std::max<int64_t>(1, std::min<int64_t>(g.nloc_c, (128 << 20) / ((int64_t)g.nloc_r * 8)));
+  double* d_panel[2] = {nullptr, nullptr};
+  double* h_panel[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  rc = DGRM_OK;
+  for (int i = 0; i < 2 && rc == DGRM_OK; ++i) {
+    if (cudaMalloc(&d_panel[i], (size_t)PC * g.nloc_r * sizeof(double)) != cudaSuccess ||
+        (!pinned && cudaHostAlloc(&h_panel[i], (size_t)PC * g.nloc_r * sizeof(double), cudaHostAllocDefault) != cudaSuccess) ||
+        cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess)
+      rc = fail(e, DGRM_E_NOMEM, "dgrm_fetch_standardised: cannot allocate the staging panels");
+  }
+  g.lld = g.nloc_r;
+  int prev = -1, p0 = 0, p1 = 0, slot = 0;
+  auto drain = [&](int sl, int lc0, int lc1) {
+    cudaEventSynchronize(done[sl]);
+    if (!pinned)
+      for (int lc = lc0; lc < lc1; ++lc)
+        memcpy(local + (int64_t)lc * lld, h_panel[sl] + (int64_t)(lc - lc0) * g.nloc_r, (size_t)g.nloc_r * sizeof(double));
+  };
+  for (int lc0 = 0; lc0 < g.nloc_c && rc == DGRM_OK; lc0 += PC, slot ^= 1) {
+    const int lc1 = std::min(lc0 + PC, g.nloc_c);
+    {
+      Prof pr(e, DGRM_K_FETCH);
+      const dim3 grid((g.nloc_r + 127) / 128, (lc1 - lc0 + 1) / 2);
+      bed_standardised_kernel<<<grid, blk, 0, e->stream>>>(a, d_panel[slot], g, lc0, lc1);
+    }
+    cudaError_t st = cudaGetLastError();
+    if (st == cudaSuccess)
+      st = pinned ? cudaMemcpy2DAsync(local + (int64_t)lc0 * lld, (size_t)lld * sizeof(double), d_panel[slot],
+                                      (size_t)g.nloc_r * sizeof(double), (size_t)g.nloc_r * sizeof(double),
+                                      (size_t)(lc1 - lc0), cudaMemcpyDeviceToHost, e->stream)
+                  : cudaMemcpyAsync(h_panel[slot], d_panel[slot], (size_t)(lc1 - lc0) * g.nloc_r * sizeof(double),
+                                    cudaMemcpyDeviceToHost, e->stream);
+    if (st != cudaSuccess) {
+      rc = fail(e, DGRM_E_CUDA, "dgrm_fetch_standardised: %s", cudaGetErrorString(st));
+      break;
+    }
+    cudaEventRecord(done[slot], e->stream);
+    if (prev >= 0) drain(prev, p0, p1);
+    prev = slot; p0 = lc0; p1 = lc1;
+  }
+  if (prev >= 0 && rc == DGRM_OK) drain(prev, p0, p1);
+  cudaStreamSynchronize(e->stream);
+  for (int i = 0; i < 2; ++i) {
+    free_dev(d_panel[i]);
+    if (h_panel[i]) cudaFreeHost(h_panel[i]);
+    if (done[i]) cudaEventDestroy(done[i]);
+  }
+  return rc;
+}
+
+// ---- (S, N) algebra --------------------------------------------------------------------------------------
+
+int dgrm_save(dgrm_engine* e, int mode) {
+  if (!e) return DGRM_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  if (mode == DGRM_SAVE_DROP) {
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaStreamSynchronize(e->out_stream));
+    free_dev(e->d_S2); e->d_S2 = nullptr;
+    free_dev(e->d_N2); e->d_N2 = nullptr;
+    e->saved = false;
+    e->view = DGRM_VIEW_CURRENT;
+    return DGRM_OK;
+  }
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  if (mode != DGRM_SAVE_COPY && mode != DGRM_SAVE_ADD) return fail(e, DGRM_E_INVALID, "dgrm_save: bad mode");
+  if (e->d_subset) return fail(e, DGRM_E_INVALID, "dgrm_save: clear the output subset first");
+  const bool flat = e->cfg.flat_norm != 0;
+  const size_t total = (size_t)e->ntiles * kTileElems;
+  if (!e->d_S2 && total > 0) {
+    CK(cudaMalloc(&e->d_S2, total * sizeof(double)));
+    if (!flat) CK(cudaMalloc(&e->d_N2, total * sizeof(int32_t)));
+  }
+  if (mode == DGRM_SAVE_ADD && e->saved) {
+    if (e->saved_flat != flat) return fail(e, DGRM_E_INVALID, "dgrm_save: flat and per-pair normalisation cannot be added");
+    if (total > 0) {
+      accumulate_store_kernel<<<e->sm_count * 8, 256, 0, e->stream>>>(e->d_S2, flat ? nullptr : e->d_N2, e->d_S, e->d_N,
+                                                                    (int64_t)total);
+      CK(cudaGetLastError());
+    }
+    e->m2 += e->m;
+  } else {
+    if (total > 0) {
+      CK(cudaMemcpyAsync(e->d_S2, e->d_S, total * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+      if (!flat) CK(cudaMemcpyAsync(e->d_N2, e->d_N, total * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+    }
+    e->m2 = e->m;
+    e->saved_flat = flat;
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  e->saved = true;
+  return DGRM_OK;
+}
+
+int dgrm_set_view(dgrm_engine* e, int view) {
+  if (!e) return DGRM_E_INVALID;
+  if (view < DGRM_VIEW_CURRENT || view > DGRM_VIEW_SAVED_PLUS_CURRENT) return fail(e, DGRM_E_INVALID, "dgrm_set_view: bad view");
+  if (view != DGRM_VIEW_CURRENT && !e->saved) return fail(e, DGRM_E_INVALID, "dgrm_set_view: nothing has been saved (dgrm_save)");
+  if (view >= DGRM_VIEW_SAVED_MINUS_CURRENT && e->saved_flat != (e->cfg.flat_norm != 0))
+    return fail(e, DGRM_E_INVALID, "dgrm_set_view: flat and per-pair normalisation cannot be combined");
+  e->view = view;
+  return DGRM_OK;
+}
+
 
 void* dgrm_host_alloc(int64_t bytes) {
   void* p = nullptr;

@@ -17,7 +17,31 @@ struct TileStore {
   int n;                  // individuals visible to fetch / pack (after an output subset)
   double flat_n;          // value of N under --grm-flat-norm
   const int32_t* subset;  // visible index -> individual (ascending), NULL = identity
+  // (S, N) algebra with the saved store (Kernel::addKernels, kernel.cpp:1705-1859); same tile layout
+  const double* S2;       // saved S (diagonal already exact)
+  const int32_t* N2;      // saved N, NULL when the saved GRM is flat-normalised
+  double flat_n2;
+  int view;               // 0 current, 1 saved, 2 saved - current, 3 saved + current
 };
+
+// Unnormalised S and N at storage element `slot` under the store's view.  `s_cur` is the current S at that
+// element (the caller may have replaced it by the exact diagonal).
+__device__ __forceinline__ void view_sn(const TileStore& ts, int64_t slot, double s_cur, double* s, double* n) {
+  const double n_cur = ts.N ? (double)ts.N[slot] : ts.flat_n;
+  if (ts.view == 0) { *s = s_cur; *n = n_cur; return; }
+  const double s2 = ts.S2[slot];
+  const double n2 = ts.N2 ? (double)ts.N2[slot] : ts.flat_n2;
+  if (ts.view == 1) { *s = s2; *n = n2; }
+  else if (ts.view == 2) { *s = __dsub_rn(s2, s_cur); *n = n2 - n_cur; }   // pdgeadd_, matrix.cpp:3005
+  else { *s = __dadd_rn(s2, s_cur); *n = n2 + n_cur; }
+}
+
+__device__ __forceinline__ double view_value(int which, double s, double n) {
+  if (which == 2) return n;
+  if (which == 1) return s;
+  // matrix.cpp:4096: m[i] *= scale / m1->m[i] with scale = 1.  -> two roundings
+  return __dmul_rn(s, __ddiv_rn(1., n));
+}
 
 __device__ __forceinline__ int64_t tile_slot(const TileStore& ts, int r, int c) {
   if (ts.subset) { r = ts.subset[r]; c = ts.subset[c]; }
@@ -30,12 +54,9 @@ __device__ __forceinline__ int64_t tile_slot(const TileStore& ts, int r, int c) 
 __device__ __forceinline__ bool tile_value(const TileStore& ts, int which, int r, int c, double* out) {
   const int64_t slot = tile_slot(ts, r, c);
   if (slot < 0) return false;
-  const double nval = ts.N ? (double)ts.N[slot] : ts.flat_n;
-  if (which == 2) { *out = nval; return true; }
-  const double s = ts.S[slot];
-  if (which == 1) { *out = s; return true; }
-  // matrix.cpp:4096: m[i] *= scale / m1->m[i] with scale = 1.  -> two roundings
-  *out = __dmul_rn(s, __ddiv_rn(1., nval));
+  double s, n;
+  view_sn(ts, slot, ts.S[slot], &s, &n);
+  *out = view_value(which, s, n);
   return true;
 }
 
@@ -94,13 +115,9 @@ __global__ void pack_rows_kernel(const TileStore ts, int which, const double* __
     const int r = gr >= gc ? gr : gc, c = gr >= gc ? gc : gr;
     const int64_t slot = tile_slot(ts, r, c);
     if (slot >= 0) {
-      const double nval = ts.N ? (double)ts.N[slot] : ts.flat_n;
-      if (which == 2) {
-        v = nval;
-      } else {
-        const double sv = (r == c) ? diag[r] : ts.S[slot];
-        v = (which == 1) ? sv : __dmul_rn(sv, __ddiv_rn(1., nval));
-      }
+      double sv, nv;
+      view_sn(ts, slot, (r == c) ? diag[ts.subset ? ts.subset[r] : r] : ts.S[slot], &sv, &nv);
+      v = view_value(which, sv, nv);
     }
   }
   stage[(int64_t)lc * (lr1 - lr0) + (lr - lr0)] = (T)v;   // T = int only for the (exact, integer) pair counts
@@ -137,6 +154,46 @@ __global__ void pack_grm_kernel(const TileStore ts, double* __restrict__ dst, in
   dst[(int64_t)(c - c0) * (ts.n + 1) + pr] = v;
 }
 
+// dgrm_save(DGRM_SAVE_ADD): saved (S, N) += current (S, N), element by element of the tile store.
+__global__ void accumulate_store_kernel(double* __restrict__ S2, int32_t* __restrict__ N2, const double* __restrict__ S,
+                                        const int32_t* __restrict__ N, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    S2[i] = __dadd_rn(S2[i], S[i]);
+    if (N2) N2[i] += N[i];
+  }
+}
+
+// Standardised genotypes (genotype.cpp:943-961) of the current GRM's SNPs straight from the resident packed rows,
+// into a block-cyclic m x n matrix (row = SNP, column = kept individual), local columns [lc0, lc1).
+struct StandardisedArgs {
+  const uint8_t* bed;      // resident store
+  int64_t pitch;
+  const int32_t* rows;     // [m] stored row of every SNP of the GRM
+  const int32_t* src_ind;  // kept individual -> .fam position, NULL = identity
+  const double* p2;
+  const double* sd;
+  int m, n;
+};
+
+__global__ void bed_standardised_kernel(const StandardisedArgs a, double* __restrict__ dst, const CyclicGeom g, int lc0,
+                                        int lc1) {
+  const int lr = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lc = lc0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (lr >= g.nloc_r || lc >= lc1) return;
+  const int snp = local_to_global(lr, g.bs_r, g.my_row, g.R);
+  const int ind = local_to_global(lc, g.bs_c, g.my_col, g.C);
+  if (snp >= a.m || ind >= a.n) return;
+  const int f = a.src_ind ? a.src_ind[ind] : ind;
+  const int pat = (a.bed[(int64_t)a.rows[snp] * a.pitch + (f >> 2)] >> (2 * (f & 3))) & 3;
+  double z = 0.;  // 01 = missing
+  if (pat != 1) {
+    const double code = pat == 0 ? 1. : (pat == 2 ? 2. : 3.);   // genotype.cpp:752-776
+    const double shift = __dadd_rn(1., __dmul_rn(2., a.p2[snp]));
+    z = __ddiv_rn(__dsub_rn(code, shift), a.sd[snp]);
+  }
+  dst[(int64_t)(lc - lc0) * g.lld + lr] = z;
+}
+
 // tile export as doubles (multi-engine gather).  ts.S / ts.N already point at the first exported element;
 // tile_rc[t] = (first global row, first global column) of storage tile tile0 + t lets the exact fp64 diagonal
 // override the tensor-core one (the tile store itself is only patched after the last tile group).
@@ -144,19 +201,14 @@ __global__ void export_tiles_kernel(const TileStore ts, int which, int64_t total
                                     const int2* __restrict__ tile_rc, int64_t tile0, const double* __restrict__ diag) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const double nval = ts.N ? (double)ts.N[i] : ts.flat_n;
-  double v;
-  if (which == 2) {
-    v = nval;
-  } else {
-    double sv = ts.S[i];
-    const int2 rc = tile_rc[tile0 + i / kTileElems];
-    const int e = (int)(i % kTileElems);
-    const int gr = rc.x + (e & 127), gc = rc.y + (e >> 7);
-    if (gr == gc && gr < ts.n) sv = diag[gr];
-    v = (which == 1) ? sv : ((nval == 0.) ? 0. : __dmul_rn(sv, __ddiv_rn(1., nval)));
-  }
-  dst[i] = v;
+  double sc = ts.S[i];
+  const int2 rc = tile_rc[tile0 + i / kTileElems];
+  const int e = (int)(i % kTileElems);
+  const int gr = rc.x + (e & 127), gc = rc.y + (e >> 7);
+  if (gr == gc && gr < ts.n) sc = diag[gr];
+  double sv, nv;
+  view_sn(ts, i, sc, &sv, &nv);
+  dst[i] = (which == 0 && nv == 0.) ? 0. : view_value(which, sv, nv);   // padding rows: N = 0
 }
 
 }  // namespace dgrm

@@ -143,6 +143,47 @@ class GrmEngine:
                                               idx.ctypes.data if idx is not None else None,
                                               len(idx) if idx is not None else 0))
 
+    # ---- resident cohort + (S, N) algebra ------------------------------------------------------------
+    def store_bed_file(self, path, m_file):
+        self._ck(self._lib.dgrm_store_bed_file(self._h, str(path).encode(), int(m_file)))
+
+    def store_bed_host(self, rows):
+        assert rows.dtype == np.uint8 and rows.ndim == 2 and rows.strides[1] == 1
+        self._ck(self._lib.dgrm_store_bed_host(self._h, rows.ctypes.data, rows.strides[0], rows.shape[0]))
+
+    def store_clear(self):
+        self._ck(self._lib.dgrm_store_clear(self._h))
+
+    @property
+    def stored_snps(self):
+        return int(self._lib.dgrm_stored_snps(self._h))
+
+    def push_stored(self, first=0, nrows=None, row_keep=None):
+        if nrows is None:
+            nrows = self.stored_snps - first
+        rk = None
+        if row_keep is not None:
+            rk = np.ascontiguousarray(row_keep, dtype=np.uint8)
+            assert rk.shape == (nrows,)
+        self._ck(self._lib.dgrm_push_stored(self._h, int(first), int(nrows), rk.ctypes.data if rk is not None else None))
+
+    def fetch_standardised(self, bs=(256, 256), grid=(1, 1), coords=(0, 0), out=None):
+        """Local block of the m x n standardised genotype matrix (row = SNP), Fortran order like Matrix::m."""
+        nr = numroc(self.num_snps, bs[0], coords[0], grid[0])
+        nc = numroc(self.num_individuals, bs[1], coords[1], grid[1])
+        if out is None:
+            out = np.full((nr, nc), np.nan, dtype=np.float64, order="F")
+        assert out.dtype == np.float64 and out.flags.f_contiguous and out.shape == (nr, nc)
+        self._ck(self._lib.dgrm_fetch_standardised(self._h, out.ctypes.data, max(nr, 1), bs[0], bs[1], coords[0],
+                                                   coords[1], grid[0], grid[1]))
+        return out
+
+    def save(self, mode="copy"):
+        self._ck(self._lib.dgrm_save(self._h, _lib.SAVE[mode]))
+
+    def set_view(self, view="current"):
+        self._ck(self._lib.dgrm_set_view(self._h, _lib.VIEW[view]))
+
     def finish(self):
         try:
             self._ck(self._lib.dgrm_finish(self._h))

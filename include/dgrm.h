@@ -194,6 +194,46 @@ int64_t dgrm_num_tiles(const dgrm_engine *e);
 int dgrm_tile_coords(const dgrm_engine *e, int32_t *tile_rc);
 int dgrm_fetch_tiles(dgrm_engine *e, int which, double *tiles /* [ntiles][128*256] */);
 
+/* ---- resident cohort: the packed .bed stays in HBM (2 bits per genotype: 12.5 GB at 100k x 500k) ----------
+ * The reference loads a Genotype once and then builds many kernels from it: one per SNP group
+ * (Analysis::makeGRM regional loop, analysis.cpp:67-110; SingleREML::computeRegional, singlereml.cpp:293-298),
+ * each time re-filtering the fp64 block-cyclic genotype matrix (genotypeOfSNPsGroup -> filterSNPsAndIndividuals,
+ * genotype.cpp:1596-1621, 972).  Here the stored rows are simply pushed again with another keep mask.
+ * dgrm_store_bed_file validates the header like dgrm_load_bed_file and appends all m_file rows;
+ * dgrm_store_bed_host appends rows from memory; dgrm_store_clear empties the store (dgrm_set_individuals keeps it
+ * while n_fam is unchanged).  dgrm_push_stored feeds stored rows [first, first + nrows) to the GRM begun by
+ * dgrm_begin, row_keep[nrows] as in dgrm_push_bed_host. */
+int dgrm_store_bed_file(dgrm_engine *e, const char *bed_path, int64_t m_file);
+int dgrm_store_bed_host(dgrm_engine *e, const uint8_t *rows, int64_t pitch, int64_t nrows);
+int dgrm_store_clear(dgrm_engine *e);
+int64_t dgrm_stored_snps(const dgrm_engine *e);
+int dgrm_push_stored(dgrm_engine *e, int64_t first, int64_t nrows, const uint8_t *row_keep);
+
+/* The standardised genotypes of the GRM's SNPs, what Genotype::normalizeGenotypes leaves in
+ * genotype->genotypes (genotype.cpp:888-961: g -= (1 + 2 p2) for non-missing, then g /= standardDev; missing
+ * stays 0) for callers that keep the Genotype (returnGenotype, auxiliar.cpp:606-613): an m x n matrix
+ * (row = SNP, column = kept individual) in the caller's block-cyclic layout, 0-ulp.  Needs every SNP of the
+ * current GRM to have come from the resident store (dgrm_push_stored). */
+int dgrm_fetch_standardised(dgrm_engine *e, double *local, int64_t lld, int bs_r, int bs_c, int my_row,
+                            int my_col, int grid_rows, int grid_cols);
+
+/* ---- (S, N) algebra between two GRMs of the same individuals (Kernel::addKernels, kernel.cpp:1705-1859) ----
+ * The reference denormalises both kernels (S = A o N), adds or subtracts S and N (pdgeadd_) and divides again;
+ * LOCO is `globalGRM->addKernels(1., grm, -1., regionalGRM)` (singlereml.cpp:298).  The engine keeps a second
+ * tile store: dgrm_save copies (DGRM_SAVE_COPY) or accumulates (DGRM_SAVE_ADD, sum of disjoint SNP groups) the
+ * finished GRM's unnormalised S, integer N and SNP count into it, and dgrm_set_view selects what every fetch /
+ * bind / write / scan sees from then on: the current GRM, the saved one, saved - current (LOCO) or
+ * saved + current.  S and N are combined exactly (fp64 / int32) before the one division. */
+#define DGRM_SAVE_COPY 0
+#define DGRM_SAVE_ADD 1
+#define DGRM_SAVE_DROP 2
+#define DGRM_VIEW_CURRENT 0
+#define DGRM_VIEW_SAVED 1
+#define DGRM_VIEW_SAVED_MINUS_CURRENT 2
+#define DGRM_VIEW_SAVED_PLUS_CURRENT 3
+int dgrm_save(dgrm_engine *e, int mode);
+int dgrm_set_view(dgrm_engine *e, int view);
+
 /* Pinned host memory helpers (Matrix::m replacement allocation for zero-staging fetches). */
 void *dgrm_host_alloc(int64_t bytes);
 void dgrm_host_free(void *p);
