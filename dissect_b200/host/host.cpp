@@ -23,10 +23,25 @@ static void engine_check(dgrm_engine* e, int rc) {
   if (rc != DGRM_OK) misc.error(dgrm_last_error(e), 0);
 }
 
+static dgrm_engine* create_engine() {
+  dgrm_config cfg;
+  dgrm_default_config(&cfg);
+  cfg.device = options.device;
+  cfg.operand = options.operand;
+  cfg.count_method = options.countMethod;
+  cfg.flat_norm = options.flatGRMNormalization ? 1 : 0;
+  cfg.chunk_snps = options.chunkSNPs;
+  cfg.cta_group = options.ctaGroup;
+  dgrm_engine* e = NULL;
+  if (dgrm_create(&cfg, &e) != DGRM_OK) misc.error(dgrm_last_error(NULL), 0);
+  return e;
+}
+
 // ------------------------------------------------------------------------------------------ Options
 Options::Options()
     : makeGRM(false), outFile("dissect"), flatGRMNormalization(false), minimumNumberOverlapingSNPs(10.),
-      maximumProportionOfElimitaedIndividuals(0.9), defaultBlockSize(256), device(0), operand(DGRM_OPERAND_FP16),
+      maximumProportionOfElimitaedIndividuals(0.9), defaultBlockSize(256), regionalAnalysis(false), regionBy(ungrouped),
+      regionSize(-1), regionOverlapping(0), minSNPsInRegions(1), writeLOCO(false), device(0), operand(DGRM_OPERAND_FP16),
       countMethod(DGRM_COUNT_FP4), chunkSNPs(16384), ctaGroup(2) {}
 
 void Options::parseOptions(int argc, char** argv) {
@@ -34,6 +49,7 @@ void Options::parseOptions(int argc, char** argv) {
     if (i + 1 >= argc) misc.error(std::string("Error: The option ") + argv[i] + " needs an argument.", 0);
     return argv[i + 1];
   };
+  bool seenRegion = false, seenGroups = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--make-grm") makeGRM = true;
@@ -56,10 +72,25 @@ void Options::parseOptions(int argc, char** argv) {
       const std::string v = need(i++);
       countMethod = v == "popc" ? DGRM_COUNT_POPC : v == "fp8" ? DGRM_COUNT_MMA : DGRM_COUNT_FP4;
     }
+    // options.cpp:975-1012
+    else if (a == "--region-size") { regionSize = atoi(need(i++).c_str()) * 1000; regionBy = byPosition; regionalAnalysis = true; seenRegion = true; }
+    else if (a == "--region-overlap") { regionOverlapping = atoi(need(i++).c_str()) * 1000; regionBy = byPosition; regionalAnalysis = true; seenRegion = true; }
+    else if (a == "--groups") { regionsFile = need(i++); regionBy = byGene; regionalAnalysis = true; seenGroups = true; }
+    else if (a == "--group-all") { regionBy = byAll; regionalAnalysis = true; }
+    else if (a == "--min-snps-region") minSNPsInRegions = atoi(need(i++).c_str());
+    else if (a == "--gpu-loco") writeLOCO = true;
     else if (a == "--gpu-chunk-snps") chunkSNPs = atoi(need(i++).c_str());
     else if (a == "--gpu-cta-group") ctaGroup = atoi(need(i++).c_str());
     else misc.error("Error: Invalid option: " + a, 0);
   }
+  // options.cpp:1582-1593
+  if (seenRegion && seenGroups)
+    misc.error("Error: Only one type of regional analysis is allowed. The options --region-overlap and --region-size or --groups can not be used together.", 0);
+  if (regionSize < 0 && regionOverlapping > 0)
+    misc.error("Error: The option --region-overlap can only be used together with --region-size.", 0);
+  if (regionalAnalysis && genotypeFile.empty())
+    misc.error("Error: To perform a regional analysis, a genotype file must be specified.", 0);
+  if (writeLOCO && !regionalAnalysis) misc.error("Error: --gpu-loco needs a regional option (e.g. --groups).", 0);
 }
 
 // ------------------------------------------------------------------------------------------- Matrix
@@ -150,7 +181,17 @@ static std::vector<std::vector<std::string> > read_table(const std::string& path
   return rows;
 }
 
-Genotype::Genotype(const std::string& fname) : nSNPs(0), nIndividuals(0), normalized(false), bedFile(fname + ".bed"), nBEDSNPs(0), nBEDIndividuals(0) {
+Genotype::Genotype()
+    : nSNPs(0), nIndividuals(0), normalized(false), nBEDSNPs(0), nBEDIndividuals(0), groupedBy(ungrouped), eng_(NULL),
+      ownsEngine_(false) {}
+
+Genotype::~Genotype() {
+  if (eng_ && ownsEngine_) dgrm_destroy(eng_);
+}
+
+Genotype::Genotype(const std::string& fname)
+    : nSNPs(0), nIndividuals(0), normalized(false), bedFile(fname + ".bed"), nBEDSNPs(0), nBEDIndividuals(0),
+      groupedBy(ungrouped), eng_(NULL), ownsEngine_(false) {
   std::set<std::string> keepSNPs, keepInds;
   if (!options.fileSNPsToKeep.empty()) {
     *misc.message << "Only SNPs specified in file [ " << options.fileSNPsToKeep << " ] will be kept." << std::endl;
@@ -164,6 +205,142 @@ Genotype::Genotype(const std::string& fname) : nSNPs(0), nIndividuals(0), normal
   readFAMFile(fname, keepInds);
   if (nSNPs == 0 || nIndividuals == 0)
     misc.error("Error: There are 0 SNPs and/or 0 individuals kept for the analysis. Aborting...", 0);
+  for (int k = 0; k < nSNPs; ++k) SNPIdsIdx[SNPIds[k]] = k;
+}
+
+
+// readBEDFile's role (genotype.cpp:548-724) for a Genotype that will feed several kernels: validate the header
+// and keep all rows of the file packed in HBM; nothing is decoded to fp64.
+void Genotype::loadResident() {
+  if (eng_) return;
+  eng_ = create_engine();
+  ownsEngine_ = true;
+  engine_check(eng_, dgrm_set_individuals(eng_, nBEDIndividuals, individualBEDIdxsMaskToKeep.data()));
+  *misc.message << "Reading genotype data from file [ " << bedFile << " ] ..." << std::endl;
+  engine_check(eng_, dgrm_store_bed_file(eng_, bedFile.c_str(), nBEDSNPs));
+  storeRows.resize((size_t)nSNPs);
+  for (int k = 0; k < nSNPs; ++k) storeRows[(size_t)k] = SNPsBEDIdxsToKeep.empty() ? k : SNPsBEDIdxsToKeep[(size_t)k];
+}
+
+// genotype.cpp:1293-1345
+void Genotype::groupSNPs(GroupBy groupBy) {
+  groupedSNPs.clear();
+  if (groupBy == byPosition) {
+    *misc.message << "Grouping SNPs in regions by position..." << std::endl;
+    groupSNPsByPosition();
+  } else if (groupBy == byGene || groupBy == byGroup) {
+    *misc.message << "Grouping SNPs in regions by group..." << std::endl;
+    groupSNPsByGene();
+  } else if (groupBy == byAll) {
+    groupedBy = byAll;
+    groupedSNPs["all"] = std::set<std::string>(SNPIds.begin(), SNPIds.end());
+  } else {
+    groupedBy = ungrouped;
+    return;
+  }
+  *misc.message << "Created " << groupedSNPs.size() << " SNP group(s)" << std::endl;
+  // groups with too few SNPs are dropped and listed in <out>.filteredregions (genotype.cpp:1328-1345)
+  std::vector<std::string> small;
+  for (auto& g : groupedSNPs)
+    if ((int)g.second.size() < options.minSNPsInRegions) small.push_back(g.first);
+  if (!small.empty()) {
+    std::ofstream f((options.outFile + ".filteredregions").c_str());
+    for (auto& g : small) {
+      f << g << " " << groupedSNPs[g].size();
+      groupedSNPs.erase(g);
+    }
+    *misc.message << small.size() << " regions with less than " << options.minSNPsInRegions
+                  << " SNPs have been filtered. Regions saved on file [ " << options.outFile << ".filteredregions ]." << std::endl;
+  }
+}
+
+// genotype.cpp:1347-1401.  Region j of a chromosome covers [j*step, j*step + regionSize) with
+// step = regionSize - regionOverlapping; a SNP belongs to every region that contains its position.
+void Genotype::groupSNPsByPosition() {
+  groupedBy = byPosition;
+  const int size = options.regionSize;
+  const int step = options.regionSize - options.regionOverlapping;
+  if (size <= 0 || step <= 0) misc.error("Error: Invalid region size / overlap.", 0);
+  for (int i = 0; i < nSNPs; ++i) {
+    const int pos = SNPs[(size_t)i].position;
+    const int last = pos / step;                               // last region starting at or before pos
+    const int first = pos < size ? 0 : (pos - size) / step + 1;  // first region ending after pos
+    for (int j = first; j <= last; ++j) {
+      std::ostringstream name;
+      name << SNPs[(size_t)i].chr << "_" << j * step << "-" << j * step + size;
+      groupedSNPs[name.str()].insert(SNPs[(size_t)i].name);
+    }
+  }
+}
+
+// genotype.cpp:1403-1446: lines `snp group [group ...]`; SNPs that are not in the genotype are skipped
+void Genotype::groupSNPsByGene() {
+  groupedBy = byGene;
+  *misc.message << "Reading SNP grouping data from file [ " << options.regionsFile << " ] ..." << std::endl;
+  std::ifstream file(options.regionsFile.c_str());
+  if (!file) misc.error("Error: The file [ " + options.regionsFile + " ] does not exist or cannot be opened.", 0);
+  std::string line;
+  while (std::getline(file, line)) {
+    std::istringstream ss(line);
+    std::string snp, group;
+    ss >> snp;
+    if (!SNPIdsIdx.count(snp)) continue;
+    while (ss >> group) {
+      if (groupedSNPs[group].count(snp))
+        *misc.message << "Warning: The group " << group << " is defined more than once for SNP " << snp << "." << std::endl;
+      groupedSNPs[group].insert(snp);
+    }
+  }
+}
+
+// genotype.cpp:1567-1594
+std::vector<std::string> Genotype::getGroup(const std::string& group, bool writeGroup) {
+  if (groupedBy == ungrouped)
+    misc.error("Error: An internal error was happened. The SNPs within a group can not be retrieved. Groups are not defined.", 0);
+  if (!groupedSNPs.count(group))
+    misc.error("Error: An internal error was happened. The group " + group + " is not a valid group.", 0);
+  std::vector<std::string> list(groupedSNPs[group].begin(), groupedSNPs[group].end());
+  if (writeGroup) {
+    std::ofstream f((options.outFile + ".region." + group).c_str());
+    for (auto& s : list) f << s << "\n";
+  }
+  return list;
+}
+
+// genotype.cpp:1596-1621 -> filterSNPsAndIndividuals(:972): same individuals, the group's SNPs in genotype order,
+// per-SNP records copied from the parent (:1111).  The fp64 matrices the reference filters here do not exist:
+// the group shares the parent's resident rows.
+void Genotype::genotypeOfSNPsGroup(const std::string& group, Genotype* g, bool writeGroup) {
+  if (g == this)
+    misc.error("Error: An internal error was happened. When getting a genotpe group, the resultat genotype must be different than the source genotype.", 0);
+  const std::vector<std::string> list = getGroup(group, writeGroup);
+  if (list.empty()) misc.error("Error: The group " + group + " is not a valid group. There are not SNPs inside this group.", 0);
+  loadResident();
+  std::vector<int> idx;
+  for (auto& sname : list) idx.push_back(SNPIdsIdx[sname]);
+  std::sort(idx.begin(), idx.end());
+  g->nIndividuals = nIndividuals;
+  g->individuals = individuals;
+  g->individualIds = individualIds;
+  g->normalized = normalized;
+  g->bedFile = bedFile;
+  g->nBEDSNPs = nBEDSNPs;
+  g->nBEDIndividuals = nBEDIndividuals;
+  g->individualBEDIdxsMaskToKeep = individualBEDIdxsMaskToKeep;
+  g->groupedBy = ungrouped;
+  g->groupedSNPs.clear();
+  g->SNPs.clear(); g->SNPIds.clear(); g->SNPIdsIdx.clear(); g->SNPsBEDIdxsToKeep.clear(); g->storeRows.clear();
+  for (int k : idx) {
+    g->SNPIdsIdx[SNPIds[(size_t)k]] = (int)g->SNPs.size();
+    g->SNPs.push_back(SNPs[(size_t)k]);
+    g->SNPIds.push_back(SNPIds[(size_t)k]);
+    g->SNPsBEDIdxsToKeep.push_back(storeRows[(size_t)k]);
+    g->storeRows.push_back(storeRows[(size_t)k]);
+  }
+  g->nSNPs = (int)g->SNPs.size();
+  if (g->eng_ && g->ownsEngine_) dgrm_destroy(g->eng_);
+  g->eng_ = eng_;
+  g->ownsEngine_ = false;
 }
 
 void Genotype::readBIMFile(const std::string& f, const std::set<std::string>& keepSNPs) {
@@ -230,7 +407,7 @@ void Genotype::readFAMFile(const std::string& f, const std::set<std::string>& ke
 // ------------------------------------------------------------------------------------------- Kernel
 Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
     : type(kernelGRM), name("default"), kernel(NULL), N(NULL), normalized(false), diagonalized(false), asymmetric(false),
-      nIndividuals(genotype->nIndividuals), eng_(NULL) {
+      nIndividuals(genotype->nIndividuals), eng_(NULL), ownsEngine_(true), isView_(false) {
   for (int i = 0; i < genotype->nIndividuals; ++i) {
     individuals.push_back(genotype->individuals[i]);
     const std::string key = genotype->individualIds[i];
@@ -243,21 +420,23 @@ Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
   randomVarNames = genotype->SNPIds;
 
   *misc.message << "Starting GRM computation..." << std::endl;
-  dgrm_config cfg;
-  dgrm_default_config(&cfg);
-  cfg.device = options.device;
-  cfg.operand = options.operand;
-  cfg.count_method = options.countMethod;
-  cfg.flat_norm = options.flatGRMNormalization ? 1 : 0;
-  cfg.chunk_snps = options.chunkSNPs;
-  cfg.cta_group = options.ctaGroup;
-  if (dgrm_create(&cfg, &eng_) != DGRM_OK) misc.error(dgrm_last_error(NULL), 0);
-  engine_check(eng_, dgrm_set_individuals(eng_, genotype->nBEDIndividuals, genotype->individualBEDIdxsMaskToKeep.data()));
-  engine_check(eng_, dgrm_begin(eng_, genotype->nSNPs));
-  *misc.message << "Reading genotype data from file [ " << genotype->bedFile << " ] ..." << std::endl;
-  std::vector<int64_t> keepIdx(genotype->SNPsBEDIdxsToKeep.begin(), genotype->SNPsBEDIdxsToKeep.end());
-  engine_check(eng_, dgrm_load_bed_file(eng_, genotype->bedFile.c_str(), genotype->nBEDSNPs,
-                                        keepIdx.empty() ? NULL : keepIdx.data(), (int64_t)keepIdx.size()));
+  if (genotype->engine()) {
+    // the Genotype keeps its packed rows in HBM (loadResident): this kernel's SNPs are re-read from there
+    eng_ = genotype->engine();
+    ownsEngine_ = false;
+    engine_check(eng_, dgrm_begin(eng_, genotype->nSNPs));
+    std::vector<uint8_t> keep((size_t)genotype->nBEDSNPs, 0);
+    for (int k = 0; k < genotype->nSNPs; ++k) keep[(size_t)genotype->storeRows[(size_t)k]] = 1;
+    engine_check(eng_, dgrm_push_stored(eng_, 0, genotype->nBEDSNPs, keep.data()));
+  } else {
+    eng_ = create_engine();
+    engine_check(eng_, dgrm_set_individuals(eng_, genotype->nBEDIndividuals, genotype->individualBEDIdxsMaskToKeep.data()));
+    engine_check(eng_, dgrm_begin(eng_, genotype->nSNPs));
+    *misc.message << "Reading genotype data from file [ " << genotype->bedFile << " ] ..." << std::endl;
+    std::vector<int64_t> keepIdx(genotype->SNPsBEDIdxsToKeep.begin(), genotype->SNPsBEDIdxsToKeep.end());
+    engine_check(eng_, dgrm_load_bed_file(eng_, genotype->bedFile.c_str(), genotype->nBEDSNPs,
+                                          keepIdx.empty() ? NULL : keepIdx.data(), (int64_t)keepIdx.size()));
+  }
   const int rc = dgrm_finish(eng_);
   // per-SNP records, as gatherSNPData leaves them on the root (genotype.cpp:859-870)
   {
@@ -293,13 +472,13 @@ Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
 
 Kernel::Kernel()
     : type(kernelGRM), name("default"), kernel(NULL), N(NULL), normalized(false), diagonalized(false), asymmetric(false),
-      nIndividuals(0), eng_(NULL) {}
+      nIndividuals(0), eng_(NULL), ownsEngine_(true), isView_(false) {}
 
 // readGRM (kernel.cpp:1023-1196): <f>.grm.ids / .grm.snps / .grm.dat -> kernel (lower) and N (lower; the file holds
 // N's upper triangle, matrix.cpp:2324-2334).  Single host rank (1 x 1 grid) only.
 Kernel::Kernel(const std::string& f)
     : type(kernelGRM), name(f), kernel(NULL), N(NULL), normalized(true), diagonalized(false), asymmetric(false),
-      nIndividuals(0), eng_(NULL) {
+      nIndividuals(0), eng_(NULL), ownsEngine_(true), isView_(false) {
   if (communicator->nProcRows != 1 || communicator->nProcCols != 1)
     misc.error("Error: reading a GRM file is implemented for a 1x1 process grid in this adapter.", 0);
   *misc.message << "Reading GRM from [ " << f << ".grm.(ids/snps/dat) ]..." << std::endl;
@@ -412,7 +591,51 @@ void Kernel::addKernels(double s1, Kernel* grm1, double s2, Kernel* grm2) {
 Kernel::~Kernel() {
   delete kernel;
   delete N;
-  if (eng_) dgrm_destroy(eng_);
+  if (eng_ && isView_) {
+    dgrm_set_output_subset(eng_, NULL, 0);
+    dgrm_set_view(eng_, DGRM_VIEW_CURRENT);
+  }
+  if (eng_ && ownsEngine_) dgrm_destroy(eng_);
+}
+
+// addKernels(1., saved, +-1., this) on the device (kernel.cpp:1705-1859): the engine combines the unnormalised S and
+// the integer N of the saved and the current GRM before the one division; SNP bookkeeping as kernel.cpp:1819-1853.
+Kernel* Kernel::combinedWithSaved(Kernel* saved, double scalingFactorThis) {
+  if (!eng_ || saved->eng_ != eng_)
+    misc.error("Error: An internal error was happened. GRMs from different engines cannot be combined on the device.", 0);
+  if (scalingFactorThis != 1. && scalingFactorThis != -1.)
+    misc.error("Error: An internal error was happened. Scaling factor when adding or substracting GRMs can only be 1 or -1.", 0);
+  if (saved->individualIds != individualIds)
+    misc.error("Error: An internal error was happened. GRMs with different individuals can not be added.", 0);
+  Kernel* r = new Kernel();
+  r->eng_ = eng_;
+  r->ownsEngine_ = false;
+  r->isView_ = true;
+  r->individuals = individuals;
+  r->individualIds = individualIds;
+  r->individualIdsIdx = individualIdsIdx;
+  r->nIndividuals = nIndividuals;
+  std::set<std::string> mine(randomVarNames.begin(), randomVarNames.end());
+  if (scalingFactorThis < 0.) {
+    size_t found = 0;
+    for (auto& sname : saved->randomVarNames) {
+      if (mine.count(sname)) ++found; else r->randomVarNames.push_back(sname);
+    }
+    if (found != mine.size())
+      misc.error("Error: Invalid operation. Two GRMs cannot be substracted if all the SNPs of one are not contained into the other.", 0);
+  } else {
+    for (auto& sname : saved->randomVarNames)
+      if (mine.count(sname))
+        misc.error("Error: Invalid operation. Two GRMs cannot be added together if the SNPs used for computing them intersect.", 0);
+    r->randomVarNames = randomVarNames;
+    r->randomVarNames.insert(r->randomVarNames.end(), saved->randomVarNames.begin(), saved->randomVarNames.end());
+  }
+  r->name = saved->name + " " + name;
+  engine_check(eng_, dgrm_set_output_subset(eng_, NULL, 0));
+  engine_check(eng_, dgrm_set_view(eng_, scalingFactorThis < 0. ? DGRM_VIEW_SAVED_MINUS_CURRENT : DGRM_VIEW_SAVED_PLUS_CURRENT));
+  r->normalized = true;
+  r->fetch();
+  return r;
 }
 
 // (Re)fill kernel and N from the device tile store in this rank's block-cyclic layout.

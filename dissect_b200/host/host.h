@@ -27,6 +27,8 @@ struct DissectError : std::runtime_error {
   explicit DissectError(const std::string& m) : std::runtime_error(m) {}
 };
 
+enum GroupBy { ungrouped, byPosition, byGene, byGroup, byOrderedFixedSize, byAll };  // genotype.h:42-50
+
 struct Options {
   bool makeGRM;
   std::string genotypeFile;            // --bfile
@@ -37,6 +39,14 @@ struct Options {
   double minimumNumberOverlapingSNPs;  // --min-overlap-snps (default 10, options.cpp:80)
   double maximumProportionOfElimitaedIndividuals;  // --min-prop-grm-inds-kept (default 0.9, options.cpp:81)
   int defaultBlockSize;                // --default-block-size (16..4096, default 256, options.cpp:244)
+  // regional analysis (options.cpp:975-1012): one GRM per SNP group, files <out>.<group>.grm.*
+  bool regionalAnalysis;
+  GroupBy regionBy;
+  std::string regionsFile;             // --groups F: lines `snp group [group ...]`
+  int regionSize, regionOverlapping;   // --region-size / --region-overlap (kb on the command line, bp here)
+  int minSNPsInRegions;                // --min-snps-region (default 1)
+  bool writeLOCO;                      // --gpu-loco: also write <out>.loco.<group> = all SNPs minus the group
+                                       // (the (S, N) algebra of singlereml.cpp:293-298, done on the device)
   // engine knobs (no counterpart in the reference)
   int device, operand, countMethod, chunkSNPs, ctaGroup;
   Options();
@@ -110,7 +120,25 @@ class Genotype {
   std::vector<int> SNPsBEDIdxsToKeep;            // empty = all (genotype.cpp:452-456)
   std::vector<int> individualBEDIdxsMaskToKeep;  // one flag per .fam line (genotype.cpp:750)
   explicit Genotype(const std::string& fname);   // genotype.cpp:110 -> load :276 (metadata; rows stream later)
+  Genotype();                                    // genotype.cpp:82-91, filled by genotypeOfSNPsGroup
+  ~Genotype();
+  // SNP groups (genotype.cpp:1293-1470) and the genotype of one group (genotype.cpp:1596-1621)
+  GroupBy groupedBy;
+  std::map<std::string, std::set<std::string> > groupedSNPs;
+  std::map<std::string, int> SNPIdsIdx;
+  void groupSNPs(GroupBy groupBy);
+  std::vector<std::string> getGroup(const std::string& group, bool writeGroup = true);
+  void genotypeOfSNPsGroup(const std::string& group, Genotype* newGenotype, bool writeGroup = true);
+  // Resident cohort: the packed .bed is uploaded once (dgrm_store_bed_file) and every Kernel built from this
+  // Genotype or from one of its groups re-reads it from HBM.  storeRows[k] = stored row of SNP k.
+  void loadResident();
+  dgrm_engine* engine() const { return eng_; }
+  std::vector<int> storeRows;
  private:
+  dgrm_engine* eng_;
+  bool ownsEngine_;
+  void groupSNPsByPosition();
+  void groupSNPsByGene();
   void readBIMFile(const std::string& f, const std::set<std::string>& keepSNPs);
   void readFAMFile(const std::string& f, const std::set<std::string>& keepIndividualIds);
 };
@@ -140,9 +168,14 @@ class Kernel {
   void denormalize();    // kernel.cpp:416-448
   bool sanitizeKernel(); // kernel.cpp:1993-2037
   void writeGRM(const std::string& f);  // kernel.cpp:893-1009 (.grm.ids / .grm.snps / .grm.dat)
+  // Device-side addKernels(1., saved, -1., this) / (1., saved, 1., this): a Kernel that reads the engine's
+  // (S, N) view `saved -/+ current` (dgrm_set_view).  `saved` must be the Kernel whose GRM was kept with
+  // dgrm_save on the same engine; the view ends when the returned Kernel is deleted.
+  Kernel* combinedWithSaved(Kernel* saved, double scalingFactorThis);
   dgrm_engine* engine() { return eng_; }
  private:
   dgrm_engine* eng_;
+  bool ownsEngine_, isView_;
   std::vector<long long> subset_;  // individuals (positions) still in the kernel after sanitizeKernel
   void fetch();
   std::vector<std::string> minimumIndividualsRemovePairs(const std::vector<int>& i1, const std::vector<int>& i2);

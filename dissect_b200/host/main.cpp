@@ -12,13 +12,47 @@ int main(int argc, char** argv) {
     communicator->nDefaultBlockRows = communicator->nDefaultBlockCols = options.defaultBlockSize;
     if (!options.makeGRM) misc.error("Error: only --make-grm is implemented by this adapter.", 0);
     if (options.genotypeFile.empty()) misc.error("Error: No genotype file(s) specified.", 0);
-    Genotype* genotype = new Genotype(options.genotypeFile);
-    Kernel* grm = new Kernel(genotype);
-    delete genotype;
-    const bool sanitized = grm->sanitizeKernel();
-    if (sanitized) grm->writeGRM(options.outFile);
-    else *misc.message << "Sorry, a problem was happened while computing the GRM. Please, check the logs." << std::endl;
-    delete grm;
+    if (!options.regionalAnalysis) {
+      Genotype* genotype = new Genotype(options.genotypeFile);
+      Kernel* grm = new Kernel(genotype);
+      delete genotype;
+      const bool sanitized = grm->sanitizeKernel();
+      if (sanitized) grm->writeGRM(options.outFile);
+      else *misc.message << "Sorry, a problem was happened while computing the GRM. Please, check the logs." << std::endl;
+      delete grm;
+    } else {
+      // analysis.cpp:67-110: one GRM per SNP group -> <out>.<group>.grm.*.  The packed cohort is uploaded once.
+      Genotype* genotype = new Genotype(options.genotypeFile);
+      genotype->groupSNPs(options.regionBy);
+      genotype->loadResident();
+      const std::string baseOutFile = options.outFile;
+      Kernel* global = NULL;
+      if (options.writeLOCO) {  // singlereml.cpp:242: the global GRM, kept on the device for global - regional
+        global = new Kernel(genotype);
+        if (dgrm_save(genotype->engine(), DGRM_SAVE_COPY) != DGRM_OK) misc.error(dgrm_last_error(genotype->engine()), 0);
+      }
+      for (auto it = genotype->groupedSNPs.begin(); it != genotype->groupedSNPs.end(); ++it) {
+        const std::string group = it->first;
+        options.outFile = baseOutFile + "." + group;
+        Genotype* regionalGenotype = new Genotype();
+        genotype->genotypeOfSNPsGroup(group, regionalGenotype);
+        Kernel* grm = new Kernel(regionalGenotype);
+        if (global) {  // singlereml.cpp:298: globalGRM->addKernels(1., grm, -1., regionalGRM), before any filtering
+          Kernel* loco = grm->combinedWithSaved(global, -1.);
+          if (loco->sanitizeKernel()) loco->writeGRM(baseOutFile + ".loco." + group);
+          else *misc.message << "WARNING: Sorry, a problem was happened while computing the LOCO GRM on region " << group << ". Please, check the logs." << std::endl;
+          delete loco;
+        }
+        const bool sanitized = grm->sanitizeKernel();
+        if (sanitized) grm->writeGRM(options.outFile);
+        else *misc.message << "WARNING: Sorry, a problem was happened while computing the GRM on region " << group << ". Please, check the logs." << std::endl;
+        delete grm;
+        delete regionalGenotype;
+      }
+      options.outFile = baseOutFile;
+      delete global;
+      delete genotype;
+    }
     return 0;
   } catch (const DissectError&) {
     return 1;  // misc.error -> MPI_Abort(-1) in the reference (misc.cpp:169)

@@ -63,3 +63,67 @@ def test_cli_badsnps(tmp_path):
     assert "same genotype for all samples" in (r.stdout + r.stderr)
     assert open(out + ".badsnps").read() == open(os.path.join(c["dir"], "ref.badsnps")).read()
     assert not os.path.exists(out + ".grm.dat")
+
+
+PARTS = os.path.join(GOLDEN, "parts")
+
+
+def _check_group_files(prefix, ref_name, n=48):
+    """<prefix>.grm.* against the files the reference wrote for the same SNP subset (tests/golden/parts)."""
+    ref = os.path.join(PARTS, ref_name)
+    assert open(prefix + ".grm.ids").read() == open(ref + ".grm.ids").read()
+    assert open(prefix + ".grm.snps").read() == open(ref + ".grm.snps").read()
+    blob, rblob = open(prefix + ".grm.dat", "rb").read(), open(ref + ".grm.dat", "rb").read()
+    assert len(blob) == len(rblob) and blob[:14] == rblob[:14]
+    A, N = orc.unpack_grm_dat(blob, n)
+    A0, N0 = orc.unpack_grm_dat(rblob, n)
+    low = lower_mask(n)
+    assert np.array_equal(N[low], N0[low])
+    m = len(open(prefix + ".grm.snps").read().split())
+    assert np.max(np.abs(A[low] - A0[low])) <= 3e-4 * max(1.0, (1000.0 / m) ** 0.5) * 2
+
+
+def test_cli_regional_groups_and_loco(tmp_path):
+    """`--make-grm --groups F` (Analysis::makeGRM regional loop, analysis.cpp:67-110): one GRM per group from
+    one upload of the .bed, plus --gpu-loco = global minus regional on the device (singlereml.cpp:293-298).
+    Reference anchors: per-group `--extract` runs of the reference binary (tests/golden/parts)."""
+    groups = tmp_path / "groups.txt"
+    with open(groups, "w") as f:
+        for k in range(160):
+            f.write(f"rs{k + 1} {'a' if k < 70 else 'b'}\n")
+        f.write("rs_not_in_bim a\n")                       # skipped like genotype.cpp:1424-1428
+    out = str(tmp_path / "reg")
+    r = run_cli(PARTS, out, ["--groups", str(groups), "--gpu-loco"])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Created 2 SNP group(s)" in r.stdout
+    _check_group_files(out + ".a", "a")
+    _check_group_files(out + ".b", "b")
+    _check_group_files(out + ".loco.a", "b")              # all SNPs minus group a == group b
+    _check_group_files(out + ".loco.b", "a")
+    # getGroup's side file (genotype.cpp:1583-1590): the group's SNPs in set order
+    listed = open(out + ".a.region.a").read().split()
+    assert listed == sorted(f"rs{k + 1}" for k in range(70))
+
+
+def test_cli_group_all_and_min_snps(tmp_path):
+    out = str(tmp_path / "all")
+    r = run_cli(PARTS, out, ["--group-all"])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    _check_group_files(out + ".all", "all")
+    groups = tmp_path / "g2.txt"
+    with open(groups, "w") as f:
+        for k in range(160):
+            f.write(f"rs{k + 1} {'big' if k >= 5 else 'small'}\n")
+    out2 = str(tmp_path / "min")
+    r = run_cli(PARTS, out2, ["--groups", str(groups), "--min-snps-region", "10"])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert os.path.exists(out2 + ".big.grm.dat") and not os.path.exists(out2 + ".small.grm.dat")
+    assert open(out2 + ".filteredregions").read().startswith("small 5")
+
+
+def test_cli_region_size_names(tmp_path):
+    """--region-size groups by position (genotype.cpp:1347-1401); the .bim of the fixture has positions 1..160."""
+    out = str(tmp_path / "pos")
+    r = run_cli(PARTS, out, ["--region-size", "1"])       # 1 kb: every SNP falls in region 0 of chromosome 1
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    _check_group_files(out + ".1_0-1000", "all")
