@@ -307,6 +307,39 @@ def run_gpu(args):
         dt = float(t.item())
     value = args.steps * W / dt
 
+    # ---- K1 (decode) kernels alone, against the HBM roofline --------------------------------------------
+    # In the timed steps above they run underneath the contraction (second stream), so their own event times
+    # are inflated by the SMs they do not get; three extra, untimed-for-`value` steps with the overlap switched
+    # off give their stand-alone bandwidth (bytes_in + bytes_out over t_K1, peak = measured copy BW).
+    k1 = None
+    if G == 1:
+        os.environ["DGRM_OVERLAP"] = "0"
+        eng1 = GrmEngine(device=local, operand=args.operand, count_method=args.count, chunk_snps=chunk,
+                         cta_group=args.cg, profile=True, resident_chunks=args.resident, resident_mb=args.resident_mb)
+        del os.environ["DGRM_OVERLAP"]
+        eng1.set_individuals(n)
+        reps = 3
+        for it in range(reps + 1):
+            eng1.begin(m_kept)
+            eng1.push_bed_device(pk_all.data_ptr(), pk_all.stride(0), m_file, row_keep=keep)
+            eng1.finish()
+            if it == 0:
+                eng1.kernel_times()
+        kt1 = eng1.kernel_times()
+        eng1.close()
+        geno = float(n) * m_kept
+        n_pad = (n + 255) // 256 * 256
+        alg = {"gather": 0.5 * geno,                                   # 1/4 B read + 1/4 B written per genotype
+               "count": 0.25 * geno + 72.0 * m_kept,                   # packed rows in, 40 B stats + 32 B table out
+               "expand": 0.25 * geno + (2.0 + (0.5 if args.count == "fp4" else 1.0 if args.count == "mma" else 0.125))
+               * n_pad * ((m_kept + 255) // 256 * 256)}                # operands are materialised: listed (§8d)
+        peaks1 = load_peaks()
+        k1 = {"bound": "hbm", "peak": peaks1["hbm_gbs"], "unit": "GB/s", "overlap": "off for this measurement",
+              "kernels": {k: {"ms_per_step": kt1[k][0] / reps, "algorithmic_bytes": alg[k],
+                              "achieved": alg[k] / (kt1[k][0] / reps * 1e-3) / 1e9,
+                              "frac": alg[k] / (kt1[k][0] / reps * 1e-3) / 1e9 / peaks1["hbm_gbs"]}
+                          for k in ("gather", "count", "expand")}}
+
     # ---- e2e: host buffers in, block-cyclic lower triangles of A and N out, every step -----------------
     e2e = None
     if G == 1 and not args.no_e2e:
@@ -442,6 +475,9 @@ def run_gpu(args):
                      "unit": "TFLOP/s", "frac": achieved / peak if achieved else None, "traffic": prof_traffic,
                      "launches": syrk_launches, "avg_launch_ms": syrk_ms / max(syrk_launches, 1)},
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()},
+        "kernel_ms_note": "decode kernels (gather/count/expand) run on a second stream underneath the contraction: "
+                          "their times here are inflated by the overlap, see roofline_k1 for them alone",
+        "roofline_k1": k1,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": e2e,
