@@ -240,12 +240,49 @@ def run_gpu(args):
             mine.append((c0, r0, r1))
         # rows are exchanged with a 16-byte aligned pitch so that the engine's row gather can use 128-bit copies
         bpr_pad = (bpr + 15) // 16 * 16
-        gather_bufs = [torch.zeros((G * shard, bpr_pad), dtype=torch.uint8, device="cuda") for _ in range(2)]
         send_bufs = [torch.zeros((shard, bpr_pad), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        # which of the G*shard gathered rows of a chunk are real and kept (shards are padded to `shard` rows)
+        rks = []
+        for (c0, r0, r1) in mine:
+            c1 = min(c0 + chunk, m_file)
+            rk = np.zeros(G * shard, np.uint8)
+            for g in range(G):
+                a = c0 + g * shard
+                b = min(a + shard, c1)
+                if b > a:
+                    rk[g * shard: g * shard + (b - a)] = keep[a:b]
+            rks.append(rk)
     host_pk = None
     if not args.no_e2e:   # the e2e leg starts from pinned host rows
         host_pk = PinnedArray((m_file, bpr), np.uint8)
         host_pk.array[:] = pk_all.cpu().numpy()
+    xch = None
+    if G > 1 and args.exchange == "p2p":
+        # copy-engine exchange (dissect_b200/exchange.py): shards go straight into every peer's gather buffer
+        from dissect_b200.exchange import NBUF, PeerExchange
+        xch = PeerExchange(shard, bpr_pad, rank, G, dist.new_group(backend="gloo"))
+        if not xch.ok:
+            if rank == 0:
+                print(f"bench.py: peer exchange unavailable ({xch.error}); using NCCL all-gather", file=sys.stderr)
+            xch = None
+    if xch is not None:
+        pk_src = torch.zeros((m_file, bpr_pad), dtype=torch.uint8, device="cuda")   # contiguous shard sources
+        pk_src[:, :bpr] = pk_all
+        del pk_all
+        torch.cuda.empty_cache()
+    elif G > 1:
+        gather_bufs = [torch.zeros((G * shard, bpr_pad), dtype=torch.uint8, device="cuda") for _ in range(2)]
+
+    def exchange_and_push(shard_src):
+        """shard_src(ci) -> (device address of this rank's contiguous shard rows of chunk ci, row count), readable in
+        xch.copy_stream order.  Shards are posted two chunks ahead; everything is stream-ordered (no host wait)."""
+        nch, posted = len(mine), 0
+        for ci in range(nch):
+            while posted < min(nch, ci + NBUF):
+                ptr, cnt = shard_src(posted)
+                xch.post(ptr, cnt)
+                posted += 1
+            xch.consume(eng, rks[ci])
 
     eng = GrmEngine(device=local, rank=rank, world=world, operand=args.operand, count_method=args.count,
                     chunk_snps=chunk, cta_group=args.cg, profile=True, resident_chunks=args.resident,
@@ -256,21 +293,16 @@ def run_gpu(args):
         if G == 1:
             eng.push_bed_device(pk_all.data_ptr(), pk_all.stride(0), m_file, row_keep=keep)
             return
+        if xch is not None:
+            exchange_and_push(lambda ci: (pk_src.data_ptr() + mine[ci][1] * bpr_pad, mine[ci][2] - mine[ci][1]))
+            return
         stream = torch.cuda.current_stream().cuda_stream
         for ci, (c0, r0, r1) in enumerate(mine):
-            c1 = min(c0 + chunk, m_file)
             gather_buf, send_buf = gather_bufs[ci & 1], send_bufs[ci & 1]
             if r1 > r0:
                 send_buf[: r1 - r0, :bpr].copy_(pk_all[r0:r1])
             dist.all_gather_into_tensor(gather_buf, send_buf)
-            # shards are padded to `shard` rows: rows beyond the chunk are dropped through row_keep
-            rk = np.zeros(G * shard, np.uint8)
-            for g in range(G):
-                a = c0 + g * shard
-                b = min(a + shard, c1)
-                if b > a:
-                    rk[g * shard: g * shard + (b - a)] = keep[a:b]
-            eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), G * shard, row_keep=rk, stream=stream)
+            eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), G * shard, row_keep=rks[ci], stream=stream)
             # two exchange buffers: the all-gather of chunk c+2 into this one is ordered after the engine read it
             eng.release_inputs(stream)
 
@@ -383,26 +415,28 @@ def run_gpu(args):
         eng.bind_tiles("A", tiles_A.ptr)      # finished tile groups stream out while later groups are contracted
         eng.bind_tiles("N", tiles_N.ptr)
 
+        def h2d_shard(ci, stream):
+            # this rank's shard of the chunk: pinned host rows -> device (row pitch padded to 16 bytes)
+            c0, r0, r1 = mine[ci]
+            send_buf = send_bufs[ci & 1]
+            if r1 > r0:
+                cudart.cudaMemcpy2DAsync(send_buf.data_ptr(), bpr_pad, host_pk.ptr + r0 * bpr, bpr, bpr, r1 - r0,
+                                         cudart.cudaMemcpyKind.cudaMemcpyHostToDevice, stream)
+            return send_buf, r1 - r0
+
         def step_e2e():
             t_a = time.perf_counter()
             eng.begin(m_kept)
-            stream = torch.cuda.current_stream().cuda_stream
-            for ci, (c0, r0, r1) in enumerate(mine):
-                c1 = min(c0 + chunk, m_file)
-                gather_buf, send_buf = gather_bufs[ci & 1], send_bufs[ci & 1]
-                if r1 > r0:
-                    # this rank's shard of the chunk: pinned host rows -> device (row pitch padded to 16 bytes)
-                    cudart.cudaMemcpy2DAsync(send_buf.data_ptr(), bpr_pad, host_pk.ptr + r0 * bpr, bpr, bpr, r1 - r0,
-                                             cudart.cudaMemcpyKind.cudaMemcpyHostToDevice, stream)
-                dist.all_gather_into_tensor(gather_buf, send_buf)
-                rk = np.zeros(G * shard, np.uint8)
-                for g in range(G):
-                    a = c0 + g * shard
-                    b = min(a + shard, c1)
-                    if b > a:
-                        rk[g * shard: g * shard + (b - a)] = keep[a:b]
-                eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), G * shard, row_keep=rk, stream=stream)
-                eng.release_inputs(stream)
+            if xch is not None:
+                exchange_and_push(lambda ci: (lambda sb_cnt: (sb_cnt[0].data_ptr(), sb_cnt[1]))(h2d_shard(ci, xch.copy_stream.cuda_stream)))
+            else:
+                stream = torch.cuda.current_stream().cuda_stream
+                for ci in range(len(mine)):
+                    gather_buf = gather_bufs[ci & 1]
+                    send_buf, _ = h2d_shard(ci, stream)
+                    dist.all_gather_into_tensor(gather_buf, send_buf)
+                    eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), G * shard, row_keep=rks[ci], stream=stream)
+                    eng.release_inputs(stream)
             t_b = time.perf_counter()
             eng.finish()
             t_c = time.perf_counter()
@@ -431,6 +465,8 @@ def run_gpu(args):
                "check_tile_sum_A": float(tiles_A.array[0, 0, 0])}
         eng.unbind_outputs()
 
+    if xch is not None:
+        xch.close()
     if rank != 0:
         eng.close()
         if world > 1:
@@ -464,7 +500,10 @@ def run_gpu(args):
                          f"1% missing, seed {SEED}" + ("" if G == 1 else f"; weak scaling: n = 20000*sqrt({G})")),
             "pair_snp_per_step": W, "chunk_snps": chunk, "cta_group": args.cg, "operand": args.operand,
             "count_method": args.count,
-            "parallelism": "1 GPU" if G == 1 else f"{G} GPUs: lower-triangle tile sets, packed chunks all-gathered (NCCL)",
+            "parallelism": "1 GPU" if G == 1 else (
+                f"{G} GPUs: lower-triangle tile sets, packed chunks all-gathered "
+                + ("by copy-engine peer writes over NVLink (CUDA IPC), gloo host barrier per chunk" if xch is not None
+                   else "with NCCL")),
             "l2": "inputs exceed L2 (packed rows + operand chunk + S/N tiles >> 126 MB)",
         },
         "pct_of_bf16_peak": {"burst": 100 * 2 * value / G / (peaks["bf16_tflops"] * 1e12),
@@ -528,6 +567,9 @@ def main():
     ap.add_argument("--n", "--individuals", dest="n", type=int, default=0, help="override individuals (default 20000*sqrt(gpus))")
     ap.add_argument("--m", "--snps", dest="m", type=int, default=0, help="override SNPs in the file (default 100000)")
     ap.add_argument("--chunk", type=int, default=16384)
+    ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
+                    help="multi-GPU chunk exchange: NCCL all-gather (default) or the experimental copy-engine peer "
+                         "writes of dissect_b200/exchange.py (correct, but measured slower so far: DESIGN.md §6)")
     ap.add_argument("--cg", type=int, default=2)
     ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16", "fp16x2"])
     ap.add_argument("--count", default="fp4", choices=["mma", "popc", "fp4"])

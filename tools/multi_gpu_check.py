@@ -25,20 +25,42 @@ def main():
     eng = GrmEngine(device=local, rank=rank, world=world, chunk_snps=chunk)
     eng.set_individuals(n)
     eng.begin(m)
-    gather_buf = torch.zeros((world * shard, bpr), dtype=torch.uint8, device="cuda")
-    send = torch.zeros((shard, bpr), dtype=torch.uint8, device="cuda")
+    mode = os.environ.get("DGRM_EXCHANGE", "nccl")
     stream = torch.cuda.current_stream().cuda_stream
-    for c0, ranges in row_shards(m, chunk, world):
-        a, b = ranges[rank]
-        send.zero_()
-        if b > a:
-            send[: b - a].copy_(torch.from_numpy(pk[a:b]))
-        dist.all_gather_into_tensor(gather_buf, send)
+    shards = row_shards(m, chunk, world)
+
+    def row_keep(ranges):
         rk = np.zeros(world * shard, np.uint8)
         for r, (ra, rb) in enumerate(ranges):
             rk[r * shard: r * shard + (rb - ra)] = 1
-        eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), world * shard, row_keep=rk, stream=stream)
-        eng.sync()
+        return rk
+
+    if mode == "p2p":
+        from dissect_b200.exchange import NBUF, PeerExchange
+        pitch = (bpr + 15) // 16 * 16
+        xch = PeerExchange(shard, pitch, rank, world, dist.new_group(backend="gloo"))
+        src = torch.zeros((m, pitch), dtype=torch.uint8, device="cuda")
+        src[:, :bpr] = torch.from_numpy(pk).cuda()
+
+        posted = 0
+        for ci, (c0, ranges) in enumerate(shards):
+            while posted < min(len(shards), ci + NBUF):
+                a, b = shards[posted][1][rank]
+                xch.post(src.data_ptr() + a * pitch, b - a)
+                posted += 1
+            xch.consume(eng, row_keep(ranges))
+    else:
+        gather_buf = torch.zeros((world * shard, bpr), dtype=torch.uint8, device="cuda")
+        send = torch.zeros((shard, bpr), dtype=torch.uint8, device="cuda")
+        for c0, ranges in shards:
+            a, b = ranges[rank]
+            send.zero_()
+            if b > a:
+                send[: b - a].copy_(torch.from_numpy(pk[a:b]))
+            dist.all_gather_into_tensor(gather_buf, send)
+            eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), world * shard, row_keep=row_keep(ranges),
+                                stream=stream)
+            eng.sync()
     eng.finish()
     rc = eng.tile_coords()
     assert sorted(map(tuple, rc.tolist())) == sorted(tiles_of_rank(n, rank, world))   # host mirror == engine
@@ -58,8 +80,10 @@ def main():
         stats_ok = np.array_equal(st["freq"], ref["stats"]["freq"]) and np.array_equal(
             st["sd"].view(np.uint64), ref["stats"]["sd"].view(np.uint64))
         ok = eN == 0.0 and eA < 1e-4 and stats_ok and not np.isnan(A[low]).any()
-        print(f"multi_gpu_check world={world}: N max err {eN}, A max err {eA:.2e}, stats bit-exact {stats_ok} -> "
+        print(f"multi_gpu_check world={world} exchange={mode}: N max err {eN}, A max err {eA:.2e}, stats bit-exact {stats_ok} -> "
               f"{'PASS' if ok else 'FAIL'}")
+    if mode == "p2p":
+        xch.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
