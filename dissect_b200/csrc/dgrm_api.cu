@@ -102,7 +102,7 @@ struct dgrm_engine {
     int lr0, lr1, lc1;      // local rectangle rows [lr0, lr1) x cols [0, lc1)
     int ev;                 // tile-group event after which the rectangle is final
     bool direct;            // copy engine writes straight into the caller's (pinned) buffer
-    bool as_int;            // pair counts cross PCIe as int32 and are widened by the host
+    int ntype;              // transport type: 0 double; 1 int32 / 2 uint16 deficiency (pair counts only), widened by the host
     bool tiles;             // tile-range job (dgrm_bind_tiles): b indexes tbind, elements [t0, t1) of the tile store
     int64_t t0, t1;
   };
@@ -163,6 +163,9 @@ struct dgrm_engine {
   int slots_evented = 0;
   double out_wait_ms = 0, out_host_ms = 0;  // DGRM_TRACE_OUT: host time waiting for / finishing output jobs
   int reserve_sms = 0;
+  int32_t* d_miss = nullptr;   // per-individual missing genotypes of the current GRM (only while streaming outputs are bound)
+  bool miss_valid = false;
+  bool n_u16 = false;          // streamed pair counts travel as 16-bit deficiencies m - N
   int overlap = 1;  // DGRM_OVERLAP=0: contract only in dgrm_finish (experiments)
 
   bool have_ind = false, begun = false, finished = false;
@@ -247,6 +250,7 @@ void release_geometry(dgrm_engine* e) {
   free_dev(e->d_S); e->d_S = nullptr;
   free_dev(e->d_N); e->d_N = nullptr;
   free_dev(e->d_diag); e->d_diag = nullptr;
+  free_dev(e->d_miss); e->d_miss = nullptr;
   free_dev(e->d_subset); e->d_subset = nullptr;
   e->n_out = 0;
   free_dev(e->d_S2); e->d_S2 = nullptr;
@@ -423,6 +427,16 @@ int process_chunk(dgrm_engine* e) {
     bed_count_stats_kernel<<<blocks, 256, 0, e->prep>>>(e->d_chunk, e->chunk_pitch, kc, (int)e->n, e->m, so, e->d_zt);
     CK(cudaGetLastError());
   }
+  if (!e->cfg.flat_norm && e->miss_valid) {
+    if (streaming_bound(e)) {
+      const int nbytes = (int)e->b_row;
+      const dim3 grid((unsigned)((nbytes + 127) / 128), (unsigned)((kc + 255) / 256));
+      bed_missing_per_individual_kernel<<<grid, 128, 0, e->prep>>>(e->d_chunk, e->chunk_pitch, kc, nbytes, (int)e->n, e->d_miss);
+      CK(cudaGetLastError());
+    } else {
+      e->miss_valid = false;   // a chunk went by uncounted: streamed pair counts fall back to int32
+    }
+  }
   {
     Prof pr(e, DGRM_K_EXPAND, e->prep);
     ExpandArgs a;
@@ -498,16 +512,25 @@ int issue_job(dgrm_engine* e, size_t k) {
     CK(cudaStreamWaitEvent(e->out_stream, e->group_ev[(size_t)j.ev], 0));
     {
       Prof pr(e, DGRM_K_FETCH, e->out_stream);
-      export_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, e->out_stream>>>(
-          ts, tb.which, cnt, (double*)e->d_out_stage[sl], e->d_tile_rc, j.t0 / kTileElems, e->d_diag);
+      const unsigned blocks = (unsigned)((cnt + 255) / 256);
+      if (j.ntype == 2)
+        export_tiles_kernel<uint16_t><<<blocks, 256, 0, e->out_stream>>>(ts, tb.which, cnt, (uint16_t*)e->d_out_stage[sl],
+                                                                        e->d_tile_rc, j.t0 / kTileElems, e->d_diag);
+      else if (j.ntype == 1)
+        export_tiles_kernel<int><<<blocks, 256, 0, e->out_stream>>>(ts, tb.which, cnt, (int*)e->d_out_stage[sl],
+                                                                   e->d_tile_rc, j.t0 / kTileElems, e->d_diag);
+      else
+        export_tiles_kernel<double><<<blocks, 256, 0, e->out_stream>>>(ts, tb.which, cnt, (double*)e->d_out_stage[sl],
+                                                                      e->d_tile_rc, j.t0 / kTileElems, e->d_diag);
       CK(cudaGetLastError());
     }
     CK(cudaEventRecord(e->stage_packed[sl], e->out_stream));
     CK(cudaStreamWaitEvent(e->d2h_stream, e->stage_packed[sl], 0));
     {
       Prof pr(e, DGRM_K_D2H, e->d2h_stream);
+      const size_t es = j.ntype == 2 ? sizeof(uint16_t) : j.ntype == 1 ? sizeof(int32_t) : sizeof(double);
       void* dst = j.direct ? (void*)(tb.host + j.t0) : e->h_out_stage[sl];
-      CK(cudaMemcpyAsync(dst, e->d_out_stage[sl], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, e->d2h_stream));
+      CK(cudaMemcpyAsync(dst, e->d_out_stage[sl], (size_t)cnt * es, cudaMemcpyDeviceToHost, e->d2h_stream));
     }
     CK(cudaEventRecord(e->stage_copied_out[sl], e->d2h_stream));
     return DGRM_OK;
@@ -521,7 +544,10 @@ int issue_job(dgrm_engine* e, size_t k) {
     Prof pr(e, DGRM_K_FETCH, e->out_stream);
     const dim3 blk(128, 2);
     const dim3 grid((unsigned)((j.lr1 - j.lr0 + 127) / 128), (unsigned)((j.lc1 + 1) / 2));
-    if (j.as_int)
+    if (j.ntype == 2)
+      pack_rows_kernel<uint16_t><<<grid, blk, 0, e->out_stream>>>(ts, bd.which, e->d_diag, (uint16_t*)e->d_out_stage[sl], g,
+                                                                 j.lr0, j.lr1, j.lc1);
+    else if (j.ntype == 1)
       pack_rows_kernel<int><<<grid, blk, 0, e->out_stream>>>(ts, bd.which, e->d_diag, (int*)e->d_out_stage[sl], g, j.lr0,
                                                             j.lr1, j.lc1);
     else
@@ -536,7 +562,7 @@ int issue_job(dgrm_engine* e, size_t k) {
     // 256-column strips that start at their own diagonal (so almost nothing above the diagonal is moved)
     Prof pr(e, DGRM_K_D2H, e->d2h_stream);
     const int h = j.lr1 - j.lr0;
-    const size_t es = j.as_int ? sizeof(int32_t) : sizeof(double);
+    const size_t es = j.ntype == 2 ? sizeof(uint16_t) : j.ntype == 1 ? sizeof(int32_t) : sizeof(double);
     auto copy_rect = [&](int lra, int lrb, int lca, int lcb) -> cudaError_t {
       if (lrb <= lra || lcb <= lca) return cudaSuccess;
       const char* src = (const char*)e->d_out_stage[sl] + ((int64_t)lca * h + (lra - j.lr0)) * es;
@@ -547,6 +573,15 @@ int issue_job(dgrm_engine* e, size_t k) {
       return cudaMemcpy2DAsync(dst, (size_t)h * es, src, (size_t)h * es, (size_t)(lrb - lra) * es, (size_t)(lcb - lca),
                                cudaMemcpyDeviceToHost, e->d2h_stream);
     };
+    if (!j.direct && es < sizeof(double)) {
+      // narrow staged elements: the rectangle is contiguous in both staging buffers, and one flat copy beats a
+      // strided one whose segments would be only h * 2 (or 4) bytes long; the few entries above the diagonal of the
+      // diagonal block ride along (the host ignores them)
+      CK(cudaMemcpyAsync(e->h_out_stage[sl], e->d_out_stage[sl], (size_t)h * (size_t)j.lc1 * es, cudaMemcpyDeviceToHost,
+                         e->d2h_stream));
+      CK(cudaEventRecord(e->stage_copied_out[sl], e->d2h_stream));
+      return DGRM_OK;
+    }
     const int lc0d = first_local_ge(j.row0, g.nloc_c, g.bs_c, g.my_col, g.C);
     CK(copy_rect(j.lr0, j.lr1, 0, lc0d));
     for (int g0 = j.row0; g0 < j.row1; g0 += 256) {
@@ -579,6 +614,29 @@ void widen_i32(double* dst, const int32_t* src, int cnt, bool stream) {
   for (int i = 0; i < cnt; ++i) dst[i] = (double)src[i];
 }
 
+// 16-bit deficiencies m - N -> fp64 pair counts (0xFFFF = no value = 0)
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void widen_u16_stream(double* dst, const uint16_t* src, int cnt, double m_total) {
+  int i = 0;
+  for (; i < cnt && ((uintptr_t)(dst + i) & 31); ++i) dst[i] = src[i] == 0xFFFF ? 0. : m_total - (double)src[i];
+  const __m256d mt = _mm256_set1_pd(m_total);
+  const __m128i sentinel = _mm_set1_epi32(0xFFFF);
+  for (; i + 4 <= cnt; i += 4) {
+    const __m128i v = _mm_cvtepu16_epi32(_mm_loadl_epi64((const __m128i*)(src + i)));
+    const __m256d none = _mm256_castsi256_pd(_mm256_cvtepi32_epi64(_mm_cmpeq_epi32(v, sentinel)));
+    _mm256_stream_pd(dst + i, _mm256_andnot_pd(none, _mm256_sub_pd(mt, _mm256_cvtepi32_pd(v))));
+  }
+  for (; i < cnt; ++i) dst[i] = src[i] == 0xFFFF ? 0. : m_total - (double)src[i];
+}
+#endif
+
+void widen_u16(double* dst, const uint16_t* src, int cnt, double m_total, bool stream) {
+#if defined(__x86_64__)
+  if (stream) return widen_u16_stream(dst, src, cnt, m_total);
+#endif
+  for (int i = 0; i < cnt; ++i) dst[i] = src[i] == 0xFFFF ? 0. : m_total - (double)src[i];
+}
+
 // Wait for job k's transfer; staged jobs are then moved (and pair counts widened to double) into the caller's
 // buffer by host threads, exactly the rows on or below the diagonal of every column.
 int finish_job(dgrm_engine* e, size_t k) {
@@ -594,13 +652,27 @@ int finish_job(dgrm_engine* e, size_t k) {
     ~Acc() { e->out_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); }
   } acc{e, tw1};
   if (j.direct) return DGRM_OK;
+#if defined(__x86_64__)
+  static const bool nt = __builtin_cpu_supports("avx2") && !getenv("DGRM_NO_NT");
+#else
+  static const bool nt = false;
+#endif
+  const double m_total = (double)e->m;
   if (j.tiles) {
-    const double* src = (const double*)e->h_out_stage[sl];
+    const void* src = e->h_out_stage[sl];
     double* dst = e->tbind[j.b].host + j.t0;
     const int64_t cnt = j.t1 - j.t0;
+    const int ntype = j.ntype;
 #pragma omp parallel for schedule(static)
-    for (int64_t o = 0; o < cnt; o += 1 << 16)
-      memcpy(dst + o, src + o, (size_t)std::min<int64_t>(1 << 16, cnt - o) * sizeof(double));
+    for (int64_t o = 0; o < cnt; o += 1 << 16) {
+      const int c = (int)std::min<int64_t>(1 << 16, cnt - o);
+      if (ntype == 2) widen_u16(dst + o, (const uint16_t*)src + o, c, m_total, nt);
+      else if (ntype == 1) widen_i32(dst + o, (const int32_t*)src + o, c, nt);
+      else memcpy(dst + o, (const double*)src + o, (size_t)c * sizeof(double));
+#if defined(__x86_64__)
+      _mm_sfence();   // non-temporal stores are weakly ordered
+#endif
+    }
     return DGRM_OK;
   }
   const dgrm_engine::Binding& bd = e->bind[j.b];
@@ -608,13 +680,8 @@ int finish_job(dgrm_engine* e, size_t k) {
   const int h = j.lr1 - j.lr0;
   const void* hs = e->h_out_stage[sl];
   double* host = bd.host;
-  const bool as_int = j.as_int;
+  const int ntype = j.ntype;
   const int lr0 = j.lr0, lr1 = j.lr1;
-#if defined(__x86_64__)
-  static const bool nt = __builtin_cpu_supports("avx2") && !getenv("DGRM_NO_NT");
-#else
-  static const bool nt = false;
-#endif
 #pragma omp parallel
   {
 #pragma omp for schedule(dynamic, 16) nowait
@@ -624,7 +691,9 @@ int finish_job(dgrm_engine* e, size_t k) {
     if (lra >= lr1) continue;
     double* dst = host + (int64_t)lc * g.lld + lra;
     const int cnt = lr1 - lra;
-    if (as_int) {
+    if (ntype == 2) {
+      widen_u16(dst, (const uint16_t*)hs + (int64_t)lc * h + (lra - lr0), cnt, m_total, nt);
+    } else if (ntype == 1) {
       widen_i32(dst, (const int32_t*)hs + (int64_t)lc * h + (lra - lr0), cnt, nt);
     } else {
       memcpy(dst, (const double*)hs + (int64_t)lc * h + (lra - lr0), (size_t)cnt * sizeof(double));
@@ -692,6 +761,17 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
     }
     if (group_end.empty() || group_end.back() != nwork) group_end.push_back(nwork);
     if (final && stream_out) {
+      // Pair counts leave the device as 16-bit deficiencies m - N_ij when the per-individual missing counts prove
+      // that every deficiency fits (m - N_ij <= missing_i + missing_j), else as int32; A always as fp64.
+      e->n_u16 = false;
+      if (e->miss_valid && !e->cfg.flat_norm && !(e->saved && e->view != DGRM_VIEW_CURRENT) && e->d_miss) {
+        std::vector<int32_t> miss((size_t)e->n);
+        CK(cudaMemcpyAsync(miss.data(), e->d_miss, (size_t)e->n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->prep));
+        CK(cudaStreamSynchronize(e->prep));
+        int64_t mx = 0;
+        for (int32_t v : miss) mx = std::max<int64_t>(mx, v);
+        e->n_u16 = 2 * mx <= 65534 && !getenv("DGRM_NO_U16");
+      }
       // output jobs: one per (raster row group, streaming binding), in the order the row groups finish
       e->jobs.clear();
       e->jobs_issued = e->jobs_done = 0;
@@ -708,8 +788,8 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
           j.lr1 = first_local_ge(row1, bd.g.nloc_r, bd.g.bs_r, bd.g.my_row, bd.g.R);
           j.lc1 = first_local_ge(row1, bd.g.nloc_c, bd.g.bs_c, bd.g.my_col, bd.g.C);
           if (j.lr1 <= j.lr0 || j.lc1 <= 0) continue;
-          j.as_int = bd.which == DGRM_FETCH_N && !e->cfg.flat_norm;
-          j.direct = bd.dev != nullptr && !j.as_int;
+          j.ntype = (bd.which == DGRM_FETCH_N && !e->cfg.flat_norm) ? (e->n_u16 ? 2 : 1) : 0;
+          j.direct = bd.dev != nullptr && j.ntype == 0;
           j.tiles = false;
           j.t0 = j.t1 = 0;
           need = std::max(need, (size_t)(j.lr1 - j.lr0) * (size_t)j.lc1 * sizeof(double));
@@ -724,7 +804,9 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
         for (size_t gi = 0; gi < group_end.size(); w0g = group_end[gi], ++gi) {
           for (int b = 0; b < e->ntbind; ++b) {
             dgrm_engine::OutJob j{};
-            j.b = b; j.ev = (int)gi; j.tiles = true; j.as_int = false; j.direct = e->tbind[b].pinned;
+            j.b = b; j.ev = (int)gi; j.tiles = true;
+            j.ntype = (e->tbind[b].which == DGRM_FETCH_N && !e->cfg.flat_norm) ? (e->n_u16 ? 2 : 1) : 0;
+            j.direct = e->tbind[b].pinned && j.ntype == 0;
             j.t0 = (int64_t)w0g * per_work;
             j.t1 = (int64_t)group_end[gi] * per_work;
             need = std::max(need, (size_t)(j.t1 - j.t0) * sizeof(double));
@@ -1189,6 +1271,7 @@ int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask
     if (!e->cfg.flat_norm) CK(cudaMalloc(&e->d_N, (size_t)e->ntiles * kTileElems * sizeof(int32_t)));
   }
   CK(cudaMalloc(&e->d_diag, (size_t)e->n_pad * sizeof(double)));
+  CK(cudaMalloc(&e->d_miss, (size_t)e->n_pad * sizeof(int32_t)));
   CK(cudaMalloc(&e->d_chunk, (size_t)kc * e->chunk_pitch));
   CK(cudaMemset(e->d_chunk, 0x55, (size_t)kc * e->chunk_pitch));
   CK(cudaMalloc(&e->d_zt, (size_t)kc * 4 * sizeof(double)));
@@ -1258,6 +1341,9 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
   // a GRM that was abandoned before dgrm_finish may still have contractions in flight
   CK(cudaEventRecord(e->mma_ev, e->stream));
   CK(cudaStreamWaitEvent(e->prep, e->mma_ev, 0));
+  CK(cudaMemsetAsync(e->d_miss, 0, (size_t)e->n_pad * sizeof(int32_t), e->prep));
+  e->miss_valid = true;
+  e->n_u16 = false;
   CK(cudaMemsetAsync(e->d_bad_count, 0, 4 * sizeof(int32_t), e->prep));
   CK(cudaMemsetAsync(e->d_diag, 0, (size_t)e->n_pad * sizeof(double), e->prep));
   e->begun = true;
@@ -1757,7 +1843,7 @@ int dgrm_fetch_tiles(dgrm_engine* e, int which, double* tiles) {
     CK(cudaStreamWaitEvent(e->stream, done[sl], 0));
     {
       Prof pr(e, DGRM_K_FETCH);
-      export_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(t2, which, cnt, d_tmp[sl], e->d_tile_rc,
+      export_tiles_kernel<double><<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(t2, which, cnt, d_tmp[sl], e->d_tile_rc,
                                                                                o / kTileElems, e->d_diag);
     }
     CK(cudaGetLastError());

@@ -102,6 +102,18 @@ __global__ void fetch_block_cyclic_kernel(const TileStore ts, int which, double*
 // the tensor cores work on later tile groups.  The rectangle belongs to one finished raster row group; entries
 // above the diagonal (inside its diagonal block) get the symmetric value, tiles this engine does not own get 0.
 // `diag` supplies the exact fp64 diagonal of S (the tile store itself is patched after the last group).
+// Transport encodings of a value leaving the device.  double: as is.  int: exact pair counts as int32.
+// uint16_t: pair counts as the deficiency m - N (the number of SNPs at which either individual is missing), used
+// when the host has established 2 * max_i(missing_i) <= 65534; 0xFFFF marks "no value" (decoded as N = 0).
+template <typename T>
+__device__ __forceinline__ T transport_encode(double v, bool valid, double m_total) {
+  return (T)v;
+}
+template <>
+__device__ __forceinline__ uint16_t transport_encode<uint16_t>(double v, bool valid, double m_total) {
+  return valid ? (uint16_t)(int)(m_total - v) : (uint16_t)0xFFFF;
+}
+
 template <typename T>
 __global__ void pack_rows_kernel(const TileStore ts, int which, const double* __restrict__ diag,
                                  T* __restrict__ stage, const CyclicGeom g, int lr0, int lr1, int lc1) {
@@ -111,6 +123,7 @@ __global__ void pack_rows_kernel(const TileStore ts, int which, const double* __
   const int gr = local_to_global(lr, g.bs_r, g.my_row, g.R);
   const int gc = local_to_global(lc, g.bs_c, g.my_col, g.C);
   double v = 0.;
+  bool valid = false;
   if (gr < ts.n && gc < ts.n) {
     const int r = gr >= gc ? gr : gc, c = gr >= gc ? gc : gr;
     const int64_t slot = tile_slot(ts, r, c);
@@ -118,9 +131,11 @@ __global__ void pack_rows_kernel(const TileStore ts, int which, const double* __
       double sv, nv;
       view_sn(ts, slot, (r == c) ? diag[ts.subset ? ts.subset[r] : r] : ts.S[slot], &sv, &nv);
       v = view_value(which, sv, nv);
+      valid = true;
     }
   }
-  stage[(int64_t)lc * (lr1 - lr0) + (lr - lr0)] = (T)v;   // T = int only for the (exact, integer) pair counts
+  // T = int / uint16_t only for the (exact, integer) pair counts
+  stage[(int64_t)lc * (lr1 - lr0) + (lr - lr0)] = transport_encode<T>(v, valid, ts.flat_n);
 }
 
 // sanitizeKernel's scan: strictly-lower pairs with -0.1 < N < min_overlap - 0.1
@@ -152,6 +167,33 @@ __global__ void pack_grm_kernel(const TileStore ts, double* __restrict__ dst, in
   if (pr <= c) tile_value(ts, 2, c, pr, &v);   // N[pr][c] = N[c][pr]
   else tile_value(ts, 0, pr - 1, c, &v);       // A[pr-1][c]
   dst[(int64_t)(c - c0) * (ts.n + 1) + pr] = v;
+}
+
+// Per-individual count of missing genotypes over a packed chunk (rows = SNPs, 4 individuals per byte, pattern 01 =
+// missing).  Bounds every pair's deficiency m - N_ij <= missing_i + missing_j, which is what lets streamed pair
+// counts cross PCIe as 16-bit values.  One thread per byte column, 256 rows per block row.
+__global__ void bed_missing_per_individual_kernel(const uint8_t* __restrict__ chunk, int64_t pitch, int kc, int nbytes,
+                                                  int n, int32_t* __restrict__ miss) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbytes) return;
+  const int r0 = blockIdx.y * 256, r1 = min(kc, r0 + 256);
+  uint32_t acc = 0;  // four 8-bit counters (<= 256 each: the last increment may carry, so flush at 255)
+  int c[4] = {0, 0, 0, 0};
+  int since = 0;
+  for (int r = r0; r < r1; ++r) {
+    const uint32_t v = chunk[(int64_t)r * pitch + b];
+    const uint32_t m = v & ~(v >> 1) & 0x55u;        // bit 2j set <=> field j == 01
+    acc += (m & 1u) | ((m & 4u) << 6) | ((m & 16u) << 12) | ((m & 64u) << 18);
+    if (++since == 255) {
+      for (int j = 0; j < 4; ++j) c[j] += (acc >> (8 * j)) & 0xFF;
+      acc = 0; since = 0;
+    }
+  }
+  for (int j = 0; j < 4; ++j) {
+    const int cnt = c[j] + (int)((acc >> (8 * j)) & 0xFF);
+    const int i = 4 * b + j;
+    if (cnt > 0 && i < n) atomicAdd(&miss[i], cnt);
+  }
 }
 
 // dgrm_save(DGRM_SAVE_ADD): saved (S, N) += current (S, N), element by element of the tile store.
@@ -197,7 +239,8 @@ __global__ void bed_standardised_kernel(const StandardisedArgs a, double* __rest
 // tile export as doubles (multi-engine gather).  ts.S / ts.N already point at the first exported element;
 // tile_rc[t] = (first global row, first global column) of storage tile tile0 + t lets the exact fp64 diagonal
 // override the tensor-core one (the tile store itself is only patched after the last tile group).
-__global__ void export_tiles_kernel(const TileStore ts, int which, int64_t total, double* __restrict__ dst,
+template <typename T>
+__global__ void export_tiles_kernel(const TileStore ts, int which, int64_t total, T* __restrict__ dst,
                                     const int2* __restrict__ tile_rc, int64_t tile0, const double* __restrict__ diag) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -208,7 +251,8 @@ __global__ void export_tiles_kernel(const TileStore ts, int which, int64_t total
   if (gr == gc && gr < ts.n) sc = diag[gr];
   double sv, nv;
   view_sn(ts, i, sc, &sv, &nv);
-  dst[i] = (which == 0 && nv == 0.) ? 0. : view_value(which, sv, nv);   // padding rows: N = 0
+  const double v = (which == 0 && nv == 0.) ? 0. : view_value(which, sv, nv);   // padding rows: N = 0
+  dst[i] = transport_encode<T>(v, gr < ts.n && gc < ts.n, ts.flat_n);
 }
 
 }  // namespace dgrm

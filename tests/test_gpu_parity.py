@@ -297,6 +297,38 @@ def test_bound_tiles_equal_fetch_tiles(pinned):
     eng.close()
 
 
+@pytest.mark.parametrize("case", ["u16", "forced_int32", "too_many_missing"])
+def test_streamed_pair_count_transport(case, monkeypatch):
+    """Streamed pair counts cross PCIe as 16-bit deficiencies m - N when the per-individual missing counts prove
+    they fit (2 max_i missing_i <= 65534), else as int32; either way the host sees exactly the device's N."""
+    if case == "too_many_missing":
+        n, m, miss = 300, 45056, 0.8      # ~36 000 missing genotypes per individual: the 16-bit bound fails
+    else:
+        n, m, miss = 600, 2048, 0.05
+    if case == "forced_int32":
+        monkeypatch.setenv("DGRM_NO_U16", "1")
+    pk = bedio.synth_packed(n, m, 77, maf_lo=0.2, missing=miss)
+    eng = GrmEngine(chunk_snps=4096)
+    eng.set_individuals(n)
+    A = PinnedArray((n, n), np.float64, order="F")
+    N = PinnedArray((n, n), np.float64, order="F")
+    eng.bind_output("A", A.ptr, n)
+    eng.bind_output("N", N.ptr, n)
+    nt = eng.num_tiles
+    T = PinnedArray((nt, 256, 128), np.float64)
+    eng.bind_tiles("N", T.ptr)
+    eng.begin(m)
+    eng.push_bed_host(pk)
+    eng.finish()
+    low = lower_mask(n)
+    assert np.array_equal(N.array[low], eng.fetch_block_cyclic("N", bs=(n, n))[low])
+    assert np.array_equal(T.array, eng.fetch_tiles("N"))
+    codes = orc.decode_rows(pk, n)
+    q = (codes != 0).astype(np.float64)
+    assert np.array_equal(N.array[low], (q.T @ q)[low])
+    eng.close()
+
+
 def test_bad_snps_are_fatal_like_the_reference():
     c = load_case("badsnp")
     eng = GrmEngine()
