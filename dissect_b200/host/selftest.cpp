@@ -5,6 +5,8 @@
 //   selftest roundtrip <in> <out>         read <in>.grm.*, write <out>.grm.*
 //   selftest add <a> <b> <out>            out = a + b
 //   selftest sub <all> <part> <out>       out = all - part
+//   selftest groups <options...>          parse the options, load the .bim/.fam metadata, group the SNPs
+//                                         (Genotype::groupSNPs, genotype.cpp:1293-1470) and print `group: snps...`
 #include <cstdio>
 #include <cstring>
 
@@ -25,7 +27,18 @@ int main(int argc, char** argv) {
       r.writeGRM(argv[4]);
       return 0;
     }
-    fprintf(stderr, "usage: selftest roundtrip|add|sub ...\n");
+    if (argc >= 2 && !strcmp(argv[1], "groups")) {
+      options.parseOptions(argc - 1, argv + 1);
+      Genotype g(options.genotypeFile);
+      g.groupSNPs(options.regionBy);
+      for (auto& grp : g.groupedSNPs) {
+        printf("GROUP %s:", grp.first.c_str());
+        for (auto& snp : g.getGroup(grp.first, false)) printf(" %s", snp.c_str());
+        printf("\n");
+      }
+      return 0;
+    }
+    fprintf(stderr, "usage: selftest roundtrip|add|sub|groups ...\n");
     return 2;
   } catch (const DissectError&) {
     return 1;
