@@ -231,12 +231,16 @@ def run_gpu(args):
     chunk = args.chunk
     # SNP rows are dealt to ranks in contiguous shards of every chunk; the packed chunk is all-gathered
     # over NVLink (the path's one exchange step), then every rank expands it locally.
-    shard = (chunk + G - 1) // G
+    # Exchange granularity: `xg` engine chunks travel in one all-gather.  The all-gather kernel cannot run underneath
+    # the persistent contraction, so every exchange is a bubble in the MMA stream; fewer, larger
+    # exchanges mean fewer bubbles, and all but the first chunk of a group are decoded underneath the contraction.
+    xchunk = chunk * max(1, args.xg)
+    shard = (xchunk + G - 1) // G
     if G > 1:
         mine = []
-        for c0 in range(0, m_file, chunk):
-            r0 = min(c0 + rank * shard, min(c0 + chunk, m_file))
-            r1 = min(r0 + shard, min(c0 + chunk, m_file))
+        for c0 in range(0, m_file, xchunk):
+            r0 = min(c0 + rank * shard, min(c0 + xchunk, m_file))
+            r1 = min(r0 + shard, min(c0 + xchunk, m_file))
             mine.append((c0, r0, r1))
         # rows are exchanged with a 16-byte aligned pitch so that the engine's row gather can use 128-bit copies
         bpr_pad = (bpr + 15) // 16 * 16
@@ -244,7 +248,7 @@ def run_gpu(args):
         # which of the G*shard gathered rows of a chunk are real and kept (shards are padded to `shard` rows)
         rks = []
         for (c0, r0, r1) in mine:
-            c1 = min(c0 + chunk, m_file)
+            c1 = min(c0 + xchunk, m_file)
             rk = np.zeros(G * shard, np.uint8)
             for g in range(G):
                 a = c0 + g * shard
@@ -498,7 +502,7 @@ def run_gpu(args):
         "config": {
             "workload": (f"make-grm {n} individuals x {m_file} SNPs ({m_kept} kept by the MAF>=0.01 extract list), "
                          f"1% missing, seed {SEED}" + ("" if G == 1 else f"; weak scaling: n = 20000*sqrt({G})")),
-            "pair_snp_per_step": W, "chunk_snps": chunk, "cta_group": args.cg, "operand": args.operand,
+            "pair_snp_per_step": W, "chunk_snps": chunk, "exchange_chunks": max(1, args.xg) if G > 1 else None, "cta_group": args.cg, "operand": args.operand,
             "count_method": args.count,
             "parallelism": "1 GPU" if G == 1 else (
                 f"{G} GPUs: lower-triangle tile sets, packed chunks all-gathered "
@@ -567,6 +571,7 @@ def main():
     ap.add_argument("--n", "--individuals", dest="n", type=int, default=0, help="override individuals (default 20000*sqrt(gpus))")
     ap.add_argument("--m", "--snps", dest="m", type=int, default=0, help="override SNPs in the file (default 100000)")
     ap.add_argument("--chunk", type=int, default=16384)
+    ap.add_argument("--xg", type=int, default=1, help="engine chunks per all-gather (multi-GPU exchange granularity)")
     ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
                     help="multi-GPU chunk exchange: NCCL all-gather (default) or the experimental copy-engine peer "
                          "writes of dissect_b200/exchange.py (correct, but measured slower so far: DESIGN.md §6)")
