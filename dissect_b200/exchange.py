@@ -19,11 +19,16 @@ chunk's rows arrived exactly when the running SYRK launch retired).  Copy engine
 Everything is stream-ordered: the host never blocks and there is no barrier; the sequence numbers are global and
 monotonic, so buffers are reused across GRMs without draining.
 
-STATUS (round 1): parity-green at 2 GPUs (tools/multi_gpu_check.py with DGRM_EXCHANGE=p2p), but EXPERIMENTAL and
-not the default: the peer copies issued here run at ~55 GB/s (2.1 ms for 2 x 58 MB, `DGRM_TRACE=1`), i.e. they are
-not taking the direct NVLink path yet, and a 2-GPU step takes 51 ms against 41.7 ms with NCCL.  `bench.py
---exchange p2p` selects it.
+STATUS (round 1): EXPERIMENTAL, not the default (`bench.py --exchange p2p`, `DGRM_EXCHANGE=p2p` for
+tools/multi_gpu_check.py).  With the peers' buffers mapped through legacy CUDA IPC (`DGRM_EXCHANGE_MAP=ipc`) the
+protocol is parity-green at 2 GPUs, but such mappings copy at only ~25 GB/s on this platform even between idle
+GPUs (tools/exp/p2p_copy_probe.py: torch copy_, cudaMemcpyAsync and cudaMemcpyPeerAsync alike; same-device
+2.6 TB/s), so a 2-GPU step took 51 ms against 41.7 ms with NCCL.  The default mapping is now torch symmetric memory
+(cuMem allocations with peer access, the NVLink path NCCL uses); that variant was written after the round's GPU
+budget was spent and has NOT run on a GPU yet.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -44,32 +49,52 @@ class PeerExchange:
         host_group: a gloo process group, used once to exchange the IPC handles."""
         from cuda.bindings import driver as cu
         from cuda.bindings import runtime as cudart
-        from torch.multiprocessing.reductions import reduce_tensor
         self.cu, self.cudart = cu, cudart
         self.rank, self.world, self.shard, self.pitch = rank, world, rows_per_rank, pitch
         self.host_group = host_group
-        self.bufs = [torch.zeros((world * rows_per_rank, pitch), dtype=torch.uint8, device="cuda") for _ in range(NBUF)]
-        self.flags = torch.zeros(2 * world, dtype=torch.int32, device="cuda")      # arrived[world] | consumed[world]
-        self.seqsrc = torch.arange(_SEQ_CAP, dtype=torch.int32, device="cuda")
-        torch.cuda.synchronize()
-        mine = [reduce_tensor(t) for t in self.bufs + [self.flags]]
-        everyone = [None] * world
-        dist.all_gather_object(everyone, mine, group=host_group)
-        self._peer_tensors = []      # keep the IPC mappings alive
-        self.peer_buf, self.peer_flag = [], []
         self.error = None
+        self._peer_tensors = []      # keep the mappings alive
+        self.peer_buf, self.peer_flag = [], []
+        self.mapping = os.environ.get("DGRM_EXCHANGE_MAP", "symm")
+        self.seqsrc = torch.arange(_SEQ_CAP, dtype=torch.int32, device="cuda")
+        nbuf_bytes = (world * rows_per_rank * pitch + 4095) // 4096 * 4096
         try:
-            for p in range(world):
-                ts = self.bufs + [self.flags] if p == rank else [fn(*args) for (fn, args) in everyone[p]]
-                self._peer_tensors.append(ts)
-                self.peer_buf.append([t.data_ptr() for t in ts[:NBUF]])
-                self.peer_flag.append(ts[NBUF].data_ptr())
-                if p != rank:
-                    dev = ts[0].device.index
-                    if not torch.cuda.can_device_access_peer(torch.cuda.current_device(), dev):
-                        raise RuntimeError(f"no peer access from device {torch.cuda.current_device()} to {dev}")
-                    cudart.cudaDeviceEnablePeerAccess(dev, 0)    # "already enabled" is fine
-                    cudart.cudaGetLastError()
+            if self.mapping == "symm":
+                # torch symmetric memory: cuMem (VMM) allocations exchanged as file descriptors and mapped with peer
+                # access -- the path NCCL itself uses, direct over NVLink.  (Legacy cudaIpc mappings, below, move only
+                # ~25 GB/s on this platform even between idle GPUs: tools/exp/p2p_copy_probe.py.)
+                import torch.distributed._symmetric_memory as symm_mem
+                dev = torch.device("cuda", torch.cuda.current_device())
+                self._symm = symm_mem.empty(NBUF * nbuf_bytes + 4096, dtype=torch.uint8, device=dev)
+                self._symm.zero_()
+                torch.cuda.synchronize()
+                self._hdl = symm_mem.rendezvous(self._symm, dist.group.WORLD)
+                base = [int(x) for x in self._hdl.buffer_ptrs]
+                nrow = world * rows_per_rank
+                self.bufs = [self._symm[k * nbuf_bytes: k * nbuf_bytes + nrow * pitch].view(nrow, pitch) for k in range(NBUF)]
+                self.flags = self._symm[NBUF * nbuf_bytes: NBUF * nbuf_bytes + 8 * world].view(torch.int32)
+                for p in range(world):
+                    self.peer_buf.append([base[p] + k * nbuf_bytes for k in range(NBUF)])
+                    self.peer_flag.append(base[p] + NBUF * nbuf_bytes)
+            else:
+                from torch.multiprocessing.reductions import reduce_tensor
+                self.bufs = [torch.zeros((world * rows_per_rank, pitch), dtype=torch.uint8, device="cuda") for _ in range(NBUF)]
+                self.flags = torch.zeros(2 * world, dtype=torch.int32, device="cuda")   # arrived[world] | consumed[world]
+                torch.cuda.synchronize()
+                mine = [reduce_tensor(t) for t in self.bufs + [self.flags]]
+                everyone = [None] * world
+                dist.all_gather_object(everyone, mine, group=host_group)
+                for p in range(world):
+                    ts = self.bufs + [self.flags] if p == rank else [fn(*args) for (fn, args) in everyone[p]]
+                    self._peer_tensors.append(ts)
+                    self.peer_buf.append([t.data_ptr() for t in ts[:NBUF]])
+                    self.peer_flag.append(ts[NBUF].data_ptr())
+                    if p != rank:
+                        dev = ts[0].device.index
+                        if not torch.cuda.can_device_access_peer(torch.cuda.current_device(), dev):
+                            raise RuntimeError(f"no peer access from device {torch.cuda.current_device()} to {dev}")
+                        cudart.cudaDeviceEnablePeerAccess(dev, 0)    # "already enabled" is fine
+                        cudart.cudaGetLastError()
         except Exception as ex:  # noqa: BLE001 - every rank must still reach the agreement below
             self.error = f"{type(ex).__name__}: {ex}"
         # all ranks agree on whether the mapping worked everywhere (callers fall back to NCCL otherwise)
@@ -81,7 +106,6 @@ class PeerExchange:
         self.rel_stream = torch.cuda.Stream()
         self.seq_post = 0
         self.seq_cons = 0
-        import os
         self._trace = [] if os.environ.get("DGRM_TRACE") else None
         self._geq = cu.CUstreamWaitValue_flags.CU_STREAM_WAIT_VALUE_GEQ
         self._d2d = cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice
@@ -144,4 +168,5 @@ class PeerExchange:
         dist.barrier(group=self.host_group)     # nobody unmaps while a peer may still be writing
         self._peer_tensors = None
         self.peer_buf = self.peer_flag = None
+        self._hdl = None
         dist.barrier(group=self.host_group)
