@@ -198,6 +198,11 @@ def run_reference(args):
 
 
 def run_gpu(args):
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; libdgrm's host threads (they widen the streamed pair counts
+    # into the caller's fp64 matrix on the e2e path) would then be one per rank.  Give each rank its share of the
+    # box's cores instead; libdgrm's OpenMP runtime reads the variable when the library is loaded, below.
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ["WORLD_SIZE"])))
     import torch
     import torch.distributed as dist
     from cuda.bindings import runtime as cudart
