@@ -28,6 +28,29 @@ def test_tile_partition_is_a_partition():
             assert max(counts) - min(counts) <= 2                       # balanced tile sets
 
 
+def test_tile_sets_are_contiguous_raster_segments():
+    """Engine r owns one contiguous segment of the raster: its concurrently running CTAs then share
+    A/B panels like on one GPU.  (Round-robin dealing gave every engine one row of each column.)"""
+    for n, world in ((5000, 3), (20000, 8), (56569, 8)):
+        n_pad = (n + 255) // 256 * 256
+        pos = {st: i for i, st in enumerate(supertile_order(n_pad))}
+        ends = []
+        for r in range(world):
+            idx = sorted({pos[(rb // 2, cp)] for rb, cp in tiles_of_rank(n, r, world)})
+            assert idx == list(range(idx[0], idx[-1] + 1))          # contiguous
+            ends.append((idx[0], idx[-1]))
+        assert ends[0][0] == 0 and ends[-1][1] == len(pos) - 1
+        assert all(ends[r + 1][0] == ends[r][1] + 1 for r in range(world - 1))
+        # panel sharing inside a window of 74 consecutive supertiles (one wave of CTA pairs): few distinct rows/columns
+        order = supertile_order(n_pad)
+        lo = ends[world // 2][0]
+        window = order[lo: lo + 74]
+        panels = len({I for I, _ in window}) + len({J for _, J in window})
+        dealt = order[world // 2:: world][:74]                       # the same wave under round-robin dealing
+        panels_rr = len({I for I, _ in dealt}) + len({J for _, J in dealt})
+        assert panels <= 32 and (len(dealt) < 74 or panels < panels_rr)
+
+
 def test_row_shards_cover_every_row_once():
     for m, chunk, world in ((1000, 256, 2), (8192, 8192, 8), (100000, 8192, 4), (5, 128, 2)):
         rows = []
