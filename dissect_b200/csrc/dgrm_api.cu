@@ -1177,11 +1177,13 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
     return DGRM_E_CUDA;
   }
   e->encode = (EncodeTiledFn)fn;
-  // The output kernels run on their own stream while grm_syrk CTAs (129 KB of shared memory, 168 registers x 256 threads each) occupy every SM: they can
-  // only be co-scheduled onto those SMs when they ask for the same L1/shared-memory split.
+  // The output kernels run on their own stream while grm_syrk CTAs (129 KB of shared memory, 168 registers x 256
+  // threads each) occupy every SM: they can only be co-scheduled onto those SMs when they ask for the same L1/shared-memory split.
   CKC(cudaFuncSetAttribute(pack_rows_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)cudaSharedmemCarveoutMaxShared));
   CKC(cudaFuncSetAttribute(pack_rows_kernel<int>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared));
+  CKC(cudaFuncSetAttribute(pack_rows_kernel<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)cudaSharedmemCarveoutMaxShared));
 #define DGRM_EXPAND_ATTR(B, S, K)                                                                          \
   CKC(cudaFuncSetAttribute(bed_expand_kernel<B, S, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem)))
