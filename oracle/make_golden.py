@@ -140,6 +140,24 @@ def main():
                 shutil.copy(os.path.join(tmp, name + e), os.path.join(dst, name + e))
         for e in (".bed", ".bim", ".fam"):
             shutil.copy(bf + e, os.path.join(dst, "in" + e))
+        # the reference's own (S, N) addition: `--bfile-list` with `--grm-join-method 0` computes one unnormalised
+        # kernel per genotype file, joins them with Kernel::addKernels and normalises (auxiliar.cpp:620-672)
+        bim = open(bf + ".bim").read().splitlines()
+        for name, (a, b) in (("pa", (0, 70)), ("pb", (70, 160))):
+            sub = os.path.join(tmp, name)
+            bedio.write_bed(sub, pk[a:b], n)
+            shutil.copy(bf + ".fam", sub + ".fam")
+            with open(sub + ".bim", "w") as f:
+                f.write("\n".join(bim[a:b]) + "\n")
+        with open(os.path.join(tmp, "list.txt"), "w") as f:
+            f.write(os.path.join(tmp, "pa") + "\n" + os.path.join(tmp, "pb") + "\n")
+        import subprocess
+        r = subprocess.run([ref_runner.DISSECT, "--make-grm", "--bfile-list", os.path.join(tmp, "list.txt"),
+                            "--grm-join-method", "0", "--out", os.path.join(tmp, "joined")], capture_output=True, text=True)
+        if r.returncode != 0 or "then add GRMs" not in r.stdout:
+            raise SystemExit("parts/joined case failed\n" + (r.stdout + r.stderr)[-3000:])
+        for e in (".grm.dat", ".grm.ids", ".grm.snps"):
+            shutil.copy(os.path.join(tmp, "joined" + e), os.path.join(dst, "joined" + e))
         with open(os.path.join(dst, "case.txt"), "w") as f:
             f.write(f"n_fam {n}\nm {m}\nsplit 70\n")
         print("parts: ok")

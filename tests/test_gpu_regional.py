@@ -1,8 +1,9 @@
 """GPU: the resident cohort and the (S, N) algebra behind regional / LOCO GRMs,
 and the standardised-genotype hand-back (§8b `dgrm_fetch_standardised`), through the C ABI.
 
-Anchors: tests/golden/parts holds GRMs the *reference binary* wrote for SNP groups a = rs1..rs70, b = rs71..rs160
-and for all 160 SNPs of one .bed (oracle/make_golden.py; per-group `--extract` runs, because the reference's own
+Anchors: tests/golden/parts holds GRMs the *reference binary* wrote for SNP groups a = rs1..rs70, b = rs71..rs160,
+for all 160 SNPs of one .bed, and for a + b joined by the reference's own Kernel::addKernels (`--bfile-list`,
+`--grm-join-method 0`) (oracle/make_golden.py; the group GRMs are per-group `--extract` runs, because the reference's own
 `--make-grm --groups` path aborts in normalizeGenotypes at this version: genotype.cpp:908-911 on a Genotype built by
 the default constructor).  Group GRMs must match those files; saved - current must reproduce the other group
 (Kernel::addKernels, kernel.cpp:1705-1859; LOCO, singlereml.cpp:298): N exactly, A within the operand tolerance."""
@@ -113,6 +114,10 @@ def test_sum_of_groups_accumulates_to_the_global_grm(eng):
     eng.set_view("saved")
     assert np.array_equal(fetch(eng, "N")[low], N_all[low])
     assert np.max(np.abs(fetch(eng, "A")[low] - A_all[low])) <= tol_for("fp16", M_FILE)
+    # ... and the file the reference wrote through its own Kernel::addKernels (--bfile-list, --grm-join-method 0)
+    A_j, N_j = ref("joined")
+    assert np.array_equal(fetch(eng, "N")[low], N_j[low])
+    assert np.max(np.abs(fetch(eng, "A")[low] - A_j[low])) <= tol_for("fp16", M_FILE)
     eng.save("drop")
     with pytest.raises(DgrmError):
         eng.set_view("saved")

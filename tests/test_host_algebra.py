@@ -150,3 +150,21 @@ def test_position_regions_multi_region(tmp_path):
     assert sorted(got) == sorted(want) and len(want) > 6
     for g in want:
         assert got[g] == sorted(want[g]), g
+
+
+def test_host_add_equals_the_references_own_join(tmp_path):
+    """tests/golden/parts/joined.* was written by the reference through its own Kernel::addKernels
+    (`--bfile-list` + `--grm-join-method 0`, auxiliar.cpp:620-672: one unnormalised kernel per genotype file, added,
+    then normalised).  The host mirror's addKernels on the two part files must reproduce it: N exactly, A to the
+    rounding of the denormalise step it needs (the parts are read back normalised)."""
+    out = str(tmp_path / "sum")
+    run("add", os.path.join(PARTS, "a"), os.path.join(PARTS, "b"), out)
+    A, N = load(out)
+    AJ, NJ = load(os.path.join(PARTS, "joined"))
+    AA, NA = load(os.path.join(PARTS, "all"))
+    low = lower_mask(48)
+    assert np.array_equal(N[low], NJ[low]) and np.array_equal(NJ[low], NA[low])
+    assert np.max(np.abs(A[low] - AJ[low])) <= 1e-13
+    assert np.max(np.abs(AJ[low] - AA[low])) <= 1e-12     # the reference's join vs its single-pass GRM
+    assert open(os.path.join(PARTS, "joined.grm.ids")).read() == open(out + ".grm.ids").read()
+    assert sorted(open(os.path.join(PARTS, "joined.grm.snps")).read().split()) == sorted(open(out + ".grm.snps").read().split())
