@@ -158,6 +158,16 @@ def main():
             raise SystemExit("parts/joined case failed\n" + (r.stdout + r.stderr)[-3000:])
         for e in (".grm.dat", ".grm.ids", ".grm.snps"):
             shutil.copy(os.path.join(tmp, "joined" + e), os.path.join(dst, "joined" + e))
+        # the reference's own LOCO subtraction and file-level addition (Kernel::addKernels, kernel.cpp:1705-1859;
+        # singlereml.cpp:298) on the files above, through oracle/_ref/grmalg (same unmodified reference objects)
+        grmalg = os.path.join(os.path.dirname(ref_runner.DISSECT), "grmalg")
+        for op, x, y, name in (("sub", "all", "a", "loco_a"), ("sub", "all", "b", "loco_b"), ("add", "a", "b", "sum_ab")):
+            r = subprocess.run([grmalg, op, os.path.join(dst, x), os.path.join(dst, y), "--out", os.path.join(tmp, name)],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                raise SystemExit(f"parts/{name} failed\n" + (r.stdout + r.stderr)[-3000:])
+            for e in (".grm.dat", ".grm.ids", ".grm.snps"):
+                shutil.copy(os.path.join(tmp, name + e), os.path.join(dst, name + e))
         with open(os.path.join(dst, "case.txt"), "w") as f:
             f.write(f"n_fam {n}\nm {m}\nsplit 70\n")
         print("parts: ok")

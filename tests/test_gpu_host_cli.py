@@ -100,6 +100,9 @@ def test_cli_regional_groups_and_loco(tmp_path):
     _check_group_files(out + ".b", "b")
     _check_group_files(out + ".loco.a", "b")              # all SNPs minus group a == group b
     _check_group_files(out + ".loco.b", "a")
+    # ... and the files the reference's own Kernel::addKernels(1., all, -1., group) wrote (oracle/_ref/grmalg)
+    _check_group_files(out + ".loco.a", "loco_a")
+    _check_group_files(out + ".loco.b", "loco_b")
     # getGroup's side file (genotype.cpp:1583-1590): the group's SNPs in set order
     listed = open(out + ".a.region.a").read().split()
     assert listed == sorted(f"rs{k + 1}" for k in range(70))

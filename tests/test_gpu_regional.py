@@ -81,6 +81,9 @@ def test_loco_view_is_global_minus_regional(eng, tmp_path):
     assert np.array_equal(fetch(eng, "N")[low], N_b[low])
     assert np.max(np.abs(fetch(eng, "A")[low] - A_b[low])) <= tol_for("fp16", M_FILE - SPLIT)
     assert np.array_equal(fetch(eng, "S")[low], (S_all - S_a)[low])      # exact fp64 subtraction of the stores
+    A_l, N_l = ref("loco_a")                          # the reference's own addKernels(1., all, -1., a) on its files
+    assert np.array_equal(fetch(eng, "N")[low], N_l[low])
+    assert np.max(np.abs(fetch(eng, "A")[low] - A_l[low])) <= tol_for("fp16", M_FILE - SPLIT)
     # every reader sees the view: the file writer and the low-overlap scan
     path = str(tmp_path / "loco.grm.dat")
     eng.write_grm_dat(path)

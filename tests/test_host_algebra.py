@@ -168,3 +168,15 @@ def test_host_add_equals_the_references_own_join(tmp_path):
     assert np.max(np.abs(AJ[low] - AA[low])) <= 1e-12     # the reference's join vs its single-pass GRM
     assert open(os.path.join(PARTS, "joined.grm.ids")).read() == open(out + ".grm.ids").read()
     assert sorted(open(os.path.join(PARTS, "joined.grm.snps")).read().split()) == sorted(open(out + ".grm.snps").read().split())
+
+
+@pytest.mark.parametrize("op,x,y,ref_name", [("sub", "all", "a", "loco_a"), ("sub", "all", "b", "loco_b"),
+                                             ("add", "a", "b", "sum_ab")])
+def test_host_algebra_reproduces_the_references_addKernels_files(op, x, y, ref_name, tmp_path):
+    """tests/golden/parts/{loco_a,loco_b,sum_ab}.* were written by the reference's own Kernel::addKernels
+    (kernel.cpp:1705-1859; LOCO: singlereml.cpp:298) on the reference's own part files, through oracle/_ref/grmalg.
+    The host mirror performs the same operations in the same order: identical files."""
+    out = str(tmp_path / "r")
+    run(op, os.path.join(PARTS, x), os.path.join(PARTS, y), out)
+    for ext in (".grm.ids", ".grm.snps", ".grm.dat"):
+        assert open(out + ext, "rb").read() == open(os.path.join(PARTS, ref_name + ext), "rb").read(), ext
