@@ -5,6 +5,7 @@ build container:  python oracle/make_golden.py
 The fixtures are committed; the GPU box never runs this script."""
 import os
 import shutil
+import subprocess
 import sys
 import tempfile
 
@@ -173,6 +174,25 @@ def main():
         print("parts: ok")
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+    # block-cyclic index arithmetic of the reference itself (Matrix::local2global / global2local, matrix.cpp:435-488)
+    # for emulated processes of R x C grids, through oracle/_ref/layoutdump
+    from dissect_b200.engine import numroc
+    layoutdump = os.path.join(os.path.dirname(ref_runner.DISSECT), "layoutdump")
+    dst = os.path.join(GOLD, "layout")
+    os.makedirs(dst, exist_ok=True)
+    with open(os.path.join(dst, "layout.txt"), "w") as out:
+        for (n, bs, grid) in ((10, (3, 2), (2, 3)), (37, (4, 4), (2, 2)), (130, (16, 8), (3, 2)), (700, (256, 256), (1, 1)),
+                              (515, (100, 64), (1, 2)), (258, (7, 5), (3, 1))):
+            for r in range(grid[0]):
+                for c in range(grid[1]):
+                    nlr, nlc = numroc(n, bs[0], r, grid[0]), numroc(n, bs[1], c, grid[1])
+                    res = subprocess.run([layoutdump] + [str(x) for x in (n, bs[0], bs[1], grid[0], grid[1], r, c, nlr, nlc)],
+                                         capture_output=True, text=True)
+                    if res.returncode != 0:
+                        raise SystemExit("layoutdump failed\n" + (res.stdout + res.stderr)[-2000:])
+                    out.write(f"CASE {n} {bs[0]} {bs[1]} {grid[0]} {grid[1]} {r} {c} {nlr} {nlc}\n")
+                    out.write("".join(l + "\n" for l in res.stdout.splitlines() if l[:2] in ("R ", "C ", "G ")))
+    print("layout: ok")
     # error-path fixture: a monomorphic SNP makes the reference abort and write <out>.badsnps
     tmp = tempfile.mkdtemp(prefix="golden_")
     try:
