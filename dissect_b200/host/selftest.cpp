@@ -5,9 +5,11 @@
 //   selftest roundtrip <in> <out>         read <in>.grm.*, write <out>.grm.*
 //   selftest add <a> <b> <out>            out = a + b
 //   selftest sub <all> <part> <out>       out = all - part
+//   selftest layout n bsR bsC R C r c     Matrix::initParameters / local2global for process (r, c) of an R x C grid
 //   selftest groups <options...>          parse the options, load the .bim/.fam metadata, group the SNPs
 //                                         (Genotype::groupSNPs, genotype.cpp:1293-1470) and print `group: snps...`
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "host.h"
@@ -38,7 +40,22 @@ int main(int argc, char** argv) {
       }
       return 0;
     }
-    fprintf(stderr, "usage: selftest roundtrip|add|sub|groups ...\n");
+    if (argc >= 9 && !strcmp(argv[1], "layout")) {
+      // selftest layout n bsR bsC R C myRow myCol: the mirror's Matrix geometry for one process of an R x C grid,
+      // in the format of oracle/_ref/layoutdump (reference: matrix.cpp:435-475, numroc: matrix.cpp:1748-1749)
+      const int n = atoi(argv[2]), bsR = atoi(argv[3]), bsC = atoi(argv[4]);
+      communicator->nProcRows = atoi(argv[5]);
+      communicator->nProcCols = atoi(argv[6]);
+      communicator->myRow = atoi(argv[7]);
+      communicator->myCol = atoi(argv[8]);
+      Matrix m(cyclicDistribution);
+      m.initParameters(n, n, bsR, bsC);
+      printf("N %d %d\n", m.nRows, m.nCols);
+      for (int l = 0; l < m.nRows; ++l) printf("R %d %d\n", l, m.local2globalRow(l));
+      for (int l = 0; l < m.nCols; ++l) printf("C %d %d\n", l, m.local2globalCol(l));
+      return 0;
+    }
+    fprintf(stderr, "usage: selftest roundtrip|add|sub|groups|layout ...\n");
     return 2;
   } catch (const DissectError&) {
     return 1;

@@ -58,3 +58,27 @@ def test_block_cyclic_local_piece_matches_the_reference_indices():
         assert loc.shape == (nlr, nlc)
         want = G[np.ix_([c["R"][l] for l in range(nlr)], [c["C"][l] for l in range(nlc)])]
         assert np.array_equal(loc, want)
+
+
+def test_host_mirror_matrix_geometry_matches_the_reference():
+    """The C++ host mirror's Matrix (dissect_b200/host: initParameters = numroc, local2globalRow/Col) against the same
+    reference output."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "dissect_b200", "host", "selftest")
+    exe = os.path.normpath(exe)
+    if not os.path.exists(exe):
+        import pytest
+        pytest.skip("host selftest not built (build())")
+    for c in _cases():
+        n, bsr, bsc, R, C, r, col, nlr, nlc = c["args"]
+        res = subprocess.run([exe, "layout"] + [str(x) for x in (n, bsr, bsc, R, C, r, col)], capture_output=True,
+                             text=True, timeout=60)
+        assert res.returncode == 0, res.stdout[-500:] + res.stderr[-500:]
+        got = {"R": {}, "C": {}}
+        for line in res.stdout.splitlines():
+            t = line.split()
+            if t[0] == "N":
+                assert (int(t[1]), int(t[2])) == (nlr, nlc)
+            elif t[0] in got:
+                got[t[0]][int(t[1])] = int(t[2])
+        assert got["R"] == c["R"] and got["C"] == c["C"]
