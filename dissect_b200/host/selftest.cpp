@@ -42,7 +42,7 @@ int main(int argc, char** argv) {
     }
     if (argc >= 9 && !strcmp(argv[1], "layout")) {
       // selftest layout n bsR bsC R C myRow myCol: the mirror's Matrix geometry for one process of an R x C grid,
-      // in the format of oracle/_ref/layoutdump (reference: matrix.cpp:435-475, numroc: matrix.cpp:1748-1749)
+      // printed as `N rows cols`, `R l g`, `C l g` (reference: matrix.cpp:435-475, numroc: matrix.cpp:1748-1749)
       const int n = atoi(argv[2]), bsR = atoi(argv[3]), bsC = atoi(argv[4]);
       communicator->nProcRows = atoi(argv[5]);
       communicator->nProcCols = atoi(argv[6]);
