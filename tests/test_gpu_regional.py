@@ -181,3 +181,26 @@ def test_standardised_needs_resident_rows():
     with pytest.raises(DgrmError):
         e.fetch_standardised()
     e.close()
+
+
+@pytest.mark.parametrize("name", ["tiny7_m40", "n37_m64"])
+def test_standardised_genotypes_equal_the_references_own_matrix(name):
+    """dgrm_fetch_standardised against ref.z.bin = genotype->genotypes as the *reference binary* left it after
+    normalizeGenotypes (dumped by oracle/snpdump.cpp): bit for bit."""
+    from tests.helpers import load_case
+    c = load_case(name)
+    zfile = os.path.join(c["dir"], "ref.z.bin")
+    if not os.path.exists(zfile):
+        pytest.skip("no ref.z.bin for this case")
+    e = GrmEngine(chunk_snps=256)
+    e.set_individuals(c["n_fam"], c["keep_mask"])
+    e.store_bed_host(np.ascontiguousarray(c["packed"]))
+    m = c["m_file"] if c["snp_keep"] is None else int(c["snp_keep"].sum())
+    e.begin(m)
+    e.push_stored(row_keep=c["snp_keep"])
+    e.finish()
+    n = e.num_individuals
+    z_ref = np.fromfile(zfile).reshape(2, m, n)[0]
+    got = e.fetch_standardised(bs=(m, n))
+    assert np.array_equal(np.ascontiguousarray(got).view(np.uint64), z_ref.view(np.uint64))
+    e.close()
