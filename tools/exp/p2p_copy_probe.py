@@ -8,8 +8,10 @@ otherwise idle pair of GPUs, by
   a) torch `Tensor.copy_`                 (what torch does for cross-device copies: enables peer access itself)
   b) cudaMemcpyAsync, kind = DeviceToDevice (what exchange.py does today)
   c) cudaMemcpyPeerAsync with explicit device ordinals
+  e) cudaMemcpyAsync into a torch symmetric-memory buffer (cuMem + peer access, what exchange.py maps now)
 and prints GB/s per method plus every return code of cudaDeviceCanAccessPeer / cudaDeviceEnablePeerAccess.
-Expected on an NVSwitch box: several hundred GB/s.  ~55 GB/s means the copy is staged through the host."""
+Expected on an NVSwitch box: several hundred GB/s.  Measured in round 1 (2 x B200, NV18): a), b), c) all 2.6 ms per
+64 MB = 25 GB/s, d) 0.025 ms = 2.6 TB/s; e) was added afterwards and has not run yet."""
 import os
 import sys
 import time
@@ -23,7 +25,7 @@ def main():
     from torch.multiprocessing.reductions import reduce_tensor
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("gloo")
+    dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
     nbytes = 64 << 20
     buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
     src = torch.full((nbytes,), rank + 1, dtype=torch.uint8, device="cuda")
@@ -77,6 +79,26 @@ def main():
     timed("b) cudaMemcpyAsync D2D (UVA) into the peer", raw_async)
     timed("c) cudaMemcpyPeerAsync into the peer", raw_peer)
     timed("d) cudaMemcpyAsync D2D, same device", local_copy)
+    # e) the mapping dissect_b200/exchange.py uses now: torch symmetric memory (cuMem allocations + peer access)
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        st = symm_mem.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", local))
+        st.zero_()
+        torch.cuda.synchronize()
+        hdl = symm_mem.rendezvous(st, dist.group.WORLD)
+        ptrs = [int(x) for x in hdl.buffer_ptrs]
+        print(f"[r{rank}] symmetric memory mapped: {len(ptrs)} buffers", file=sys.stderr)
+
+        def symm_copy():
+            (e,) = cudart.cudaMemcpyAsync(ptrs[peer_rank], src.data_ptr(), nbytes, d2d, stream.cuda_stream)
+            assert int(e) == 0, e
+
+        timed("e) cudaMemcpyAsync into the peer's symm_mem buffer", symm_copy)
+        torch.cuda.synchronize()
+        dist.barrier()
+        print(f"[r{rank}] symm buffer holds {int(st[0])} / {int(st[-1])} (expected {(rank - 1) % world + 1})", file=sys.stderr)
+    except Exception as ex:  # noqa: BLE001
+        print(f"[r{rank}] symmetric memory path failed: {type(ex).__name__}: {ex}", file=sys.stderr)
     torch.cuda.synchronize()
     dist.barrier()
     # what arrived: the peer's last write must be visible here
