@@ -75,7 +75,7 @@ typedef struct dgrm_config {
   int32_t chunk_snps;    /* SNPs contracted per launch (fp32 in-chunk, fp64 across); mult. of 256 */
   int32_t cta_group;     /* 1 = one-SM MMA 128x256 tiles, 2 = CTA-pair MMA 256x256 tiles     */
   int32_t profile;       /* 1 = record CUDA events around every kernel launch                */
-  int32_t resident_chunks; /* SNP chunks whose operands stay resident and are contracted tile-major (0 = auto) */
+  int32_t resident_chunks; /* operand slots: SNP chunks whose tensor-core operands stay in HBM at once (0 = auto) */
   int32_t resident_mb;   /* memory budget (MiB) for resident operands when resident_chunks == 0     */
   int32_t reserve_sms;   /* SMs the persistent contraction leaves free for the caller's own kernels (e.g. NCCL
                             all-gather CTAs, which cannot co-reside with it); -1 or 0 = none.  Measured at 2 GPUs:

@@ -21,6 +21,18 @@ def test_header_and_binding_agree():
     assert declared_symbols() == sorted(_lib.SYMBOLS)
 
 
+def test_config_struct_layout_matches_the_binding():
+    """dgrm_config in the header and the ctypes mirror: same fields, same order, all int32 (64 bytes)."""
+    txt = open(os.path.join(ROOT, "include", "dgrm.h")).read()
+    body = re.search(r"typedef struct dgrm_config \{(.*?)\} dgrm_config;", txt, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"int32_t\s+([a-z_]+)(\[\d+\])?\s*;", body)
+    want = [(n, int(a[1:-1]) if a else 1) for n, a in fields]
+    got = [(n, C.sizeof(t) // 4) for n, t in _lib.Config._fields_]
+    assert got == want
+    assert C.sizeof(_lib.Config) == 4 * sum(k for _, k in want) == 64
+
+
 def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared_symbols():
