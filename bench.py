@@ -31,8 +31,11 @@ import numpy as np  # noqa: E402
 # N > 1: same SNP set, individuals scaled by sqrt(N) so that the pair work per GPU stays fixed (weak scaling);
 #        N = 8 gives 56,568 individuals, between configs[1] and configs[2].
 BASE_N, BASE_M, MISSING, MAF_LO, MAF_HI, MAF_MIN, SEED = 20000, 100000, 0.01, 0.001, 0.5, 0.01, 2
-# bounded CPU sample of the same workload for the reference arm (about 10-30 s of host work)
-CPU_N, CPU_M = 4000, 16000
+# bounded CPU sample of the same workload for the reference arm: the SAME 20,000 individuals (the reference's cost
+# split between its O(n m) loader and its O(n^2 m) dsyrk depends on n), the SNP count cut to ~10 s of host work
+# (measured: the reference spends ~16 ms per SNP at n = 20000 on 8 cores, linear in the SNP count).  The reference
+# ARM repeats its sample steps + 1 times, so it uses fewer SNPs than the single cpu_baseline run of the GPU arm.
+CPU_N, CPU_M, CPU_M_ARM = 20000, 3000, 1500
 
 
 def load_peaks():
@@ -139,8 +142,9 @@ def cpu_threads():
 
 def sample_desc(r, threads):
     return (f"reference Genotype load + Kernel ctor (oracle/_ref/grmtime, unmodified reference sources, 1 MPI rank "
-            f"on a 1x1 BLACS shim, OpenBLAS dsyrk, {threads} threads) on n={r['n']} x m={r['m']} kept SNPs of the same "
-            f"synthetic family (1% missing, MAF>=0.01 extract list): load {r['load_s']:.2f}s + compute "
+            f"on a 1x1 BLACS shim, OpenBLAS dsyrk, {threads} threads) on n={r['n']} individuals x m={r['m']} kept SNPs: "
+            f"configs[1]'s 20000 individuals with the SNP count cut from 100000 (same "
+            f"distributions, 1% missing, MAF>=0.01 extract list): load {r['load_s']:.2f}s + compute "
             f"{r['compute_s']:.2f}s; the full config needs >= 42 GB and ~10 min on one rank")
 
 
@@ -153,9 +157,9 @@ def run_reference(args):
     base = {"impl": "reference", "metric": "grm_pair_snp_per_s", "unit": "pair*SNP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
-    # the sample shrinks with K so that the whole --steps K --warmup W run stays within a few minutes
+    # every step is the same bounded sample (n = 20000, CPU_M SNPs in the file), whatever K is: ~8 s per step
     runs = args.steps + min(args.warmup, 1)
-    m_s = max(2000, min(CPU_M, int(CPU_M * 6 / max(runs, 1))))
+    m_s = CPU_M_ARM
     if not os.path.exists(exe):
         # the reference-built oracle travels prebuilt; without it fall back to the plain-C port
         from oracle import c_oracle
@@ -164,14 +168,14 @@ def run_reference(args):
             base.update({"unavailable": "neither oracle/_ref/grmtime nor oracle/_ref/libgrm_oracle.so is built"})
             emit(base)
             return
-        pk = bedio.synth_packed(CPU_N // 2, m_s // 4, SEED, maf_lo=0.05, maf_hi=MAF_HI, missing=MISSING)
+        pn, pm = 2000, 1000      # the scalar plain-C port is O(n^2 m) on one core: a smaller sample of the family
+        pk = bedio.synth_packed(pn, pm, SEED, maf_lo=0.05, maf_hi=MAF_HI, missing=MISSING)
         res = []
         for i in range(runs):
             t0 = time.time()
-            c_oracle.grm(pk, CPU_N // 2)
+            c_oracle.grm(pk, pn)
             if i >= runs - args.steps:
-                res.append({"n": CPU_N // 2, "m": m_s // 4, "load_s": 0.0, "compute_s": time.time() - t0,
-                            "W": (CPU_N // 2) * (CPU_N // 2 + 1) / 2 * (m_s // 4)})
+                res.append({"n": pn, "m": pm, "load_s": 0.0, "compute_s": time.time() - t0, "W": pn * (pn + 1) / 2 * pm})
         kind = "port"
     else:
         kind = "reference"
@@ -185,10 +189,15 @@ def run_reference(args):
     val = W / t
     base.update({
         "value": val, "ms_per_step": 1e3 * t / len(res),
-        "config": {"workload": f"make-grm {res[-1]['n']}x{m_s if kind == 'reference' else res[-1]['m']} bounded CPU sample "
-                               "of configs[1] (20000x100000, 1% missing, MAF filter)",
+        "config": {"workload": f"make-grm {res[-1]['n']} individuals x {m_s if kind == 'reference' else res[-1]['m']} SNPs "
+                               f"({res[-1]['m']} kept): bounded CPU sample of configs[1] (20000 individuals x 100000 SNPs, 1% "
+                               "missing, MAF filter) with the SNP count cut, the same sample every step",
                    "parallelism": f"1 MPI rank, {threads} OpenMP/BLAS threads"},
+        "load_s_per_step": sum(r["load_s"] for r in res) / len(res),
+        "compute_s_per_step": sum(r["compute_s"] for r in res) / len(res),
         "cpu_baseline": {"value": val, "unit": "pair*SNP/s", "cores": threads, "kind": kind,
+                         "load_s": sum(r["load_s"] for r in res) / len(res),
+                         "compute_s": sum(r["compute_s"] for r in res) / len(res),
                          "sample": sample_desc(res[-1], threads) if kind == "reference" else
                          f"plain-C restatement oracle/grm_oracle.c on n={res[-1]['n']} x m={res[-1]['m']}"},
         "e2e": {"value": val, "unit": "pair*SNP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -197,17 +206,66 @@ def run_reference(args):
     emit(base)
 
 
+def parity_block(rank, world, local, args, dist):
+    """Outside the timed region: the n = 1500 x m = 3000 oracle case through the SAME driver the timed steps use
+    (dissect_b200.multi.MultiGpuGrm, same exchange, same operand / count method), tiles gathered on rank 0 and
+    compared with the numpy oracle."""
+    import torch
+    from dissect_b200 import bedio
+    from dissect_b200.engine import assemble_from_tiles
+    from dissect_b200.multi import DeviceRows, MultiGpuGrm
+    n, m, chunk = 1500, 3000, 1024
+    pk = bedio.synth_packed(n, m, 17, missing=0.02)         # same seed everywhere; a rank only reads its shards
+    mg = MultiGpuGrm(n, rank=rank, world=world, device=local, chunk_snps=chunk, xg=1, exchange=args.exchange,
+                     operand=args.operand, count_method=args.count, cta_group=args.cg)
+    dev_pk = torch.zeros((m, mg.pitch), dtype=torch.uint8, device="cuda")
+    dev_pk[:, : pk.shape[1]] = torch.from_numpy(pk).cuda()
+    mg.build(DeviceRows(dev_pk), m)
+    st = mg.eng.snp_stats()
+    sets = {k: mg.gather_tiles(k) for k in ("A", "N")}
+    out = None
+    if rank == 0:
+        from oracle import grm_oracle as orc
+        ref = orc.grm(orc.decode_rows(pk, n))
+        low = np.tril(np.ones((n, n), bool))
+        N = assemble_from_tiles(n, sets["N"])
+        A = assemble_from_tiles(n, sets["A"])
+        stats_ok = bool(np.array_equal(st["freq"], ref["stats"]["freq"]) and all(
+            np.array_equal(st[k].view(np.uint64), ref["stats"][k].view(np.uint64)) for k in ("p1", "p2", "sd")))
+        covered = not (np.isnan(A[low]).any() or np.isnan(N[low]).any())
+        eN = float(np.nanmax(np.abs(N[low] - ref["N"][low])))
+        eA = float(np.nanmax(np.abs(A[low] - ref["A"][low])))
+        tolA = {"fp16": 1e-4, "bf16": 1e-3, "fp16x2": 5e-6}[args.operand]
+        out = {"case": f"n={n} m={m} chunk={chunk}, 2% missing, seed 17, {world} rank(s), exchange {args.exchange if world > 1 else 'none'}",
+               "oracle": "oracle/grm_oracle.py (numpy restatement pinned to the reference binary)",
+               "N_exact": covered and eN == 0.0, "A_max_err": eA, "A_tol": tolA, "stats_bitexact": stats_ok,
+               "triangle_covered_once": covered, "ok": bool(covered and eN == 0.0 and eA <= tolA and stats_ok)}
+    mg.close()
+    del dev_pk
+    torch.cuda.empty_cache()
+    return out
+
+
+CONFIGS = {
+    # name: individuals, SNPs in the file, seed, SNP groups (BASELINE.json configs[1..4])
+    "c2": dict(n=20000, m=100000, seed=2, groups=0),
+    "c3": dict(n=100000, m=500000, seed=3, groups=0),
+    "c4": dict(n=50000, m=300000, seed=4, groups=22),
+    "c5": dict(n=50000, m=200000, seed=5, groups=0),
+}
+
+
 def run_gpu(args):
     # torchrun exports OMP_NUM_THREADS=1 to every rank; libdgrm's host threads (they widen the streamed pair counts
     # into the caller's fp64 matrix on the e2e path) would then be one per rank.  Give each rank its share of the
     # box's cores instead; libdgrm's OpenMP runtime reads the variable when the library is loaded, below.
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ["WORLD_SIZE"])))
+        os.environ["OMP_NUM_THREADS"] = str(max(1, cpu_threads() // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
     import torch
     import torch.distributed as dist
-    from cuda.bindings import runtime as cudart
     from dissect_b200 import GrmEngine
     from dissect_b200.engine import PinnedArray
+    from dissect_b200.multi import DeviceRows, HostRows, MultiGpuGrm
     from dissect_b200.synth import synth_packed_cuda
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,106 +277,70 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     G = world
-    n = args.n if args.n else int(round(BASE_N * math.sqrt(G)))
-    m_file = args.m if args.m else BASE_M
+    cfgd = CONFIGS[args.config]
+    weak = args.config == "c2" and not args.n
+    n = args.n if args.n else (int(round(BASE_N * math.sqrt(G))) if weak else cfgd["n"])
+    m_file = args.m if args.m else cfgd["m"]
+    seed = cfgd["seed"]
+    if cfgd["groups"] and G > 1:
+        raise SystemExit("bench.py: --config c4 (SNP-group GRMs from one resident cohort) runs on one GPU")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- synthetic cohort (same seed on every rank -> identical data; rank r keeps its row shard) ----------
-    pk_all, maf = synth_packed_cuda(n, m_file, SEED, maf_lo=MAF_LO, maf_hi=MAF_HI, missing=MISSING)
+    chunk = args.chunk
+    mg = MultiGpuGrm(n, rank=rank, world=world, device=local, chunk_snps=chunk, xg=args.xg, exchange=args.exchange,
+                     operand=args.operand, count_method=args.count, cta_group=args.cg, profile=True,
+                     resident_chunks=args.resident, resident_mb=args.resident_mb, a_transport=args.a_transport)
+    eng = mg.eng
+    # ---- synthetic cohort (same seed on every rank -> identical data; a rank only READS its own row shards) ----
+    pk_raw, maf = synth_packed_cuda(n, m_file, seed, maf_lo=MAF_LO, maf_hi=MAF_HI, missing=MISSING)
     keep = (maf >= MAF_MIN).cpu().numpy().astype(np.uint8)          # "MAF filter" = --extract list
     m_kept = int(keep.sum())
+    bpr = pk_raw.shape[1]
+    if G > 1 and mg.pitch != bpr:     # rows at the exchange pitch: shards go out without staging
+        pk_all = torch.zeros((m_file, mg.pitch), dtype=torch.uint8, device="cuda")
+        pk_all[:, :bpr] = pk_raw
+        del pk_raw
+        torch.cuda.empty_cache()
+    else:
+        pk_all = pk_raw
     W = n * (n + 1) / 2 * m_kept
-    bpr = pk_all.shape[1]
-    chunk = args.chunk
-    # SNP rows are dealt to ranks in contiguous shards of every chunk; the packed chunk is all-gathered
-    # over NVLink (the path's one exchange step), then every rank expands it locally.
-    # Exchange granularity: `xg` engine chunks travel in one all-gather.  The all-gather kernel cannot run underneath
-    # the persistent contraction, so every exchange is a bubble in the MMA stream; fewer, larger
-    # exchanges mean fewer bubbles, and all but the first chunk of a group are decoded underneath the contraction.
-    xchunk = chunk * max(1, args.xg)
-    shard = (xchunk + G - 1) // G
-    if G > 1:
-        mine = []
-        for c0 in range(0, m_file, xchunk):
-            r0 = min(c0 + rank * shard, min(c0 + xchunk, m_file))
-            r1 = min(r0 + shard, min(c0 + xchunk, m_file))
-            mine.append((c0, r0, r1))
-        # rows are exchanged with a 16-byte aligned pitch so that the engine's row gather can use 128-bit copies
-        bpr_pad = (bpr + 15) // 16 * 16
-        send_bufs = [torch.zeros((shard, bpr_pad), dtype=torch.uint8, device="cuda") for _ in range(2)]
-        # which of the G*shard gathered rows of a chunk are real and kept (shards are padded to `shard` rows)
-        rks = []
-        for (c0, r0, r1) in mine:
-            c1 = min(c0 + xchunk, m_file)
-            rk = np.zeros(G * shard, np.uint8)
-            for g in range(G):
-                a = c0 + g * shard
-                b = min(a + shard, c1)
-                if b > a:
-                    rk[g * shard: g * shard + (b - a)] = keep[a:b]
-            rks.append(rk)
+    plan = mg.prepare(m_file, keep)
     host_pk = None
     if not args.no_e2e:   # the e2e leg starts from pinned host rows
         host_pk = PinnedArray((m_file, bpr), np.uint8)
-        host_pk.array[:] = pk_all.cpu().numpy()
-    xch = None
-    if G > 1 and args.exchange == "p2p":
-        # copy-engine exchange (dissect_b200/exchange.py): shards go straight into every peer's gather buffer
-        from dissect_b200.exchange import NBUF, PeerExchange
-        xch = PeerExchange(shard, bpr_pad, rank, G, dist.new_group(backend="gloo"))
-        if not xch.ok:
-            if rank == 0:
-                print(f"bench.py: peer exchange unavailable ({xch.error}); using NCCL all-gather", file=sys.stderr)
-            xch = None
-    if xch is not None:
-        pk_src = torch.zeros((m_file, bpr_pad), dtype=torch.uint8, device="cuda")   # contiguous shard sources
-        pk_src[:, :bpr] = pk_all
-        del pk_all
-        torch.cuda.empty_cache()
-    elif G > 1:
-        gather_bufs = [torch.zeros((G * shard, bpr_pad), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        host_pk.array[:] = pk_all[:, :bpr].cpu().numpy()
+    dev_src = DeviceRows(pk_all)
 
-    def exchange_and_push(shard_src):
-        """shard_src(ci) -> (device address of this rank's contiguous shard rows of chunk ci, row count), readable in
-        xch.copy_stream order.  Shards are posted two chunks ahead; everything is stream-ordered (no host wait)."""
-        nch, posted = len(mine), 0
-        for ci in range(nch):
-            while posted < min(nch, ci + NBUF):
-                ptr, cnt = shard_src(posted)
-                xch.post(ptr, cnt)
-                posted += 1
-            xch.consume(eng, rks[ci])
-
-    eng = GrmEngine(device=local, rank=rank, world=world, operand=args.operand, count_method=args.count,
-                    chunk_snps=chunk, cta_group=args.cg, profile=True, resident_chunks=args.resident,
-                    resident_mb=args.resident_mb)
-    eng.set_individuals(n)
-
-    def push_device_resident():
-        if G == 1:
-            eng.push_bed_device(pk_all.data_ptr(), pk_all.stride(0), m_file, row_keep=keep)
-            return
-        if xch is not None:
-            exchange_and_push(lambda ci: (pk_src.data_ptr() + mine[ci][1] * bpr_pad, mine[ci][2] - mine[ci][1]))
-            return
-        stream = torch.cuda.current_stream().cuda_stream
-        for ci, (c0, r0, r1) in enumerate(mine):
-            gather_buf, send_buf = gather_bufs[ci & 1], send_bufs[ci & 1]
-            if r1 > r0:
-                send_buf[: r1 - r0, :bpr].copy_(pk_all[r0:r1])
-            dist.all_gather_into_tensor(gather_buf, send_buf)
-            eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), G * shard, row_keep=rks[ci], stream=stream)
-            # two exchange buffers: the all-gather of chunk c+2 into this one is ordered after the engine read it
-            eng.release_inputs(stream)
+    groups = None
+    if cfgd["groups"]:
+        # C4: 22 SNP groups with sizes proportional to the human chromosome lengths
+        chr_len = np.array([248, 242, 198, 190, 181, 171, 159, 145, 138, 133, 135, 133, 114, 107, 102, 90, 83, 80, 58, 64,
+                            46, 50], dtype=np.float64)[: cfgd["groups"]]
+        edges = np.concatenate([[0], np.round(np.cumsum(chr_len) / chr_len.sum() * m_file).astype(np.int64)])
+        groups = [(int(edges[g]), int(edges[g + 1])) for g in range(len(chr_len))]
+        eng.store_bed_device(pk_all.data_ptr(), pk_all.stride(0), m_file)
+        W = W * 2      # the global GRM plus every group GRM again for its leave-one-chromosome-out view
 
     def step_device():
+        if groups is None:
+            mg.build(dev_src, m_file, keep)
+            return
+        # global GRM from the resident cohort, kept as (S, N); then per chromosome: group GRM and its LOCO view
         eng.begin(m_kept)
-        push_device_resident()
+        eng.push_stored(0, m_file, row_keep=keep)
         eng.finish()
+        eng.save("copy")
+        for (g0, g1) in groups:
+            eng.begin(max(1, int(keep[g0:g1].sum())))
+            eng.push_stored(g0, g1 - g0, row_keep=keep[g0:g1])
+            eng.finish()
+            eng.set_view("saved-current")        # global - chromosome (singlereml.cpp:298)
+            eng.low_overlap_pairs(10.0, cap=16)  # a reader of the LOCO view: sanitizeKernel's scan over (S, N)
+            eng.set_view("current")
 
     # ---- value: device-resident inputs ------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -353,7 +375,7 @@ def run_gpu(args):
     # are inflated by the SMs they do not get; three extra, untimed-for-`value` steps with the overlap switched
     # off give their stand-alone bandwidth (bytes_in + bytes_out over t_K1, peak = measured copy BW).
     k1 = None
-    if G == 1:
+    if G == 1 and groups is None and not args.no_k1:
         os.environ["DGRM_OVERLAP"] = "0"
         eng1 = GrmEngine(device=local, operand=args.operand, count_method=args.count, chunk_snps=chunk,
                          cta_group=args.cg, profile=True, resident_chunks=args.resident, resident_mb=args.resident_mb)
@@ -370,37 +392,43 @@ def run_gpu(args):
         eng1.close()
         geno = float(n) * m_kept
         n_pad = (n + 255) // 256 * 256
-        alg = {"gather": 0.5 * geno,                                   # 1/4 B read + 1/4 B written per genotype
-               "count": 0.25 * geno + 72.0 * m_kept,                   # packed rows in, 40 B stats + 32 B table out
-               "expand": 0.25 * geno + (2.0 + (0.5 if args.count == "fp4" else 1.0 if args.count == "mma" else 0.125))
+        qb = 0.5 if args.count == "fp4" else 1.0 if args.count == "mma" else 0.125
+        alg = {"decode": 0.25 * geno + 0.25 * geno + 72.0 * m_kept,     # packed rows in, aligned chunk + 40 B stats + 32 B table out
+               "expand": 0.25 * geno + (2.0 * (2 if args.operand == "fp16x2" else 1) + qb)
                * n_pad * ((m_kept + 255) // 256 * 256)}                # operands are materialised: listed (§8d)
+        names = {"decode": ("gather", "count"), "expand": ("expand",)}
         peaks1 = load_peaks()
+        kern = {}
+        for k, parts in names.items():
+            ms = sum(kt1[p][0] for p in parts) / reps
+            if ms > 0:
+                kern[k] = {"ms_per_step": ms, "algorithmic_bytes": alg[k], "achieved": alg[k] / (ms * 1e-3) / 1e9,
+                           "frac": alg[k] / (ms * 1e-3) / 1e9 / peaks1["hbm_gbs"],
+                           "launches_per_step": sum(kt1[p][1] for p in parts) / reps}
         k1 = {"bound": "hbm", "peak": peaks1["hbm_gbs"], "unit": "GB/s", "overlap": "off for this measurement",
-              "kernels": {k: {"ms_per_step": kt1[k][0] / reps, "algorithmic_bytes": alg[k],
-                              "achieved": alg[k] / (kt1[k][0] / reps * 1e-3) / 1e9,
-                              "frac": alg[k] / (kt1[k][0] / reps * 1e-3) / 1e9 / peaks1["hbm_gbs"]}
-                          for k in ("gather", "count", "expand")}}
+              "kernels": kern}
 
-    # ---- e2e: host buffers in, block-cyclic lower triangles of A and N out, every step -----------------
+    # ---- e2e: host buffers in, A and N (lower triangle / this rank's tiles) out, every step ------------------
     e2e = None
-    if G == 1 and not args.no_e2e:
+    tiles_A = tiles_N = None
+    if groups is not None:
+        pass
+    elif G == 1 and not args.no_e2e:
         A_host = PinnedArray((n, n), np.float64, order="F")
         N_host = PinnedArray((n, n), np.float64, order="F")
-
         # the caller's Matrix::m buffers are bound once; every dgrm_finish streams the finished tile groups
         # into them while later groups are still on the tensor cores
         eng.bind_output("A", A_host.ptr, n, bs=(256, 256), uplo="L")
         eng.bind_output("N", N_host.ptr, n, bs=(256, 256), uplo="L")
+        host_src = HostRows(host_pk.ptr, bpr)
 
         def step_e2e():
-            eng.begin(m_kept)
-            eng.push_bed_host(host_pk.ptr, row_keep=keep, pitch=bpr, nrows=m_file)
-            eng.finish()
+            mg.build(host_src, m_file, keep)
 
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
         barrier()
-        ke = max(1, min(args.steps, 3))
+        ke = max(1, args.steps)
         ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ee0.record()
         for _ in range(ke):
@@ -408,54 +436,29 @@ def run_gpu(args):
         ee1.record()
         barrier()
         dte = ee0.elapsed_time(ee1) * 1e-3
-        tri = n * (n + 1) // 2
-        e2e = {"value": ke * W / dte, "unit": "pair*SNP/s", "ms_per_step": 1e3 * dte / ke,
-               "h2d_bytes_per_step": int(m_file * bpr), "d2h_bytes_per_step": int(2 * tri * 8),
-               "result": "A and N lower triangles (fp64) into pinned block-cyclic Matrix::m buffers, bs 256, 1x1 grid",
+        e2e = {"value": ke * W / dte, "unit": "pair*SNP/s", "ms_per_step": 1e3 * dte / ke, "steps": ke,
+               "h2d_bytes_per_step": int(m_file * bpr), "d2h_bytes_per_step": int(eng.last_d2h_bytes),
+               "result": "A and N lower triangles as fp64 in pinned block-cyclic Matrix::m buffers (bs 256, 1x1 grid); "
+                         "d2h_bytes_per_step = bytes the copy engine really moved (A as " + args.a_transport +
+                         ", N as 16-bit deficiencies m - N or int32, widened to fp64 by host threads)",
                "check_trace_A": float(np.trace(A_host.array[:2000, :2000]))}
         eng.unbind_outputs()
+        del A_host, N_host
     elif G > 1 and not args.no_e2e:
         # per-rank H2D of its row shards + all-gather + compute + D2H of the tiles this rank owns
         ntl = eng.num_tiles
         tiles_A = PinnedArray((max(ntl, 1), 256, 128), np.float64)
         tiles_N = PinnedArray((max(ntl, 1), 256, 128), np.float64)
-
-        dbg = os.environ.get("DGRM_BENCH_DEBUG") and rank == 0
         eng.bind_tiles("A", tiles_A.ptr)      # finished tile groups stream out while later groups are contracted
         eng.bind_tiles("N", tiles_N.ptr)
-
-        def h2d_shard(ci, stream):
-            # this rank's shard of the chunk: pinned host rows -> device (row pitch padded to 16 bytes)
-            c0, r0, r1 = mine[ci]
-            send_buf = send_bufs[ci & 1]
-            if r1 > r0:
-                cudart.cudaMemcpy2DAsync(send_buf.data_ptr(), bpr_pad, host_pk.ptr + r0 * bpr, bpr, bpr, r1 - r0,
-                                         cudart.cudaMemcpyKind.cudaMemcpyHostToDevice, stream)
-            return send_buf, r1 - r0
+        host_src = HostRows(host_pk.ptr, bpr)
 
         def step_e2e():
-            t_a = time.perf_counter()
-            eng.begin(m_kept)
-            if xch is not None:
-                exchange_and_push(lambda ci: (lambda sb_cnt: (sb_cnt[0].data_ptr(), sb_cnt[1]))(h2d_shard(ci, xch.copy_stream.cuda_stream)))
-            else:
-                stream = torch.cuda.current_stream().cuda_stream
-                for ci in range(len(mine)):
-                    gather_buf = gather_bufs[ci & 1]
-                    send_buf, _ = h2d_shard(ci, stream)
-                    dist.all_gather_into_tensor(gather_buf, send_buf)
-                    eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), G * shard, row_keep=rks[ci], stream=stream)
-                    eng.release_inputs(stream)
-            t_b = time.perf_counter()
-            eng.finish()
-            t_c = time.perf_counter()
-            if dbg:
-                print(f"[e2e rank0] push {1e3*(t_b-t_a):.1f} ms, finish (compute + streamed tiles) {1e3*(t_c-t_b):.1f} ms",
-                      file=sys.stderr)
+            mg.build(host_src, m_file, keep)
 
         step_e2e()
         barrier()
-        ke = max(1, min(args.steps, 2))
+        ke = max(1, args.steps)
         ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ee0.record()
         for _ in range(ke):
@@ -466,18 +469,33 @@ def run_gpu(args):
         t = torch.tensor([dte], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dte = float(t.item())
-        e2e = {"value": ke * W / dte, "unit": "pair*SNP/s", "ms_per_step": 1e3 * dte / ke,
-               "h2d_bytes_per_step": int(sum(r1 - r0 for (_, r0, r1) in mine) * bpr),
-               "d2h_bytes_per_step": int(2 * ntl * 128 * 256 * 8),
-               "result": "per rank: its packed row shards in, its owned 128x256 tiles of A and N (fp64) streamed out "
-                         "into bound pinned buffers",
-               "check_tile_sum_A": float(tiles_A.array[0, 0, 0])}
+        e2e = {"value": ke * W / dte, "unit": "pair*SNP/s", "ms_per_step": 1e3 * dte / ke, "steps": ke,
+               "h2d_bytes_per_step": int(plan.rows_of(rank) * bpr), "d2h_bytes_per_step": int(eng.last_d2h_bytes),
+               "bytes_are": "this rank's; every rank moves about the same",
+               "result": "per rank: its packed row shards in, its owned 128x256 tiles of A and N as fp64 in bound pinned "
+                         "buffers; d2h_bytes_per_step = bytes the copy engine really moved (A as " + args.a_transport +
+                         ", N as 16-bit deficiencies or int32, widened by host threads)"}
         eng.unbind_outputs()
 
-    if xch is not None:
-        xch.close()
+    # ---- correctness of what was just timed (outside the timed regions) --------------------------------------
+    checks = None
+    if not args.no_check and groups is None:
+        from tools import fullsize_checks
+        if tiles_A is None:       # no e2e leg (or one GPU): take the tiles of the last timed GRM
+            tA, tN = eng.fetch_tiles("A"), eng.fetch_tiles("N")
+        else:
+            tA, tN = tiles_A.array, tiles_N.array
+        checks = fullsize_checks.run(pk_all, keep, n, m_kept, eng.tile_coords(), tA, tN, eng.snp_stats(), rank, world,
+                                     torch.device("cuda", local), operand=args.operand, dist=dist)
+        del tA, tN
+    tiles_A = tiles_N = None
+    del pk_all
+    dev_src = None
+    torch.cuda.empty_cache()
+    parity = None if args.no_check else parity_block(rank, world, local, args, dist)
+
     if rank != 0:
-        eng.close()
+        mg.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -485,34 +503,40 @@ def run_gpu(args):
 
     peaks = load_peaks()
     syrk_ms, syrk_launches = kt["syrk"]
+    pc_ms, pc_launches = kt["paircnt"]
     launches = sum(v[1] for k, v in kt.items() if k != "d2h")
     # algorithmic flops of the contraction: 2 per pair*SNP, lower triangle incl. diagonal;
     # with G ranks each rank's launches cover 1/G of the triangle.
     flops_total = 2.0 * W * args.steps / G
     achieved = flops_total / (syrk_ms * 1e-3) / 1e12 if syrk_ms else None
     peak = peaks["bf16_tflops_sustained"]
-    prof_traffic = None
+    prof_traffic = traffic_src = None
     pj = os.path.join(ROOT, "profiles", "syrk_traffic.json")
-    if os.path.exists(pj):
-        prof_traffic = json.load(open(pj)).get("dram_bytes_per_launch")
+    if os.path.exists(pj) and G == 1 and args.config == "c2" and not args.n and not args.m:
+        tj = json.load(open(pj))
+        if tj.get("chunk_snps", 16384) == chunk and tj.get("operand", "fp16") == args.operand:
+            prof_traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = tj.get("source", "profiles/syrk_traffic.json") + " (one ncu --set full capture of this command's kernel, not measured in this run)"
     out = {
         "metric": "grm_pair_snp_per_s", "value": value, "unit": "pair*SNP/s", "n_gpus": G, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "wall_ms_per_step": 1e3 * wall_dt / args.steps,
         "timing": "CUDA events on the rank's stream around the K steps (each step ends in dgrm_finish, which drains the "
-                  "engine's streams), max over ranks", "higher_is_better": True, "scaling": "weak",
+                  "engine's streams), max over ranks", "higher_is_better": True, "scaling": "weak" if weak or G == 1 else "strong",
         "vs_baseline": None, "dtype": {"fp16": "f16 operands / f32 chunk accum / f64 across chunks; counts exact int32",
                                        "bf16": "bf16 operands / f32 / f64; counts exact int32",
                                        "fp16x2": "f16 hi+lo split (3 MMAs) / f32 / f64"}[args.operand],
         "data": "synthetic",
         "config": {
             "workload": (f"make-grm {n} individuals x {m_file} SNPs ({m_kept} kept by the MAF>=0.01 extract list), "
-                         f"1% missing, seed {SEED}" + ("" if G == 1 else f"; weak scaling: n = 20000*sqrt({G})")),
-            "pair_snp_per_step": W, "chunk_snps": chunk, "exchange_chunks": max(1, args.xg) if G > 1 else None, "cta_group": args.cg, "operand": args.operand,
-            "count_method": args.count,
+                         f"1% missing, seed {seed} (BASELINE configs[{int(args.config[1]) - 1}])"
+                         + (f"; weak scaling: n = 20000*sqrt({G})" if weak and G > 1 else "")
+                         + (f"; global GRM + {len(groups)} chromosome GRMs and their LOCO views from one resident cohort" if groups else "")),
+            "pair_snp_per_step": W, "chunk_snps": chunk, "exchange_chunks": mg.xg if G > 1 else None, "cta_group": args.cg,
+            "operand": args.operand, "count_method": args.count,
             "parallelism": "1 GPU" if G == 1 else (
                 f"{G} GPUs: lower-triangle tile sets, packed chunks all-gathered "
-                + ("by copy-engine peer writes over NVLink (CUDA IPC), gloo host barrier per chunk" if xch is not None
-                   else "with NCCL")),
+                + ("by copy-engine peer writes over NVLink, stream-ordered" if args.exchange == "p2p" else "with NCCL")
+                + " (dissect_b200/multi.py)"),
             "l2": "inputs exceed L2 (packed rows + operand chunk + S/N tiles >> 126 MB)",
         },
         "pct_of_bf16_peak": {"burst": 100 * 2 * value / G / (peaks["bf16_tflops"] * 1e12),
@@ -521,7 +545,17 @@ def run_gpu(args):
         "roofline": {"kernel": "grm_syrk_kernel (tcgen05 kind::f16)", "bound": "tensor", "achieved": achieved,
                      "peak": peak, "peak_kind": f"bf16 sustained, {peaks['source']} (burst {peaks['bf16_tflops']})",
                      "unit": "TFLOP/s", "frac": achieved / peak if achieved else None, "traffic": prof_traffic,
+                     "traffic_source": traffic_src,
                      "launches": syrk_launches, "avg_launch_ms": syrk_ms / max(syrk_launches, 1)},
+        "roofline_k4": None if not pc_ms else {
+            "kernel": {"fp4": "grm_syrk_kernel<.,2,int> (tcgen05 kind::mxf4, e2m1 0/1 operands)",
+                       "mma": "grm_syrk_kernel<.,1,int> (tcgen05 kind::f8f6f4)", "popc": "pair_count_popc_kernel"}[args.count],
+            "bound": "tensor", "unit": "pair*SNP/s", "achieved": W * args.steps / G / (pc_ms * 1e-3),
+            "peak": 4 * peaks["bf16_tflops_sustained"] * 1e12 / 2 if args.count == "fp4" else
+                    2 * peaks["bf16_tflops_sustained"] * 1e12 / 2 if args.count == "mma" else None,
+            "peak_kind": "dense fp4 (fp8) MMA rate taken as 4x (2x) the measured sustained bf16 rate at 2 flop per "
+                         "pair*SNP: nominal ratio, no fp4 GEMM measurement exists in MEASURED_PEAKS.json",
+            "launches": pc_launches, "avg_launch_ms": pc_ms / max(pc_launches, 1)},
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()},
         "kernel_ms_note": "decode kernels (gather/count/expand) run on a second stream underneath the contraction: "
                           "their times here are inflated by the overlap, see roofline_k1 for them alone",
@@ -529,7 +563,11 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": e2e,
+        "parity": parity,
+        "fullsize_checks": checks,
     }
+    if out["roofline_k4"] and out["roofline_k4"]["peak"]:
+        out["roofline_k4"]["frac"] = out["roofline_k4"]["achieved"] / out["roofline_k4"]["peak"]
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------------
     if G == 1 and not args.no_cpu:
         try:
@@ -539,12 +577,14 @@ def run_gpu(args):
                 r = reference_step(wd, threads)
             v = r["W"] / (r["load_s"] + r["compute_s"])
             out["cpu_baseline"] = {"value": v, "unit": "pair*SNP/s", "cores": threads, "kind": "reference",
+                                   "load_s": r["load_s"], "compute_s": r["compute_s"],
+                                   "value_compute_only": r["W"] / r["compute_s"] if r["compute_s"] else None,
                                    "sample": sample_desc(r, threads)}
         except Exception as ex:  # the baseline is reported, never required
             out["cpu_baseline"] = {"value": None, "unit": "pair*SNP/s", "cores": cpu_threads(), "kind": "reference",
                                    "sample": f"unavailable: {ex}"[:300]}
     emit(out)
-    eng.close()
+    mg.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -575,8 +615,18 @@ def main():
     ap.add_argument("--impl", default="dgrm", choices=["dgrm", "reference"])
     ap.add_argument("--n", "--individuals", dest="n", type=int, default=0, help="override individuals (default 20000*sqrt(gpus))")
     ap.add_argument("--m", "--snps", dest="m", type=int, default=0, help="override SNPs in the file (default 100000)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
+                    help="BASELINE.json workload: c2 = configs[1] (the default, the one the metric is quoted on; individuals "
+                         "scale with sqrt(gpus)), c3 / c5 = configs[2] / configs[4] at their full sizes, c4 = configs[3] "
+                         "(22 chromosome GRMs + LOCO views from one resident cohort, one GPU)")
     ap.add_argument("--chunk", type=int, default=16384)
-    ap.add_argument("--xg", type=int, default=1, help="engine chunks per all-gather (multi-GPU exchange granularity)")
+    ap.add_argument("--xg", type=int, default=0, help="engine chunks per all-gather (multi-GPU exchange granularity); "
+                                                      "0 = as many as a 2 GB exchange-buffer budget allows")
+    ap.add_argument("--a-transport", default="fp32", choices=["fp64", "fp32"],
+                    help="how streamed A values cross PCIe on the e2e path: fp32 (+ the exact fp64 diagonal; adds <= 6e-8 "
+                         "relative, the caller still receives fp64) or fp64")
+    ap.add_argument("--no-k1", action="store_true", help="skip the stand-alone decode-kernel measurement")
+    ap.add_argument("--no-check", action="store_true", help="skip the parity block and the full-size checks")
     ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
                     help="multi-GPU chunk exchange: NCCL all-gather (default) or the experimental copy-engine peer "
                          "writes of dissect_b200/exchange.py (correct, but measured slower so far: DESIGN.md §6)")

@@ -11,16 +11,17 @@ K_NAMES = ("count", "expand", "syrk", "paircnt", "final", "fetch", "gather", "d2
 OPERANDS = {"fp16": 0, "bf16": 1, "fp16x2": 2}
 COUNT_METHODS = {"mma": 0, "popc": 1, "fp4": 2}
 FETCH = {"A": 0, "S": 1, "N": 2}
+TRANSPORT = {"fp64": 0, "fp32": 1}
 
 # every symbol include/dgrm.h declares
 SYMBOLS = (
     "dgrm_default_config", "dgrm_create", "dgrm_destroy", "dgrm_last_error", "dgrm_abi_version",
     "dgrm_set_individuals", "dgrm_begin", "dgrm_push_bed_host", "dgrm_push_bed_device", "dgrm_release_inputs",
     "dgrm_load_bed_file", "dgrm_finish", "dgrm_sync", "dgrm_num_snps", "dgrm_num_individuals",
-    "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_bind_output", "dgrm_unbind_outputs", "dgrm_bind_tiles", "dgrm_low_overlap_pairs",
-    "dgrm_set_output_subset", "dgrm_write_grm_dat", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles",
+    "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_fetch_block_cyclic_cols", "dgrm_bind_output", "dgrm_unbind_outputs", "dgrm_bind_tiles", "dgrm_low_overlap_pairs",
+    "dgrm_set_output_subset", "dgrm_write_grm_dat", "dgrm_write_grm_dat_part", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles",
     "dgrm_host_alloc", "dgrm_host_free", "dgrm_kernel_times",
-    "dgrm_store_bed_file", "dgrm_store_bed_host", "dgrm_store_clear", "dgrm_stored_snps", "dgrm_push_stored",
+    "dgrm_store_bed_file", "dgrm_store_bed_host", "dgrm_store_bed_device", "dgrm_last_d2h_bytes", "dgrm_store_clear", "dgrm_stored_snps", "dgrm_push_stored",
     "dgrm_fetch_standardised", "dgrm_save", "dgrm_set_view",
 )
 SAVE = {"copy": 0, "add": 1, "drop": 2}
@@ -32,7 +33,7 @@ class Config(C.Structure):
         ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("operand", C.c_int32),
         ("count_method", C.c_int32), ("flat_norm", C.c_int32), ("chunk_snps", C.c_int32),
         ("cta_group", C.c_int32), ("profile", C.c_int32), ("resident_chunks", C.c_int32), ("resident_mb", C.c_int32),
-        ("reserve_sms", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("reserve_sms", C.c_int32), ("a_transport", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -73,12 +74,14 @@ def load():
     lib.dgrm_snp_stats.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.dgrm_bad_snps.argtypes = [vp, vp, i64, P(i64)]
     lib.dgrm_fetch_block_cyclic.argtypes = [vp, i32, vp, i64, i32, i32, i32, i32, i32, i32, C.c_char]
+    lib.dgrm_fetch_block_cyclic_cols.argtypes = [vp, i32, vp, i64, i32, i32, i32, i32, i32, i32, C.c_char, i64, i64]
     lib.dgrm_bind_output.argtypes = [vp, i32, vp, i64, i32, i32, i32, i32, i32, i32, C.c_char]
     lib.dgrm_unbind_outputs.argtypes = [vp]
     lib.dgrm_bind_tiles.argtypes = [vp, i32, vp]
     lib.dgrm_low_overlap_pairs.argtypes = [vp, dbl, vp, i64, P(i64)]
     lib.dgrm_set_output_subset.argtypes = [vp, vp, i64]
     lib.dgrm_write_grm_dat.argtypes = [vp, C.c_char_p]
+    lib.dgrm_write_grm_dat_part.argtypes = [vp, C.c_char_p, i32]
     lib.dgrm_num_tiles.argtypes = [vp]
     lib.dgrm_num_tiles.restype = i64
     lib.dgrm_tile_coords.argtypes = [vp, vp]
@@ -90,6 +93,9 @@ def load():
     lib.dgrm_kernel_times.argtypes = [vp, P(dbl * K_NUM), P(i64 * K_NUM)]
     lib.dgrm_store_bed_file.argtypes = [vp, C.c_char_p, i64]
     lib.dgrm_store_bed_host.argtypes = [vp, vp, i64, i64]
+    lib.dgrm_store_bed_device.argtypes = [vp, vp, i64, i64, vp]
+    lib.dgrm_last_d2h_bytes.argtypes = [vp]
+    lib.dgrm_last_d2h_bytes.restype = i64
     lib.dgrm_store_clear.argtypes = [vp]
     lib.dgrm_stored_snps.argtypes = [vp]
     lib.dgrm_stored_snps.restype = i64

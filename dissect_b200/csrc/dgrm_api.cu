@@ -13,6 +13,9 @@
 #include <string>
 #include <vector>
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -60,6 +63,8 @@ struct dgrm_engine {
   std::vector<int4> work;       // launch work list (CG form)
   std::vector<int4> work_cg1;   // 128x256 form (popcount kernel)
   std::vector<int32_t> tile_rc; // [ntiles][2]
+  std::vector<int32_t> h_index; // host copy of d_index: [nrb][ncp] -> storage tile or -1 (not owned)
+  std::vector<int32_t> h_subset; // host copy of d_subset
   int4* d_work = nullptr;
   int4* d_work_cg1 = nullptr;
   int32_t* d_index = nullptr;
@@ -102,12 +107,15 @@ struct dgrm_engine {
     int lr0, lr1, lc1;      // local rectangle rows [lr0, lr1) x cols [0, lc1)
     int ev;                 // tile-group event after which the rectangle is final
     bool direct;            // copy engine writes straight into the caller's (pinned) buffer
-    int ntype;              // transport type: 0 double; 1 int32 / 2 uint16 deficiency (pair counts only), widened by the host
+    int ntype;              // transport type: 0 double; 1 int32 / 2 uint16 deficiency (pair counts only), 3 float (A, cfg.a_transport); 1-3 are widened by the host
     bool tiles;             // tile-range job (dgrm_bind_tiles): b indexes tbind, elements [t0, t1) of the tile store
     int64_t t0, t1;
   };
   std::vector<OutJob> jobs;
   size_t jobs_issued = 0, jobs_done = 0;
+  int64_t d2h_bytes = 0;      // bytes the copy engine moved for the streamed outputs of the last dgrm_finish
+  double* d_diag_a = nullptr; // fp32 transport: exact fp64 A_ii of the visible individuals, delivered after the last job
+  double* h_diag_a = nullptr;
   std::vector<int> rg_end;    // per raster row group: end index in `work` of its last owned supertile
   std::vector<int> rg_row1;   // per raster row group: one past its last global row
 
@@ -251,7 +259,11 @@ void release_geometry(dgrm_engine* e) {
   free_dev(e->d_N); e->d_N = nullptr;
   free_dev(e->d_diag); e->d_diag = nullptr;
   free_dev(e->d_miss); e->d_miss = nullptr;
+  free_dev(e->d_diag_a); e->d_diag_a = nullptr;
+  if (e->h_diag_a) cudaFreeHost(e->h_diag_a);
+  e->h_diag_a = nullptr;
   free_dev(e->d_subset); e->d_subset = nullptr;
+  e->h_subset.clear();
   e->n_out = 0;
   free_dev(e->d_S2); e->d_S2 = nullptr;
   free_dev(e->d_N2); e->d_N2 = nullptr;
@@ -301,7 +313,7 @@ int make_tmap(dgrm_engine* e, CUtensorMap* map, void* base, int elem_bytes, int6
 // K supertiles: equal work (every tile costs the same), and its concurrent CTAs share A/B panels exactly as on
 // one GPU (dealing tiles round-robin gave each engine one row of every column: 1 + 74 panels per k-block
 // instead of 8 + 9, and the contraction ran 20 % slower at 8 GPUs).
-void build_tiles(dgrm_engine* e) {
+int build_tiles(dgrm_engine* e) {
   const int T = (int)(e->n_pad / 256);
   const int GR = 8;
   e->nrb = 2 * T;
@@ -309,7 +321,8 @@ void build_tiles(dgrm_engine* e) {
   e->work.clear();
   e->work_cg1.clear();
   e->tile_rc.clear();
-  std::vector<int32_t> index((size_t)e->nrb * e->ncp, -1);
+  std::vector<int32_t>& index = e->h_index;   // host copy: ownership tests of the multi-engine readers
+  index.assign((size_t)e->nrb * e->ncp, -1);
   e->rg_end.clear();
   e->rg_row1.clear();
   int64_t s = 0, ls = 0;
@@ -338,20 +351,21 @@ void build_tiles(dgrm_engine* e) {
   for (int g = 0; g < T; g += GR) e->rg_row1.push_back(std::min(g + GR, T) * 256);
   e->ntiles = 2 * ls;
   // upload
-  cudaMalloc(&e->d_index, index.size() * sizeof(int32_t));
-  cudaMemcpy(e->d_index, index.data(), index.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  CK(cudaMalloc(&e->d_index, index.size() * sizeof(int32_t)));
+  CK(cudaMemcpy(e->d_index, index.data(), index.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   if (!e->work_cg1.empty()) {
     std::vector<int2> rc(e->work_cg1.size());
     for (size_t t = 0; t < e->work_cg1.size(); ++t) rc[(size_t)e->work_cg1[t].z] = make_int2(e->work_cg1[t].x, e->work_cg1[t].y);
-    cudaMalloc(&e->d_tile_rc, rc.size() * sizeof(int2));
-    cudaMemcpy(e->d_tile_rc, rc.data(), rc.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    CK(cudaMalloc(&e->d_tile_rc, rc.size() * sizeof(int2)));
+    CK(cudaMemcpy(e->d_tile_rc, rc.data(), rc.size() * sizeof(int2), cudaMemcpyHostToDevice));
   }
   if (!e->work.empty()) {
-    cudaMalloc(&e->d_work, e->work.size() * sizeof(int4));
-    cudaMemcpy(e->d_work, e->work.data(), e->work.size() * sizeof(int4), cudaMemcpyHostToDevice);
-    cudaMalloc(&e->d_work_cg1, e->work_cg1.size() * sizeof(int4));
-    cudaMemcpy(e->d_work_cg1, e->work_cg1.data(), e->work_cg1.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    CK(cudaMalloc(&e->d_work, e->work.size() * sizeof(int4)));
+    CK(cudaMemcpy(e->d_work, e->work.data(), e->work.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&e->d_work_cg1, e->work_cg1.size() * sizeof(int4)));
+    CK(cudaMemcpy(e->d_work_cg1, e->work_cg1.data(), e->work_cg1.size() * sizeof(int4), cudaMemcpyHostToDevice));
   }
+  return DGRM_OK;
 }
 
 TileStore tile_store(const dgrm_engine* e) {
@@ -373,12 +387,7 @@ TileStore tile_store(const dgrm_engine* e) {
 template <int CG, int KIND, typename OutT>
 int launch_syrk(dgrm_engine* e, const CUtensorMap& tmap, const SyrkParams& p) {
   using Cfg = SyrkCfg<CG>;
-  auto kern = grm_syrk_kernel<CG, KIND, OutT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  auto kern = grm_syrk_kernel<CG, KIND, OutT>;   // its dynamic shared memory limit is raised per device in dgrm_create
   const int units = std::min<int>(p.work_end - p.work_begin, (e->sm_count - e->reserve_sms) / CG);
   if (units <= 0) return DGRM_OK;
   cudaLaunchConfig_t lc{};
@@ -477,12 +486,22 @@ int process_chunk(dgrm_engine* e) {
   return DGRM_OK;
 }
 
-bool binding_streams(const dgrm_engine::Binding& bd) { return bd.uplo == 0; }
+// Rectangles of a block-cyclic binding stream out row group by row group only when this engine owns the whole
+// triangle: a partial owner would have to leave the other engines' entries of the caller's buffer alone, which the
+// strided copy-engine transfers cannot do.  With world > 1 such bindings are filled at the end of dgrm_finish
+// (owned entries only); dgrm_bind_tiles is the streaming egress of a multi-engine run.
+bool binding_streams(const dgrm_engine* e, const dgrm_engine::Binding& bd) { return bd.uplo == 0 && e->cfg.world == 1; }
 
 bool streaming_bound(const dgrm_engine* e) {
   bool s = e->ntbind > 0;
-  for (int b = 0; b < e->nbind; ++b) s |= binding_streams(e->bind[b]);
+  for (int b = 0; b < e->nbind; ++b) s |= binding_streams(e, e->bind[b]);
   return s;
+}
+
+// Does this engine own the tile that holds lower-triangle element (r >= c) of the visible matrix?
+inline bool owns_element(const dgrm_engine* e, int r, int c) {
+  if (!e->h_subset.empty()) { r = e->h_subset[(size_t)r]; c = e->h_subset[(size_t)c]; }
+  return e->h_index[(size_t)(r >> 7) * e->ncp + (c >> 8)] >= 0;
 }
 
 // first local index whose global index is >= target (block-cyclic, monotone)
@@ -494,6 +513,10 @@ int first_local_ge(int target, int nloc, int bs, int me, int P) {
     if (gidx >= target) b = mid; else a = mid + 1;
   }
   return a;
+}
+
+inline size_t transport_size(int ntype) {
+  return ntype == 2 ? sizeof(uint16_t) : (ntype == 1 || ntype == 3) ? sizeof(int32_t) : sizeof(double);
 }
 
 // Issue output job k: pack kernel (out_stream) -> device staging -> copy engine (d2h_stream) -> either the
@@ -519,6 +542,9 @@ int issue_job(dgrm_engine* e, size_t k) {
       else if (j.ntype == 1)
         export_tiles_kernel<int><<<blocks, 256, 0, e->out_stream>>>(ts, tb.which, cnt, (int*)e->d_out_stage[sl],
                                                                    e->d_tile_rc, j.t0 / kTileElems, e->d_diag);
+      else if (j.ntype == 3)
+        export_tiles_kernel<float><<<blocks, 256, 0, e->out_stream>>>(ts, tb.which, cnt, (float*)e->d_out_stage[sl],
+                                                                     e->d_tile_rc, j.t0 / kTileElems, e->d_diag);
       else
         export_tiles_kernel<double><<<blocks, 256, 0, e->out_stream>>>(ts, tb.which, cnt, (double*)e->d_out_stage[sl],
                                                                       e->d_tile_rc, j.t0 / kTileElems, e->d_diag);
@@ -528,9 +554,10 @@ int issue_job(dgrm_engine* e, size_t k) {
     CK(cudaStreamWaitEvent(e->d2h_stream, e->stage_packed[sl], 0));
     {
       Prof pr(e, DGRM_K_D2H, e->d2h_stream);
-      const size_t es = j.ntype == 2 ? sizeof(uint16_t) : j.ntype == 1 ? sizeof(int32_t) : sizeof(double);
+      const size_t es = transport_size(j.ntype);
       void* dst = j.direct ? (void*)(tb.host + j.t0) : e->h_out_stage[sl];
       CK(cudaMemcpyAsync(dst, e->d_out_stage[sl], (size_t)cnt * es, cudaMemcpyDeviceToHost, e->d2h_stream));
+      e->d2h_bytes += (int64_t)cnt * (int64_t)es;
     }
     CK(cudaEventRecord(e->stage_copied_out[sl], e->d2h_stream));
     return DGRM_OK;
@@ -550,6 +577,9 @@ int issue_job(dgrm_engine* e, size_t k) {
     else if (j.ntype == 1)
       pack_rows_kernel<int><<<grid, blk, 0, e->out_stream>>>(ts, bd.which, e->d_diag, (int*)e->d_out_stage[sl], g, j.lr0,
                                                             j.lr1, j.lc1);
+    else if (j.ntype == 3)
+      pack_rows_kernel<float><<<grid, blk, 0, e->out_stream>>>(ts, bd.which, e->d_diag, (float*)e->d_out_stage[sl], g, j.lr0,
+                                                              j.lr1, j.lc1);
     else
       pack_rows_kernel<double><<<grid, blk, 0, e->out_stream>>>(ts, bd.which, e->d_diag, (double*)e->d_out_stage[sl], g,
                                                                j.lr0, j.lr1, j.lc1);
@@ -562,9 +592,10 @@ int issue_job(dgrm_engine* e, size_t k) {
     // 256-column strips that start at their own diagonal (so almost nothing above the diagonal is moved)
     Prof pr(e, DGRM_K_D2H, e->d2h_stream);
     const int h = j.lr1 - j.lr0;
-    const size_t es = j.ntype == 2 ? sizeof(uint16_t) : j.ntype == 1 ? sizeof(int32_t) : sizeof(double);
+    const size_t es = transport_size(j.ntype);
     auto copy_rect = [&](int lra, int lrb, int lca, int lcb) -> cudaError_t {
       if (lrb <= lra || lcb <= lca) return cudaSuccess;
+      e->d2h_bytes += (int64_t)(lrb - lra) * (lcb - lca) * (int64_t)es;
       const char* src = (const char*)e->d_out_stage[sl] + ((int64_t)lca * h + (lra - j.lr0)) * es;
       if (j.direct)
         return cudaMemcpy2DAsync(bd.host + (int64_t)lca * g.lld + lra, (size_t)g.lld * sizeof(double), src, (size_t)h * es,
@@ -579,6 +610,7 @@ int issue_job(dgrm_engine* e, size_t k) {
       // diagonal block ride along (the host ignores them)
       CK(cudaMemcpyAsync(e->h_out_stage[sl], e->d_out_stage[sl], (size_t)h * (size_t)j.lc1 * es, cudaMemcpyDeviceToHost,
                          e->d2h_stream));
+      e->d2h_bytes += (int64_t)h * j.lc1 * (int64_t)es;
       CK(cudaEventRecord(e->stage_copied_out[sl], e->d2h_stream));
       return DGRM_OK;
     }
@@ -610,6 +642,23 @@ __attribute__((target("avx2"))) void widen_i32_stream(double* dst, const int32_t
 void widen_i32(double* dst, const int32_t* src, int cnt, bool stream) {
 #if defined(__x86_64__)
   if (stream) return widen_i32_stream(dst, src, cnt);
+#endif
+  for (int i = 0; i < cnt; ++i) dst[i] = (double)src[i];
+}
+
+// fp32 transport of A -> the caller's fp64 matrix
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void widen_f32_stream(double* dst, const float* src, int cnt) {
+  int i = 0;
+  for (; i < cnt && ((uintptr_t)(dst + i) & 31); ++i) dst[i] = (double)src[i];
+  for (; i + 4 <= cnt; i += 4) _mm256_stream_pd(dst + i, _mm256_cvtps_pd(_mm_loadu_ps(src + i)));
+  for (; i < cnt; ++i) dst[i] = (double)src[i];
+}
+#endif
+
+void widen_f32(double* dst, const float* src, int cnt, bool stream) {
+#if defined(__x86_64__)
+  if (stream) return widen_f32_stream(dst, src, cnt);
 #endif
   for (int i = 0; i < cnt; ++i) dst[i] = (double)src[i];
 }
@@ -668,6 +717,7 @@ int finish_job(dgrm_engine* e, size_t k) {
       const int c = (int)std::min<int64_t>(1 << 16, cnt - o);
       if (ntype == 2) widen_u16(dst + o, (const uint16_t*)src + o, c, m_total, nt);
       else if (ntype == 1) widen_i32(dst + o, (const int32_t*)src + o, c, nt);
+      else if (ntype == 3) widen_f32(dst + o, (const float*)src + o, c, nt);
       else memcpy(dst + o, (const double*)src + o, (size_t)c * sizeof(double));
 #if defined(__x86_64__)
       _mm_sfence();   // non-temporal stores are weakly ordered
@@ -695,6 +745,8 @@ int finish_job(dgrm_engine* e, size_t k) {
       widen_u16(dst, (const uint16_t*)hs + (int64_t)lc * h + (lra - lr0), cnt, m_total, nt);
     } else if (ntype == 1) {
       widen_i32(dst, (const int32_t*)hs + (int64_t)lc * h + (lra - lr0), cnt, nt);
+    } else if (ntype == 3) {
+      widen_f32(dst, (const float*)hs + (int64_t)lc * h + (lra - lr0), cnt, nt);
     } else {
       memcpy(dst, (const double*)hs + (int64_t)lc * h + (lra - lr0), (size_t)cnt * sizeof(double));
     }
@@ -702,6 +754,59 @@ int finish_job(dgrm_engine* e, size_t k) {
 #if defined(__x86_64__)
   _mm_sfence();
 #endif
+  }
+  return DGRM_OK;
+}
+
+// fp32 transport: the streamed A values were rounded to fp32 on their way out; the diagonal (which the engine
+// holds as the exact fp64 sum of squares) is delivered separately as doubles and patched into the bound buffers.
+int deliver_exact_diagonal(dgrm_engine* e) {
+  if (e->cfg.a_transport != DGRM_TRANSPORT_FP32) return DGRM_OK;
+  bool any_rect = false, any_tiles = false;
+  for (int b = 0; b < e->nbind; ++b) any_rect |= binding_streams(e, e->bind[b]) && e->bind[b].which == DGRM_FETCH_A;
+  for (int b = 0; b < e->ntbind; ++b) any_tiles |= e->tbind[b].which == DGRM_FETCH_A;
+  if (!any_rect && !any_tiles) return DGRM_OK;
+  if (!e->d_diag_a) {
+    CK(cudaMalloc(&e->d_diag_a, (size_t)e->n_pad * sizeof(double)));
+    CK(cudaHostAlloc(&e->h_diag_a, (size_t)e->n_pad * sizeof(double), cudaHostAllocDefault));
+  }
+  // stream order puts this after the last tile group; cnt values of A_ii as doubles
+  auto fetch_diag = [&](const TileStore& ts, int cnt) -> int {
+    diag_values_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(ts, DGRM_FETCH_A, e->d_diag, e->d_diag_a, cnt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_diag_a, e->d_diag_a, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->d2h_bytes += (int64_t)cnt * 8;
+    return DGRM_OK;
+  };
+  if (any_rect) {   // block-cyclic bindings see the visible individuals (output subset)
+    const int n_vis = (int)(e->d_subset ? e->n_out : e->n);
+    const int rc = fetch_diag(tile_store(e), n_vis);
+    if (rc) return rc;
+    for (int b = 0; b < e->nbind; ++b) {
+      const dgrm_engine::Binding& bd = e->bind[b];
+      if (!binding_streams(e, bd) || bd.which != DGRM_FETCH_A) continue;
+      const CyclicGeom& g = bd.g;
+      for (int i = 0; i < n_vis; ++i) {
+        if ((i / g.bs_r) % g.R != g.my_row || (i / g.bs_c) % g.C != g.my_col || !owns_element(e, i, i)) continue;
+        const int lr = (i / g.bs_r / g.R) * g.bs_r + i % g.bs_r, lc = (i / g.bs_c / g.C) * g.bs_c + i % g.bs_c;
+        bd.host[(int64_t)lc * g.lld + lr] = e->h_diag_a[i];
+      }
+    }
+  }
+  if (any_tiles) {  // tile bindings hold the engine's own tiles: every individual, no subset
+    TileStore ts = tile_store(e);
+    ts.subset = nullptr;
+    ts.n = (int)e->n;
+    const int rc = fetch_diag(ts, (int)e->n);
+    if (rc) return rc;
+    for (int b = 0; b < e->ntbind; ++b) {
+      if (e->tbind[b].which != DGRM_FETCH_A) continue;
+      for (int i = 0; i < (int)e->n; ++i) {
+        const int sidx = e->h_index[(size_t)(i >> 7) * e->ncp + (i >> 8)];
+        if (sidx >= 0) e->tbind[b].host[(int64_t)sidx * kTileElems + (int64_t)(i & 255) * kTileM + (i & 127)] = e->h_diag_a[i];
+      }
+    }
   }
   return DGRM_OK;
 }
@@ -775,20 +880,22 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
       // output jobs: one per (raster row group, streaming binding), in the order the row groups finish
       e->jobs.clear();
       e->jobs_issued = e->jobs_done = 0;
+      e->d2h_bytes = 0;
       size_t need = 0;
       for (size_t rg = 0; rg < e->rg_row1.size(); ++rg) {
         const int row0 = rg == 0 ? 0 : e->rg_row1[rg - 1], row1 = std::min<int>(e->rg_row1[rg], (int)e->n);
         if (row0 >= row1) continue;
         for (int b = 0; b < e->nbind; ++b) {
           const dgrm_engine::Binding& bd = e->bind[b];
-          if (!binding_streams(bd)) continue;
+          if (!binding_streams(e, bd)) continue;
           dgrm_engine::OutJob j;
-          j.b = b; j.row0 = row0; j.row1 = row1; j.ev = rg_group[rg];
+          j.b = b; j.row0 = row0; j.row1 = row1; j.ev = std::max(0, rg_group[rg]);
           j.lr0 = first_local_ge(row0, bd.g.nloc_r, bd.g.bs_r, bd.g.my_row, bd.g.R);
           j.lr1 = first_local_ge(row1, bd.g.nloc_r, bd.g.bs_r, bd.g.my_row, bd.g.R);
           j.lc1 = first_local_ge(row1, bd.g.nloc_c, bd.g.bs_c, bd.g.my_col, bd.g.C);
           if (j.lr1 <= j.lr0 || j.lc1 <= 0) continue;
-          j.ntype = (bd.which == DGRM_FETCH_N && !e->cfg.flat_norm) ? (e->n_u16 ? 2 : 1) : 0;
+          j.ntype = (bd.which == DGRM_FETCH_N && !e->cfg.flat_norm) ? (e->n_u16 ? 2 : 1)
+                    : (bd.which == DGRM_FETCH_A && e->cfg.a_transport == DGRM_TRANSPORT_FP32) ? 3 : 0;
           j.direct = bd.dev != nullptr && j.ntype == 0;
           j.tiles = false;
           j.t0 = j.t1 = 0;
@@ -805,7 +912,8 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
           for (int b = 0; b < e->ntbind; ++b) {
             dgrm_engine::OutJob j{};
             j.b = b; j.ev = (int)gi; j.tiles = true;
-            j.ntype = (e->tbind[b].which == DGRM_FETCH_N && !e->cfg.flat_norm) ? (e->n_u16 ? 2 : 1) : 0;
+            j.ntype = (e->tbind[b].which == DGRM_FETCH_N && !e->cfg.flat_norm) ? (e->n_u16 ? 2 : 1)
+                      : (e->tbind[b].which == DGRM_FETCH_A && e->cfg.a_transport == DGRM_TRANSPORT_FP32) ? 3 : 0;
             j.direct = e->tbind[b].pinned && j.ntype == 0;
             j.t0 = (int64_t)w0g * per_work;
             j.t1 = (int64_t)group_end[gi] * per_work;
@@ -913,6 +1021,10 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
         rc = finish_job(e, e->jobs_done);
         if (rc) return rc;
         e->jobs_done++;
+      }
+      {
+        const int rc = deliver_exact_diagonal(e);
+        if (rc) return rc;
       }
       if (getenv("DGRM_TRACE_OUT"))
         fprintf(stderr, "[dgrm] %zu output jobs: waited %.2f ms for the copy engine, %.2f ms in host conversion\n",
@@ -1098,6 +1210,7 @@ int dgrm_default_config(dgrm_config* cfg) {
   cfg->resident_chunks = 0;  // auto
   cfg->resident_mb = 16384;
   cfg->reserve_sms = -1;
+  cfg->a_transport = DGRM_TRANSPORT_FP64;
   return DGRM_OK;
 }
 
@@ -1118,6 +1231,8 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   if (cfg->operand < 0 || cfg->operand > DGRM_OPERAND_FP16X2 || cfg->count_method < 0 ||
       cfg->count_method > DGRM_COUNT_FP4)
     return fail(nullptr, DGRM_E_INVALID, "dgrm_create: bad operand/count_method");
+  if (cfg->a_transport != DGRM_TRANSPORT_FP64 && cfg->a_transport != DGRM_TRANSPORT_FP32)
+    return fail(nullptr, DGRM_E_INVALID, "dgrm_create: bad a_transport");
   int ndev = 0;
   cudaError_t st = cudaGetDeviceCount(&ndev);
   if (st != cudaSuccess || ndev == 0)
@@ -1185,6 +1300,15 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
                            (int)cudaSharedmemCarveoutMaxShared));
   CKC(cudaFuncSetAttribute(pack_rows_kernel<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)cudaSharedmemCarveoutMaxShared));
+  CKC(cudaFuncSetAttribute(pack_rows_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared));
+  // kernel attributes are per device: every engine sets them for its own (a process may drive several GPUs)
+#define DGRM_SYRK_ATTR(CG, KIND, T)                                                                          \
+  CKC(cudaFuncSetAttribute(grm_syrk_kernel<CG, KIND, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SyrkCfg<CG>::kSmemBytes))
+  DGRM_SYRK_ATTR(1, 0, double); DGRM_SYRK_ATTR(2, 0, double);
+  DGRM_SYRK_ATTR(1, 1, int); DGRM_SYRK_ATTR(2, 1, int);
+  DGRM_SYRK_ATTR(1, 2, int); DGRM_SYRK_ATTR(2, 2, int);
+#undef DGRM_SYRK_ATTR
 #define DGRM_EXPAND_ATTR(B, S, K)                                                                          \
   CKC(cudaFuncSetAttribute(bed_expand_kernel<B, S, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem)))
   DGRM_EXPAND_ATTR(false, false, 0); DGRM_EXPAND_ATTR(false, false, 1); DGRM_EXPAND_ATTR(false, false, 2); DGRM_EXPAND_ATTR(false, false, 3);
@@ -1265,8 +1389,10 @@ int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask
     CK(cudaMalloc(&e->d_src_ind, src.size() * sizeof(int32_t)));
     CK(cudaMemcpy(e->d_src_ind, src.data(), src.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
-  build_tiles(e);
-  CK(cudaGetLastError());
+  {
+    const int rc = build_tiles(e);
+    if (rc) return rc;
+  }
   const int kc = e->kc_max;
   if (e->ntiles > 0) {
     CK(cudaMalloc(&e->d_S, (size_t)e->ntiles * kTileElems * sizeof(double)));
@@ -1338,6 +1464,7 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
     CK(cudaStreamSynchronize(e->stream));
     free_dev(e->d_subset);
     e->d_subset = nullptr;
+    e->h_subset.clear();
     e->n_out = 0;
   }
   // a GRM that was abandoned before dgrm_finish may still have contractions in flight
@@ -1376,8 +1503,11 @@ int dgrm_push_bed_device(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, i
 int dgrm_release_inputs(dgrm_engine* e, void* consumer_stream) {
   if (!e) return DGRM_E_INVALID;
   CK(cudaSetDevice(e->cfg.device));
-  // the row gather into the chunk buffer is the only reader of caller memory and runs on the decode stream
+  // readers of caller memory: the row gather into the chunk buffer (decode stream) and the host-to-device copies
+  // of dgrm_push_bed_host (copy stream)
   CK(cudaEventRecord(e->producer_ev, e->prep));
+  CK(cudaStreamWaitEvent((cudaStream_t)consumer_stream, e->producer_ev, 0));
+  CK(cudaEventRecord(e->producer_ev, e->copy_stream));
   CK(cudaStreamWaitEvent((cudaStream_t)consumer_stream, e->producer_ev, 0));
   return DGRM_OK;
 }
@@ -1488,7 +1618,7 @@ int dgrm_finish(dgrm_engine* e) {
     // bindings that could not stream (pageable memory, uplo U/B, or nothing was contracted): fill them now
     for (int b = 0; b < e->nbind; ++b) {
       const dgrm_engine::Binding& bd = e->bind[b];
-      if (binding_streams(bd) && e->chunks_done > 0 && !e->work.empty()) continue;
+      if (binding_streams(e, bd) && e->chunks_done > 0 && !e->work.empty()) continue;
       const char up = bd.uplo == 0 ? 'L' : bd.uplo == 1 ? 'U' : 'B';
       rc = dgrm_fetch_block_cyclic(e, bd.which, bd.host, bd.g.lld, bd.g.bs_r, bd.g.bs_c, bd.g.my_row, bd.g.my_col, bd.g.R,
                                    bd.g.C, up);
@@ -1617,8 +1747,9 @@ int dgrm_bad_snps(dgrm_engine* e, int64_t* idx, int64_t cap, int64_t* count) {
   return DGRM_OK;
 }
 
-int dgrm_fetch_block_cyclic(dgrm_engine* e, int which, double* local, int64_t lld, int bs_r, int bs_c, int my_row,
-                            int my_col, int R, int C, char uplo) {
+// local columns [lcb, lce) of the caller's block (lce < 0: all of them); `local` points at column lcb
+int dgrm_fetch_block_cyclic_cols(dgrm_engine* e, int which, double* local, int64_t lld, int bs_r, int bs_c, int my_row,
+                                 int my_col, int R, int C, char uplo, int64_t lcb, int64_t lce) {
   int rc = check_ready(e, true);
   if (rc) return rc;
   if (!local || which < 0 || which > 2 || bs_r < 1 || bs_c < 1 || R < 1 || C < 1 || my_row < 0 || my_row >= R ||
@@ -1634,76 +1765,106 @@ int dgrm_fetch_block_cyclic(dgrm_engine* e, int which, double* local, int64_t ll
   g.nloc_c = numroc(n_vis, bs_c, my_col, C);
   if (g.nloc_r == 0 || g.nloc_c == 0) return DGRM_OK;
   if (lld < g.nloc_r) return fail(e, DGRM_E_INVALID, "dgrm_fetch_block_cyclic: lld %lld < local rows %d", (long long)lld, g.nloc_r);
+  if (lce < 0) { lcb = 0; lce = g.nloc_c; }
+  if (lcb < 0 || lce > g.nloc_c || lcb > lce)
+    return fail(e, DGRM_E_INVALID, "dgrm_fetch_block_cyclic_cols: bad local column range [%lld, %lld) of %d", (long long)lcb,
+                (long long)lce, g.nloc_c);
+  if (lcb == lce) return DGRM_OK;
+  const int lc_begin = (int)lcb, lc_end = (int)lce;
   const TileStore ts = tile_store(e);
   const dim3 blk(128, 2);
 
   cudaPointerAttributes attr;
-  const bool pinned = cudaPointerGetAttributes(&attr, local) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
-                      attr.devicePointer != nullptr;
+  const bool have_attr = cudaPointerGetAttributes(&attr, local) == cudaSuccess;
   cudaGetLastError();
-  if (pinned) {
-    // zero-copy: the kernel stores straight into the caller's pinned Matrix::m over PCIe
+  const bool on_device = have_attr && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) &&
+                         attr.devicePointer != nullptr;
+  const bool pinned = have_attr && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+  if (pinned || on_device) {
+    // pinned host memory: zero-copy, the kernel stores straight into the caller's Matrix::m over PCIe.
+    // device memory (a multi-engine caller's exchange panel, dgrm.h): plain stores.  Either way only entries of
+    // tiles this engine owns are written.
     Prof pr(e, DGRM_K_FETCH);
     g.lld = lld;
     const int PC = 4096;
-    for (int lc0 = 0; lc0 < g.nloc_c; lc0 += PC) {
-      const int lc1 = std::min(lc0 + PC, g.nloc_c);
+    for (int lc0 = lc_begin; lc0 < lc_end; lc0 += PC) {
+      const int lc1 = std::min(lc0 + PC, lc_end);
       const dim3 grid((g.nloc_r + 127) / 128, (lc1 - lc0 + 1) / 2);
-      fetch_block_cyclic_kernel<<<grid, blk, 0, e->stream>>>(ts, which, (double*)attr.devicePointer + (int64_t)lc0 * lld,
+      fetch_block_cyclic_kernel<<<grid, blk, 0, e->stream>>>(ts, which, (double*)attr.devicePointer + (int64_t)(lc0 - lc_begin) * lld,
                                                             g, lc0, lc1, up);
       CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(e->stream));
     return DGRM_OK;
   }
-  // pageable destination: device panel -> pinned panel -> memcpy of exactly the requested rows
-  const int PC = (int)std::max<int64_t>(1, std::min<int64_t>(g.nloc_c, (64 << 20) / ((int64_t)g.nloc_r * 8)));
-  double* d_panel[2] = {nullptr, nullptr};
-  double* h_panel[2] = {nullptr, nullptr};
-  cudaEvent_t done[2];
+  // pageable destination: device panel -> pinned panel -> memcpy of exactly the requested (and owned) rows
+  const int PC = (int)std::max<int64_t>(1, std::min<int64_t>(lc_end - lc_begin, (64 << 20) / ((int64_t)g.nloc_r * 8)));
+  struct Panels {
+    double* d[2] = {nullptr, nullptr};
+    double* h[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    ~Panels() {
+      for (int i = 0; i < 2; ++i) {
+        if (d[i]) cudaFree(d[i]);
+        if (h[i]) cudaFreeHost(h[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+      }
+    }
+  } pn;
   for (int i = 0; i < 2; ++i) {
-    CK(cudaMalloc(&d_panel[i], (size_t)PC * g.nloc_r * sizeof(double)));
-    CK(cudaHostAlloc(&h_panel[i], (size_t)PC * g.nloc_r * sizeof(double), cudaHostAllocDefault));
-    CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    CK(cudaMalloc(&pn.d[i], (size_t)PC * g.nloc_r * sizeof(double)));
+    CK(cudaHostAlloc(&pn.h[i], (size_t)PC * g.nloc_r * sizeof(double), cudaHostAllocDefault));
+    CK(cudaEventCreateWithFlags(&pn.done[i], cudaEventDisableTiming));
   }
   g.lld = g.nloc_r;
+  const bool partial = e->cfg.world > 1;   // then only the runs of owned tiles may touch the caller's buffer
+  auto first_ge = [&](int target) { return first_local_ge(target, g.nloc_r, bs_r, my_row, R); };
   auto drain = [&](int slot, int lc0, int lc1) -> int {
-    CK(cudaEventSynchronize(done[slot]));
+    CK(cudaEventSynchronize(pn.done[slot]));
     for (int lc = lc0; lc < lc1; ++lc) {
       const int gc = ((lc / bs_c) * C + my_col) * bs_c + lc % bs_c;
       int lo = 0, hi = g.nloc_r;  // local row range to copy
-      if (up != 2) {
-        // first local row whose global index is >= gc (+1 for strict)
-        auto first_ge = [&](int target) {
-          int a = 0, b = g.nloc_r;
-          while (a < b) {
-            const int mid = (a + b) / 2;
-            const int gr = ((mid / bs_r) * R + my_row) * bs_r + mid % bs_r;
-            if (gr >= target) b = mid; else a = mid + 1;
-          }
-          return a;
-        };
-        if (up == 0) lo = first_ge(gc); else hi = first_ge(gc + 1);
+      if (up == 0) lo = first_ge(gc); else if (up == 1) hi = first_ge(gc + 1);
+      if (hi <= lo) continue;
+      double* dst = local + (int64_t)(lc - lc_begin) * lld;
+      const double* src = pn.h[slot] + (int64_t)(lc - lc0) * g.nloc_r;
+      if (!partial) {
+        memcpy(dst + lo, src + lo, (size_t)(hi - lo) * sizeof(double));
+        continue;
       }
-      if (hi > lo)
-        memcpy(local + (int64_t)lc * lld + lo, h_panel[slot] + (int64_t)(lc - lc0) * g.nloc_r + lo,
-               (size_t)(hi - lo) * sizeof(double));
+      if (!e->h_subset.empty()) {   // ownership follows the individuals behind the subset: element by element
+        for (int lr = lo; lr < hi; ++lr) {
+          const int gr = ((lr / bs_r) * R + my_row) * bs_r + lr % bs_r;
+          if (owns_element(e, std::max(gr, gc), std::min(gr, gc))) dst[lr] = src[lr];
+        }
+        continue;
+      }
+      // runs inside one block-cyclic block, one 128-row tile and one side of the diagonal share an owner
+      for (int lr = lo; lr < hi;) {
+        const int gr = ((lr / bs_r) * R + my_row) * bs_r + lr % bs_r;
+        int run = std::min(hi - lr, bs_r - lr % bs_r);
+        run = std::min(run, 128 - (gr & 127));
+        if (gr < gc) run = std::min(run, gc - gr);
+        if (owns_element(e, std::max(gr, gc), std::min(gr, gc)))
+          memcpy(dst + lr, src + lr, (size_t)run * sizeof(double));
+        lr += run;
+      }
     }
     return DGRM_OK;
   };
   int prev_slot = -1, prev0 = 0, prev1 = 0, slot = 0;
-  for (int lc0 = 0; lc0 < g.nloc_c; lc0 += PC, slot ^= 1) {
-    const int lc1 = std::min(lc0 + PC, g.nloc_c);
+  for (int lc0 = lc_begin; lc0 < lc_end; lc0 += PC, slot ^= 1) {
+    const int lc1 = std::min(lc0 + PC, lc_end);
     {
       Prof pr(e, DGRM_K_FETCH);
-      CK(cudaMemsetAsync(d_panel[slot], 0, (size_t)(lc1 - lc0) * g.nloc_r * sizeof(double), e->stream));
+      CK(cudaMemsetAsync(pn.d[slot], 0, (size_t)(lc1 - lc0) * g.nloc_r * sizeof(double), e->stream));
       const dim3 grid((g.nloc_r + 127) / 128, (lc1 - lc0 + 1) / 2);
-      fetch_block_cyclic_kernel<<<grid, blk, 0, e->stream>>>(ts, which, d_panel[slot], g, lc0, lc1, up);
+      fetch_block_cyclic_kernel<<<grid, blk, 0, e->stream>>>(ts, which, pn.d[slot], g, lc0, lc1, up);
       CK(cudaGetLastError());
     }
-    CK(cudaMemcpyAsync(h_panel[slot], d_panel[slot], (size_t)(lc1 - lc0) * g.nloc_r * sizeof(double),
+    CK(cudaMemcpyAsync(pn.h[slot], pn.d[slot], (size_t)(lc1 - lc0) * g.nloc_r * sizeof(double),
                        cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaEventRecord(done[slot], e->stream));
+    CK(cudaEventRecord(pn.done[slot], e->stream));
     if (prev_slot >= 0) {
       rc = drain(prev_slot, prev0, prev1);
       if (rc) return rc;
@@ -1711,12 +1872,12 @@ int dgrm_fetch_block_cyclic(dgrm_engine* e, int which, double* local, int64_t ll
     prev_slot = slot; prev0 = lc0; prev1 = lc1;
   }
   if (prev_slot >= 0) rc = drain(prev_slot, prev0, prev1);
-  for (int i = 0; i < 2; ++i) {
-    cudaFree(d_panel[i]);
-    cudaFreeHost(h_panel[i]);
-    cudaEventDestroy(done[i]);
-  }
   return rc;
+}
+
+int dgrm_fetch_block_cyclic(dgrm_engine* e, int which, double* local, int64_t lld, int bs_r, int bs_c, int my_row,
+                            int my_col, int R, int C, char uplo) {
+  return dgrm_fetch_block_cyclic_cols(e, which, local, lld, bs_r, bs_c, my_row, my_col, R, C, uplo, 0, -1);
 }
 
 int dgrm_low_overlap_pairs(dgrm_engine* e, double min_overlap, int64_t* pairs, int64_t cap, int64_t* count) {
@@ -1724,68 +1885,132 @@ int dgrm_low_overlap_pairs(dgrm_engine* e, double min_overlap, int64_t* pairs, i
   if (rc) return rc;
   if (cap < 0 || (cap > 0 && !pairs) || !count) return fail(e, DGRM_E_INVALID, "dgrm_low_overlap_pairs: bad arguments");
   CK(cudaSetDevice(e->cfg.device));
-  int64_t* d_pairs = nullptr;
-  unsigned long long* d_count = nullptr;
-  CK(cudaMalloc(&d_count, sizeof(unsigned long long)));
-  if (cap > 0) CK(cudaMalloc(&d_pairs, (size_t)cap * 2 * sizeof(int64_t)));
-  CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), e->stream));
+  struct Bufs {
+    int64_t* pairs = nullptr;
+    unsigned long long* count = nullptr;
+    ~Bufs() { if (pairs) cudaFree(pairs); if (count) cudaFree(count); }
+  } bf;
+  CK(cudaMalloc(&bf.count, sizeof(unsigned long long)));
+  if (cap > 0) CK(cudaMalloc(&bf.pairs, (size_t)cap * 2 * sizeof(int64_t)));
+  CK(cudaMemsetAsync(bf.count, 0, sizeof(unsigned long long), e->stream));
   const int64_t n_vis = e->d_subset ? e->n_out : e->n;
   const dim3 grid((unsigned)((n_vis + 255) / 256), (unsigned)std::min<int64_t>(n_vis, 32768));
-  low_overlap_kernel<<<grid, 256, 0, e->stream>>>(tile_store(e), min_overlap, d_pairs, cap, d_count);
+  low_overlap_kernel<<<grid, 256, 0, e->stream>>>(tile_store(e), min_overlap, bf.pairs, cap, bf.count);
   CK(cudaGetLastError());
   unsigned long long c = 0;
-  CK(cudaMemcpyAsync(&c, d_count, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(&c, bf.count, sizeof c, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   *count = (int64_t)c;
   if (cap > 0 && c > 0)
-    CK(cudaMemcpy(pairs, d_pairs, (size_t)std::min<int64_t>(cap, (int64_t)c) * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost));
-  cudaFree(d_count);
-  if (d_pairs) cudaFree(d_pairs);
+    CK(cudaMemcpy(pairs, bf.pairs, (size_t)std::min<int64_t>(cap, (int64_t)c) * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  return DGRM_OK;
+}
+
+// Owned runs of file column c of the packed (n+1) x n array: rows pr <= c hold N[c][pr] (tile of (c, pr)), rows
+// pr > c hold A[pr-1][c] (tile of (pr-1, c)).  Appends [begin, end) row ranges, merged where adjacent.
+static void grm_dat_owned_runs(const dgrm_engine* e, int n, int c, std::vector<std::pair<int, int>>* runs) {
+  auto add = [&](int a, int b) {
+    if (!runs->empty() && runs->back().second == a) runs->back().second = b;
+    else runs->push_back({a, b});
+  };
+  if (e->cfg.world == 1) { add(0, n + 1); return; }
+  if (!e->h_subset.empty()) {  // ownership follows the individuals behind the subset: element by element
+    for (int pr = 0; pr <= n; ++pr)
+      if (pr <= c ? owns_element(e, c, pr) : owns_element(e, pr - 1, c)) add(pr, pr + 1);
+    return;
+  }
+  for (int pr = 0; pr <= c; pr += 256)
+    if (owns_element(e, c, pr)) add(pr, std::min(pr + 256, c + 1));
+  for (int r = c; r < n; r = (r | 127) + 1)
+    if (owns_element(e, r, c)) add(r + 1, std::min((r | 127) + 1, n) + 1);
+}
+
+int dgrm_write_grm_dat_part(dgrm_engine* e, const char* path, int create) {
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  if (!path) return fail(e, DGRM_E_INVALID, "dgrm_write_grm_dat: null path");
+  CK(cudaSetDevice(e->cfg.device));
+  const int n = (int)(e->d_subset ? e->n_out : e->n);
+  const int64_t col_elems = (int64_t)n + 1;
+  struct Res {
+    int fd = -1;
+    bool created = false, ok = false;
+    std::string path;
+    double* d_panel = nullptr;
+    double* h_panel = nullptr;
+    ~Res() {
+      if (d_panel) cudaFree(d_panel);
+      if (h_panel) cudaFreeHost(h_panel);
+      if (fd >= 0) close(fd);
+      if (created && !ok) unlink(path.c_str());   // no half-written <out>.grm.dat left behind by its creator
+    }
+  } rs;
+  rs.path = path;
+  rs.fd = create ? open(path, O_CREAT | O_TRUNC | O_WRONLY, 0644) : open(path, O_WRONLY);
+  if (rs.fd < 0) return fail(e, DGRM_E_IO, "cannot open [ %s ] for writing", path);
+  rs.created = create != 0;
+  if (create) {
+    // kernel.cpp:944-966
+    const unsigned char header[14] = {'G', 'R', 'M', 0, 0x5A, 0x99, 0x2, 0x1, (unsigned char)sizeof(double), 0x1, 0, 0, 0, 0};
+    if (pwrite(rs.fd, header, 14, 0) != 14 || ftruncate(rs.fd, 14 + col_elems * (int64_t)n * 8) != 0)
+      return fail(e, DGRM_E_IO, "short write to [ %s ]", path);
+  }
+  const int PC = (int)std::max<int64_t>(1, std::min<int64_t>(n, (64 << 20) / (col_elems * 8)));
+  CK(cudaMalloc(&rs.d_panel, (size_t)PC * col_elems * sizeof(double)));
+  CK(cudaHostAlloc(&rs.h_panel, (size_t)PC * col_elems * sizeof(double), cudaHostAllocDefault));
+  const TileStore ts = tile_store(e);
+  std::vector<std::vector<std::pair<int, int>>> runs((size_t)PC);
+  for (int c0 = 0; c0 < n; c0 += PC) {
+    const int c1 = std::min(c0 + PC, n);
+    // the row range of P this engine has anything in, over the panel's columns (the whole column when world == 1)
+    int pr0 = n + 1, pr1 = 0;
+    for (int c = c0; c < c1; ++c) {
+      auto& rv = runs[(size_t)(c - c0)];
+      rv.clear();
+      grm_dat_owned_runs(e, n, c, &rv);
+      if (!rv.empty()) { pr0 = std::min(pr0, rv.front().first); pr1 = std::max(pr1, rv.back().second); }
+    }
+    if (pr1 <= pr0) continue;
+    const int h = pr1 - pr0;
+    const dim3 grid((unsigned)((h + 255) / 256), (unsigned)(c1 - c0));
+    pack_grm_kernel<<<grid, 256, 0, e->stream>>>(ts, rs.d_panel, c0, c1, pr0, pr1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rs.h_panel, rs.d_panel, (size_t)(c1 - c0) * h * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->cfg.world == 1) {   // one contiguous piece of the file
+      const size_t bytes = (size_t)(c1 - c0) * col_elems * sizeof(double);
+      const char* src = (const char*)rs.h_panel;
+      for (size_t off = 0; off < bytes;) {
+        const ssize_t w = pwrite(rs.fd, src + off, bytes - off, 14 + (int64_t)c0 * col_elems * 8 + (int64_t)off);
+        if (w <= 0) return fail(e, DGRM_E_IO, "short write to [ %s ]", path);
+        off += (size_t)w;
+      }
+      continue;
+    }
+    for (int c = c0; c < c1; ++c)
+      for (const auto& r : runs[(size_t)(c - c0)]) {
+        const char* src = (const char*)(rs.h_panel + (int64_t)(c - c0) * h + (r.first - pr0));
+        const size_t bytes = (size_t)(r.second - r.first) * sizeof(double);
+        for (size_t off = 0; off < bytes;) {
+          const ssize_t w = pwrite(rs.fd, src + off, bytes - off, 14 + ((int64_t)c * col_elems + r.first) * 8 + (int64_t)off);
+          if (w <= 0) return fail(e, DGRM_E_IO, "short write to [ %s ]", path);
+          off += (size_t)w;
+        }
+      }
+  }
+  const int fd = rs.fd;
+  rs.fd = -1;
+  if (close(fd) != 0) return fail(e, DGRM_E_IO, "close failed on [ %s ]", path);
+  rs.ok = true;
   return DGRM_OK;
 }
 
 int dgrm_write_grm_dat(dgrm_engine* e, const char* path) {
-  int rc = check_ready(e, true);
-  if (rc) return rc;
-  if (e->cfg.world != 1) return fail(e, DGRM_E_INVALID, "dgrm_write_grm_dat needs the whole triangle (world == 1)");
-  if (!path) return fail(e, DGRM_E_INVALID, "dgrm_write_grm_dat: null path");
-  CK(cudaSetDevice(e->cfg.device));
-  FILE* f = fopen(path, "wb");
-  if (!f) return fail(e, DGRM_E_IO, "cannot open [ %s ] for writing", path);
-  // kernel.cpp:944-966
-  const unsigned char header[14] = {'G', 'R', 'M', 0, 0x5A, 0x99, 0x2, 0x1, (unsigned char)sizeof(double), 0x1, 0, 0, 0, 0};
-  if (fwrite(header, 1, 14, f) != 14) {
-    fclose(f);
-    return fail(e, DGRM_E_IO, "short write to [ %s ]", path);
-  }
-  const int n = (int)(e->d_subset ? e->n_out : e->n);
-  const int64_t col_elems = (int64_t)n + 1;
-  const int PC = (int)std::max<int64_t>(1, std::min<int64_t>(n, (64 << 20) / (col_elems * 8)));
-  double* d_panel = nullptr;
-  double* h_panel = nullptr;
-  CK(cudaMalloc(&d_panel, (size_t)PC * col_elems * sizeof(double)));
-  CK(cudaHostAlloc(&h_panel, (size_t)PC * col_elems * sizeof(double), cudaHostAllocDefault));
-  const TileStore ts = tile_store(e);
-  rc = DGRM_OK;
-  for (int c0 = 0; c0 < n; c0 += PC) {
-    const int c1 = std::min(c0 + PC, n);
-    const dim3 grid((unsigned)((col_elems + 255) / 256), (unsigned)(c1 - c0));
-    pack_grm_kernel<<<grid, 256, 0, e->stream>>>(ts, d_panel, c0, c1);
-    cudaMemcpyAsync(h_panel, d_panel, (size_t)(c1 - c0) * col_elems * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
-    if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
-      rc = fail(e, DGRM_E_CUDA, "pack_grm failed: %s", cudaGetErrorString(cudaGetLastError()));
-      break;
-    }
-    const size_t cnt = (size_t)(c1 - c0) * col_elems;
-    if (fwrite(h_panel, sizeof(double), cnt, f) != cnt) {
-      rc = fail(e, DGRM_E_IO, "short write to [ %s ]", path);
-      break;
-    }
-  }
-  cudaFree(d_panel);
-  cudaFreeHost(h_panel);
-  if (fclose(f) != 0 && rc == DGRM_OK) rc = fail(e, DGRM_E_IO, "close failed on [ %s ]", path);
-  return rc;
+  if (e && e->cfg.world != 1)
+    return fail(e, DGRM_E_INVALID,
+                "dgrm_write_grm_dat needs the whole triangle (world == 1); engines of a partition write their own "
+                "entries with dgrm_write_grm_dat_part");
+  return dgrm_write_grm_dat_part(e, path, 1);
 }
 
 int dgrm_set_output_subset(dgrm_engine* e, const int64_t* idx, int64_t count) {
@@ -1795,6 +2020,7 @@ int dgrm_set_output_subset(dgrm_engine* e, const int64_t* idx, int64_t count) {
   CK(cudaStreamSynchronize(e->stream));
   free_dev(e->d_subset);
   e->d_subset = nullptr;
+  e->h_subset.clear();
   e->n_out = 0;
   if (!idx || count <= 0) return DGRM_OK;
   std::vector<int32_t> v((size_t)count);
@@ -1807,6 +2033,7 @@ int dgrm_set_output_subset(dgrm_engine* e, const int64_t* idx, int64_t count) {
   }
   CK(cudaMalloc(&e->d_subset, (size_t)count * sizeof(int32_t)));
   CK(cudaMemcpy(e->d_subset, v.data(), (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice));
+  e->h_subset = v;
   e->n_out = count;
   return DGRM_OK;
 }
@@ -1871,9 +2098,13 @@ static int store_reserve(dgrm_engine* e, int64_t rows_total) {
   uint8_t* nb = nullptr;
   CK(cudaMalloc(&nb, (size_t)cap * pitch));
   if (e->d_bed && e->bed_rows > 0) {
-    CK(cudaStreamSynchronize(e->copy_stream));
-    CK(cudaStreamSynchronize(e->prep));
-    CK(cudaMemcpy(nb, e->d_bed, (size_t)e->bed_rows * pitch, cudaMemcpyDeviceToDevice));
+    cudaError_t st = cudaStreamSynchronize(e->copy_stream);
+    if (st == cudaSuccess) st = cudaStreamSynchronize(e->prep);
+    if (st == cudaSuccess) st = cudaMemcpy(nb, e->d_bed, (size_t)e->bed_rows * pitch, cudaMemcpyDeviceToDevice);
+    if (st != cudaSuccess) {
+      cudaFree(nb);
+      return fail(e, DGRM_E_CUDA, "growing the resident store failed: %s", cudaGetErrorString(st));
+    }
   }
   free_dev(e->d_bed);
   e->d_bed = nb;
@@ -1917,6 +2148,28 @@ int dgrm_store_bed_host(dgrm_engine* e, const uint8_t* rows, int64_t pitch, int6
   e->bed_rows += nrows;
   return DGRM_OK;
 }
+
+int dgrm_store_bed_device(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64_t nrows, void* producer_stream) {
+  if (!e) return DGRM_E_INVALID;
+  if (!e->have_ind) return fail(e, DGRM_E_INVALID, "dgrm_store_bed_device: call dgrm_set_individuals first");
+  if (!d_rows || nrows < 0 || pitch < e->b_fam) return fail(e, DGRM_E_INVALID, "dgrm_store_bed_device: bad rows/pitch");
+  if (e->bed_rows + nrows > INT32_MAX) return fail(e, DGRM_E_INVALID, "dgrm_store_bed_device: too many rows");
+  CK(cudaSetDevice(e->cfg.device));
+  const int rc = store_reserve(e, e->bed_rows + nrows);
+  if (rc) return rc;
+  if (nrows > 0) {
+    CK(cudaEventRecord(e->producer_ev, (cudaStream_t)producer_stream));
+    CK(cudaStreamWaitEvent(e->copy_stream, e->producer_ev, 0));
+    CK(cudaMemcpy2DAsync(e->d_bed + e->bed_rows * e->bed_pitch, (size_t)e->bed_pitch, d_rows, (size_t)pitch,
+                         (size_t)e->b_fam, (size_t)nrows, cudaMemcpyDeviceToDevice, e->copy_stream));
+    CK(cudaEventRecord(e->bed_ev, e->copy_stream));
+    CK(cudaStreamSynchronize(e->copy_stream));
+  }
+  e->bed_rows += nrows;
+  return DGRM_OK;
+}
+
+int64_t dgrm_last_d2h_bytes(const dgrm_engine* e) { return e ? e->d2h_bytes : 0; }
 
 int dgrm_store_bed_file(dgrm_engine* e, const char* bed_path, int64_t m_file) {
   if (!e) return DGRM_E_INVALID;

@@ -114,6 +114,27 @@ __device__ __forceinline__ uint16_t transport_encode<uint16_t>(double v, bool va
   return valid ? (uint16_t)(int)(m_total - v) : (uint16_t)0xFFFF;
 }
 
+template <>
+__device__ __forceinline__ float transport_encode<float>(double v, bool valid, double m_total) {
+  return valid ? (float)v : 0.f;
+}
+
+// out[i] = matrix `which` at (i, i) of the visible individuals under the store's view, from the exact fp64 diagonal
+// of S (0 when this engine does not own the diagonal tile).
+__global__ void diag_values_kernel(const TileStore ts, int which, const double* __restrict__ diag, double* __restrict__ out,
+                                   int n_vis) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_vis) return;
+  double v = 0.;
+  const int64_t slot = tile_slot(ts, i, i);
+  if (slot >= 0) {
+    double sv, nv;
+    view_sn(ts, slot, diag[ts.subset ? ts.subset[i] : i], &sv, &nv);
+    v = view_value(which, sv, nv);
+  }
+  out[i] = v;
+}
+
 template <typename T>
 __global__ void pack_rows_kernel(const TileStore ts, int which, const double* __restrict__ diag,
                                  T* __restrict__ stage, const CyclicGeom g, int lr0, int lr1, int lc1) {
@@ -159,14 +180,16 @@ __global__ void low_overlap_kernel(const TileStore ts, double min_overlap, int64
 // Packed (n+1) x n column-major array of packMatrices (matrix.cpp:2324-2334), columns [c0, c1):
 //   P[r][c] = N[r][c]   r = 0..c       (upper triangle of N incl. diagonal)
 //   P[r+1][c] = A[r][c] r = c..n-1     (lower triangle of A incl. diagonal)
-__global__ void pack_grm_kernel(const TileStore ts, double* __restrict__ dst, int c0, int c1) {
-  const int pr = blockIdx.x * blockDim.x + threadIdx.x;  // row of P, 0..n
+// Only rows [pr0, pr1) of P are produced (pitch pr1 - pr0): an engine of a partition packs just the row range its
+// tiles reach.  Entries of tiles the engine does not own are written as 0 and never leave the host staging.
+__global__ void pack_grm_kernel(const TileStore ts, double* __restrict__ dst, int c0, int c1, int pr0, int pr1) {
+  const int pr = pr0 + blockIdx.x * blockDim.x + threadIdx.x;  // row of P, 0..n
   const int c = c0 + blockIdx.y;
-  if (pr > ts.n || c >= c1) return;
+  if (pr >= pr1 || c >= c1) return;
   double v = 0.;
   if (pr <= c) tile_value(ts, 2, c, pr, &v);   // N[pr][c] = N[c][pr]
   else tile_value(ts, 0, pr - 1, c, &v);       // A[pr-1][c]
-  dst[(int64_t)(c - c0) * (ts.n + 1) + pr] = v;
+  dst[(int64_t)(c - c0) * (pr1 - pr0) + (pr - pr0)] = v;
 }
 
 // Per-individual count of missing genotypes over a packed chunk (rows = SNPs, 4 individuals per byte, pattern 01 =

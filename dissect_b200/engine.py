@@ -56,7 +56,7 @@ class PinnedArray:
 class GrmEngine:
     def __init__(self, device=0, rank=0, world=1, operand="fp16", count_method="fp4", flat_norm=False,
                  chunk_snps=16384, cta_group=2, profile=False, resident_chunks=0, resident_mb=16384,
-                 reserve_sms=-1):
+                 reserve_sms=-1, a_transport="fp64"):
         self._lib = _lib.load()
         cfg = _lib.Config()
         self._lib.dgrm_default_config(C.byref(cfg))
@@ -70,6 +70,7 @@ class GrmEngine:
         cfg.resident_chunks = resident_chunks
         cfg.resident_mb = resident_mb
         cfg.reserve_sms = reserve_sms
+        cfg.a_transport = _lib.TRANSPORT[a_transport]
         self.cfg = cfg
         h = C.c_void_p()
         rc = self._lib.dgrm_create(C.byref(cfg), C.byref(h))
@@ -151,6 +152,13 @@ class GrmEngine:
         assert rows.dtype == np.uint8 and rows.ndim == 2 and rows.strides[1] == 1
         self._ck(self._lib.dgrm_store_bed_host(self._h, rows.ctypes.data, rows.strides[0], rows.shape[0]))
 
+    def store_bed_device(self, ptr, pitch, nrows, stream=None):
+        self._ck(self._lib.dgrm_store_bed_device(self._h, int(ptr), int(pitch), int(nrows), stream))
+
+    @property
+    def last_d2h_bytes(self):
+        return int(self._lib.dgrm_last_d2h_bytes(self._h))
+
     def store_clear(self):
         self._ck(self._lib.dgrm_store_clear(self._h))
 
@@ -231,9 +239,16 @@ class GrmEngine:
                                                    uplo.encode()))
         return out
 
-    def fetch_into(self, which, ptr, lld, bs=(256, 256), grid=(1, 1), coords=(0, 0), uplo="L"):
-        self._ck(self._lib.dgrm_fetch_block_cyclic(self._h, _lib.FETCH[which], int(ptr), lld, bs[0], bs[1],
-                                                   coords[0], coords[1], grid[0], grid[1], uplo.encode()))
+    def fetch_into(self, which, ptr, lld, bs=(256, 256), grid=(1, 1), coords=(0, 0), uplo="L", cols=None):
+        """Fill caller memory at `ptr` (pageable / pinned host, or device memory of this GPU); `cols` = (lc0, lc1)
+        restricts to those local columns, `ptr` then addresses column lc0."""
+        if cols is None:
+            self._ck(self._lib.dgrm_fetch_block_cyclic(self._h, _lib.FETCH[which], int(ptr), lld, bs[0], bs[1],
+                                                       coords[0], coords[1], grid[0], grid[1], uplo.encode()))
+        else:
+            self._ck(self._lib.dgrm_fetch_block_cyclic_cols(self._h, _lib.FETCH[which], int(ptr), lld, bs[0], bs[1],
+                                                            coords[0], coords[1], grid[0], grid[1], uplo.encode(),
+                                                            int(cols[0]), int(cols[1])))
 
     def bind_output(self, which, ptr, lld, bs=(256, 256), grid=(1, 1), coords=(0, 0), uplo="L"):
         self._ck(self._lib.dgrm_bind_output(self._h, _lib.FETCH[which], int(ptr), lld, bs[0], bs[1], coords[0],
@@ -263,6 +278,10 @@ class GrmEngine:
 
     def write_grm_dat(self, path):
         self._ck(self._lib.dgrm_write_grm_dat(self._h, str(path).encode()))
+
+    def write_grm_dat_part(self, path, create):
+        """This engine's entries of <path> (multi-engine writer); `create` on exactly one engine, first."""
+        self._ck(self._lib.dgrm_write_grm_dat_part(self._h, str(path).encode(), int(bool(create))))
 
     @property
     def num_tiles(self):

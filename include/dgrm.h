@@ -47,6 +47,12 @@ extern "C" {
 #define DGRM_COUNT_POPC  1  /* AND + popcount over bit-packed non-missing masks               */
 #define DGRM_COUNT_FP4   2  /* 0/1 e2m1 operands through block-scaled tcgen05 kind::mxf4 (all scales 1.0), exact in fp32 */
 
+/* transport of streamed A values: fp64 as they are (default), or rounded to fp32 on the device and widened back by
+ * the library's host threads; the diagonal always arrives as the exact fp64 value.  fp32 adds a relative error
+ * <= 2^-24 = 6e-8 to A_ij (three orders below the operand tolerance) and halves the bytes of the largest stream. */
+#define DGRM_TRANSPORT_FP64 0
+#define DGRM_TRANSPORT_FP32 1
+
 /* which matrix dgrm_fetch_* returns */
 #define DGRM_FETCH_A  0  /* normalised GRM  A = S * (1/N)     (matrix.cpp:4096)               */
 #define DGRM_FETCH_S  1  /* unnormalised    S = Z^T Z         (kernel.cpp:94)                 */
@@ -80,7 +86,9 @@ typedef struct dgrm_config {
   int32_t reserve_sms;   /* SMs the persistent contraction leaves free for the caller's own kernels (e.g. NCCL
                             all-gather CTAs, which cannot co-reside with it); -1 or 0 = none.  Measured at 2 GPUs:
                             no net gain (the contraction loses what the exchange wins), so the default is 0 */
-  int32_t reserved[4];
+  int32_t a_transport;   /* DGRM_TRANSPORT_*: how STREAMED values of A (dgrm_bind_output / dgrm_bind_tiles) cross
+                            PCIe; the caller's buffer always receives doubles                                 */
+  int32_t reserved[3];
 } dgrm_config;
 
 /* Fill *cfg with defaults (device 0, rank 0/1, fp16 operands, fp4 pair count, chunk 16384, cta_group 2). */
@@ -110,16 +118,18 @@ int dgrm_begin(dgrm_engine *e, int64_t m_capacity);
  * Replaces readBEDFile's decode loop + parseSNP/parseSNPbyte (genotype.cpp:639-787),
  * normalizeGenotypes (genotype.cpp:888-961) and both pdsyrk_ calls (kernel.cpp:94,100) for
  * these rows.  The host variant copies host->device itself (asynchronously when `rows` is
- * pinned); the device variant reads rows already in HBM once `producer_stream` (a
- * cudaStream_t; NULL = the legacy default stream) reaches the point of the call. */
+ * pinned: a pinned `rows` buffer must then stay unchanged until dgrm_finish / dgrm_sync returns, or until a
+ * stream that dgrm_release_inputs has ordered after the engine's reads gets there); the device variant reads
+ * rows already in HBM once `producer_stream` (a cudaStream_t; NULL = the legacy default stream) reaches the
+ * point of the call. */
 int dgrm_push_bed_host(dgrm_engine *e, const uint8_t *rows, int64_t pitch, int64_t nrows,
                        const uint8_t *row_keep);
 int dgrm_push_bed_device(dgrm_engine *e, const uint8_t *d_rows, int64_t pitch, int64_t nrows,
                          const uint8_t *row_keep, void *producer_stream);
 
 /* Make `consumer_stream` (a cudaStream_t; NULL = legacy default stream) wait until the engine has read every
- * buffer handed to dgrm_push_bed_device so far, so that the caller may overwrite those buffers (e.g. with the
- * next NCCL all-gather) without a host synchronisation. */
+ * buffer handed to dgrm_push_bed_device / dgrm_push_bed_host so far, so that the caller may overwrite those
+ * buffers (e.g. with the next NCCL all-gather) without a host synchronisation. */
 int dgrm_release_inputs(dgrm_engine *e, void *consumer_stream);
 
 /* Whole-file convenience: validates the 3-byte header exactly as genotype.cpp:578-605 and
@@ -149,10 +159,20 @@ int dgrm_bad_snps(dgrm_engine *e, int64_t *idx, int64_t cap, int64_t *count);
  * 1748-1758; grid R x C row-major, source process (0,0)): global (gr,gc) owned by
  * ((gr/bs_r)%R, (gc/bs_c)%C) lands at local[lc*lld + lr].  uplo 'L' writes only gc <= gr
  * (what pdsyrk_('L',..) leaves defined, matrix.cpp:2679-2682), 'U' only gc >= gr, 'B' both.
- * With world > 1 only entries of tiles this engine owns are written. */
+ * With world > 1 only entries of tiles this engine owns are written (everything else in `local` is left as it
+ * was), so the engines of a partition can fill one buffer in turn, or each fill a zeroed panel that the caller
+ * then sums over the engines (every entry has exactly one owner: x + 0 + ... + 0 is exact).  `local` may be
+ * pageable or pinned host memory, or DEVICE memory of this engine's GPU: the multi-GPU egress reduces such
+ * device panels over NVLink to the engine whose host rank owns the block. */
 int dgrm_fetch_block_cyclic(dgrm_engine *e, int which, double *local, int64_t lld, int bs_r,
                             int bs_c, int my_row, int my_col, int grid_rows, int grid_cols,
                             char uplo);
+/* Same, restricted to local columns [lc_begin, lc_end) of that block; `local` points at column lc_begin.
+ * Lets a caller move a large block through a bounded panel (the reference moves one bs x bs block at a time,
+ * matrix.cpp:2297-2341). */
+int dgrm_fetch_block_cyclic_cols(dgrm_engine *e, int which, double *local, int64_t lld, int bs_r,
+                                 int bs_c, int my_row, int my_col, int grid_rows, int grid_cols,
+                                 char uplo, int64_t lc_begin, int64_t lc_end);
 
 /* Bind a caller-owned local block-cyclic buffer (same arguments as dgrm_fetch_block_cyclic) that
  * dgrm_finish fills with matrix `which`.  When the buffer is pinned (dgrm_host_alloc) the tiles are
@@ -188,6 +208,14 @@ int dgrm_set_output_subset(dgrm_engine *e, const int64_t *idx, int64_t count);
  * the packed (n+1) x n column-major array of matrix.cpp:2324-2334.  world must be 1. */
 int dgrm_write_grm_dat(dgrm_engine *e, const char *path);
 
+/* Multi-engine form of the writer (the reference funnels every block through rank 0: packMatrices
+ * matrix.cpp:2262-2349 + writeMatrixMPI :2168-2219).  Every engine of a partition writes, at their offsets in
+ * the same file, exactly the entries whose tiles it owns (per file column at most a few contiguous runs), so an
+ * 80 GB result needs no gather.  Exactly one engine calls it with create != 0 FIRST (creates / truncates the
+ * file, writes the header, sizes the file); the others call it with create == 0 after that call has returned
+ * (the caller's barrier).  With world == 1 and create != 0 it is dgrm_write_grm_dat. */
+int dgrm_write_grm_dat_part(dgrm_engine *e, const char *path, int create);
+
 /* Raw tile export for multi-engine runs: this engine's 128x256 tiles, column-major inside a
  * tile.  tile_rc[ntiles][2] = (row block of 128, column panel of 256). */
 int64_t dgrm_num_tiles(const dgrm_engine *e);
@@ -205,6 +233,8 @@ int dgrm_fetch_tiles(dgrm_engine *e, int which, double *tiles /* [ntiles][128*25
  * dgrm_begin, row_keep[nrows] as in dgrm_push_bed_host. */
 int dgrm_store_bed_file(dgrm_engine *e, const char *bed_path, int64_t m_file);
 int dgrm_store_bed_host(dgrm_engine *e, const uint8_t *rows, int64_t pitch, int64_t nrows);
+/* same, from rows already in this GPU's memory, readable once `producer_stream` reaches the point of the call */
+int dgrm_store_bed_device(dgrm_engine *e, const uint8_t *d_rows, int64_t pitch, int64_t nrows, void *producer_stream);
 int dgrm_store_clear(dgrm_engine *e);
 int64_t dgrm_stored_snps(const dgrm_engine *e);
 int dgrm_push_stored(dgrm_engine *e, int64_t first, int64_t nrows, const uint8_t *row_keep);
@@ -233,6 +263,9 @@ int dgrm_fetch_standardised(dgrm_engine *e, double *local, int64_t lld, int bs_r
 #define DGRM_VIEW_SAVED_PLUS_CURRENT 3
 int dgrm_save(dgrm_engine *e, int mode);
 int dgrm_set_view(dgrm_engine *e, int view);
+
+/* Bytes the copy engine moved device -> host for the streamed (bound) outputs of the last dgrm_finish. */
+int64_t dgrm_last_d2h_bytes(const dgrm_engine *e);
 
 /* Pinned host memory helpers (Matrix::m replacement allocation for zero-staging fetches). */
 void *dgrm_host_alloc(int64_t bytes);

@@ -1,14 +1,5 @@
-"""CPU: host logic of the multi-GPU path with world_size = 2 over gloo — the packed-row shards of every chunk
-are all-gathered exactly as bench.py does over NCCL, and the tile partition covers the lower triangle once."""
-import os
-import socket
-
-import numpy as np
-import torch
-import torch.distributed as dist
-import torch.multiprocessing as mp
-
-from dissect_b200 import bedio
+"""CPU: index arithmetic of the multi-GPU path — the tile partition covers the lower triangle once, in contiguous
+raster segments.  (The exchange loop itself runs over gloo in tests/test_multi_driver_cpu.py.)"""
 from dissect_b200.partition import row_shards, supertile_order, tiles_of_rank
 
 
@@ -58,43 +49,3 @@ def test_row_shards_cover_every_row_once():
             for a, b in ranges:
                 rows += list(range(a, b))
         assert rows == list(range(m))
-
-
-def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
-
-
-def _worker(rank, world, port, m, n, chunk, out_dir):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    pk = bedio.synth_packed(n, m, 5, missing=0.02)          # same seed on every rank
-    bpr = pk.shape[1]
-    shard = (chunk + world - 1) // world
-    rebuilt = []
-    for c0, ranges in row_shards(m, chunk, world):
-        a, b = ranges[rank]
-        send = torch.zeros((shard, bpr), dtype=torch.uint8)
-        if b > a:
-            send[: b - a] = torch.from_numpy(pk[a:b])
-        gathered = [torch.zeros_like(send) for _ in range(world)]
-        dist.all_gather(gathered, send)
-        for r, (ra, rb) in enumerate(ranges):
-            rebuilt.append(gathered[r][: rb - ra].numpy())
-    full = np.concatenate(rebuilt, axis=0)
-    ok = np.array_equal(full, pk)
-    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok), len(tiles_of_rank(n, rank, world))]))
-    dist.barrier()
-    dist.destroy_process_group()
-
-
-def test_two_rank_gloo_exchange(tmp_path):
-    world, m, n, chunk = 2, 700, 300, 256
-    mp.spawn(_worker, args=(world, _free_port(), m, n, chunk, str(tmp_path)), nprocs=world, join=True)
-    res = [np.load(str(tmp_path / f"ok{r}.npy")) for r in range(world)]
-    assert all(r[0] == 1 for r in res)               # every rank reassembled every chunk bit for bit
-    T = 2
-    assert sum(int(r[1]) for r in res) == T * (T + 1)
