@@ -141,6 +141,102 @@ bed_count_stats_kernel(const uint8_t* __restrict__ chunk, int64_t pitch, int nro
   }
 }
 
+// lane 0 of the counting warp: statistics in the reference's operation order (genotype.cpp:735-738, 922-959)
+__device__ __forceinline__ void snp_stats_finish(int c0, int c2, int c3, int n, int64_t g, int row, const SnpStatsOut& o,
+                                                 double* __restrict__ zt) {
+  const int c1 = n - c0 - c2 - c3;  // 00 hom A1
+  o.freq[g * 4 + 0] = c0;
+  o.freq[g * 4 + 1] = c1;
+  o.freq[g * 4 + 2] = c2;
+  o.freq[g * 4 + 3] = c3;
+  const int nn = c1 + c2 + c3;
+  o.nn[g] = nn;
+  const double den = __dmul_rn(2., (double)nn);
+  const double p1 = __ddiv_rn(__dadd_rn(__dmul_rn(2., (double)c1), (double)c2), den);
+  const double p2 = __ddiv_rn(__dadd_rn(__dmul_rn(2., (double)c3), (double)c2), den);
+  const double sd = __dsqrt_rn(__dmul_rn(__dmul_rn(2., p1), __dsub_rn(1., p1)));
+  o.p1[g] = p1;
+  o.p2[g] = p2;
+  o.sd[g] = sd;
+  const double shift = __dadd_rn(1., __dmul_rn(2., p2));
+  double z1 = __ddiv_rn(__dsub_rn(1., shift), sd);
+  double z2 = __ddiv_rn(__dsub_rn(2., shift), sd);
+  double z3 = __ddiv_rn(__dsub_rn(3., shift), sd);
+  const bool nan_snp = (nn == 0);
+  const bool zero_sd = !nan_snp && (sd == 0.);
+  if (nan_snp || zero_sd) {
+    z1 = z2 = z3 = 0.;  // keep NaN/Inf out of the accumulators; dgrm_finish reports the error
+    atomicAdd(&o.bad_count[nan_snp ? 1 : 0], 1);
+    const int total = atomicAdd(&o.bad_count[2], 1);
+    if (total < o.bad_cap) o.bad_list[total] = nan_snp ? -(g + 1) : g;
+  }
+  double* z = zt + (int64_t)row * 4;
+  z[0] = z1;  // 00
+  z[1] = 0.;  // 01 missing
+  z[2] = z2;  // 10
+  z[3] = z3;  // 11
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a+b fused: ONE pass over the caller's rows does the row selection / alignment copy into the chunk buffer
+// (bed_gather_kernel) and the per-SNP counts and statistics (bed_count_stats_kernel): one warp per kept row,
+// VecT loads chosen by the host from the alignment of (src, src_pitch), popcounts on the lo/hi bit planes with the
+// padding bits of the last byte masked, warp-shuffle reduction, lane 0 finishes the statistics.
+// 1/4 B read + 1/4 B written per genotype instead of 1/4 + 1/4 (gather) + 1/4 (count).
+// ------------------------------------------------------------------------------------------------
+template <typename VecT>
+__global__ void __launch_bounds__(256)
+bed_decode_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const int32_t* __restrict__ rows, int64_t row0,
+                  int nrows, uint8_t* __restrict__ dst, int64_t dst_pitch, int nbytes, int n, int64_t snp0, SnpStatsOut o,
+                  double* __restrict__ zt, int zt_row0) {
+  constexpr int V = (int)sizeof(VecT);
+  constexpr int W = V / 4;  // 32-bit words per vector
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const int64_t srow = rows ? (int64_t)rows[row] : row0 + row;
+  const uint8_t* s = src + srow * src_pitch;
+  uint8_t* d = dst + (int64_t)row * dst_pitch;
+  const int nvec = nbytes / V;
+  int c0 = 0, c2 = 0, c3 = 0;
+  auto count_word = [&](uint32_t w, int i0) {   // 16 individuals starting at i0
+    int valid = n - i0;
+    valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
+    const uint32_t km = (valid == 16) ? 0x55555555u : (((1u << (2 * valid)) - 1u) & 0x55555555u);
+    const uint32_t lo = w & 0x55555555u;
+    const uint32_t hi = (w >> 1) & 0x55555555u;
+    c3 += __popc(lo & hi & km);   // 11 hom A2
+    c2 += __popc(hi & ~lo & km);  // 10 het
+    c0 += __popc(lo & ~hi & km);  // 01 missing
+  };
+#pragma unroll 4
+  for (int j = lane; j < nvec; j += 32) {
+    const VecT v = __ldg(reinterpret_cast<const VecT*>(s) + j);
+    reinterpret_cast<VecT*>(d)[j] = v;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int t = 0; t < W; ++t) count_word(w[t], (j * W + t) * 16);
+  }
+  for (int b = nvec * V + lane; b < nbytes; b += 32) {   // the row's last nbytes % V bytes, 4 individuals each
+    const uint32_t v = s[b];
+    d[b] = (uint8_t)v;
+    int valid = n - b * 4;
+    valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
+    const uint32_t km = ((1u << (2 * valid)) - 1u) & 0x55u;
+    const uint32_t lo = v & 0x55u, hi = (v >> 1) & 0x55u;
+    c3 += __popc(lo & hi & km);
+    c2 += __popc(hi & ~lo & km);
+    c0 += __popc(lo & ~hi & km);
+  }
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, sft);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, sft);
+    c3 += __shfl_xor_sync(0xffffffffu, c3, sft);
+  }
+  if (lane == 0) snp_stats_finish(c0, c2, c3, n, snp0 + row, zt_row0 + row, o, zt);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1c: expand one chunk into tensor-core operands.
 //   Z  [n_pad][z_pitch] 16-bit, K-major: Z[i][k] = round16(zt[k][pattern(k,i)])         (hi part)

@@ -123,6 +123,11 @@ struct dgrm_engine {
   int slots = 0;
   int chunks_in_super = 0;
   int launched_s = 0, launched_n = 0;  // resident chunks of this super already contracted into S / N
+  // streaming outputs: the first tile groups (work items [0, pre_end)) are contracted chunk by chunk while the rows
+  // are still arriving, so that the tensor cores are not idle during the host-to-device phase of an e2e build
+  int pre_end = -1;                    // -1 = not decided yet for this GRM, 0 = no prefix
+  int pre_s = 0, pre_n = 0;            // resident chunks already contracted over the prefix
+  int prefix_pct = 30;                 // DGRM_PREFIX_PCT
   int64_t supers_done = 0;
   int slot_kpad[kMaxChunks] = {0};
   int l2_policy = 3;  // see SyrkParams::l2_policy (DGRM_L2_POLICY overrides, for experiments)
@@ -175,6 +180,7 @@ struct dgrm_engine {
   bool miss_valid = false;
   bool n_u16 = false;          // streamed pair counts travel as 16-bit deficiencies m - N
   int overlap = 1;  // DGRM_OVERLAP=0: contract only in dgrm_finish (experiments)
+  int fused_decode = 1;  // DGRM_FUSED_DECODE=0: separate gather and count kernels (A/B measurements)
 
   bool have_ind = false, begun = false, finished = false;
 
@@ -409,6 +415,7 @@ int launch_syrk(dgrm_engine* e, const CUtensorMap& tmap, const SyrkParams& p) {
 constexpr int kCountMergeSnps = 32768;  // SNPs per pair-count accumulation (exact in fp32: << 2^24)
 
 int flush_super(dgrm_engine* e, bool final, bool wrap = false);
+int flush_prefix(dgrm_engine* e);
 bool streaming_bound(const dgrm_engine* e);
 
 // One chunk of packed rows: per-SNP statistics, then expansion into resident operand slot `chunks_in_super`.
@@ -429,13 +436,8 @@ int process_chunk(dgrm_engine* e) {
   const int64_t col0 = (int64_t)slot * e->kc_max;
   if (e->supers_done > 0) CK(cudaStreamWaitEvent(e->prep, e->slot_ev[slot], 0));  // the slot's previous chunk is contracted
 
-  {
-    Prof pr(e, DGRM_K_COUNT, e->prep);
-    SnpStatsOut so{e->d_freq, e->d_nn, e->d_p1, e->d_p2, e->d_sd, e->d_bad_count, e->d_bad_list, dgrm_engine::kBadCap};
-    const int blocks = (kc * 32 + 255) / 256;
-    bed_count_stats_kernel<<<blocks, 256, 0, e->prep>>>(e->d_chunk, e->chunk_pitch, kc, (int)e->n, e->m, so, e->d_zt);
-    CK(cudaGetLastError());
-  }
+  // (per-SNP counts, statistics and the zt table of these rows were produced while the rows were gathered into the
+  // chunk buffer: bed_decode_kernel in push_device_rows)
   if (!e->cfg.flat_norm && e->miss_valid) {
     if (streaming_bound(e)) {
       const int nbytes = (int)e->b_row;
@@ -483,6 +485,7 @@ int process_chunk(dgrm_engine* e) {
   // the next chunk (prep stream) overlaps it; with them the contraction waits for dgrm_finish, which walks the
   // tiles group by group so that finished groups leave the device early.
   if (e->overlap && !streaming_bound(e)) return flush_super(e, false);
+  if (e->overlap) return flush_prefix(e);
   return DGRM_OK;
 }
 
@@ -822,6 +825,131 @@ int issue_ready_jobs(dgrm_engine* e, int gi) {
   return DGRM_OK;
 }
 
+// Tile groups of a streamed build: one per raster row group, ends rounded up to whole waves of the persistent grid
+// (no ragged tail, and a row group is final as soon as its launches are done).
+void stream_groups(const dgrm_engine* e, std::vector<int>* group_end, std::vector<int>* rg_group) {
+  const int nwork = (int)e->work.size();
+  const int units = std::max(1, (e->sm_count - e->reserve_sms) / e->cfg.cta_group);
+  group_end->clear();
+  rg_group->assign(e->rg_end.size(), 0);
+  for (size_t rg = 0; rg < e->rg_end.size(); ++rg) {
+    const int end = std::min(nwork, (e->rg_end[rg] + units - 1) / units * units);
+    if (end > (group_end->empty() ? 0 : group_end->back())) group_end->push_back(end);
+    (*rg_group)[rg] = std::max(0, (int)group_end->size() - 1);
+  }
+  if (group_end->empty() || group_end->back() != nwork) group_end->push_back(nwork);
+}
+
+// S += Z^T Z of resident chunk j0 over work items [w0, w1)
+int contract_s(dgrm_engine* e, int w0, int w1, int j0) {
+  const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
+  const bool bf16 = e->cfg.operand == DGRM_OPERAND_BF16;
+  const int lo = e->slots * e->kc_max;
+  Prof pr(e, DGRM_K_SYRK);
+  SyrkParams p{};
+  p.work = e->d_work;
+  p.l2_policy = e->l2_policy;
+  p.work_begin = w0;
+  p.work_end = w1;
+  p.nchunks = 1;
+  p.chunk_col[0] = j0 * e->kc_max;
+  p.chunk_kpad[0] = e->slot_kpad[j0];
+  p.accumulate = e->supers_done > 0 || j0 > 0;
+  p.npass = split ? 3 : 1;
+  p.a_off[0] = 0; p.a_off[1] = lo; p.a_off[2] = 0;
+  p.b_off[0] = 0; p.b_off[1] = 0; p.b_off[2] = lo;
+  p.out = e->d_S;
+  p.idesc = make_idesc(e->cfg.cta_group, bf16 ? 1 : 0);
+  return e->cfg.cta_group == 2 ? launch_syrk<2, 0, double>(e, e->tmap_z, p) : launch_syrk<1, 0, double>(e, e->tmap_z, p);
+}
+
+// N += M^T M of the resident chunks [j0, j1) (one accumulation: at most 32768 SNPs) over work items [w0, w1)
+int contract_n(dgrm_engine* e, int w0, int w1, int j0, int j1) {
+  const bool count_fp4 = e->cfg.count_method == DGRM_COUNT_FP4;
+  Prof pr(e, DGRM_K_PAIRCNT);
+  if (e->cfg.count_method == DGRM_COUNT_POPC) {
+    const int nw1 = w1 * e->cfg.cta_group, nw0 = w0 * e->cfg.cta_group;  // 128-row tiles of this group
+    pair_count_popc_kernel<<<std::min(nw1 - nw0, e->sm_count * 2), 256, 0, e->stream>>>(
+        e->d_MB + (int64_t)j0 * e->kc_max / 32, e->mb_pitch, e->slot_kpad[j0] / 32, e->d_work_cg1 + nw0, nw1 - nw0,
+        e->d_N, e->supers_done > 0 || j0 > 0);
+    CK(cudaGetLastError());
+    return DGRM_OK;
+  }
+  int kpad = 0;
+  for (int j = j0; j < j1; ++j) kpad += e->slot_kpad[j];   // slots are adjacent; only the last can be short
+  SyrkParams p{};
+  p.work = e->d_work;
+  p.l2_policy = e->l2_policy;
+  p.work_begin = w0;
+  p.work_end = w1;
+  p.nchunks = 1;
+  p.npass = 1;
+  p.a_off[0] = p.b_off[0] = 0;
+  p.out = e->d_N;
+  p.accumulate = e->supers_done > 0 || j0 > 0;
+  if (count_fp4) {  // operand addressed in bytes: two SNPs per byte
+    p.chunk_col[0] = j0 * e->kc_max / 2;
+    p.chunk_kpad[0] = kpad / 2;
+    p.idesc = make_idesc_mxf4(e->cfg.cta_group);
+    return e->cfg.cta_group == 2 ? launch_syrk<2, 2, int>(e, e->tmap_q4, p) : launch_syrk<1, 2, int>(e, e->tmap_q4, p);
+  }
+  p.chunk_col[0] = j0 * e->kc_max;
+  p.chunk_kpad[0] = kpad;
+  p.idesc = make_idesc(e->cfg.cta_group, 0 /* e4m3 */);
+  return e->cfg.cta_group == 2 ? launch_syrk<2, 1, int>(e, e->tmap_q, p) : launch_syrk<1, 1, int>(e, e->tmap_q, p);
+}
+
+inline int count_merge(const dgrm_engine* e) {
+  // pair count: 0/1 products accumulate exactly in fp32 up to 2^24, so resident chunks are merged up to
+  // 32768 SNPs per TMEM accumulation (one int32 read-modify-write of the tile per merged group)
+  const bool mma = !e->cfg.flat_norm && (e->cfg.count_method == DGRM_COUNT_MMA || e->cfg.count_method == DGRM_COUNT_FP4);
+  return mma ? std::max(1, kCountMergeSnps / e->kc_max) : 1;
+}
+
+// Resident chunks [from_s, nch) into S and merged groups [from_n, n_to) into N, over work items [w0, w1).
+int contract_range(dgrm_engine* e, int w0, int w1, int from_s, int from_n, int nch, int n_to) {
+  if (w1 <= w0) return DGRM_OK;
+  const int merge = count_merge(e);
+  for (int j0 = std::min(from_s, from_n); j0 < nch; ++j0) {
+    if (j0 >= from_s) {
+      const int rc = contract_s(e, w0, w1, j0);
+      if (rc) return rc;
+    }
+    if (e->cfg.flat_norm || j0 < from_n || j0 >= n_to || j0 % merge != 0) continue;
+    const int rc = contract_n(e, w0, w1, j0, std::min(n_to, j0 + merge));
+    if (rc) return rc;
+  }
+  return DGRM_OK;
+}
+
+// Streamed build, while rows are still being pushed: contract the chunks that are resident so far over the prefix
+// of the work list.  dgrm_finish then has less left to do for the first tile groups, whose outputs leave first.
+int flush_prefix(dgrm_engine* e) {
+  const int nwork = (int)e->work.size();
+  if (e->pre_end < 0) {
+    e->pre_end = 0;
+    if (e->prefix_pct > 0 && nwork > 0) {
+      std::vector<int> group_end, rg_group;
+      stream_groups(e, &group_end, &rg_group);
+      for (int end : group_end)
+        if ((int64_t)end * 100 >= (int64_t)nwork * e->prefix_pct) {
+          if (end < nwork) e->pre_end = end;
+          break;
+        }
+    }
+  }
+  if (e->pre_end <= 0) return DGRM_OK;
+  const int nch = e->chunks_in_super, merge = count_merge(e);
+  CK(cudaEventRecord(e->prep_ev, e->prep));
+  CK(cudaStreamWaitEvent(e->stream, e->prep_ev, 0));
+  const int n_to = nch / merge * merge;
+  const int rc = contract_range(e, 0, e->pre_end, e->pre_s, e->pre_n, nch, n_to);
+  if (rc) return rc;
+  e->pre_s = nch;
+  e->pre_n = std::max(e->pre_n, n_to);
+  return DGRM_OK;
+}
+
 // Contract resident chunks that have not been contracted yet (fp32 in TMEM per chunk, fp64 / int32
 // read-modify-write of the tile across chunks).  S: chunks [launched_s, nch); N: merged groups from launched_n up to
 // the last complete group (every chunk when `final` or `wrap`).
@@ -831,43 +959,29 @@ int issue_ready_jobs(dgrm_engine* e, int gi) {
 int flush_super(dgrm_engine* e, bool final, bool wrap) {
   const int nch = e->chunks_in_super;
   if (nch == 0) return DGRM_OK;
-  const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
-  const bool bf16 = e->cfg.operand == DGRM_OPERAND_BF16;
-  const bool count_fp4 = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_FP4;
-  const bool count_mma = !e->cfg.flat_norm && (e->cfg.count_method == DGRM_COUNT_MMA || count_fp4);
-  const bool count_popc = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_POPC;
-  // pair count: 0/1 products accumulate exactly in fp32 up to 2^24, so resident chunks are merged up to
-  // 32768 SNPs per TMEM accumulation (one int32 read-modify-write of the tile per merged group)
-  const int merge = count_mma ? std::max(1, kCountMergeSnps / e->kc_max) : 1;
+  const int merge = count_merge(e);
   const int ls = e->launched_s, ln = e->launched_n;
   const int n_to = (final || wrap) ? nch : nch / merge * merge;
   const int nwork = (int)e->work.size();
+  const int pre_end = std::max(0, e->pre_end);   // work items [0, pre_end) are ahead by (pre_s, pre_n): flush_prefix
   // the operands of every chunk expanded so far must be complete before the MMA stream reads them
   CK(cudaEventRecord(e->prep_ev, e->prep));
   CK(cudaStreamWaitEvent(e->stream, e->prep_ev, 0));
   const bool stream_out = streaming_bound(e);
-  if (nwork > 0 && (ls < nch || ln < n_to || (final && stream_out))) {
-    SyrkParams p{};
-    p.work = e->d_work;
-    p.l2_policy = e->l2_policy;
-    const int lo = e->slots * e->kc_max;
-    // tile groups: whole waves of the persistent grid, so that no launch has a ragged tail
-    const int units = (e->sm_count - e->reserve_sms) / e->cfg.cta_group;
-    // Tile groups.  Streaming outputs: one group per raster row group, its end rounded up to whole waves of
-    // the persistent grid (no ragged tail, and the row group is final as soon as its launches are done).
+  if (nwork > 0) {
+    // Tile groups.  Streaming outputs: one group per raster row group (stream_groups); otherwise one launch range
+    // (two when a prefix of the work list is ahead of the rest).
     std::vector<int> group_end;
     std::vector<int> rg_group(e->rg_end.size(), 0);
     if (final && stream_out) {
-      for (size_t rg = 0; rg < e->rg_end.size(); ++rg) {
-        const int end = std::min(nwork, (e->rg_end[rg] + units - 1) / units * units);
-        if (end > (group_end.empty() ? 0 : group_end.back())) group_end.push_back(end);
-        rg_group[rg] = (int)group_end.size() - 1;
-      }
+      stream_groups(e, &group_end, &rg_group);
+    } else {
+      if (pre_end > 0 && pre_end < nwork) group_end.push_back(pre_end);
+      group_end.push_back(nwork);
     }
-    if (group_end.empty() || group_end.back() != nwork) group_end.push_back(nwork);
     if (final && stream_out) {
       // Pair counts leave the device as 16-bit deficiencies m - N_ij when the per-individual missing counts prove
-      // that every deficiency fits (m - N_ij <= missing_i + missing_j), else as int32; A always as fp64.
+      // that every deficiency fits (m - N_ij <= missing_i + missing_j), else as int32; A as fp64 or fp32 (cfg).
       e->n_u16 = false;
       if (e->miss_valid && !e->cfg.flat_norm && !(e->saved && e->view != DGRM_VIEW_CURRENT) && e->d_miss) {
         std::vector<int32_t> miss((size_t)e->n);
@@ -951,56 +1065,9 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
     int w0 = 0;
     for (size_t gi = 0; gi < group_end.size(); w0 = group_end[gi], ++gi) {
       const int w1 = group_end[gi];
-      p.work_begin = w0;
-      p.work_end = w1;
-      for (int j0 = std::min(ls, ln); j0 < nch; ++j0) {
-        if (j0 >= ls) {
-          Prof pr(e, DGRM_K_SYRK);
-          p.nchunks = 1;
-          p.chunk_col[0] = j0 * e->kc_max;
-          p.chunk_kpad[0] = e->slot_kpad[j0];
-          p.accumulate = e->supers_done > 0 || j0 > 0;
-          p.npass = split ? 3 : 1;
-          p.a_off[0] = 0; p.a_off[1] = lo; p.a_off[2] = 0;
-          p.b_off[0] = 0; p.b_off[1] = 0; p.b_off[2] = lo;
-          p.out = e->d_S;
-          p.idesc = make_idesc(e->cfg.cta_group, bf16 ? 1 : 0);
-          const int rc = e->cfg.cta_group == 2 ? launch_syrk<2, 0, double>(e, e->tmap_z, p)
-                                               : launch_syrk<1, 0, double>(e, e->tmap_z, p);
-          if (rc) return rc;
-        }
-        if (j0 < ln || j0 >= n_to || j0 % merge != 0) continue;
-        Prof pr(e, DGRM_K_PAIRCNT);
-        if (count_popc) {
-          const int nw1 = w1 * e->cfg.cta_group, nw0 = w0 * e->cfg.cta_group;  // 128-row tiles of this group
-          pair_count_popc_kernel<<<std::min(nw1 - nw0, e->sm_count * 2), 256, 0, e->stream>>>(
-              e->d_MB + (int64_t)j0 * e->kc_max / 32, e->mb_pitch, e->slot_kpad[j0] / 32, e->d_work_cg1 + nw0, nw1 - nw0,
-              e->d_N, e->supers_done > 0 || j0 > 0);
-          CK(cudaGetLastError());
-        } else if (count_mma) {
-          const int j1 = std::min(n_to, j0 + merge);
-          int kpad = 0;
-          for (int j = j0; j < j1; ++j) kpad += e->slot_kpad[j];   // slots are adjacent; only the last can be short
-          p.nchunks = 1;
-          p.npass = 1;
-          p.a_off[0] = p.b_off[0] = 0;
-          p.out = e->d_N;
-          p.accumulate = e->supers_done > 0 || j0 > 0;
-          int rc;
-          if (count_fp4) {  // operand addressed in bytes: two SNPs per byte
-            p.chunk_col[0] = j0 * e->kc_max / 2;
-            p.chunk_kpad[0] = kpad / 2;
-            p.idesc = make_idesc_mxf4(e->cfg.cta_group);
-            rc = e->cfg.cta_group == 2 ? launch_syrk<2, 2, int>(e, e->tmap_q4, p) : launch_syrk<1, 2, int>(e, e->tmap_q4, p);
-          } else {
-            p.chunk_col[0] = j0 * e->kc_max;
-            p.chunk_kpad[0] = kpad;
-            p.idesc = make_idesc(e->cfg.cta_group, 0 /* e4m3 */);
-            rc = e->cfg.cta_group == 2 ? launch_syrk<2, 1, int>(e, e->tmap_q, p) : launch_syrk<1, 1, int>(e, e->tmap_q, p);
-          }
-          if (rc) return rc;
-        }
-      }
+      const bool ahead = w1 <= pre_end;   // this group belongs to the prefix that flush_prefix already advanced
+      const int rc0 = contract_range(e, w0, w1, ahead ? e->pre_s : ls, ahead ? e->pre_n : ln, nch, n_to);
+      if (rc0) return rc0;
       if (final && stream_out) {
         while (e->group_ev.size() <= gi) {
           cudaEvent_t ev;
@@ -1033,6 +1100,8 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
   }
   e->launched_s = nch;
   e->launched_n = n_to;
+  e->pre_s = nch;
+  e->pre_n = n_to;
   // slots whose contractions are all queued can be overwritten once the MMA stream gets here: process_chunk makes
   // the decode stream wait for the slot's own event only, so the decode of the next super overlaps the rest of this one
   const int done = e->cfg.flat_norm ? nch : std::min(nch, n_to);
@@ -1044,6 +1113,7 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
   if (final || wrap) {
     e->chunks_in_super = 0;
     e->launched_s = e->launched_n = 0;
+    e->pre_s = e->pre_n = 0;
     e->slots_evented = 0;
     e->supers_done++;
   }
@@ -1077,22 +1147,45 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
       d_idx = e->d_rowidx[s];
     }
     {
-      Prof pr(e, DGRM_K_GATHER, e->prep);
       const int nbytes = (int)(e->d_src_ind ? e->b_row : e->b_fam);
       uint8_t* dst = e->d_chunk + (int64_t)e->fill * e->chunk_pitch;
       const uint64_t align = (uint64_t)(uintptr_t)d_rows | (uint64_t)pitch;
       const int vec = e->d_src_ind ? 1 : (align % 16 == 0 ? 16 : align % 8 == 0 ? 8 : align % 4 == 0 ? 4 : 1);
-      const int per_row = (nbytes / vec + 255) / 256;
-      const dim3 grid((unsigned)std::max(1, std::min(per_row, 64)), (unsigned)take);
+      SnpStatsOut so{e->d_freq, e->d_nn, e->d_p1, e->d_p2, e->d_sd, e->d_bad_count, e->d_bad_list, dgrm_engine::kBadCap};
+      const int64_t snp0 = e->m + e->fill;
+      if (vec > 1 && e->fused_decode) {
+        // one pass: row selection / alignment copy + per-SNP counts and statistics, one warp per row
+        Prof pr(e, DGRM_K_GATHER, e->prep);
+        const int blocks = (take * 32 + 255) / 256;
+#define DGRM_DECODE(T)                                                                                          \
+  bed_decode_kernel<T><<<blocks, 256, 0, e->prep>>>(d_rows, pitch, d_idx, pos, take, dst, e->chunk_pitch, nbytes, \
+                                                    (int)e->n, snp0, so, e->d_zt, e->fill)
+        if (vec == 16) DGRM_DECODE(uint4);
+        else if (vec == 8) DGRM_DECODE(uint2);
+        else DGRM_DECODE(uint32_t);
+#undef DGRM_DECODE
+        CK(cudaGetLastError());
+      } else {
+        // --keep compaction of individuals, or rows that are not even 4-byte aligned: gather, then count
+        {
+          Prof pr(e, DGRM_K_GATHER, e->prep);
+          const int per_row = (nbytes / vec + 255) / 256;
+          const dim3 grid((unsigned)std::max(1, std::min(per_row, 64)), (unsigned)take);
 #define DGRM_GATHER(T)                                                                                            \
   bed_gather_kernel<T><<<grid, 256, 0, e->prep>>>(d_rows, pitch, d_idx, pos, take, dst, e->chunk_pitch, nbytes, \
                                                   e->d_src_ind, (int)e->n)
-      if (vec == 16) DGRM_GATHER(uint4);
-      else if (vec == 8) DGRM_GATHER(uint2);
-      else if (vec == 4) DGRM_GATHER(uint32_t);
-      else DGRM_GATHER(uint8_t);
+          if (vec == 16) DGRM_GATHER(uint4);
+          else if (vec == 8) DGRM_GATHER(uint2);
+          else if (vec == 4) DGRM_GATHER(uint32_t);
+          else DGRM_GATHER(uint8_t);
 #undef DGRM_GATHER
-      CK(cudaGetLastError());
+          CK(cudaGetLastError());
+        }
+        Prof pr(e, DGRM_K_COUNT, e->prep);
+        bed_count_stats_kernel<<<(take * 32 + 255) / 256, 256, 0, e->prep>>>(dst, e->chunk_pitch, take, (int)e->n, snp0, so,
+                                                                            e->d_zt + (int64_t)e->fill * 4);
+        CK(cudaGetLastError());
+      }
       if (row_keep) CK(cudaEventRecord(e->rowidx_free[e->rowidx_i ^ 1], e->prep));
     }
     e->fill += take;
@@ -1252,6 +1345,8 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   e->kc_max = cfg->chunk_snps;
   if (const char* pol = getenv("DGRM_L2_POLICY")) e->l2_policy = atoi(pol);
   if (const char* ov = getenv("DGRM_OVERLAP")) e->overlap = atoi(ov);
+  if (const char* fd = getenv("DGRM_FUSED_DECODE")) e->fused_decode = atoi(fd);
+  if (const char* pp = getenv("DGRM_PREFIX_PCT")) e->prefix_pct = std::max(0, std::min(90, atoi(pp)));
   e->reserve_sms = cfg->reserve_sms > 0 ? cfg->reserve_sms : 0;
   if (const char* rs = getenv("DGRM_RESERVE_SMS")) e->reserve_sms = atoi(rs);
   e->reserve_sms = std::max(0, std::min(e->reserve_sms, e->sm_count - 2));
@@ -1455,6 +1550,8 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
   e->chunks_done = 0;
   e->chunks_in_super = 0;
   e->launched_s = e->launched_n = 0;
+  e->pre_s = e->pre_n = 0;
+  e->pre_end = -1;
   e->slots_evented = 0;
   e->supers_done = 0;
   e->finished = false;

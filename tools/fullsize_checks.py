@@ -105,10 +105,11 @@ def tile_matvecs(tile_rc, tiles_A, tiles_N, n, w_pm, w01, device, slab=512):
 
 
 def s_tolerance(n, m, operand="fp16"):
-    """|(S w)_i - ref_i| / m allowed: 8 x the rms of sum_j w_j dA_ij for independent operand-rounding errors
-    (rms dA = 3.5e-6 * sqrt(1e4 / m) for fp16 operands, 8x that for bf16)."""
+    """|(S w)_i - ref_i| / m allowed: 16 x the rms of sum_j w_j dA_ij for independent operand-rounding errors
+    (rms dA = 3.5e-6 * sqrt(1e4 / m) for fp16 operands, 8x that for bf16).  Measured on B200 at
+    C2 (n = 20000, m = 98107, fp16): max over the rows = 4.2 x that rms; a dropped 128 x 256 tile gives 320 x."""
     rms = {"fp16": 3.5e-6, "bf16": 2.8e-5, "fp16x2": 3.5e-6}[operand] * math.sqrt(1e4 / max(m, 1))
-    return 8. * rms * math.sqrt(n)
+    return 16. * rms * math.sqrt(n)
 
 
 def run(pk, keep, n, m_kept, tile_rc, tiles_A, tiles_N, engine_stats, rank, world, device, operand="fp16", seed=12345,
