@@ -22,7 +22,7 @@ SYMBOLS = (
     "dgrm_set_output_subset", "dgrm_write_grm_dat", "dgrm_write_grm_dat_part", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles",
     "dgrm_host_alloc", "dgrm_host_free", "dgrm_kernel_times",
     "dgrm_store_bed_file", "dgrm_store_bed_host", "dgrm_store_bed_device", "dgrm_last_d2h_bytes", "dgrm_store_clear", "dgrm_stored_snps", "dgrm_push_stored",
-    "dgrm_fetch_standardised", "dgrm_save", "dgrm_set_view",
+    "dgrm_fetch_standardised", "dgrm_save", "dgrm_set_view", "dgrm_ld_begin", "dgrm_ld_pairs",
 )
 SAVE = {"copy": 0, "add": 1, "drop": 2}
 VIEW = {"current": 0, "saved": 1, "saved-current": 2, "saved+current": 3}
@@ -95,6 +95,8 @@ def load():
     lib.dgrm_store_bed_host.argtypes = [vp, vp, i64, i64]
     lib.dgrm_store_bed_device.argtypes = [vp, vp, i64, i64, vp]
     lib.dgrm_last_d2h_bytes.argtypes = [vp]
+    lib.dgrm_ld_begin.argtypes = [vp, i64, vp, i64]
+    lib.dgrm_ld_pairs.argtypes = [vp, dbl, vp, i64, P(i64)]
     lib.dgrm_last_d2h_bytes.restype = i64
     lib.dgrm_store_clear.argtypes = [vp]
     lib.dgrm_stored_snps.argtypes = [vp]

@@ -444,6 +444,80 @@ __global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// LD mode (GWAS::getLessSignificantCorrelatedSNPs, gwas.cpp:1163-1165: genotypes * genotypes^T, missings * missings^T):
+// the operands are SNP-major, which is the .bed's own order — row k of the chunk becomes operand row k with the
+// individuals along K, no transposition:
+//   Z [row][i] = round16(zt[row][pattern(row, i)]),  Q/Q4/MB [row][i] = (pattern != 01)
+//   diag[row]  = f1 z1^2 + f2 z2^2 + f3 z3^2   (sum over the individuals of z^2 in fp64, from the exact counts)
+// One thread expands 8 individuals (two packed bytes): a 16-byte Z store, 4 bytes of e2m1 nibbles.
+// ------------------------------------------------------------------------------------------------
+struct LdExpandArgs {
+  const uint8_t* chunk;
+  int64_t pitch;
+  int kc;              // SNP rows in the chunk
+  int n;               // individuals per row
+  const double* zt;    // [kc][4]
+  const int32_t* freq; // [kc][4] counts of the chunk's SNPs (missing, hom A1, het, hom A2)
+  uint16_t* Z;         // operand row of the chunk's first SNP
+  int64_t z_pitch;     // elements
+  int64_t lo_off;      // element offset of the lo part (SPLIT)
+  uint8_t* Q;
+  int64_t q_pitch;
+  uint8_t* Q4;
+  int64_t q4_pitch;
+  uint32_t* MB;
+  int64_t mb_pitch;    // 32-bit words
+  double* diag;        // [kc]
+};
+
+template <bool BF16, bool SPLIT>
+__global__ void __launch_bounds__(256) ld_expand_kernel(const LdExpandArgs a) {
+  const int row = blockIdx.y;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;   // group of 8 individuals
+  const int ngroups = (a.n + 7) >> 3;
+  const double* zp = a.zt + (int64_t)row * 4;
+  const double z0 = zp[0], z2 = zp[2], z3 = zp[3];
+  if (g == 0) {
+    const int32_t* f = a.freq + (int64_t)row * 4;
+    a.diag[row] = __dadd_rn(__dadd_rn(__dmul_rn((double)f[1], __dmul_rn(z0, z0)), __dmul_rn((double)f[2], __dmul_rn(z2, z2))),
+                            __dmul_rn((double)f[3], __dmul_rn(z3, z3)));
+  }
+  if (g >= ngroups) return;
+  uint32_t hi[4], lo[4];
+  {
+    const double zz[4] = {z0, 0., z2, z3};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      hi[c] = round16<BF16>(zz[c]);
+      lo[c] = SPLIT ? round16<BF16>(zz[c] - widen16<BF16>((uint16_t)hi[c])) : 0u;
+    }
+  }
+  const uint8_t* src = a.chunk + (int64_t)row * a.pitch + 2 * g;
+  uint32_t w = src[0];
+  if (8 * g + 4 < a.n) w |= (uint32_t)src[1] << 8;
+  const int valid = min(8, a.n - 8 * g);
+  if (valid < 8) w = (w & ((1u << (2 * valid)) - 1u)) | (0x5555u & ~((1u << (2 * valid)) - 1u));   // past n: missing
+  uint32_t oh[4], ol[4], q4 = 0, q8lo = 0, q8hi = 0, bits = 0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const uint32_t code = (w >> (2 * t)) & 3u;
+    const uint32_t vh = hi[code], vl = lo[code];
+    if (t & 1) { oh[t >> 1] |= vh << 16; ol[t >> 1] |= vl << 16; } else { oh[t >> 1] = vh; ol[t >> 1] = vl; }
+    const uint32_t present = code != 1u;
+    q4 |= present << (4 * t + 1);          // e2m1 1.0 = 0b0010 in nibble t
+    if (t < 4) q8lo |= (present * 0x38u) << (8 * t); else q8hi |= (present * 0x38u) << (8 * (t - 4));   // e4m3 1.0
+    bits |= present << t;
+  }
+  // padding individuals (i >= n) inside the last group must not contribute: their pattern was forced to 01
+  uint16_t* zrow = a.Z + (int64_t)row * a.z_pitch + 8 * g;
+  *reinterpret_cast<uint4*>(zrow) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+  if (SPLIT) *reinterpret_cast<uint4*>(zrow + a.lo_off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  if (a.Q4) *reinterpret_cast<uint32_t*>(a.Q4 + (int64_t)row * a.q4_pitch + 4 * g) = q4;
+  if (a.Q) *reinterpret_cast<uint2*>(a.Q + (int64_t)row * a.q_pitch + 8 * g) = make_uint2(q8lo, q8hi);
+  if (a.MB) reinterpret_cast<uint8_t*>(a.MB + (int64_t)row * a.mb_pitch)[g] = (uint8_t)bits;
+}
+
 // diag[i] += sum_kt diag_part[kt][i], fixed order (deterministic).
 __global__ void diag_reduce_kernel(const double* __restrict__ part, int nkt, int n_pad, double* __restrict__ diag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -52,7 +52,9 @@ struct dgrm_engine {
   EncodeTiledFn encode = nullptr;
 
   // cohort geometry
-  int64_t n_fam = 0, n = 0, n_pad = 0;
+  int64_t n_fam = 0, n = 0, n_pad = 0;   // n = dimension of the output matrices (individuals; SNPs of the group in LD mode)
+  int64_t n_row = 0;        // individuals per compacted packed row (== n except in LD mode)
+  bool ld_mode = false;     // dgrm_ld_begin: SNP x SNP correlations, the contraction runs over the individuals
   int64_t b_fam = 0;        // bytes per raw .bed row
   int64_t b_row = 0;        // bytes per compacted row
   int64_t chunk_pitch = 0;  // device chunk row pitch (multiple of 128)
@@ -422,6 +424,28 @@ bool streaming_bound(const dgrm_engine* e);
 int process_chunk(dgrm_engine* e) {
   const int kc = e->fill;
   if (kc == 0) return DGRM_OK;
+  if (e->ld_mode) {
+    // LD mode: the chunk's SNP rows become operand ROWS [m, m + kc), all individuals along K
+    Prof pr(e, DGRM_K_EXPAND, e->prep);
+    LdExpandArgs a;
+    a.chunk = e->d_chunk; a.pitch = e->chunk_pitch; a.kc = kc; a.n = (int)e->n_row; a.zt = e->d_zt;
+    a.freq = e->d_freq + e->m * 4;
+    a.Z = e->d_Z + e->m * e->z_pitch; a.z_pitch = e->z_pitch; a.lo_off = (int64_t)e->slots * e->kc_max;
+    a.Q = e->d_Q ? e->d_Q + e->m * e->q_pitch : nullptr; a.q_pitch = e->q_pitch;
+    a.Q4 = e->d_Q4 ? e->d_Q4 + e->m * e->q4_pitch : nullptr; a.q4_pitch = e->q4_pitch;
+    a.MB = e->d_MB ? e->d_MB + e->m * e->mb_pitch : nullptr; a.mb_pitch = e->mb_pitch;
+    a.diag = e->d_diag + e->m;
+    const dim3 grid((unsigned)(((e->n_row + 7) / 8 + 255) / 256), (unsigned)kc);
+    const int op = e->cfg.operand;
+    if (op == DGRM_OPERAND_BF16) ld_expand_kernel<true, false><<<grid, 256, 0, e->prep>>>(a);
+    else if (op == DGRM_OPERAND_FP16X2) ld_expand_kernel<false, true><<<grid, 256, 0, e->prep>>>(a);
+    else ld_expand_kernel<false, false><<<grid, 256, 0, e->prep>>>(a);
+    CK(cudaGetLastError());
+    e->m += kc;
+    e->chunks_done++;
+    e->fill = 0;
+    return DGRM_OK;
+  }
   const int kc_pad = (int)round_up(kc, 256);  // whole 128-byte k-blocks for every operand width (fp4: 256 SNPs)
   const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
   const bool bf16 = e->cfg.operand == DGRM_OPERAND_BF16;
@@ -442,7 +466,7 @@ int process_chunk(dgrm_engine* e) {
     if (streaming_bound(e)) {
       const int nbytes = (int)e->b_row;
       const dim3 grid((unsigned)((nbytes + 127) / 128), (unsigned)((kc + 255) / 256));
-      bed_missing_per_individual_kernel<<<grid, 128, 0, e->prep>>>(e->d_chunk, e->chunk_pitch, kc, nbytes, (int)e->n, e->d_miss);
+      bed_missing_per_individual_kernel<<<grid, 128, 0, e->prep>>>(e->d_chunk, e->chunk_pitch, kc, nbytes, (int)e->n_row, e->d_miss);
       CK(cudaGetLastError());
     } else {
       e->miss_valid = false;   // a chunk went by uncounted: streamed pair counts fall back to int32
@@ -451,7 +475,7 @@ int process_chunk(dgrm_engine* e) {
   {
     Prof pr(e, DGRM_K_EXPAND, e->prep);
     ExpandArgs a;
-    a.chunk = e->d_chunk; a.pitch = e->chunk_pitch; a.kc = kc; a.n = (int)e->n; a.zt = e->d_zt;
+    a.chunk = e->d_chunk; a.pitch = e->chunk_pitch; a.kc = kc; a.n = (int)e->n_row; a.zt = e->d_zt;
     a.Z = e->d_Z + col0; a.z_pitch = e->z_pitch; a.lo_off = (int64_t)e->slots * e->kc_max;
     a.Q = count_mma ? e->d_Q + col0 : nullptr; a.q_pitch = e->q_pitch;
     a.Q4 = count_fp4 ? e->d_Q4 + col0 / 2 : nullptr; a.q4_pitch = e->q4_pitch;
@@ -1159,7 +1183,7 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
         const int blocks = (take * 32 + 255) / 256;
 #define DGRM_DECODE(T)                                                                                          \
   bed_decode_kernel<T><<<blocks, 256, 0, e->prep>>>(d_rows, pitch, d_idx, pos, take, dst, e->chunk_pitch, nbytes, \
-                                                    (int)e->n, snp0, so, e->d_zt, e->fill)
+                                                    (int)e->n_row, snp0, so, e->d_zt, e->fill)
         if (vec == 16) DGRM_DECODE(uint4);
         else if (vec == 8) DGRM_DECODE(uint2);
         else DGRM_DECODE(uint32_t);
@@ -1173,7 +1197,7 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
           const dim3 grid((unsigned)std::max(1, std::min(per_row, 64)), (unsigned)take);
 #define DGRM_GATHER(T)                                                                                            \
   bed_gather_kernel<T><<<grid, 256, 0, e->prep>>>(d_rows, pitch, d_idx, pos, take, dst, e->chunk_pitch, nbytes, \
-                                                  e->d_src_ind, (int)e->n)
+                                                  e->d_src_ind, (int)e->n_row)
           if (vec == 16) DGRM_GATHER(uint4);
           else if (vec == 8) DGRM_GATHER(uint2);
           else if (vec == 4) DGRM_GATHER(uint32_t);
@@ -1182,7 +1206,7 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
           CK(cudaGetLastError());
         }
         Prof pr(e, DGRM_K_COUNT, e->prep);
-        bed_count_stats_kernel<<<(take * 32 + 255) / 256, 256, 0, e->prep>>>(dst, e->chunk_pitch, take, (int)e->n, snp0, so,
+        bed_count_stats_kernel<<<(take * 32 + 255) / 256, 256, 0, e->prep>>>(dst, e->chunk_pitch, take, (int)e->n_row, snp0, so,
                                                                             e->d_zt + (int64_t)e->fill * 4);
         CK(cudaGetLastError());
       }
@@ -1453,7 +1477,9 @@ void dgrm_destroy(dgrm_engine* e) {
   delete e;
 }
 
-int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask) {
+// Cohort + output geometry.  out_dim == 0: GRM mode, the output matrices are individuals x individuals;
+// out_dim > 0: LD mode, they are out_dim x out_dim (SNPs of a group) and the individuals are the contraction axis.
+static int setup_geometry(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask, int64_t out_dim) {
   if (!e) return DGRM_E_INVALID;
   if (n_fam <= 0 || n_fam > (1 << 30)) return fail(e, DGRM_E_INVALID, "dgrm_set_individuals: bad n_fam");
   CK(cudaSetDevice(e->cfg.device));
@@ -1474,11 +1500,13 @@ int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask
       if (keep_mask[f]) src.push_back((int32_t)f); else identity = false;
   }
   e->n_fam = n_fam;
-  e->n = (keep_mask && !identity) ? (int64_t)src.size() : n_fam;
-  if (e->n <= 0) return fail(e, DGRM_E_INVALID, "dgrm_set_individuals: no individual kept");
+  e->n_row = (keep_mask && !identity) ? (int64_t)src.size() : n_fam;
+  if (e->n_row <= 0) return fail(e, DGRM_E_INVALID, "dgrm_set_individuals: no individual kept");
+  e->ld_mode = out_dim > 0;
+  e->n = e->ld_mode ? out_dim : e->n_row;
   e->n_pad = round_up(e->n, 256);
   e->b_fam = (n_fam + 3) / 4;
-  e->b_row = (e->n + 3) / 4;
+  e->b_row = (e->n_row + 3) / 4;
   e->chunk_pitch = round_up(std::max(e->b_fam, e->b_row), 128);
   if (keep_mask && !identity) {
     CK(cudaMalloc(&e->d_src_ind, src.size() * sizeof(int32_t)));
@@ -1516,9 +1544,32 @@ int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask
   return DGRM_OK;
 }
 
+int dgrm_set_individuals(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask) {
+  return setup_geometry(e, n_fam, keep_mask, 0);
+}
+
+static int begin_common(dgrm_engine* e, int64_t m_capacity);
+
 int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
   if (!e) return DGRM_E_INVALID;
   if (!e->have_ind) return fail(e, DGRM_E_INVALID, "dgrm_begin: call dgrm_set_individuals first");
+  if (e->ld_mode) return fail(e, DGRM_E_INVALID, "dgrm_begin: the engine is in LD mode (dgrm_ld_begin); call dgrm_set_individuals for a GRM");
+  return begin_common(e, m_capacity);
+}
+
+// LD mode (GWAS::getLessSignificantCorrelatedSNPs, gwas.cpp:1156-1172): correlations between the m_group SNPs that
+// the following pushes deliver.  The operands are SNP-major (row = SNP, K = individuals, every individual chunk
+// resident at once), the tile store is m_group x m_group, everything downstream of the contraction is shared.
+int dgrm_ld_begin(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask, int64_t m_group) {
+  if (!e) return DGRM_E_INVALID;
+  if (m_group <= 0 || m_group > (1 << 30)) return fail(e, DGRM_E_INVALID, "dgrm_ld_begin: bad m_group");
+  if (e->cfg.flat_norm) return fail(e, DGRM_E_INVALID, "dgrm_ld_begin: flat normalisation does not exist for SNP correlations");
+  int rc = setup_geometry(e, n_fam, keep_mask, m_group);
+  if (rc) return rc;
+  return begin_common(e, m_group);
+}
+
+static int begin_common(dgrm_engine* e, int64_t m_capacity) {
   if (m_capacity <= 0) return fail(e, DGRM_E_INVALID, "dgrm_begin: m_capacity must be positive");
   CK(cudaSetDevice(e->cfg.device));
   if (m_capacity > e->m_cap) {
@@ -1532,7 +1583,23 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
     CK(cudaMalloc(&e->d_sd, (size_t)m_capacity * sizeof(double)));
     e->m_cap = m_capacity;
   }
-  {
+  if (e->ld_mode) {
+    // every individual chunk is resident: slots cover the padded individual count
+    const int64_t kpad = round_up(e->n_row, 256);
+    const int64_t need = (kpad + e->kc_max - 1) / e->kc_max;
+    if (need > kMaxChunks)
+      return fail(e, DGRM_E_INVALID, "dgrm_ld_begin: %lld individuals need more than %d chunks of %d", (long long)e->n_row,
+                  kMaxChunks, e->kc_max);
+    const int rc = ensure_operands(e, (int)need);
+    if (rc) return rc;
+    // rows past the group's SNPs and columns past the individuals must contribute nothing
+    const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
+    CK(cudaMemsetAsync(e->d_Z, 0, (size_t)e->n_pad * e->z_pitch * sizeof(uint16_t), e->prep));
+    if (e->d_Q) CK(cudaMemsetAsync(e->d_Q, 0, (size_t)e->n_pad * e->q_pitch, e->prep));
+    if (e->d_Q4) CK(cudaMemsetAsync(e->d_Q4, 0, (size_t)e->n_pad * e->q4_pitch, e->prep));
+    if (e->d_MB) CK(cudaMemsetAsync(e->d_MB, 0, (size_t)e->n_pad * e->mb_pitch * sizeof(uint32_t), e->prep));
+    (void)split;
+  } else {
     // resident operand slots: as many chunks as the SNP count needs, bounded by the memory budget
     const int64_t need = (m_capacity + e->kc_max - 1) / e->kc_max;
     const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
@@ -1568,7 +1635,7 @@ int dgrm_begin(dgrm_engine* e, int64_t m_capacity) {
   CK(cudaEventRecord(e->mma_ev, e->stream));
   CK(cudaStreamWaitEvent(e->prep, e->mma_ev, 0));
   CK(cudaMemsetAsync(e->d_miss, 0, (size_t)e->n_pad * sizeof(int32_t), e->prep));
-  e->miss_valid = true;
+  e->miss_valid = !e->ld_mode;
   e->n_u16 = false;
   CK(cudaMemsetAsync(e->d_bad_count, 0, 4 * sizeof(int32_t), e->prep));
   CK(cudaMemsetAsync(e->d_diag, 0, (size_t)e->n_pad * sizeof(double), e->prep));
@@ -1690,6 +1757,11 @@ int dgrm_finish(dgrm_engine* e) {
   if (!e->finished) {
     rc = process_chunk(e);
     if (rc) return rc;
+    if (e->ld_mode) {   // every individual chunk is resident: contract them all now
+      const int64_t kpad = round_up(e->n_row, 256);
+      e->chunks_in_super = e->chunks_done > 0 ? e->slots : 0;
+      for (int j = 0; j < e->slots; ++j) e->slot_kpad[j] = (int)std::min<int64_t>(e->kc_max, kpad - (int64_t)j * e->kc_max);
+    }
     rc = flush_super(e, true);
     if (rc) return rc;
     CK(cudaEventRecord(e->prep_ev, e->prep));  // statistics, bad-SNP list and the exact diagonal live on the decode stream
@@ -1993,6 +2065,33 @@ int dgrm_low_overlap_pairs(dgrm_engine* e, double min_overlap, int64_t* pairs, i
   const int64_t n_vis = e->d_subset ? e->n_out : e->n;
   const dim3 grid((unsigned)((n_vis + 255) / 256), (unsigned)std::min<int64_t>(n_vis, 32768));
   low_overlap_kernel<<<grid, 256, 0, e->stream>>>(tile_store(e), min_overlap, bf.pairs, cap, bf.count);
+  CK(cudaGetLastError());
+  unsigned long long c = 0;
+  CK(cudaMemcpyAsync(&c, bf.count, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  *count = (int64_t)c;
+  if (cap > 0 && c > 0)
+    CK(cudaMemcpy(pairs, bf.pairs, (size_t)std::min<int64_t>(cap, (int64_t)c) * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  return DGRM_OK;
+}
+
+int dgrm_ld_pairs(dgrm_engine* e, double threshold, int64_t* pairs, int64_t cap, int64_t* count) {
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  if (!e->ld_mode) return fail(e, DGRM_E_INVALID, "dgrm_ld_pairs: the engine is not in LD mode (dgrm_ld_begin)");
+  if (cap < 0 || (cap > 0 && !pairs) || !count) return fail(e, DGRM_E_INVALID, "dgrm_ld_pairs: bad arguments");
+  CK(cudaSetDevice(e->cfg.device));
+  struct Bufs {
+    int64_t* pairs = nullptr;
+    unsigned long long* count = nullptr;
+    ~Bufs() { if (pairs) cudaFree(pairs); if (count) cudaFree(count); }
+  } bf;
+  CK(cudaMalloc(&bf.count, sizeof(unsigned long long)));
+  if (cap > 0) CK(cudaMalloc(&bf.pairs, (size_t)cap * 2 * sizeof(int64_t)));
+  CK(cudaMemsetAsync(bf.count, 0, sizeof(unsigned long long), e->stream));
+  const int64_t n_vis = e->d_subset ? e->n_out : e->n;
+  const dim3 grid((unsigned)((n_vis + 255) / 256), (unsigned)std::min<int64_t>(n_vis, 32768));
+  outside_range_kernel<<<grid, 256, 0, e->stream>>>(tile_store(e), threshold, bf.pairs, cap, bf.count);
   CK(cudaGetLastError());
   unsigned long long c = 0;
   CK(cudaMemcpyAsync(&c, bf.count, sizeof c, cudaMemcpyDeviceToHost, e->stream));

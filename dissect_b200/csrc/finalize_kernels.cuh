@@ -177,6 +177,26 @@ __global__ void low_overlap_kernel(const TileStore ts, double min_overlap, int64
   }
 }
 
+// LD mode: strictly-lower pairs whose value lies outside [-threshold, threshold] — what
+// Matrix::getGlobalIndexOutsideRange(-t, t) reports for a symmetric 'L' matrix (matrix.cpp:4279-4307) and
+// GWAS::getLessSignificantCorrelatedSNPs then keeps (idxS1 > idxS2, gwas.cpp:1191).  NaN compares false, as there.
+__global__ void outside_range_kernel(const TileStore ts, double threshold, int64_t* __restrict__ pairs, int64_t cap,
+                                     unsigned long long* __restrict__ count) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= ts.n) return;
+  for (int c = blockIdx.y; c < r; c += gridDim.y) {
+    double v;
+    if (!tile_value(ts, 0, r, c, &v)) continue;
+    if (v < -threshold || v > threshold) {
+      const unsigned long long k = atomicAdd(count, 1ull);
+      if ((int64_t)k < cap) {
+        pairs[2 * k] = r;
+        pairs[2 * k + 1] = c;
+      }
+    }
+  }
+}
+
 // Packed (n+1) x n column-major array of packMatrices (matrix.cpp:2324-2334), columns [c0, c1):
 //   P[r][c] = N[r][c]   r = 0..c       (upper triangle of N incl. diagonal)
 //   P[r+1][c] = A[r][c] r = c..n-1     (lower triangle of A incl. diagonal)

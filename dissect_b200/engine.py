@@ -109,6 +109,20 @@ class GrmEngine:
             assert km.shape == (n_fam,)
         self._ck(self._lib.dgrm_set_individuals(self._h, n_fam, km.ctypes.data if km is not None else None))
 
+    def ld_begin(self, n_fam, m_group, keep_mask=None):
+        """LD mode: the following pushes deliver the m_group SNPs whose correlations are wanted (gwas.cpp:1156-1172)."""
+        km = None
+        if keep_mask is not None:
+            km = np.ascontiguousarray(keep_mask, dtype=np.int32)
+            assert km.shape == (n_fam,)
+        self._ck(self._lib.dgrm_ld_begin(self._h, int(n_fam), km.ctypes.data if km is not None else None, int(m_group)))
+
+    def ld_pairs(self, threshold, cap=1 << 20):
+        pairs = np.zeros((cap, 2), np.int64)
+        cnt = C.c_int64(0)
+        self._ck(self._lib.dgrm_ld_pairs(self._h, float(threshold), pairs.ctypes.data, cap, C.byref(cnt)))
+        return sorted(map(tuple, pairs[: min(cap, cnt.value)].tolist())), cnt.value
+
     def begin(self, m_capacity):
         self._ck(self._lib.dgrm_begin(self._h, int(m_capacity)))
 

@@ -145,7 +145,7 @@ int dgrm_finish(dgrm_engine *e);
 int dgrm_sync(dgrm_engine *e);
 
 int64_t dgrm_num_snps(const dgrm_engine *e);         /* SNPs pushed and kept so far          */
-int64_t dgrm_num_individuals(const dgrm_engine *e);  /* individuals kept                     */
+int64_t dgrm_num_individuals(const dgrm_engine *e);  /* individuals kept = dimension of the output matrices (LD mode: SNPs of the group) */
 
 /* What `struct SNP` holds on the root rank after readBEDFile/gatherSNPData
  * (genotype.h:65-69, genotype.cpp:735-738, 859-870): bit-exact counts, 0-ulp doubles.
@@ -263,6 +263,23 @@ int dgrm_fetch_standardised(dgrm_engine *e, double *local, int64_t lld, int bs_r
 #define DGRM_VIEW_SAVED_PLUS_CURRENT 3
 int dgrm_save(dgrm_engine *e, int mode);
 int dgrm_set_view(dgrm_engine *e, int view);
+
+/* ---- LD mode: SNP x SNP correlations of a group of SNPs ---------------------------------
+ * Replaces the contraction of GWAS::getLessSignificantCorrelatedSNPs (gwas.cpp:1156-1172; igwas.cpp:979-995):
+ *     correlations->multiply(genotypes, 'N', genotypes, 'T')      G G^T     (pdsyrk_('L','N'), matrix.cpp:2677-2683)
+ *     normalization->multiply(missings, 'N', missings, 'T')       M M^T
+ *     correlations->elementWiseDivision(normalization)            matrix.cpp:4091-4098
+ *     correlations->getGlobalIndexOutsideRange(-t, t, ...)        matrix.cpp:4265-4330
+ * on the standardised genotypes (gwas.cpp:149) of the m_group SNPs pushed after dgrm_ld_begin with the ordinary
+ * dgrm_push_bed_host / dgrm_push_bed_device calls (SNP rows in group order; row_keep as usual).  Same kernels as
+ * the GRM with the roles of SNPs and individuals exchanged: the contraction runs over the kept individuals.
+ * After dgrm_finish every reader works on the m_group x m_group matrices: dgrm_fetch_block_cyclic(DGRM_FETCH_A) is
+ * `correlations`, DGRM_FETCH_N the shared non-missing counts, dgrm_snp_stats the group's struct SNP values, and
+ * dgrm_ld_pairs lists the strictly-lower (row, col) pairs with value < -threshold or > threshold, the pairs
+ * gwas.cpp:1191 acts on (pairs is [cap][2]; *count receives the total found, which may exceed cap).
+ * dgrm_set_individuals returns the engine to GRM mode. */
+int dgrm_ld_begin(dgrm_engine *e, int64_t n_fam, const int32_t *keep_mask, int64_t m_group);
+int dgrm_ld_pairs(dgrm_engine *e, double threshold, int64_t *pairs, int64_t cap, int64_t *count);
 
 /* Bytes the copy engine moved device -> host for the streamed (bound) outputs of the last dgrm_finish. */
 int64_t dgrm_last_d2h_bytes(const dgrm_engine *e);

@@ -1,0 +1,99 @@
+"""GPU: LD mode through the C ABI — the SNP x SNP correlation step of the reference's GWAS
+(gwas.cpp:1156-1172) against (a) the matrices and index lists the reference's own objects produced
+(tests/golden/ld_*, oracle/_ref/ldcorr) and (b) the numpy restatement on seeded inputs.
+Bars: per-SNP statistics and the shared non-missing counts N bit-exact; correlations within the operand tolerance
+(stated below, absolute: correlations are O(1)); the outside-range pair list identical wherever the reference's value
+is not within that tolerance of the threshold."""
+import numpy as np
+import pytest
+
+from dissect_b200 import GrmEngine, bedio
+from oracle import grm_oracle as orc
+from tests.helpers import load_ld_case, lower_mask
+
+pytestmark = pytest.mark.gpu
+
+LD_CASES = ["ld_n61_m40", "ld_n130_m90_keep_extract", "ld_n300_m270"]
+# max |C_gpu - C_ref| over the lower triangle.  The contraction length is the number of individuals K: operand rounding
+# gives about 2^-11 / sqrt(K) per entry for fp16 (measured 3e-5 at K = 300), 8x that for bf16, 1e-6 for the split.
+TOL_C = {"fp16": 2e-4, "bf16": 2e-3, "fp16x2": 5e-6}
+
+
+def ld_build(rows, n_fam, keep_mask=None, **kw):
+    eng = GrmEngine(**kw)
+    eng.ld_begin(n_fam, rows.shape[0], keep_mask)
+    eng.push_bed_host(np.ascontiguousarray(rows))
+    eng.finish()
+    return eng
+
+
+def check_pairs(got, ref_strict, ref_C, thr, tol):
+    sure = {p for p in ref_strict if abs(abs(ref_C[p]) - thr) > tol}
+    near = {(r, c) for r in range(ref_C.shape[0]) for c in range(r) if abs(abs(ref_C[r, c]) - thr) <= tol}
+    assert sure <= set(got) <= sure | near
+
+
+@pytest.mark.parametrize("operand", ["fp16", "fp16x2"])
+@pytest.mark.parametrize("name", LD_CASES)
+def test_ld_golden_reference_outputs(name, operand):
+    c = load_ld_case(name)
+    eng = ld_build(c["rows"], c["n_fam"], c["keep_mask"], operand=operand, chunk_snps=256)
+    m = c["rows"].shape[0]
+    assert eng.num_snps == m and eng.num_individuals == m
+    codes = orc.decode_rows(c["rows"], c["n_fam"], c["keep_mask"])
+    want = orc.ld(codes, c["threshold"])
+    st = eng.snp_stats()
+    assert np.array_equal(st["freq"], want["stats"]["freq"])
+    for k in ("p1", "p2", "sd"):
+        assert np.array_equal(st[k].view(np.uint64), want["stats"][k].view(np.uint64)), k
+    low = lower_mask(m)
+    C = eng.fetch_block_cyclic("A", bs=(m, m))
+    N = eng.fetch_block_cyclic("N", bs=(m, m))
+    assert np.array_equal(N[low], want["N"][low])
+    assert np.max(np.abs(C[low] - c["ref_C"][low])) <= TOL_C[operand]
+    assert np.max(np.abs(np.diag(C) - np.diag(c["ref_C"]))) <= 1e-12        # exact fp64 diagonal
+    pairs, cnt = eng.ld_pairs(c["threshold"])
+    assert cnt == len(pairs)
+    ref_strict = sorted({(r, cc) for r, cc in c["ref_pairs"] if r > cc})
+    check_pairs(pairs, ref_strict, c["ref_C"], c["threshold"], TOL_C[operand])
+    eng.close()
+
+
+@pytest.mark.parametrize("operand,count,cg", [("fp16", "fp4", 2), ("fp16", "fp4", 1), ("bf16", "mma", 2), ("fp16", "popc", 2)])
+def test_ld_vs_oracle_seeded(operand, count, cg):
+    """3000 individuals (three 1024-individual chunks along K, ragged last byte), 700 SNPs, 3 % missing."""
+    n, m = 2999, 700
+    pk = bedio.synth_packed(n, m, 71, maf_lo=0.1, missing=0.03)
+    keep = np.ones(n, np.int32)
+    keep[::11] = 0
+    eng = ld_build(pk, n, keep, operand=operand, count_method=count, cta_group=cg, chunk_snps=1024)
+    want = orc.ld(orc.decode_rows(pk, n, keep), 0.08)
+    low = lower_mask(m)
+    N = eng.fetch_block_cyclic("N", bs=(m, m))
+    C = eng.fetch_block_cyclic("A", bs=(m, m))
+    assert np.array_equal(N[low], want["N"][low])
+    assert np.max(np.abs(C[low] - want["C"][low])) <= TOL_C[operand]
+    pairs, _ = eng.ld_pairs(0.08)
+    check_pairs(pairs, want["pairs"], np.nan_to_num(want["C"]), 0.08, TOL_C[operand])
+    assert len(want["pairs"]) > 10
+    eng.close()
+
+
+def test_ld_then_grm_on_the_same_engine():
+    """dgrm_set_individuals returns an engine from LD mode to GRM mode."""
+    n, m = 300, 400
+    pk = bedio.synth_packed(n, m, 72, missing=0.02)
+    eng = GrmEngine(chunk_snps=256)
+    eng.ld_begin(n, 100)
+    eng.push_bed_host(np.ascontiguousarray(pk[:100]))
+    eng.finish()
+    with pytest.raises(Exception):
+        eng.begin(m)                                  # still in LD mode
+    eng.set_individuals(n)
+    eng.begin(m)
+    eng.push_bed_host(pk)
+    eng.finish()
+    ref = orc.grm(orc.decode_rows(pk, n))
+    low = lower_mask(n)
+    assert np.array_equal(eng.fetch_block_cyclic("N", bs=(n, n))[low], ref["N"][low])
+    eng.close()
