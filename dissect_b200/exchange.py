@@ -55,7 +55,7 @@ class PeerExchange:
         self.error = None
         self._peer_tensors = []      # keep the mappings alive
         self.peer_buf, self.peer_flag = [], []
-        self.mapping = os.environ.get("DGRM_EXCHANGE_MAP", "symm")
+        self.mapping = os.environ.get("DGRM_EXCHANGE_MAP", "ipc")
         self.seqsrc = torch.arange(_SEQ_CAP, dtype=torch.int32, device="cuda")
         nbuf_bytes = (world * rows_per_rank * pitch + 4095) // 4096 * 4096
         try:
