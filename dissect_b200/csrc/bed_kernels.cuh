@@ -238,6 +238,124 @@ bed_decode_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const int3
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1a+b, GRM mode: the same single pass (row selection + per-SNP counts), but the chunk leaves it TRANSPOSED in
+// 16-SNP groups:   T[kg][i] = one 32-bit word = the 2-bit patterns of SNPs 16 kg .. 16 kg + 15 of individual i
+// (SNP t at bits 2t).  bed_expand, whose threads run along individuals, then needs ONE coalesced 32-bit global load
+// per 16 genotypes instead of sixteen byte loads from a staged shared-memory tile, and the word's nibbles index the
+// SNP-pair tables directly.  Same 1/4 byte per genotype as the row-major chunk.
+// Thread = (16-row group, word column j = individuals 16 j .. 16 j + 15): 16 coalesced 32-bit loads (one per row),
+// a 16 x 16 transpose of 2-bit fields in registers (4 butterfly stages), 64 contiguous bytes out.
+// Rows arrive in arbitrary batches: a launch covers chunk rows [fill, fill + nrows); a group whose first row is in
+// this launch starts from "all missing" (01), otherwise the word written by the previous launch is updated.
+// Per-row counts are reduced over the warp, then the block, then added to counts[row][3] with atomics;
+// bed_stats_finish_kernel turns them into struct SNP values once the rows are complete.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void transpose16x16_2bit(uint32_t (&w)[16]) {
+#define DGRM_TSTAGE(S, MASK)                                   \
+  _Pragma("unroll") for (int j = 0; j < 16; ++j)               \
+    if ((j & S) == 0) {                                        \
+      const uint32_t t = ((w[j] >> (2 * S)) ^ w[j + S]) & MASK; \
+      w[j + S] ^= t;                                           \
+      w[j] ^= t << (2 * S);                                    \
+    }
+  DGRM_TSTAGE(8, 0x0000FFFFu)
+  DGRM_TSTAGE(4, 0x00FF00FFu)
+  DGRM_TSTAGE(2, 0x0F0F0F0Fu)
+  DGRM_TSTAGE(1, 0x33333333u)
+#undef DGRM_TSTAGE
+}
+
+__global__ void __launch_bounds__(256)
+bed_decode_t_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const int32_t* __restrict__ rows, int64_t row0,
+                    int fill, int nrows, uint32_t* __restrict__ T, int64_t t_pitch, int nbytes, int n,
+                    int32_t* __restrict__ counts /* [chunk rows][4]: missing, -, het, hom A2 */) {
+  __shared__ int s_cnt[16][3];
+  const int kg = (fill >> 4) + blockIdx.y;          // 16-row group of the chunk
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nwords = (n + 15) >> 4;
+  const int g0 = kg << 4;                           // first chunk row of the group
+  const int ra = max(g0, fill), rb = min(g0 + 16, fill + nrows);   // chunk rows of this group delivered by this launch
+  if (threadIdx.x < 48) s_cnt[threadIdx.x / 3][threadIdx.x % 3] = 0;
+  __syncthreads();
+  uint32_t w[16];
+  int c0[16], c2[16], c3[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) { w[t] = 0x55555555u; c0[t] = c2[t] = c3[t] = 0; }
+  if (j < nwords) {
+    const int valid = min(16, n - 16 * j);
+    const uint32_t keep = valid == 16 ? 0xFFFFFFFFu : ((1u << (2 * valid)) - 1u);
+    const bool whole = 4 * j + 4 <= nbytes;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int r = g0 + t;
+      if (r < ra || r >= rb) continue;
+      const int64_t srow = rows ? (int64_t)rows[r - fill] : row0 + (r - fill);
+      const uint8_t* s = src + srow * src_pitch + 4 * j;
+      uint32_t v;
+      if (whole) {
+        v = __ldg(reinterpret_cast<const uint32_t*>(s));
+      } else {
+        v = 0;
+        for (int b = 0; 4 * j + b < nbytes; ++b) v |= (uint32_t)s[b] << (8 * b);
+      }
+      v = (v & keep) | (0x55555555u & ~keep);       // individuals past n read as missing and are not counted
+      const uint32_t lo = v & 0x55555555u, hi = (v >> 1) & 0x55555555u, km = keep & 0x55555555u;
+      c3[t] = __popc(lo & hi & km);
+      c2[t] = __popc(hi & ~lo & km);
+      c0[t] = __popc(lo & ~hi & km);
+      w[t] = v;
+    }
+    transpose16x16_2bit(w);                         // w[c] = individual 16 j + c, SNP t at bits 2t
+    uint32_t* out = T + (int64_t)kg * t_pitch + 16 * j;
+    if (ra == g0 && rb == g0 + 16) {                // the whole group in one launch: plain 16-byte stores
+#pragma unroll
+      for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(out)[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    } else {
+      // rows [ra, rb) of the group: merge into what earlier launches wrote (or into "all missing" when this launch
+      // delivers the group's first row)
+      const uint32_t lo_bits = (ra - g0) == 0 ? 0u : ((1u << (2 * (ra - g0))) - 1u);
+      const uint32_t hi_bits = (rb - g0) == 16 ? 0xFFFFFFFFu : ((1u << (2 * (rb - g0))) - 1u);
+      const uint32_t mine = hi_bits & ~lo_bits;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const uint32_t old = ra == g0 ? 0x55555555u : out[c];
+        out[c] = (old & ~mine) | (w[c] & mine);
+      }
+    }
+  }
+  // counts: warp reduce (two 16-bit counters per register: <= 16 * 32 each), block reduce in shared memory, atomics out
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    uint32_t a = (uint32_t)c0[t] | ((uint32_t)c2[t] << 16), b = (uint32_t)c3[t];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, sft);
+      b += __shfl_xor_sync(0xffffffffu, b, sft);
+    }
+    if ((threadIdx.x & 31) == 0 && (a | b)) {
+      atomicAdd(&s_cnt[t][0], (int)(a & 0xFFFFu));
+      atomicAdd(&s_cnt[t][1], (int)(a >> 16));
+      atomicAdd(&s_cnt[t][2], (int)b);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 48) {
+    const int t = threadIdx.x / 3, k = threadIdx.x % 3;
+    const int v = s_cnt[t][k];
+    if (v) atomicAdd(&counts[(int64_t)(g0 + t) * 4 + (k == 0 ? 0 : k + 1)], v);
+  }
+}
+
+// struct SNP values of chunk rows [fill, fill + nrows) from their complete counts (reference operation order)
+__global__ void bed_stats_finish_kernel(const int32_t* __restrict__ counts, int fill, int nrows, int n, int64_t snp0,
+                                        SnpStatsOut o, double* __restrict__ zt) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const int32_t* c = counts + (int64_t)(fill + r) * 4;
+  snp_stats_finish(c[0], c[2], c[3], n, snp0 + r, fill + r, o, zt);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1c: expand one chunk into tensor-core operands.
 //   Z  [n_pad][z_pitch] 16-bit, K-major: Z[i][k] = round16(zt[k][pattern(k,i)])         (hi part)
 //      with SPLIT also Z[i][lo_off + k] = round16(zt - hi)                                 (lo part)
@@ -445,6 +563,201 @@ __global__ void __launch_bounds__(256) bed_expand_kernel(const ExpandArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1c, GRM mode, from the transposed chunk T (bed_decode_t_kernel): same outputs as bed_expand_kernel.
+// A thread owns one individual and walks 16-SNP words: one coalesced 32-bit global load per 16 genotypes; each nibble
+// of the word (the patterns of two adjacent SNPs) indexes a 16-entry table of the SNP PAIR: two 16-bit operand
+// values in one 32-bit shared-memory read, and the sum of the two exact squares in one 64-bit read.  That is 1.5
+// shared-memory wavefronts per genotype instead of ~4 (byte + 16-bit + 64-bit lookups per genotype), which was what
+// bounded the row-major kernel (61 M wavefronts per 16384-SNP chunk, profiles/r1b_ncu_full_summary.csv).
+// Also emits, per individual, the number of missing genotypes of the tile (the bound that lets streamed pair counts
+// travel as 16-bit values), which used to be a third pass over the chunk.
+// ------------------------------------------------------------------------------------------------
+struct ExpandTArgs {
+  const uint32_t* T;   // [kc / 16][t_pitch]
+  int64_t t_pitch;     // words
+  int kc;              // valid SNP rows in the chunk
+  int n;               // individuals
+  const double* zt;    // [kc][4]
+  uint16_t* Z;
+  int64_t z_pitch;
+  int64_t lo_off;
+  uint8_t* Q;
+  int64_t q_pitch;
+  uint8_t* Q4;
+  int64_t q4_pitch;
+  uint32_t* MB;
+  int64_t mb_pitch;
+  double* diag_part;   // [ktiles][n_pad]
+  int32_t* miss_part;  // [ktiles][n_pad] or NULL
+  int n_pad;
+};
+
+template <int QK>
+struct ExpandTSmem {
+  uint16_t lut_hi[kExpK][4];
+  uint16_t lut_lo[kExpK][4];
+  double lut_sq[kExpK][4];
+  uint32_t pair_hi[kExpK / 2][16];   // operand values of SNPs (2p, 2p+1): low half-word = SNP 2p
+  uint32_t pair_lo[kExpK / 2][16];
+  double pair_sq[kExpK / 2][16];
+  double dpart[2][kExpI];
+  int mpart[2][kExpI];
+  uint8_t outz[kExpI * kExpZPitch];
+  uint8_t outq[kExpI * (QK == 1 ? kExpQPitch : QK == 2 ? kExpQ4Pitch : kExpMPitch)];
+};
+
+template <bool BF16, bool SPLIT, int QK>
+__global__ void __launch_bounds__(256) bed_expand_t_kernel(const ExpandTArgs a) {
+  extern __shared__ __align__(16) uint8_t expand_smem_raw[];
+  ExpandTSmem<QK>& sm = *reinterpret_cast<ExpandTSmem<QK>*>(expand_smem_raw);
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * kExpI;
+  const int k0 = blockIdx.y * kExpK;
+  if (tid < kExpK) {
+    double z[4] = {0., 0., 0., 0.};
+    if (k0 + tid < a.kc) {
+      const double* zp = a.zt + (int64_t)(k0 + tid) * 4;
+      z[0] = zp[0]; z[2] = zp[2]; z[3] = zp[3];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint16_t hi = round16<BF16>(z[c]);
+      sm.lut_hi[tid][c] = hi;
+      sm.lut_lo[tid][c] = SPLIT ? round16<BF16>(z[c] - widen16<BF16>(hi)) : (uint16_t)0;
+      sm.lut_sq[tid][c] = __dmul_rn(z[c], z[c]);
+    }
+  }
+  __syncthreads();
+  // pair tables: entry idx = pattern(SNP 2p) + 4 * pattern(SNP 2p + 1); 64 pairs x 16 entries, 4 per thread
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int ent = tid * 4 + q, p = ent >> 4, idx = ent & 15;
+    const int ca = idx & 3, cb = idx >> 2;
+    sm.pair_hi[p][idx] = (uint32_t)sm.lut_hi[2 * p][ca] | ((uint32_t)sm.lut_hi[2 * p + 1][cb] << 16);
+    if (SPLIT) sm.pair_lo[p][idx] = (uint32_t)sm.lut_lo[2 * p][ca] | ((uint32_t)sm.lut_lo[2 * p + 1][cb] << 16);
+    sm.pair_sq[p][idx] = __dadd_rn(sm.lut_sq[2 * p][ca], sm.lut_sq[2 * p + 1][cb]);
+  }
+  __syncthreads();
+
+  const int il = tid & (kExpI - 1);
+  const int kh = tid >> 7;
+  const bool real = i0 + il < a.n;
+  // the individual's 8 words of this tile (16 SNPs each); groups past the chunk and individuals past n: all missing
+  uint32_t words[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int kgl = kh + 2 * j;                 // 16-SNP group within the tile
+    words[j] = 0x55555555u;
+    if (real && k0 + 16 * kgl < a.kc) words[j] = __ldg(a.T + (int64_t)((k0 >> 4) + kgl) * a.t_pitch + i0 + il);
+  }
+  double dsum = 0.;
+  int msum = 0;
+#pragma unroll 1
+  for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+    const uint32_t* ptab = part == 0 ? &sm.pair_hi[0][0] : &sm.pair_lo[0][0];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kgl = kh + 2 * j;
+      const uint32_t w = words[j];
+      uint32_t h[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const uint32_t idx = (w >> (4 * p)) & 15u;
+        h[p] = ptab[(kgl * 8 + p) * 16 + idx];
+        if (part == 0) dsum = __dadd_rn(dsum, sm.pair_sq[kgl * 8 + p][idx]);
+      }
+      uint4* oz = reinterpret_cast<uint4*>(&sm.outz[il * kExpZPitch + kgl * 32]);
+      oz[0] = make_uint4(h[0], h[1], h[2], h[3]);
+      oz[1] = make_uint4(h[4], h[5], h[6], h[7]);
+      if (part == 0) {
+        const uint32_t lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+        msum += __popc(lo & ~hi);
+        if (QK != 0) {
+          // present <=> pattern != 01; one flag per SNP at bit 2t (16 SNPs)
+          const uint32_t x = (hi | (lo ^ 0x55555555u)) & 0x55555555u;
+          if constexpr (QK == 2) {
+            // spread flag t from bit 2t to bit 4t + 1 (e2m1 1.0 = 0b0010 in nibble t), 8 SNPs per 32-bit word
+            uint32_t out2[2];
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              uint32_t y = (x >> (16 * hlf)) & 0xFFFFu;
+              y = (y & 0xFFu) | ((y & 0xFF00u) << 8);
+              y = (y & 0x000F000Fu) | ((y & 0x00F000F0u) << 4);
+              y = (y & 0x01010101u) | ((y & 0x04040404u) << 2);
+              out2[hlf] = y << 1;
+            }
+            uint32_t* oq = reinterpret_cast<uint32_t*>(&sm.outq[il * kExpQ4Pitch + kgl * 8]);   // 68-byte pitch: 4-byte aligned
+            oq[0] = out2[0];
+            oq[1] = out2[1];
+          } else {
+            uint32_t y = x;                      // compress the 16 flags to adjacent bits
+            y = (y | (y >> 1)) & 0x33333333u;
+            y = (y | (y >> 2)) & 0x0F0F0F0Fu;
+            y = (y | (y >> 4)) & 0x00FF00FFu;
+            y = (y | (y >> 8)) & 0x0000FFFFu;
+            if constexpr (QK == 3) {
+              *reinterpret_cast<uint16_t*>(&sm.outq[il * kExpMPitch + kgl * 2]) = (uint16_t)y;
+            } else {                             // e4m3 1.0 = 0x38, one byte per SNP
+              uint32_t qb[4];
+#pragma unroll
+              for (int v = 0; v < 4; ++v) qb[v] = ((((y >> (4 * v)) & 0xFu) * 0x00204081u) & 0x01010101u) * 0x38u;
+              uint2* oq = reinterpret_cast<uint2*>(&sm.outq[il * kExpQPitch + kgl * 16]);         // 136-byte pitch: 8-byte aligned
+              oq[0] = make_uint2(qb[0], qb[1]);
+              oq[1] = make_uint2(qb[2], qb[3]);
+            }
+          }
+        }
+      }
+    }
+    if (part == 0) { sm.dpart[kh][il] = dsum; sm.mpart[kh][il] = msum; }
+    __syncthreads();
+    // write-out: full rows, 16 lanes per row
+    {
+      const int c = tid & 15;
+      uint16_t* zbase = a.Z + (part == 0 ? 0 : a.lo_off) + k0;
+#pragma unroll
+      for (int ps = 0; ps < kExpI / 16; ++ps) {
+        const int r = ps * 16 + (tid >> 4);
+        const uint4 v = *reinterpret_cast<const uint4*>(&sm.outz[r * kExpZPitch + c * 16]);
+        *reinterpret_cast<uint4*>(zbase + (int64_t)(i0 + r) * a.z_pitch + c * 8) = v;
+      }
+      if (part == 0) {
+        if constexpr (QK == 1) {
+#pragma unroll
+          for (int ps = 0; ps < kExpI / 16; ++ps) {
+            const int r = ps * 16 + (tid >> 4);
+            const uint2 v = *reinterpret_cast<const uint2*>(&sm.outq[r * kExpQPitch + c * 8]);
+            *reinterpret_cast<uint2*>(a.Q + (int64_t)(i0 + r) * a.q_pitch + k0 + c * 8) = v;
+          }
+        }
+        if constexpr (QK == 2) {
+#pragma unroll
+          for (int ps = 0; ps < kExpI / 16; ++ps) {
+            const int r = ps * 16 + (tid >> 4);
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(&sm.outq[r * kExpQ4Pitch + c * 4]);
+            *reinterpret_cast<uint32_t*>(a.Q4 + (int64_t)(i0 + r) * a.q4_pitch + (k0 >> 1) + c * 4) = v;
+          }
+        }
+        if constexpr (QK == 3) {
+          if (tid < kExpI) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.outq[tid * kExpMPitch]);
+            *reinterpret_cast<uint4*>(a.MB + (int64_t)(i0 + tid) * a.mb_pitch + (k0 >> 5)) =
+                make_uint4(src[0], src[1], src[2], src[3]);
+          }
+        }
+        if (tid < kExpI) {
+          a.diag_part[(int64_t)blockIdx.y * a.n_pad + i0 + tid] = __dadd_rn(sm.dpart[0][tid], sm.dpart[1][tid]);
+          if (a.miss_part)   // padding individuals and SNP rows past the chunk were read as "missing": not real ones
+            a.miss_part[(int64_t)blockIdx.y * a.n_pad + i0 + tid] =
+                (i0 + tid < a.n) ? sm.mpart[0][tid] + sm.mpart[1][tid] - max(0, min(kExpK, k0 + kExpK - a.kc)) : 0;
+        }
+      }
+    }
+    if (SPLIT) __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LD mode (GWAS::getLessSignificantCorrelatedSNPs, gwas.cpp:1163-1165: genotypes * genotypes^T, missings * missings^T):
 // the operands are SNP-major, which is the .bed's own order — row k of the chunk becomes operand row k with the
 // individuals along K, no transposition:
@@ -519,12 +832,18 @@ __global__ void __launch_bounds__(256) ld_expand_kernel(const LdExpandArgs a) {
 }
 
 // diag[i] += sum_kt diag_part[kt][i], fixed order (deterministic).
-__global__ void diag_reduce_kernel(const double* __restrict__ part, int nkt, int n_pad, double* __restrict__ diag) {
+__global__ void diag_reduce_kernel(const double* __restrict__ part, int nkt, int n_pad, double* __restrict__ diag,
+                                   const int32_t* __restrict__ miss_part = nullptr, int32_t* __restrict__ miss = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pad) return;
   double s = diag[i];
   for (int kt = 0; kt < nkt; ++kt) s = __dadd_rn(s, part[(int64_t)kt * n_pad + i]);
   diag[i] = s;
+  if (miss_part) {   // per-individual missing genotypes of the chunk (exact integers)
+    int mc = miss[i];
+    for (int kt = 0; kt < nkt; ++kt) mc += miss_part[(int64_t)kt * n_pad + i];
+    miss[i] = mc;
+  }
 }
 
 }  // namespace dgrm

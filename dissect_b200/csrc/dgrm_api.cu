@@ -183,6 +183,11 @@ struct dgrm_engine {
   bool n_u16 = false;          // streamed pair counts travel as 16-bit deficiencies m - N
   int overlap = 1;  // DGRM_OVERLAP=0: contract only in dgrm_finish (experiments)
   int fused_decode = 1;  // DGRM_FUSED_DECODE=0: separate gather and count kernels (A/B measurements)
+  int k1_transposed = 1; // DGRM_K1_TRANSPOSED=0: row-major chunk + bed_expand_kernel (round-1 decode path, A/B measurements)
+  uint32_t* d_chunkT = nullptr;   // transposed chunk: [kc_max / 16][t_pitch] words (GRM mode)
+  int64_t t_pitch = 0;
+  int32_t* d_counts = nullptr;    // [kc_max][4] per-row pattern counts being accumulated
+  int32_t* d_miss_part = nullptr; // [kc_max / 128][n_pad]
 
   bool have_ind = false, begun = false, finished = false;
 
@@ -278,6 +283,9 @@ void release_geometry(dgrm_engine* e) {
   e->saved = false;
   e->view = DGRM_VIEW_CURRENT;
   free_dev(e->d_chunk); e->d_chunk = nullptr;
+  free_dev(e->d_chunkT); e->d_chunkT = nullptr;
+  free_dev(e->d_counts); e->d_counts = nullptr;
+  free_dev(e->d_miss_part); e->d_miss_part = nullptr;
   free_dev(e->d_Z); e->d_Z = nullptr;
   free_dev(e->d_Q); e->d_Q = nullptr;
   free_dev(e->d_Q4); e->d_Q4 = nullptr;
@@ -462,7 +470,8 @@ int process_chunk(dgrm_engine* e) {
 
   // (per-SNP counts, statistics and the zt table of these rows were produced while the rows were gathered into the
   // chunk buffer: bed_decode_kernel in push_device_rows)
-  if (!e->cfg.flat_norm && e->miss_valid) {
+  const bool transposed = e->d_chunkT != nullptr;
+  if (!transposed && !e->cfg.flat_norm && e->miss_valid) {
     if (streaming_bound(e)) {
       const int nbytes = (int)e->b_row;
       const dim3 grid((unsigned)((nbytes + 127) / 128), (unsigned)((kc + 255) / 256));
@@ -474,31 +483,56 @@ int process_chunk(dgrm_engine* e) {
   }
   {
     Prof pr(e, DGRM_K_EXPAND, e->prep);
-    ExpandArgs a;
-    a.chunk = e->d_chunk; a.pitch = e->chunk_pitch; a.kc = kc; a.n = (int)e->n_row; a.zt = e->d_zt;
-    a.Z = e->d_Z + col0; a.z_pitch = e->z_pitch; a.lo_off = (int64_t)e->slots * e->kc_max;
-    a.Q = count_mma ? e->d_Q + col0 : nullptr; a.q_pitch = e->q_pitch;
-    a.Q4 = count_fp4 ? e->d_Q4 + col0 / 2 : nullptr; a.q4_pitch = e->q4_pitch;
-    a.MB = count_popc ? e->d_MB + col0 / 32 : nullptr; a.mb_pitch = e->mb_pitch;
-    a.diag_part = e->d_diag_part; a.n_pad = (int)e->n_pad;
     const dim3 grid((unsigned)(e->n_pad / kExpI), (unsigned)(kc_pad / kExpK));
-    const size_t smem = sizeof(ExpandSmem);
     const int qk = count_mma ? 1 : count_fp4 ? 2 : count_popc ? 3 : 0;
+    if (transposed) {
+      ExpandTArgs a;
+      a.T = e->d_chunkT; a.t_pitch = e->t_pitch; a.kc = kc; a.n = (int)e->n_row; a.zt = e->d_zt;
+      a.Z = e->d_Z + col0; a.z_pitch = e->z_pitch; a.lo_off = (int64_t)e->slots * e->kc_max;
+      a.Q = count_mma ? e->d_Q + col0 : nullptr; a.q_pitch = e->q_pitch;
+      a.Q4 = count_fp4 ? e->d_Q4 + col0 / 2 : nullptr; a.q4_pitch = e->q4_pitch;
+      a.MB = count_popc ? e->d_MB + col0 / 32 : nullptr; a.mb_pitch = e->mb_pitch;
+      a.diag_part = e->d_diag_part; a.miss_part = e->cfg.flat_norm ? nullptr : e->d_miss_part; a.n_pad = (int)e->n_pad;
+#define DGRM_EXPAND_T(B, S, K) bed_expand_t_kernel<B, S, K><<<grid, 256, sizeof(ExpandTSmem<K>), e->prep>>>(a)
+#define DGRM_EXPAND_TQ(B, S)                                                   \
+  do {                                                                         \
+    if (qk == 0) DGRM_EXPAND_T(B, S, 0); else if (qk == 1) DGRM_EXPAND_T(B, S, 1); \
+    else if (qk == 2) DGRM_EXPAND_T(B, S, 2); else DGRM_EXPAND_T(B, S, 3);     \
+  } while (0)
+      if (bf16) DGRM_EXPAND_TQ(true, false);
+      else if (split) DGRM_EXPAND_TQ(false, true);
+      else DGRM_EXPAND_TQ(false, false);
+#undef DGRM_EXPAND_TQ
+#undef DGRM_EXPAND_T
+      CK(cudaGetLastError());
+      diag_reduce_kernel<<<(unsigned)((e->n_pad + 255) / 256), 256, 0, e->prep>>>(
+          e->d_diag_part, kc_pad / kExpK, (int)e->n_pad, e->d_diag, a.miss_part, a.miss_part ? e->d_miss : nullptr);
+      CK(cudaGetLastError());
+    } else {
+      ExpandArgs a;
+      a.chunk = e->d_chunk; a.pitch = e->chunk_pitch; a.kc = kc; a.n = (int)e->n_row; a.zt = e->d_zt;
+      a.Z = e->d_Z + col0; a.z_pitch = e->z_pitch; a.lo_off = (int64_t)e->slots * e->kc_max;
+      a.Q = count_mma ? e->d_Q + col0 : nullptr; a.q_pitch = e->q_pitch;
+      a.Q4 = count_fp4 ? e->d_Q4 + col0 / 2 : nullptr; a.q4_pitch = e->q4_pitch;
+      a.MB = count_popc ? e->d_MB + col0 / 32 : nullptr; a.mb_pitch = e->mb_pitch;
+      a.diag_part = e->d_diag_part; a.n_pad = (int)e->n_pad;
+      const size_t smem = sizeof(ExpandSmem);
 #define DGRM_EXPAND(B, S, K) bed_expand_kernel<B, S, K><<<grid, 256, smem, e->prep>>>(a)
 #define DGRM_EXPAND_Q(B, S)                                              \
   do {                                                                   \
     if (qk == 0) DGRM_EXPAND(B, S, 0); else if (qk == 1) DGRM_EXPAND(B, S, 1); \
     else if (qk == 2) DGRM_EXPAND(B, S, 2); else DGRM_EXPAND(B, S, 3);   \
   } while (0)
-    if (bf16) DGRM_EXPAND_Q(true, false);
-    else if (split) DGRM_EXPAND_Q(false, true);
-    else DGRM_EXPAND_Q(false, false);
+      if (bf16) DGRM_EXPAND_Q(true, false);
+      else if (split) DGRM_EXPAND_Q(false, true);
+      else DGRM_EXPAND_Q(false, false);
 #undef DGRM_EXPAND_Q
 #undef DGRM_EXPAND
-    CK(cudaGetLastError());
-    diag_reduce_kernel<<<(unsigned)((e->n_pad + 255) / 256), 256, 0, e->prep>>>(e->d_diag_part, kc_pad / kExpK,
-                                                                              (int)e->n_pad, e->d_diag);
-    CK(cudaGetLastError());
+      CK(cudaGetLastError());
+      diag_reduce_kernel<<<(unsigned)((e->n_pad + 255) / 256), 256, 0, e->prep>>>(e->d_diag_part, kc_pad / kExpK,
+                                                                                (int)e->n_pad, e->d_diag);
+      CK(cudaGetLastError());
+    }
   }
   e->slot_kpad[slot] = kc_pad;
   e->m += kc;
@@ -1177,7 +1211,33 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
       const int vec = e->d_src_ind ? 1 : (align % 16 == 0 ? 16 : align % 8 == 0 ? 8 : align % 4 == 0 ? 4 : 1);
       SnpStatsOut so{e->d_freq, e->d_nn, e->d_p1, e->d_p2, e->d_sd, e->d_bad_count, e->d_bad_list, dgrm_engine::kBadCap};
       const int64_t snp0 = e->m + e->fill;
-      if (vec > 1 && e->fused_decode) {
+      if (e->d_chunkT) {
+        // GRM mode: one pass produces the transposed chunk (16-SNP words per individual) and the per-row counts;
+        // sources that cannot be read with aligned 32-bit loads (or need the --keep compaction of individuals) are
+        // first gathered into the row-major chunk buffer
+        Prof pr(e, DGRM_K_GATHER, e->prep);
+        if (e->fill == 0) CK(cudaMemsetAsync(e->d_counts, 0, (size_t)e->kc_max * 4 * sizeof(int32_t), e->prep));
+        const uint8_t* tsrc = d_rows;
+        int64_t tpitch = pitch, trow0 = pos;
+        const int32_t* tidx = d_idx;
+        if (vec < 4) {
+          const int per_row = (nbytes / vec + 255) / 256;
+          const dim3 grid((unsigned)std::max(1, std::min(per_row, 64)), (unsigned)take);
+          bed_gather_kernel<uint8_t><<<grid, 256, 0, e->prep>>>(d_rows, pitch, d_idx, pos, take, dst, e->chunk_pitch, nbytes,
+                                                                e->d_src_ind, (int)e->n_row);
+          CK(cudaGetLastError());
+          tsrc = dst; tpitch = e->chunk_pitch; trow0 = 0; tidx = nullptr;
+        }
+        const int tbytes = (int)(e->d_src_ind ? e->b_row : nbytes);
+        const int nwords = (int)((e->n_row + 15) / 16);
+        const int groups = ((e->fill + take - 1) >> 4) - (e->fill >> 4) + 1;
+        bed_decode_t_kernel<<<dim3((unsigned)((nwords + 255) / 256), (unsigned)groups), 256, 0, e->prep>>>(
+            tsrc, tpitch, tidx, trow0, e->fill, take, e->d_chunkT, e->t_pitch, tbytes, (int)e->n_row, e->d_counts);
+        CK(cudaGetLastError());
+        bed_stats_finish_kernel<<<(take + 255) / 256, 256, 0, e->prep>>>(e->d_counts, e->fill, take, (int)e->n_row, snp0, so,
+                                                                        e->d_zt);
+        CK(cudaGetLastError());
+      } else if (vec > 1 && e->fused_decode) {
         // one pass: row selection / alignment copy + per-SNP counts and statistics, one warp per row
         Prof pr(e, DGRM_K_GATHER, e->prep);
         const int blocks = (take * 32 + 255) / 256;
@@ -1370,6 +1430,7 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   if (const char* pol = getenv("DGRM_L2_POLICY")) e->l2_policy = atoi(pol);
   if (const char* ov = getenv("DGRM_OVERLAP")) e->overlap = atoi(ov);
   if (const char* fd = getenv("DGRM_FUSED_DECODE")) e->fused_decode = atoi(fd);
+  if (const char* kt = getenv("DGRM_K1_TRANSPOSED")) e->k1_transposed = atoi(kt);
   if (const char* pp = getenv("DGRM_PREFIX_PCT")) e->prefix_pct = std::max(0, std::min(90, atoi(pp)));
   e->reserve_sms = cfg->reserve_sms > 0 ? cfg->reserve_sms : 0;
   if (const char* rs = getenv("DGRM_RESERVE_SMS")) e->reserve_sms = atoi(rs);
@@ -1434,6 +1495,12 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   DGRM_EXPAND_ATTR(true, false, 0); DGRM_EXPAND_ATTR(true, false, 1); DGRM_EXPAND_ATTR(true, false, 2); DGRM_EXPAND_ATTR(true, false, 3);
   DGRM_EXPAND_ATTR(false, true, 0); DGRM_EXPAND_ATTR(false, true, 1); DGRM_EXPAND_ATTR(false, true, 2); DGRM_EXPAND_ATTR(false, true, 3);
 #undef DGRM_EXPAND_ATTR
+#define DGRM_EXPAND_T_ATTR(B, S, K)                                                                          \
+  CKC(cudaFuncSetAttribute(bed_expand_t_kernel<B, S, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandTSmem<K>)))
+  DGRM_EXPAND_T_ATTR(false, false, 0); DGRM_EXPAND_T_ATTR(false, false, 1); DGRM_EXPAND_T_ATTR(false, false, 2); DGRM_EXPAND_T_ATTR(false, false, 3);
+  DGRM_EXPAND_T_ATTR(true, false, 0); DGRM_EXPAND_T_ATTR(true, false, 1); DGRM_EXPAND_T_ATTR(true, false, 2); DGRM_EXPAND_T_ATTR(true, false, 3);
+  DGRM_EXPAND_T_ATTR(false, true, 0); DGRM_EXPAND_T_ATTR(false, true, 1); DGRM_EXPAND_T_ATTR(false, true, 2); DGRM_EXPAND_T_ATTR(false, true, 3);
+#undef DGRM_EXPAND_T_ATTR
 #undef CKC
   *out = e;
   return DGRM_OK;
@@ -1526,6 +1593,12 @@ static int setup_geometry(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mas
   CK(cudaMalloc(&e->d_chunk, (size_t)kc * e->chunk_pitch));
   CK(cudaMemset(e->d_chunk, 0x55, (size_t)kc * e->chunk_pitch));
   CK(cudaMalloc(&e->d_zt, (size_t)kc * 4 * sizeof(double)));
+  if (!e->ld_mode && e->k1_transposed) {
+    e->t_pitch = round_up(e->n_row, 32);
+    CK(cudaMalloc(&e->d_chunkT, (size_t)(kc / 16) * e->t_pitch * sizeof(uint32_t)));
+    CK(cudaMalloc(&e->d_counts, (size_t)kc * 4 * sizeof(int32_t)));
+    CK(cudaMalloc(&e->d_miss_part, (size_t)(kc / kExpK) * e->n_pad * sizeof(int32_t)));
+  }
   CK(cudaMalloc(&e->d_diag_part, (size_t)(kc / kExpK) * e->n_pad * sizeof(double)));
   e->slots = 0;  // operand slots are sized by dgrm_begin, once the SNP count is known
   // host staging: slabs of up to kc rows

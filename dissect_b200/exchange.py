@@ -19,13 +19,12 @@ chunk's rows arrived exactly when the running SYRK launch retired).  Copy engine
 Everything is stream-ordered: the host never blocks and there is no barrier; the sequence numbers are global and
 monotonic, so buffers are reused across GRMs without draining.
 
-STATUS (round 1): EXPERIMENTAL, not the default (`bench.py --exchange p2p`, `DGRM_EXCHANGE=p2p` for
-tools/multi_gpu_check.py).  With the peers' buffers mapped through legacy CUDA IPC (`DGRM_EXCHANGE_MAP=ipc`) the
-protocol is parity-green at 2 GPUs, but such mappings copy at only ~25 GB/s on this platform even between idle
-GPUs (tools/exp/p2p_copy_probe.py: torch copy_, cudaMemcpyAsync and cudaMemcpyPeerAsync alike; same-device
-2.6 TB/s), so a 2-GPU step took 51 ms against 41.7 ms with NCCL.  The default mapping is now torch symmetric memory
-(cuMem allocations with peer access, the NVLink path NCCL uses); that variant was written after the round's GPU
-budget was spent and has NOT run on a GPU yet.
+STATUS (round 2): the default exchange of dissect_b200/multi.py (`exchange="auto"`).  The peers' buffers are mapped
+through torch symmetric memory (cuMem allocations with peer access, the NVLink path NCCL itself uses); parity-green at
+2 GPUs (tools/multi_gpu_check.py --exchange p2p: tiles vs oracle, block-cyclic egress, parallel writer) and faster than
+NCCL: 38.15 vs 40.10 ms per step at 2 GPUs (profiles/r2_bench_n2_p2p_symm.json vs r2_bench_n2_xg1.json), i.e. the
+2-GPU step costs what the 1-GPU step costs.  Legacy CUDA-IPC mappings (`DGRM_EXCHANGE_MAP=ipc`) also pass parity but
+copy at only ~25 GB/s on this platform (52.7 ms per step): kept for boxes without symmetric memory support.
 """
 import os
 
@@ -55,7 +54,7 @@ class PeerExchange:
         self.error = None
         self._peer_tensors = []      # keep the mappings alive
         self.peer_buf, self.peer_flag = [], []
-        self.mapping = os.environ.get("DGRM_EXCHANGE_MAP", "ipc")
+        self.mapping = os.environ.get("DGRM_EXCHANGE_MAP", "symm")
         self.seqsrc = torch.arange(_SEQ_CAP, dtype=torch.int32, device="cuda")
         nbuf_bytes = (world * rows_per_rank * pitch + 4095) // 4096 * 4096
         try:

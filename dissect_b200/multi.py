@@ -53,17 +53,20 @@ class ShardPlan:
         return sum(b - a for _, ranges, _ in self.groups for (a, b) in [ranges[rank]])
 
 
-def auto_xg(n, world, chunk_snps, m_file, budget_bytes=2 << 30):
-    """Chunks per all-gather: as many as the exchange buffers (2 send + 2 gather, `budget_bytes` together) allow.
-    The all-gather kernel cannot run underneath the persistent contraction, so every exchange is a bubble in the
-    MMA stream: fewer, larger exchanges mean fewer bubbles, and all chunks of a group but the first are decoded
-    underneath the contraction."""
-    if world == 1:
+def auto_xg(n, world, chunk_snps, m_file, exchange="nccl", budget_bytes=2 << 30):
+    """Engine chunks per exchange.  The copy-engine exchange (p2p) runs underneath the contraction, so one chunk per
+    exchange pipelines best.  An NCCL all-gather is a kernel and cannot run underneath the persistent contraction:
+    every exchange is then a bubble in the MMA stream, and for large cohorts (>= 128 MB per chunk) fewer, larger
+    exchanges win (measured r1: C3 on 8 GPUs 779 -> 696 ms with 4 chunks per all-gather; for the 28k-individual
+    2-GPU case one chunk per exchange is 2.5 % faster than six, r2)."""
+    if world == 1 or exchange == "p2p":
         return 1
     pitch = ((n + 3) // 4 + 15) // 16 * 16
+    if chunk_snps * pitch < (128 << 20):
+        return 1
     per_chunk = 2 * (1 + 1.0 / world) * chunk_snps * pitch
     nchunks = max(1, math.ceil(m_file / chunk_snps))
-    return int(max(1, min(8, nchunks, budget_bytes // max(1, int(per_chunk)))))
+    return int(max(1, min(4, nchunks, budget_bytes // max(1, int(per_chunk)))))
 
 
 class DeviceRows:
@@ -96,8 +99,11 @@ class HostRows:
 class MultiGpuGrm:
     """One per rank.  `engine` is this rank's GrmEngine (its tile set); `build` runs the whole GRM."""
 
-    def __init__(self, n, *, rank, world, device, chunk_snps=16384, xg=0, exchange="nccl", group=None,
+    def __init__(self, n, *, rank, world, device, chunk_snps=16384, xg=0, exchange="auto", group=None,
                  engine=None, **engine_kw):
+        """exchange: "p2p" = copy-engine peer writes over NVLink (dissect_b200/exchange.py, SM-free, runs underneath the
+        contraction), "nccl" = all_gather_into_tensor, "auto" = p2p when every rank can map its peers' buffers
+        (torch symmetric memory), else nccl."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -111,6 +117,11 @@ class MultiGpuGrm:
         # device = "cpu" (with a stand-in engine and a gloo group) runs the same loop in the CPU tests of the host logic
         self._cuda = device != "cpu"
         self._dev = torch.device("cuda", device) if self._cuda else torch.device("cpu")
+        if exchange == "auto":
+            exchange = "p2p" if (self._cuda and world > 1) else "nccl"
+            self._exchange_fallback = True
+        else:
+            self._exchange_fallback = False
         self.exchange = exchange if world > 1 else "none"
         self.plan = None
         self._bufs = None
@@ -119,7 +130,17 @@ class MultiGpuGrm:
     # -- planning / buffers -----------------------------------------------------------------------------------
     def prepare(self, m_file, keep=None):
         """Builds the shard plan and (re)allocates the exchange buffers; idempotent for the same cohort."""
-        xg = self.xg_arg if self.xg_arg > 0 else auto_xg(self.n, self.world, self.chunk, m_file)
+        if self.world > 1 and self.exchange == "p2p" and self._xch is None and self._exchange_fallback and not getattr(self, "_p2p_probed", False):
+            # decide once, collectively, whether the peer mapping works on this box
+            from .exchange import PeerExchange
+            self._p2p_probed = True
+            self._host_group = self.dist.new_group(backend="gloo")
+            probe = PeerExchange(1, 16, self.rank, self.world, self._host_group)
+            ok = probe.ok
+            probe.close()
+            if not ok:
+                self.exchange = "nccl"
+        xg = self.xg_arg if self.xg_arg > 0 else auto_xg(self.n, self.world, self.chunk, m_file, self.exchange)
         if self.plan is not None and self.plan.m_file == m_file and self.plan.xchunk == self.chunk * xg and (
                 (keep is None and self.plan.m_kept == m_file) or (keep is not None and np.array_equal(self.plan.keep, keep))):
             return self.plan
@@ -132,7 +153,8 @@ class MultiGpuGrm:
             self._close_exchange()
             if self.exchange == "p2p":
                 from .exchange import PeerExchange
-                self._host_group = self.dist.new_group(backend="gloo")
+                if getattr(self, "_host_group", None) is None:
+                    self._host_group = self.dist.new_group(backend="gloo")
                 self._xch = PeerExchange(sh, self.pitch, self.rank, self.world, self._host_group)
                 if not self._xch.ok:
                     raise RuntimeError(f"peer exchange unavailable: {self._xch.error}")
