@@ -53,7 +53,7 @@ class ShardPlan:
         return sum(b - a for _, ranges, _ in self.groups for (a, b) in [ranges[rank]])
 
 
-def auto_xg(n, world, chunk_snps, m_file, exchange="nccl", budget_bytes=2 << 30):
+def auto_xg(n, world, chunk_snps, m_file, exchange="nccl", budget_bytes=4 << 30):
     """Engine chunks per exchange.  The copy-engine exchange (p2p) runs underneath the contraction, so one chunk per
     exchange pipelines best.  An NCCL all-gather is a kernel and cannot run underneath the persistent contraction:
     every exchange is then a bubble in the MMA stream, and for large cohorts (>= 128 MB per chunk) fewer, larger
