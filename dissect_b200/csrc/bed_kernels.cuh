@@ -270,39 +270,48 @@ bed_decode_t_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const in
                     int fill, int nrows, uint32_t* __restrict__ T, int64_t t_pitch, int nbytes, int n,
                     int32_t* __restrict__ counts /* [chunk rows][4]: missing, -, het, hom A2 */) {
   __shared__ int s_cnt[16][3];
+  __shared__ int64_t s_off[16];                     // byte offset of the group's source rows, -1 = not in this launch
   const int kg = (fill >> 4) + blockIdx.y;          // 16-row group of the chunk
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int nwords = (n + 15) >> 4;
   const int g0 = kg << 4;                           // first chunk row of the group
   const int ra = max(g0, fill), rb = min(g0 + 16, fill + nrows);   // chunk rows of this group delivered by this launch
   if (threadIdx.x < 48) s_cnt[threadIdx.x / 3][threadIdx.x % 3] = 0;
+  if (threadIdx.x < 16) {
+    const int r = g0 + threadIdx.x;
+    s_off[threadIdx.x] = (r >= ra && r < rb) ? (rows ? (int64_t)rows[r - fill] : row0 + (r - fill)) * src_pitch : -1;
+  }
   __syncthreads();
   uint32_t w[16];
-  int c0[16], c2[16], c3[16];
-#pragma unroll
-  for (int t = 0; t < 16; ++t) { w[t] = 0x55555555u; c0[t] = c2[t] = c3[t] = 0; }
+  uint32_t cnt[16];                                 // per row: missing | het << 10 | hom A2 << 20 (<= 16 each per lane)
   if (j < nwords) {
     const int valid = min(16, n - 16 * j);
     const uint32_t keep = valid == 16 ? 0xFFFFFFFFu : ((1u << (2 * valid)) - 1u);
-    const bool whole = 4 * j + 4 <= nbytes;
+    const uint32_t km = keep & 0x55555555u;
+    if (4 * j + 4 <= nbytes) {                      // sixteen independent, coalesced 32-bit loads
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int64_t off = s_off[t];
+        w[t] = off >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(src + off + 4 * j)) : 0x55555555u;
+      }
+    } else {                                        // the row's last, partial word
+#pragma unroll 1
+      for (int t = 0; t < 16; ++t) {
+        const int64_t off = s_off[t];
+        uint32_t v = 0x55555555u;
+        if (off >= 0) {
+          v = 0;
+          for (int b = 0; 4 * j + b < nbytes; ++b) v |= (uint32_t)src[off + 4 * j + b] << (8 * b);
+        }
+        w[t] = v;
+      }
+    }
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-      const int r = g0 + t;
-      if (r < ra || r >= rb) continue;
-      const int64_t srow = rows ? (int64_t)rows[r - fill] : row0 + (r - fill);
-      const uint8_t* s = src + srow * src_pitch + 4 * j;
-      uint32_t v;
-      if (whole) {
-        v = __ldg(reinterpret_cast<const uint32_t*>(s));
-      } else {
-        v = 0;
-        for (int b = 0; 4 * j + b < nbytes; ++b) v |= (uint32_t)s[b] << (8 * b);
-      }
-      v = (v & keep) | (0x55555555u & ~keep);       // individuals past n read as missing and are not counted
-      const uint32_t lo = v & 0x55555555u, hi = (v >> 1) & 0x55555555u, km = keep & 0x55555555u;
-      c3[t] = __popc(lo & hi & km);
-      c2[t] = __popc(hi & ~lo & km);
-      c0[t] = __popc(lo & ~hi & km);
+      const uint32_t v = (w[t] & keep) | (0x55555555u & ~keep);   // individuals past n read as missing, not counted
+      const uint32_t lo = v & 0x55555555u, hi = (v >> 1) & 0x55555555u;
+      const uint32_t kmt = s_off[t] >= 0 ? km : 0u;
+      cnt[t] = (uint32_t)__popc(lo & ~hi & kmt) | ((uint32_t)__popc(hi & ~lo & kmt) << 10) | ((uint32_t)__popc(lo & hi & kmt) << 20);
       w[t] = v;
     }
     transpose16x16_2bit(w);                         // w[c] = individual 16 j + c, SNP t at bits 2t
@@ -322,20 +331,20 @@ bed_decode_t_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const in
         out[c] = (old & ~mine) | (w[c] & mine);
       }
     }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) cnt[t] = 0;
   }
-  // counts: warp reduce (two 16-bit counters per register: <= 16 * 32 each), block reduce in shared memory, atomics out
+  // counts: warp reduce (three 10-bit counters per register: <= 16 * 32 each), block reduce in shared memory, atomics out
 #pragma unroll
   for (int t = 0; t < 16; ++t) {
-    uint32_t a = (uint32_t)c0[t] | ((uint32_t)c2[t] << 16), b = (uint32_t)c3[t];
+    uint32_t a = cnt[t];
 #pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, sft);
-      b += __shfl_xor_sync(0xffffffffu, b, sft);
-    }
-    if ((threadIdx.x & 31) == 0 && (a | b)) {
-      atomicAdd(&s_cnt[t][0], (int)(a & 0xFFFFu));
-      atomicAdd(&s_cnt[t][1], (int)(a >> 16));
-      atomicAdd(&s_cnt[t][2], (int)b);
+    for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+    if ((threadIdx.x & 31) == 0 && a) {
+      if (a & 0x3FFu) atomicAdd(&s_cnt[t][0], (int)(a & 0x3FFu));
+      if ((a >> 10) & 0x3FFu) atomicAdd(&s_cnt[t][1], (int)((a >> 10) & 0x3FFu));
+      if (a >> 20) atomicAdd(&s_cnt[t][2], (int)(a >> 20));
     }
   }
   __syncthreads();
