@@ -15,7 +15,7 @@ TRANSPORT = {"fp64": 0, "fp32": 1}
 
 # every symbol include/dgrm.h declares
 SYMBOLS = (
-    "dgrm_default_config", "dgrm_create", "dgrm_destroy", "dgrm_last_error", "dgrm_abi_version",
+    "dgrm_default_config", "dgrm_device_count", "dgrm_validate_bed_header", "dgrm_create", "dgrm_destroy", "dgrm_last_error", "dgrm_abi_version",
     "dgrm_set_individuals", "dgrm_begin", "dgrm_push_bed_host", "dgrm_push_bed_device", "dgrm_release_inputs",
     "dgrm_load_bed_file", "dgrm_finish", "dgrm_sync", "dgrm_num_snps", "dgrm_num_individuals",
     "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_fetch_block_cyclic_cols", "dgrm_bind_output", "dgrm_unbind_outputs", "dgrm_bind_tiles", "dgrm_low_overlap_pairs",
@@ -59,6 +59,8 @@ def load():
     lib.dgrm_last_error.argtypes = [vp]
     lib.dgrm_last_error.restype = C.c_char_p
     lib.dgrm_abi_version.argtypes = []
+    lib.dgrm_device_count.argtypes = []
+    lib.dgrm_validate_bed_header.argtypes = [vp, C.c_char_p]
     lib.dgrm_set_individuals.argtypes = [vp, i64, vp]
     lib.dgrm_begin.argtypes = [vp, i64]
     lib.dgrm_push_bed_host.argtypes = [vp, vp, i64, i64, vp]

@@ -269,14 +269,14 @@ __global__ void __launch_bounds__(256)
 bed_decode_t_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const int32_t* __restrict__ rows, int64_t row0,
                     int fill, int nrows, uint32_t* __restrict__ T, int64_t t_pitch, int nbytes, int n,
                     int32_t* __restrict__ counts /* [chunk rows][4]: missing, -, het, hom A2 */) {
-  __shared__ int s_cnt[16][3];
+  __shared__ uint32_t s_w[8][16];                   // per warp: packed counts of the group's 16 rows
   __shared__ int64_t s_off[16];                     // byte offset of the group's source rows, -1 = not in this launch
   const int kg = (fill >> 4) + blockIdx.y;          // 16-row group of the chunk
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const int nwords = (n + 15) >> 4;
   const int g0 = kg << 4;                           // first chunk row of the group
   const int ra = max(g0, fill), rb = min(g0 + 16, fill + nrows);   // chunk rows of this group delivered by this launch
-  if (threadIdx.x < 48) s_cnt[threadIdx.x / 3][threadIdx.x % 3] = 0;
   if (threadIdx.x < 16) {
     const int r = g0 + threadIdx.x;
     s_off[threadIdx.x] = (r >= ra && r < rb) ? (rows ? (int64_t)rows[r - fill] : row0 + (r - fill)) * src_pitch : -1;
@@ -286,12 +286,12 @@ bed_decode_t_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const in
   uint32_t cnt[16];                                 // per row: missing | het << 10 | hom A2 << 20 (<= 16 each per lane)
   if (j < nwords) {
     const int valid = min(16, n - 16 * j);
-    const uint32_t keep = valid == 16 ? 0xFFFFFFFFu : ((1u << (2 * valid)) - 1u);
-    const uint32_t km = keep & 0x55555555u;
+    uint32_t act = 0;                               // rows delivered by this launch
     if (4 * j + 4 <= nbytes) {                      // sixteen independent, coalesced 32-bit loads
 #pragma unroll
       for (int t = 0; t < 16; ++t) {
         const int64_t off = s_off[t];
+        act |= (off >= 0 ? 1u : 0u) << t;
         w[t] = off >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(src + off + 4 * j)) : 0x55555555u;
       }
     } else {                                        // the row's last, partial word
@@ -300,19 +300,25 @@ bed_decode_t_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const in
         const int64_t off = s_off[t];
         uint32_t v = 0x55555555u;
         if (off >= 0) {
+          act |= 1u << t;
           v = 0;
           for (int b = 0; 4 * j + b < nbytes; ++b) v |= (uint32_t)src[off + 4 * j + b] << (8 * b);
         }
         w[t] = v;
       }
     }
+    if (valid < 16) {                               // individuals past n read as missing (and so are never counted as data)
+      const uint32_t keep = (1u << (2 * valid)) - 1u;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) w[t] = (w[t] & keep) | (0x55555555u & ~keep);
+    }
+    const int pad = 16 - valid;                     // those padding fields count as "missing" below: taken out again
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-      const uint32_t v = (w[t] & keep) | (0x55555555u & ~keep);   // individuals past n read as missing, not counted
+      const uint32_t v = w[t];
       const uint32_t lo = v & 0x55555555u, hi = (v >> 1) & 0x55555555u;
-      const uint32_t kmt = s_off[t] >= 0 ? km : 0u;
-      cnt[t] = (uint32_t)__popc(lo & ~hi & kmt) | ((uint32_t)__popc(hi & ~lo & kmt) << 10) | ((uint32_t)__popc(lo & hi & kmt) << 20);
-      w[t] = v;
+      const uint32_t c = (uint32_t)(__popc(lo & ~hi) - pad) | ((uint32_t)__popc(hi & ~lo) << 10) | ((uint32_t)__popc(lo & hi) << 20);
+      cnt[t] = ((act >> t) & 1u) ? c : 0u;
     }
     transpose16x16_2bit(w);                         // w[c] = individual 16 j + c, SNP t at bits 2t
     uint32_t* out = T + (int64_t)kg * t_pitch + 16 * j;
@@ -335,22 +341,28 @@ bed_decode_t_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const in
 #pragma unroll
     for (int t = 0; t < 16; ++t) cnt[t] = 0;
   }
-  // counts: warp reduce (three 10-bit counters per register: <= 16 * 32 each), block reduce in shared memory, atomics out
-#pragma unroll
-  for (int t = 0; t < 16; ++t) {
-    uint32_t a = cnt[t];
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
-    if ((threadIdx.x & 31) == 0 && a) {
-      if (a & 0x3FFu) atomicAdd(&s_cnt[t][0], (int)(a & 0x3FFu));
-      if ((a >> 10) & 0x3FFu) atomicAdd(&s_cnt[t][1], (int)((a >> 10) & 0x3FFu));
-      if (a >> 20) atomicAdd(&s_cnt[t][2], (int)(a >> 20));
-    }
+  // counts: butterfly over the warp that halves the values a lane carries at every step (16 shuffles instead of 80);
+  // lane l ends with the warp total of row l >> 1 (three 10-bit counters per register, <= 16 * 32 each)
+#define DGRM_BFLY(H, BIT)                                                        \
+  _Pragma("unroll") for (int i = 0; i < H; ++i) {                                \
+    const bool up = (lane & BIT) != 0;                                           \
+    const uint32_t send = up ? cnt[i] : cnt[i + H];                              \
+    const uint32_t mine = up ? cnt[i + H] : cnt[i];                              \
+    cnt[i] = mine + __shfl_xor_sync(0xffffffffu, send, BIT);                     \
   }
+  DGRM_BFLY(8, 16)
+  DGRM_BFLY(4, 8)
+  DGRM_BFLY(2, 4)
+  DGRM_BFLY(1, 2)
+#undef DGRM_BFLY
+  const uint32_t tot = cnt[0] + __shfl_xor_sync(0xffffffffu, cnt[0], 1);
+  if ((lane & 1) == 0) s_w[threadIdx.x >> 5][lane >> 1] = tot;
   __syncthreads();
   if (threadIdx.x < 48) {
     const int t = threadIdx.x / 3, k = threadIdx.x % 3;
-    const int v = s_cnt[t][k];
+    int v = 0;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) v += (int)((s_w[wp][t] >> (10 * k)) & 0x3FFu);
     if (v) atomicAdd(&counts[(int64_t)(g0 + t) * 4 + (k == 0 ? 0 : k + 1)], v);
   }
 }
@@ -601,24 +613,27 @@ struct ExpandTArgs {
   int n_pad;
 };
 
-template <int QK>
+constexpr int kExpTThreads = 512;    // 16 warps per block: the 64 KB of staging then carry 48 warps per SM
+constexpr int kExpTKh = kExpTThreads / kExpI;   // threads per individual (each takes every kExpTKh-th 16-SNP word)
+
+template <int QK, bool SPLIT>
 struct ExpandTSmem {
   uint16_t lut_hi[kExpK][4];
-  uint16_t lut_lo[kExpK][4];
+  uint16_t lut_lo[SPLIT ? kExpK : 1][4];
   double lut_sq[kExpK][4];
   uint32_t pair_hi[kExpK / 2][16];   // operand values of SNPs (2p, 2p+1): low half-word = SNP 2p
-  uint32_t pair_lo[kExpK / 2][16];
+  uint32_t pair_lo[SPLIT ? kExpK / 2 : 1][16];
   double pair_sq[kExpK / 2][16];
-  double dpart[2][kExpI];
-  int mpart[2][kExpI];
+  double dpart[kExpTKh][kExpI];
+  int mpart[kExpTKh][kExpI];
   uint8_t outz[kExpI * kExpZPitch];
   uint8_t outq[kExpI * (QK == 1 ? kExpQPitch : QK == 2 ? kExpQ4Pitch : kExpMPitch)];
 };
 
 template <bool BF16, bool SPLIT, int QK>
-__global__ void __launch_bounds__(256) bed_expand_t_kernel(const ExpandTArgs a) {
+__global__ void __launch_bounds__(kExpTThreads) bed_expand_t_kernel(const ExpandTArgs a) {
   extern __shared__ __align__(16) uint8_t expand_smem_raw[];
-  ExpandTSmem<QK>& sm = *reinterpret_cast<ExpandTSmem<QK>*>(expand_smem_raw);
+  ExpandTSmem<QK, SPLIT>& sm = *reinterpret_cast<ExpandTSmem<QK, SPLIT>*>(expand_smem_raw);
   const int tid = threadIdx.x;
   const int i0 = blockIdx.x * kExpI;
   const int k0 = blockIdx.y * kExpK;
@@ -632,15 +647,15 @@ __global__ void __launch_bounds__(256) bed_expand_t_kernel(const ExpandTArgs a) 
     for (int c = 0; c < 4; ++c) {
       const uint16_t hi = round16<BF16>(z[c]);
       sm.lut_hi[tid][c] = hi;
-      sm.lut_lo[tid][c] = SPLIT ? round16<BF16>(z[c] - widen16<BF16>(hi)) : (uint16_t)0;
+      if (SPLIT) sm.lut_lo[tid][c] = round16<BF16>(z[c] - widen16<BF16>(hi));
       sm.lut_sq[tid][c] = __dmul_rn(z[c], z[c]);
     }
   }
   __syncthreads();
-  // pair tables: entry idx = pattern(SNP 2p) + 4 * pattern(SNP 2p + 1); 64 pairs x 16 entries, 4 per thread
+  // pair tables: entry idx = pattern(SNP 2p) + 4 * pattern(SNP 2p + 1); 64 pairs x 16 entries, 2 per thread
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int ent = tid * 4 + q, p = ent >> 4, idx = ent & 15;
+  for (int q = 0; q < 1024 / kExpTThreads; ++q) {
+    const int ent = tid * (1024 / kExpTThreads) + q, p = ent >> 4, idx = ent & 15;
     const int ca = idx & 3, cb = idx >> 2;
     sm.pair_hi[p][idx] = (uint32_t)sm.lut_hi[2 * p][ca] | ((uint32_t)sm.lut_hi[2 * p + 1][cb] << 16);
     if (SPLIT) sm.pair_lo[p][idx] = (uint32_t)sm.lut_lo[2 * p][ca] | ((uint32_t)sm.lut_lo[2 * p + 1][cb] << 16);
@@ -651,11 +666,12 @@ __global__ void __launch_bounds__(256) bed_expand_t_kernel(const ExpandTArgs a) 
   const int il = tid & (kExpI - 1);
   const int kh = tid >> 7;
   const bool real = i0 + il < a.n;
-  // the individual's 8 words of this tile (16 SNPs each); groups past the chunk and individuals past n: all missing
-  uint32_t words[4];
+  constexpr int kWords = (kExpK / 16) / kExpTKh;   // 16-SNP words per thread
+  // the individual's words of this tile (16 SNPs each); groups past the chunk and individuals past n: all missing
+  uint32_t words[kWords];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int kgl = kh + 2 * j;                 // 16-SNP group within the tile
+  for (int j = 0; j < kWords; ++j) {
+    const int kgl = kh + kExpTKh * j;           // 16-SNP group within the tile
     words[j] = 0x55555555u;
     if (real && k0 + 16 * kgl < a.kc) words[j] = __ldg(a.T + (int64_t)((k0 >> 4) + kgl) * a.t_pitch + i0 + il);
   }
@@ -665,8 +681,8 @@ __global__ void __launch_bounds__(256) bed_expand_t_kernel(const ExpandTArgs a) 
   for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
     const uint32_t* ptab = part == 0 ? &sm.pair_hi[0][0] : &sm.pair_lo[0][0];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int kgl = kh + 2 * j;
+    for (int j = 0; j < kWords; ++j) {
+      const int kgl = kh + kExpTKh * j;
       const uint32_t w = words[j];
       uint32_t h[8];
 #pragma unroll
@@ -725,24 +741,24 @@ __global__ void __launch_bounds__(256) bed_expand_t_kernel(const ExpandTArgs a) 
       const int c = tid & 15;
       uint16_t* zbase = a.Z + (part == 0 ? 0 : a.lo_off) + k0;
 #pragma unroll
-      for (int ps = 0; ps < kExpI / 16; ++ps) {
-        const int r = ps * 16 + (tid >> 4);
+      for (int ps = 0; ps < kExpI / (kExpTThreads / 16); ++ps) {
+        const int r = ps * (kExpTThreads / 16) + (tid >> 4);
         const uint4 v = *reinterpret_cast<const uint4*>(&sm.outz[r * kExpZPitch + c * 16]);
         *reinterpret_cast<uint4*>(zbase + (int64_t)(i0 + r) * a.z_pitch + c * 8) = v;
       }
       if (part == 0) {
         if constexpr (QK == 1) {
 #pragma unroll
-          for (int ps = 0; ps < kExpI / 16; ++ps) {
-            const int r = ps * 16 + (tid >> 4);
+          for (int ps = 0; ps < kExpI / (kExpTThreads / 16); ++ps) {
+            const int r = ps * (kExpTThreads / 16) + (tid >> 4);
             const uint2 v = *reinterpret_cast<const uint2*>(&sm.outq[r * kExpQPitch + c * 8]);
             *reinterpret_cast<uint2*>(a.Q + (int64_t)(i0 + r) * a.q_pitch + k0 + c * 8) = v;
           }
         }
         if constexpr (QK == 2) {
 #pragma unroll
-          for (int ps = 0; ps < kExpI / 16; ++ps) {
-            const int r = ps * 16 + (tid >> 4);
+          for (int ps = 0; ps < kExpI / (kExpTThreads / 16); ++ps) {
+            const int r = ps * (kExpTThreads / 16) + (tid >> 4);
             const uint32_t v = *reinterpret_cast<const uint32_t*>(&sm.outq[r * kExpQ4Pitch + c * 4]);
             *reinterpret_cast<uint32_t*>(a.Q4 + (int64_t)(i0 + r) * a.q4_pitch + (k0 >> 1) + c * 4) = v;
           }
@@ -755,10 +771,14 @@ __global__ void __launch_bounds__(256) bed_expand_t_kernel(const ExpandTArgs a) 
           }
         }
         if (tid < kExpI) {
-          a.diag_part[(int64_t)blockIdx.y * a.n_pad + i0 + tid] = __dadd_rn(sm.dpart[0][tid], sm.dpart[1][tid]);
+          double ds = sm.dpart[0][tid];
+          int ms = sm.mpart[0][tid];
+#pragma unroll
+          for (int h2 = 1; h2 < kExpTKh; ++h2) { ds = __dadd_rn(ds, sm.dpart[h2][tid]); ms += sm.mpart[h2][tid]; }
+          a.diag_part[(int64_t)blockIdx.y * a.n_pad + i0 + tid] = ds;
           if (a.miss_part)   // padding individuals and SNP rows past the chunk were read as "missing": not real ones
             a.miss_part[(int64_t)blockIdx.y * a.n_pad + i0 + tid] =
-                (i0 + tid < a.n) ? sm.mpart[0][tid] + sm.mpart[1][tid] - max(0, min(kExpK, k0 + kExpK - a.kc)) : 0;
+                (i0 + tid < a.n) ? ms - max(0, min(kExpK, k0 + kExpK - a.kc)) : 0;
         }
       }
     }
@@ -841,17 +861,33 @@ __global__ void __launch_bounds__(256) ld_expand_kernel(const LdExpandArgs a) {
 }
 
 // diag[i] += sum_kt diag_part[kt][i], fixed order (deterministic).
-__global__ void diag_reduce_kernel(const double* __restrict__ part, int nkt, int n_pad, double* __restrict__ diag,
-                                   const int32_t* __restrict__ miss_part = nullptr, int32_t* __restrict__ miss = nullptr) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pad) return;
-  double s = diag[i];
-  for (int kt = 0; kt < nkt; ++kt) s = __dadd_rn(s, part[(int64_t)kt * n_pad + i]);
-  diag[i] = s;
-  if (miss_part) {   // per-individual missing genotypes of the chunk (exact integers)
-    int mc = miss[i];
-    for (int kt = 0; kt < nkt; ++kt) mc += miss_part[(int64_t)kt * n_pad + i];
-    miss[i] = mc;
+// Block = 32 individuals x 8 warps; warp w sums the k-tiles w, w + 8, ... (coalesced 256-byte reads), the eight
+// partial sums are then combined in warp order: the summation order is fixed by the launch geometry alone.
+__global__ void __launch_bounds__(256)
+diag_reduce_kernel(const double* __restrict__ part, int nkt, int n_pad, double* __restrict__ diag,
+                   const int32_t* __restrict__ miss_part = nullptr, int32_t* __restrict__ miss = nullptr) {
+  __shared__ double s_d[8][32];
+  __shared__ int s_m[8][32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  double s = 0.;
+  int mc = 0;
+  if (i < n_pad) {
+    for (int kt = wp; kt < nkt; kt += 8) {
+      s = __dadd_rn(s, part[(int64_t)kt * n_pad + i]);
+      if (miss_part) mc += miss_part[(int64_t)kt * n_pad + i];
+    }
+  }
+  s_d[wp][lane] = s;
+  s_m[wp][lane] = mc;
+  __syncthreads();
+  if (wp == 0 && i < n_pad) {
+    double t = diag[i];
+    int m = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { t = __dadd_rn(t, s_d[q][lane]); m += s_m[q][lane]; }
+    diag[i] = t;
+    if (miss_part) miss[i] += m;   // per-individual missing genotypes of the chunk (exact integers)
   }
 }
 

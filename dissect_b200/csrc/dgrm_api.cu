@@ -493,7 +493,7 @@ int process_chunk(dgrm_engine* e) {
       a.Q4 = count_fp4 ? e->d_Q4 + col0 / 2 : nullptr; a.q4_pitch = e->q4_pitch;
       a.MB = count_popc ? e->d_MB + col0 / 32 : nullptr; a.mb_pitch = e->mb_pitch;
       a.diag_part = e->d_diag_part; a.miss_part = e->cfg.flat_norm ? nullptr : e->d_miss_part; a.n_pad = (int)e->n_pad;
-#define DGRM_EXPAND_T(B, S, K) bed_expand_t_kernel<B, S, K><<<grid, 256, sizeof(ExpandTSmem<K>), e->prep>>>(a)
+#define DGRM_EXPAND_T(B, S, K) bed_expand_t_kernel<B, S, K><<<grid, kExpTThreads, sizeof(ExpandTSmem<K, S>), e->prep>>>(a)
 #define DGRM_EXPAND_TQ(B, S)                                                   \
   do {                                                                         \
     if (qk == 0) DGRM_EXPAND_T(B, S, 0); else if (qk == 1) DGRM_EXPAND_T(B, S, 1); \
@@ -505,7 +505,7 @@ int process_chunk(dgrm_engine* e) {
 #undef DGRM_EXPAND_TQ
 #undef DGRM_EXPAND_T
       CK(cudaGetLastError());
-      diag_reduce_kernel<<<(unsigned)((e->n_pad + 255) / 256), 256, 0, e->prep>>>(
+      diag_reduce_kernel<<<(unsigned)((e->n_pad + 31) / 32), 256, 0, e->prep>>>(
           e->d_diag_part, kc_pad / kExpK, (int)e->n_pad, e->d_diag, a.miss_part, a.miss_part ? e->d_miss : nullptr);
       CK(cudaGetLastError());
     } else {
@@ -529,8 +529,8 @@ int process_chunk(dgrm_engine* e) {
 #undef DGRM_EXPAND_Q
 #undef DGRM_EXPAND
       CK(cudaGetLastError());
-      diag_reduce_kernel<<<(unsigned)((e->n_pad + 255) / 256), 256, 0, e->prep>>>(e->d_diag_part, kc_pad / kExpK,
-                                                                                (int)e->n_pad, e->d_diag);
+      diag_reduce_kernel<<<(unsigned)((e->n_pad + 31) / 32), 256, 0, e->prep>>>(e->d_diag_part, kc_pad / kExpK,
+                                                                               (int)e->n_pad, e->d_diag);
       CK(cudaGetLastError());
     }
   }
@@ -1372,6 +1372,23 @@ extern "C" {
 
 int dgrm_abi_version(void) { return DGRM_ABI_VERSION; }
 
+int dgrm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int dgrm_validate_bed_header(dgrm_engine* e, const char* bed_path) {
+  if (!e || !bed_path) return DGRM_E_INVALID;
+  FILE* f = nullptr;
+  const int rc = open_bed(e, bed_path, &f);
+  if (f) fclose(f);
+  return rc;
+}
+
 int dgrm_default_config(dgrm_config* cfg) {
   if (!cfg) return DGRM_E_INVALID;
   memset(cfg, 0, sizeof *cfg);
@@ -1496,7 +1513,7 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   DGRM_EXPAND_ATTR(false, true, 0); DGRM_EXPAND_ATTR(false, true, 1); DGRM_EXPAND_ATTR(false, true, 2); DGRM_EXPAND_ATTR(false, true, 3);
 #undef DGRM_EXPAND_ATTR
 #define DGRM_EXPAND_T_ATTR(B, S, K)                                                                          \
-  CKC(cudaFuncSetAttribute(bed_expand_t_kernel<B, S, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandTSmem<K>)))
+  CKC(cudaFuncSetAttribute(bed_expand_t_kernel<B, S, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandTSmem<K, S>)))
   DGRM_EXPAND_T_ATTR(false, false, 0); DGRM_EXPAND_T_ATTR(false, false, 1); DGRM_EXPAND_T_ATTR(false, false, 2); DGRM_EXPAND_T_ATTR(false, false, 3);
   DGRM_EXPAND_T_ATTR(true, false, 0); DGRM_EXPAND_T_ATTR(true, false, 1); DGRM_EXPAND_T_ATTR(true, false, 2); DGRM_EXPAND_T_ATTR(true, false, 3);
   DGRM_EXPAND_T_ATTR(false, true, 0); DGRM_EXPAND_T_ATTR(false, true, 1); DGRM_EXPAND_T_ATTR(false, true, 2); DGRM_EXPAND_T_ATTR(false, true, 3);

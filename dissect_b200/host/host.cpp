@@ -23,10 +23,13 @@ static void engine_check(dgrm_engine* e, int rc) {
   if (rc != DGRM_OK) misc.error(dgrm_last_error(e), 0);
 }
 
-static dgrm_engine* create_engine() {
+static dgrm_engine* create_engine(int rank = 0, int world = 1) {
   dgrm_config cfg;
   dgrm_default_config(&cfg);
-  cfg.device = options.device;
+  const int ndev = std::max(1, dgrm_device_count());
+  cfg.device = (options.device + rank) % ndev;
+  cfg.rank = rank;
+  cfg.world = world;
   cfg.operand = options.operand;
   cfg.count_method = options.countMethod;
   cfg.flat_norm = options.flatGRMNormalization ? 1 : 0;
@@ -42,7 +45,7 @@ Options::Options()
     : makeGRM(false), outFile("dissect"), flatGRMNormalization(false), minimumNumberOverlapingSNPs(10.),
       maximumProportionOfElimitaedIndividuals(0.9), defaultBlockSize(256), regionalAnalysis(false), regionBy(ungrouped),
       regionSize(-1), regionOverlapping(0), minSNPsInRegions(1), writeLOCO(false), device(0), operand(DGRM_OPERAND_FP16),
-      countMethod(DGRM_COUNT_FP4), chunkSNPs(16384), ctaGroup(2) {}
+      countMethod(DGRM_COUNT_FP4), chunkSNPs(16384), ctaGroup(2), engines(1), lazyHostMatrices(false) {}
 
 void Options::parseOptions(int argc, char** argv) {
   auto need = [&](int i) -> std::string {
@@ -80,6 +83,11 @@ void Options::parseOptions(int argc, char** argv) {
     else if (a == "--min-snps-region") minSNPsInRegions = atoi(need(i++).c_str());
     else if (a == "--gpu-loco") writeLOCO = true;
     else if (a == "--gpu-chunk-snps") chunkSNPs = atoi(need(i++).c_str());
+    else if (a == "--gpu-engines") {
+      engines = atoi(need(i++).c_str());
+      if (engines < 1 || engines > 64) misc.error("Error: --gpu-engines is out of the range [1, 64].", 0);
+    } else if (a == "--gpu-lazy-host") lazyHostMatrices = true;
+    else if (a == "--gpu-eager-host") lazyHostMatrices = false;
     else if (a == "--gpu-cta-group") ctaGroup = atoi(need(i++).c_str());
     else misc.error("Error: Invalid option: " + a, 0);
   }
@@ -91,6 +99,8 @@ void Options::parseOptions(int argc, char** argv) {
   if (regionalAnalysis && genotypeFile.empty())
     misc.error("Error: To perform a regional analysis, a genotype file must be specified.", 0);
   if (writeLOCO && !regionalAnalysis) misc.error("Error: --gpu-loco needs a regional option (e.g. --groups).", 0);
+  if (engines > 1 && regionalAnalysis)
+    misc.error("Error: --gpu-engines > 1 is implemented for a single GRM (no regional option) in this adapter.", 0);
 }
 
 // ------------------------------------------------------------------------------------------- Matrix
@@ -423,21 +433,61 @@ Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
   if (genotype->engine()) {
     // the Genotype keeps its packed rows in HBM (loadResident): this kernel's SNPs are re-read from there
     eng_ = genotype->engine();
+    engs_.push_back(eng_);
     ownsEngine_ = false;
     engine_check(eng_, dgrm_begin(eng_, genotype->nSNPs));
     std::vector<uint8_t> keep((size_t)genotype->nBEDSNPs, 0);
     for (int k = 0; k < genotype->nSNPs; ++k) keep[(size_t)genotype->storeRows[(size_t)k]] = 1;
     engine_check(eng_, dgrm_push_stored(eng_, 0, genotype->nBEDSNPs, keep.data()));
-  } else {
+  } else if (options.engines <= 1) {
     eng_ = create_engine();
+    engs_.push_back(eng_);
     engine_check(eng_, dgrm_set_individuals(eng_, genotype->nBEDIndividuals, genotype->individualBEDIdxsMaskToKeep.data()));
     engine_check(eng_, dgrm_begin(eng_, genotype->nSNPs));
     *misc.message << "Reading genotype data from file [ " << genotype->bedFile << " ] ..." << std::endl;
     std::vector<int64_t> keepIdx(genotype->SNPsBEDIdxsToKeep.begin(), genotype->SNPsBEDIdxsToKeep.end());
     engine_check(eng_, dgrm_load_bed_file(eng_, genotype->bedFile.c_str(), genotype->nBEDSNPs,
                                           keepIdx.empty() ? NULL : keepIdx.data(), (int64_t)keepIdx.size()));
+  } else {
+    // The lower triangle split over several engines (GPUs), all fed by this host rank: the .bed is read once and
+    // every slab of rows is handed to every engine (each contracts its own tile set; the per-SNP statistics are the
+    // same integers everywhere).  The reference distributes fp64 genotype blocks over BLACS instead (genotype.cpp:639-707).
+    const int G = options.engines;
+    for (int r = 0; r < G; ++r) {
+      dgrm_engine* e = create_engine(r, G);
+      engs_.push_back(e);
+      engine_check(e, dgrm_set_individuals(e, genotype->nBEDIndividuals, genotype->individualBEDIdxsMaskToKeep.data()));
+      engine_check(e, dgrm_begin(e, genotype->nSNPs));
+    }
+    eng_ = engs_[0];
+    *misc.message << "Reading genotype data from file [ " << genotype->bedFile << " ] ..." << std::endl;
+    engine_check(eng_, dgrm_validate_bed_header(eng_, genotype->bedFile.c_str()));   // genotype.cpp:578-605
+    std::vector<uint8_t> keep;
+    if (!genotype->SNPsBEDIdxsToKeep.empty()) {
+      keep.assign((size_t)genotype->nBEDSNPs, 0);
+      for (size_t k = 0; k < genotype->SNPsBEDIdxsToKeep.size(); ++k) keep[(size_t)genotype->SNPsBEDIdxsToKeep[k]] = 1;
+    }
+    FILE* f = fopen(genotype->bedFile.c_str(), "rb");
+    if (!f || fseek(f, 3, SEEK_SET) != 0) misc.error("Error: The file [ " + genotype->bedFile + " ] does not exist or cannot be opened.", 0);
+    const int64_t bpr = ((int64_t)genotype->nBEDIndividuals + 3) / 4;
+    const int64_t slab = std::max<int64_t>(1, (64ll << 20) / bpr);
+    std::vector<uint8_t> buf((size_t)(slab * bpr));   // pageable: the copy is staged before the push returns
+    for (int64_t r0 = 0; r0 < genotype->nBEDSNPs; r0 += slab) {
+      const int64_t cnt = std::min<int64_t>(slab, genotype->nBEDSNPs - r0);
+      if ((int64_t)fread(buf.data(), (size_t)bpr, (size_t)cnt, f) != cnt) {
+        fclose(f);
+        misc.error("Error: An internal error has happened when reading the genotypes file.", 0);   // genotype.cpp:693-696
+      }
+      for (int r = 0; r < G; ++r)
+        engine_check(engs_[r], dgrm_push_bed_host(engs_[r], buf.data(), bpr, cnt, keep.empty() ? NULL : keep.data() + r0));
+    }
+    fclose(f);
   }
-  const int rc = dgrm_finish(eng_);
+  int rc = DGRM_OK;
+  for (size_t r = 0; r < engs_.size(); ++r) {
+    const int rcr = dgrm_finish(engs_[r]);
+    if (rc == DGRM_OK) rc = rcr;
+  }
   // per-SNP records, as gatherSNPData leaves them on the root (genotype.cpp:859-870)
   {
     const int m = genotype->nSNPs;
@@ -466,7 +516,7 @@ Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
   else
     *misc.message << "GRM will be normalized for all individuals by the total number of SNPs: " << double(genotype->nSNPs) << "." << std::endl;
   normalized = normalizeGRM;
-  fetch();
+  if (!options.lazyHostMatrices) fetch();
   *misc.message << "GRM computation finished." << std::endl;
 }
 
@@ -595,7 +645,14 @@ Kernel::~Kernel() {
     dgrm_set_output_subset(eng_, NULL, 0);
     dgrm_set_view(eng_, DGRM_VIEW_CURRENT);
   }
-  if (eng_ && ownsEngine_) dgrm_destroy(eng_);
+  if (ownsEngine_) {
+    if (engs_.empty() && eng_) dgrm_destroy(eng_);
+    for (size_t r = 0; r < engs_.size(); ++r) dgrm_destroy(engs_[r]);
+  }
+}
+
+void Kernel::ensureHost() {
+  if (!kernel && eng_) fetch();
 }
 
 // addKernels(1., saved, +-1., this) on the device (kernel.cpp:1705-1859): the engine combines the unnormalised S and
@@ -609,6 +666,7 @@ Kernel* Kernel::combinedWithSaved(Kernel* saved, double scalingFactorThis) {
     misc.error("Error: An internal error was happened. GRMs with different individuals can not be added.", 0);
   Kernel* r = new Kernel();
   r->eng_ = eng_;
+  r->engs_ = engs_;
   r->ownsEngine_ = false;
   r->isView_ = true;
   r->individuals = individuals;
@@ -634,7 +692,7 @@ Kernel* Kernel::combinedWithSaved(Kernel* saved, double scalingFactorThis) {
   engine_check(eng_, dgrm_set_output_subset(eng_, NULL, 0));
   engine_check(eng_, dgrm_set_view(eng_, scalingFactorThis < 0. ? DGRM_VIEW_SAVED_MINUS_CURRENT : DGRM_VIEW_SAVED_PLUS_CURRENT));
   r->normalized = true;
-  r->fetch();
+  if (!options.lazyHostMatrices) r->fetch();
   return r;
 }
 
@@ -648,16 +706,21 @@ void Kernel::fetch() {
   N->initParameters(nIndividuals, nIndividuals, bs, communicator->nDefaultBlockCols);
   kernel->symmetric = N->symmetric = true;
   kernel->uplo = N->uplo = 'L';  // matrix.cpp:2679-2680; kernel.cpp:105-108 for the flat case
-  engine_check(eng_, dgrm_fetch_block_cyclic(eng_, normalized ? DGRM_FETCH_A : DGRM_FETCH_S, kernel->m, std::max(kernel->nRows, 1),
-                                             kernel->nBlockRows, kernel->nBlockCols, communicator->myRow, communicator->myCol,
-                                             communicator->nProcRows, communicator->nProcCols, 'L'));
-  engine_check(eng_, dgrm_fetch_block_cyclic(eng_, DGRM_FETCH_N, N->m, std::max(N->nRows, 1), N->nBlockRows, N->nBlockCols,
-                                             communicator->myRow, communicator->myCol, communicator->nProcRows,
-                                             communicator->nProcCols, 'L'));
+  // every engine of the partition writes the entries of the tiles it owns (dgrm.h) into the same local block
+  for (size_t r = 0; r < engs_.size(); ++r) {
+    dgrm_engine* e = engs_[r];
+    engine_check(e, dgrm_fetch_block_cyclic(e, normalized ? DGRM_FETCH_A : DGRM_FETCH_S, kernel->m, std::max(kernel->nRows, 1),
+                                            kernel->nBlockRows, kernel->nBlockCols, communicator->myRow, communicator->myCol,
+                                            communicator->nProcRows, communicator->nProcCols, 'L'));
+    engine_check(e, dgrm_fetch_block_cyclic(e, DGRM_FETCH_N, N->m, std::max(N->nRows, 1), N->nBlockRows, N->nBlockCols,
+                                            communicator->myRow, communicator->myCol, communicator->nProcRows,
+                                            communicator->nProcCols, 'L'));
+  }
 }
 
 void Kernel::normalize() {
   if (normalized) return;
+  ensureHost();
   if (diagonalized) misc.error("Error: Diagonalized Kernel cannot be normalized.", 0);
   if (!N) misc.error("Error: An internal error was happened. GRM cannot be normalized because normalization matrix is not present.", 0);
   if (N->uplo != kernel->uplo)
@@ -668,6 +731,7 @@ void Kernel::normalize() {
 
 void Kernel::denormalize() {
   if (!normalized) return;
+  ensureHost();
   if (diagonalized) misc.error("Error: Diagonalized Kernel cannot be unnormalized.", 0);
   kernel->elementWiseMultiplication(N);
   normalized = false;
@@ -696,13 +760,15 @@ std::vector<std::string> Kernel::minimumIndividualsRemovePairs(const std::vector
 
 bool Kernel::sanitizeKernel() {
   if (!eng_) misc.error("Error: sanitizeKernel on a host-only GRM is not implemented in this adapter.", 0);
-  if (!N) misc.error("Error: An internal error was happened. Kernel cannot be checked without the normalization matrix.", 0);
-  int64_t cnt = 0;
-  engine_check(eng_, dgrm_low_overlap_pairs(eng_, options.minimumNumberOverlapingSNPs, NULL, 0, &cnt));
-  std::vector<int64_t> pairs((size_t)std::max<int64_t>(cnt, 1) * 2);
-  if (cnt > 0) engine_check(eng_, dgrm_low_overlap_pairs(eng_, options.minimumNumberOverlapingSNPs, pairs.data(), cnt, &cnt));
   std::vector<std::pair<int, int> > hits;  // (col, row) so that sorting gives the column-major scan order
-  for (int64_t i = 0; i < cnt; ++i) hits.push_back(std::make_pair((int)pairs[2 * i + 1], (int)pairs[2 * i]));
+  for (size_t r = 0; r < engs_.size(); ++r) {   // every engine scans the tiles it owns
+    dgrm_engine* e = engs_[r];
+    int64_t cnt = 0;
+    engine_check(e, dgrm_low_overlap_pairs(e, options.minimumNumberOverlapingSNPs, NULL, 0, &cnt));
+    std::vector<int64_t> pairs((size_t)std::max<int64_t>(cnt, 1) * 2);
+    if (cnt > 0) engine_check(e, dgrm_low_overlap_pairs(e, options.minimumNumberOverlapingSNPs, pairs.data(), cnt, &cnt));
+    for (int64_t i = 0; i < cnt; ++i) hits.push_back(std::make_pair((int)pairs[2 * i + 1], (int)pairs[2 * i]));
+  }
   std::sort(hits.begin(), hits.end());
   std::vector<int> i1, i2;
   for (size_t i = 0; i < hits.size(); ++i) {
@@ -746,14 +812,14 @@ void Kernel::filterIndividuals(const std::vector<std::string>& keepIds) {
   for (size_t i = 0; i < ids.size(); ++i) individualIdsIdx[ids[i]] = (int)i;
   nIndividuals = (int)ids.size();
   std::vector<int64_t> idx(subset_.begin(), subset_.end());
-  engine_check(eng_, dgrm_set_output_subset(eng_, idx.data(), (int64_t)idx.size()));
-  fetch();
+  for (size_t r = 0; r < engs_.size(); ++r) engine_check(engs_[r], dgrm_set_output_subset(engs_[r], idx.data(), (int64_t)idx.size()));
+  if (kernel || !options.lazyHostMatrices) fetch();
 }
 
 void Kernel::writeGRM(const std::string& f) {
   if (asymmetric) misc.error("Error: An internal error was happened. This operation can not be performed on an asymmetric GRM", 0);
   if (!normalized) misc.error("Error: An internal error was happened. GRM can only be stored in normalized form.", 0);
-  if (!N) misc.error("Error: An internal error was happened. GRM can only be stored when N information is stored.", 0);
+  if (!N && !eng_) misc.error("Error: An internal error was happened. GRM can only be stored when N information is stored.", 0);
   *misc.message << "Writing GRM on [ " << f << ".grm.(ids/snps/dat) ]..." << std::endl;
   if (communicator->mpiRoot) {
     std::ofstream ids((f + ".grm.ids").c_str());
@@ -764,7 +830,9 @@ void Kernel::writeGRM(const std::string& f) {
   if (eng_) {
     // packMatrices + writeMatrixMPI funnel every block through rank 0 in the reference (matrix.cpp:2308-2341);
     // here the device packs the (n+1) x n array directly
-    engine_check(eng_, dgrm_write_grm_dat(eng_, (f + ".grm.dat").c_str()));
+    // (and with several engines every engine writes the runs of the file that its tiles hold)
+    for (size_t r = 0; r < engs_.size(); ++r)
+      engine_check(engs_[r], dgrm_write_grm_dat_part(engs_[r], (f + ".grm.dat").c_str(), r == 0 ? 1 : 0));
   } else {
     // host-only kernel (read from file / addKernels result): kernel.cpp:944-974 + matrix.cpp:2324-2334 on one rank
     if (communicator->nProcRows != 1 || communicator->nProcCols != 1)

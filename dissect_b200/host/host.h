@@ -49,6 +49,11 @@ struct Options {
                                        // (the (S, N) algebra of singlereml.cpp:293-298, done on the device)
   // engine knobs (no counterpart in the reference)
   int device, operand, countMethod, chunkSNPs, ctaGroup;
+  int engines;                         // --gpu-engines G: the lower triangle is split over G engines (GPU device +
+                                       // r mod the number of devices for engine r), all driven by this one host rank
+  bool lazyHostMatrices;               // --gpu-lazy-host: kernel / N are only brought to the host when asked for
+                                       // (ensureHost); --make-grm itself needs files only, so a 50k or 100k GRM never
+                                       // has to fit the INT_MAX local-matrix limit of a 1 x 1 grid (matrix.cpp:1773-1779)
   Options();
   void parseOptions(int argc, char** argv);
 };
@@ -173,8 +178,10 @@ class Kernel {
   // dgrm_save on the same engine; the view ends when the returned Kernel is deleted.
   Kernel* combinedWithSaved(Kernel* saved, double scalingFactorThis);
   dgrm_engine* engine() { return eng_; }
+  void ensureHost();  // materialise kernel / N on the host (no-op when they are there already)
  private:
-  dgrm_engine* eng_;
+  dgrm_engine* eng_;                  // engine 0 (owner of the per-SNP statistics; every engine computes the same)
+  std::vector<dgrm_engine*> engs_;    // all engines of the partition (engs_[0] == eng_)
   bool ownsEngine_, isView_;
   std::vector<long long> subset_;  // individuals (positions) still in the kernel after sanitizeKernel
   void fetch();

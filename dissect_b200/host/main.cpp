@@ -8,6 +8,7 @@ using namespace dgrm_host;
 
 int main(int argc, char** argv) {
   try {
+    options.lazyHostMatrices = true;   // --make-grm only writes files: kernel / N stay on the device (--gpu-eager-host undoes it)
     options.parseOptions(argc, argv);
     communicator->nDefaultBlockRows = communicator->nDefaultBlockCols = options.defaultBlockSize;
     if (!options.makeGRM) misc.error("Error: only --make-grm is implemented by this adapter.", 0);

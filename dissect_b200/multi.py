@@ -15,6 +15,8 @@ block-cyclic local matrix into a zeroed device panel and the panels are summed o
 (every entry has exactly one owner, so the sum is exact), or every engine writes its own runs of the .grm.dat.
 """
 import math
+import os
+import time
 
 import numpy as np
 
@@ -184,6 +186,8 @@ class MultiGpuGrm:
         Everything is stream-ordered on torch's current stream; the host never waits inside the loop."""
         plan = self.prepare(m_file, keep)
         eng, torch = self.eng, self.torch
+        trace = os.environ.get("DGRM_BUILD_TRACE") and self.rank == 0
+        t0 = time.perf_counter()
         eng.begin(max(plan.m_kept, 1))
         stream = torch.cuda.current_stream().cuda_stream if self._cuda else None
         if self.world == 1:
@@ -207,8 +211,13 @@ class MultiGpuGrm:
                 eng.push_bed_device(gather_buf.data_ptr(), gather_buf.stride(0), self.world * plan.shard, row_keep=rk,
                                     stream=stream)
                 eng.release_inputs(stream)
+        t1 = time.perf_counter()
         if finish:
             eng.finish()
+        if trace:
+            import sys
+            print(f"[multi r0] push phase {1e3 * (t1 - t0):.2f} ms (host time to enqueue), finish {1e3 * (time.perf_counter() - t1):.2f} ms, "
+                  f"groups {len(plan.groups)}, exchange {self.exchange}", file=sys.stderr)
 
     def _build_p2p(self, source, plan):
         """Copy-engine exchange (dissect_b200/exchange.py): shards are posted up to NBUF groups ahead."""

@@ -104,6 +104,9 @@ const char *dgrm_last_error(const dgrm_engine *e);
 
 int dgrm_abi_version(void);
 
+/* Number of CUDA devices visible to the process (0 when there is none or the runtime fails). */
+int dgrm_device_count(void);
+
 /* Cohort geometry.  n_fam = individuals in the .fam; keep_mask[n_fam] != 0 keeps individual f
  * (individualBEDIdxsMaskToKeep, genotype.cpp:750); NULL keeps everyone. */
 int dgrm_set_individuals(dgrm_engine *e, int64_t n_fam, const int32_t *keep_mask);
@@ -137,6 +140,10 @@ int dgrm_release_inputs(dgrm_engine *e, void *consumer_stream);
  * m_file rows (SNPsBEDIdxsToKeep). */
 int dgrm_load_bed_file(dgrm_engine *e, const char *bed_path, int64_t m_file,
                        const int64_t *snp_keep_idx, int64_t m_keep);
+
+/* The 3-byte header checks of readBEDFile alone (genotype.cpp:578-605), with the reference's messages: for hosts that
+ * read the file themselves (one reader feeding several engines). */
+int dgrm_validate_bed_header(dgrm_engine *e, const char *bed_path);
 
 /* Flush the last partial chunk, finish S and N.  Fails with DGRM_E_BADSNP / DGRM_E_NANSNP
  * when a kept SNP is monomorphic / entirely missing (genotype.cpp:924-939); the offending
