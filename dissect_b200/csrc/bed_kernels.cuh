@@ -620,14 +620,14 @@ template <int QK, bool SPLIT>
 struct ExpandTSmem {
   uint16_t lut_hi[kExpK][4];
   uint16_t lut_lo[SPLIT ? kExpK : 1][4];
-  double lut_sq[kExpK][4];
+  alignas(16) double lut_sq[kExpK][4];
   uint32_t pair_hi[kExpK / 2][16];   // operand values of SNPs (2p, 2p+1): low half-word = SNP 2p
   uint32_t pair_lo[SPLIT ? kExpK / 2 : 1][16];
-  double pair_sq[kExpK / 2][16];
+  alignas(16) double pair_sq[kExpK / 2][16];
   double dpart[kExpTKh][kExpI];
   int mpart[kExpTKh][kExpI];
-  uint8_t outz[kExpI * kExpZPitch];
-  uint8_t outq[kExpI * (QK == 1 ? kExpQPitch : QK == 2 ? kExpQ4Pitch : kExpMPitch)];
+  alignas(16) uint8_t outz[kExpI * kExpZPitch];
+  alignas(16) uint8_t outq[kExpI * (QK == 1 ? kExpQPitch : QK == 2 ? kExpQ4Pitch : kExpMPitch)];
 };
 
 template <bool BF16, bool SPLIT, int QK>

@@ -45,18 +45,24 @@ Options::Options()
     : makeGRM(false), outFile("dissect"), flatGRMNormalization(false), minimumNumberOverlapingSNPs(10.),
       maximumProportionOfElimitaedIndividuals(0.9), defaultBlockSize(256), regionalAnalysis(false), regionBy(ungrouped),
       regionSize(-1), regionOverlapping(0), minSNPsInRegions(1), writeLOCO(false), device(0), operand(DGRM_OPERAND_FP16),
-      countMethod(DGRM_COUNT_FP4), chunkSNPs(16384), ctaGroup(2), engines(1), lazyHostMatrices(false) {}
+      countMethod(DGRM_COUNT_FP4), chunkSNPs(16384), ctaGroup(2), engines(1), lazyHostMatrices(false), GRMJoinMethod(0) {}
 
 void Options::parseOptions(int argc, char** argv) {
   auto need = [&](int i) -> std::string {
     if (i + 1 >= argc) misc.error(std::string("Error: The option ") + argv[i] + " needs an argument.", 0);
     return argv[i + 1];
   };
-  bool seenRegion = false, seenGroups = false;
+  bool seenRegion = false, seenGroups = false, seenJoin = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--make-grm") makeGRM = true;
     else if (a == "--bfile") genotypeFile = need(i++);
+    else if (a == "--bfile-list") genotypeListFile = need(i++);                 // options.cpp:414-417
+    else if (a == "--grm-join-method") {                                        // options.cpp:497-500
+      GRMJoinMethod = atoi(need(i++).c_str());
+      seenJoin = true;
+      if (GRMJoinMethod < 0 || GRMJoinMethod > 1) misc.error("Error: --grm-join-method is out of the range [0, 1].", 0);
+    }
     else if (a == "--out") outFile = need(i++);
     else if (a == "--extract") fileSNPsToKeep = need(i++);
     else if (a == "--keep") fileIndividualsToKeep = need(i++);
@@ -96,6 +102,10 @@ void Options::parseOptions(int argc, char** argv) {
     misc.error("Error: Only one type of regional analysis is allowed. The options --region-overlap and --region-size or --groups can not be used together.", 0);
   if (regionSize < 0 && regionOverlapping > 0)
     misc.error("Error: The option --region-overlap can only be used together with --region-size.", 0);
+  if (!genotypeListFile.empty() && !genotypeFile.empty())   // options.cpp:1193-1196
+    misc.error("Error: A genotype file and a genotype list of files can not be specified at the same time.", 0);
+  if (seenJoin && genotypeListFile.empty())                   // options.cpp:1288-1291
+    misc.error("Error: The option --grm-join-method can only be used together with --bfile-list.", 0);
   if (regionalAnalysis && genotypeFile.empty())
     misc.error("Error: To perform a regional analysis, a genotype file must be specified.", 0);
   if (writeLOCO && !regionalAnalysis) misc.error("Error: --gpu-loco needs a regional option (e.g. --groups).", 0);
@@ -418,6 +428,23 @@ void Genotype::readFAMFile(const std::string& f, const std::set<std::string>& ke
 Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
     : type(kernelGRM), name("default"), kernel(NULL), N(NULL), normalized(false), diagonalized(false), asymmetric(false),
       nIndividuals(genotype->nIndividuals), eng_(NULL), ownsEngine_(true), isView_(false) {
+  std::vector<Genotype*> one(1, genotype);
+  compute(one, normalizeGRM);
+}
+
+// One GRM from several genotype files with the same individuals and disjoint SNPs (--bfile-list): what
+// loadGRMUsingOptions builds by adding per-file kernels (method 0, auxiliar.cpp:620-672) or by joining the genotypes
+// first (method 1, :673-690).  On the device both are the same thing: S and N simply keep accumulating over the files'
+// SNP chunks before the one division.
+Kernel::Kernel(const std::vector<Genotype*>& genotypes, bool normalizeGRM)
+    : type(kernelGRM), name("default"), kernel(NULL), N(NULL), normalized(false), diagonalized(false), asymmetric(false),
+      nIndividuals(genotypes.empty() ? 0 : genotypes[0]->nIndividuals), eng_(NULL), ownsEngine_(true), isView_(false) {
+  if (genotypes.empty()) misc.error("Error: No genotype file(s) specified.", 0);
+  compute(genotypes, normalizeGRM);
+}
+
+void Kernel::compute(const std::vector<Genotype*>& genotypes, bool normalizeGRM) {
+  Genotype* genotype = genotypes[0];
   for (int i = 0; i < genotype->nIndividuals; ++i) {
     individuals.push_back(genotype->individuals[i]);
     const std::string key = genotype->individualIds[i];
@@ -427,10 +454,24 @@ Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
                  genotype->individuals[i].individualID + " appears more than one time in the genotypes.", 0);
     individualIdsIdx[key] = i;
   }
-  randomVarNames = genotype->SNPIds;
+  int totalSNPs = 0;
+  for (size_t g = 0; g < genotypes.size(); ++g) {
+    if (g > 0) {
+      if (genotypes[g]->individualIds != individualIds || genotypes[g]->nBEDIndividuals != genotype->nBEDIndividuals ||
+          genotypes[g]->individualBEDIdxsMaskToKeep != genotype->individualBEDIdxsMaskToKeep)
+        misc.error("Error: An internal error was happened. GRMs with different individuals can not be added.", 0);   // kernel.cpp:1740
+      std::set<std::string> seen(randomVarNames.begin(), randomVarNames.end());
+      for (size_t k = 0; k < genotypes[g]->SNPIds.size(); ++k)
+        if (seen.count(genotypes[g]->SNPIds[k]))   // auxiliar.cpp:651-655
+          misc.error("Error: When computing a GRM from multiple genotype files. There are SNPs repeated in different files.", 0);
+    }
+    randomVarNames.insert(randomVarNames.end(), genotypes[g]->SNPIds.begin(), genotypes[g]->SNPIds.end());
+    totalSNPs += genotypes[g]->nSNPs;
+  }
 
   *misc.message << "Starting GRM computation..." << std::endl;
   if (genotype->engine()) {
+    if (genotypes.size() != 1) misc.error("Error: An internal error was happened. A resident genotype cannot be joined with others.", 0);
     // the Genotype keeps its packed rows in HBM (loadResident): this kernel's SNPs are re-read from there
     eng_ = genotype->engine();
     engs_.push_back(eng_);
@@ -439,49 +480,50 @@ Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
     std::vector<uint8_t> keep((size_t)genotype->nBEDSNPs, 0);
     for (int k = 0; k < genotype->nSNPs; ++k) keep[(size_t)genotype->storeRows[(size_t)k]] = 1;
     engine_check(eng_, dgrm_push_stored(eng_, 0, genotype->nBEDSNPs, keep.data()));
-  } else if (options.engines <= 1) {
-    eng_ = create_engine();
-    engs_.push_back(eng_);
-    engine_check(eng_, dgrm_set_individuals(eng_, genotype->nBEDIndividuals, genotype->individualBEDIdxsMaskToKeep.data()));
-    engine_check(eng_, dgrm_begin(eng_, genotype->nSNPs));
-    *misc.message << "Reading genotype data from file [ " << genotype->bedFile << " ] ..." << std::endl;
-    std::vector<int64_t> keepIdx(genotype->SNPsBEDIdxsToKeep.begin(), genotype->SNPsBEDIdxsToKeep.end());
-    engine_check(eng_, dgrm_load_bed_file(eng_, genotype->bedFile.c_str(), genotype->nBEDSNPs,
-                                          keepIdx.empty() ? NULL : keepIdx.data(), (int64_t)keepIdx.size()));
   } else {
-    // The lower triangle split over several engines (GPUs), all fed by this host rank: the .bed is read once and
-    // every slab of rows is handed to every engine (each contracts its own tile set; the per-SNP statistics are the
-    // same integers everywhere).  The reference distributes fp64 genotype blocks over BLACS instead (genotype.cpp:639-707).
-    const int G = options.engines;
+    // One engine, or the lower triangle split over several engines (GPUs) that are all fed by this host rank: each
+    // contracts its own tile set; the per-SNP statistics are the same integers everywhere.  The reference distributes
+    // fp64 genotype blocks over BLACS instead (genotype.cpp:639-707).
+    const int G = std::max(1, options.engines);
     for (int r = 0; r < G; ++r) {
       dgrm_engine* e = create_engine(r, G);
       engs_.push_back(e);
       engine_check(e, dgrm_set_individuals(e, genotype->nBEDIndividuals, genotype->individualBEDIdxsMaskToKeep.data()));
-      engine_check(e, dgrm_begin(e, genotype->nSNPs));
+      engine_check(e, dgrm_begin(e, totalSNPs));
     }
     eng_ = engs_[0];
-    *misc.message << "Reading genotype data from file [ " << genotype->bedFile << " ] ..." << std::endl;
-    engine_check(eng_, dgrm_validate_bed_header(eng_, genotype->bedFile.c_str()));   // genotype.cpp:578-605
-    std::vector<uint8_t> keep;
-    if (!genotype->SNPsBEDIdxsToKeep.empty()) {
-      keep.assign((size_t)genotype->nBEDSNPs, 0);
-      for (size_t k = 0; k < genotype->SNPsBEDIdxsToKeep.size(); ++k) keep[(size_t)genotype->SNPsBEDIdxsToKeep[k]] = 1;
-    }
-    FILE* f = fopen(genotype->bedFile.c_str(), "rb");
-    if (!f || fseek(f, 3, SEEK_SET) != 0) misc.error("Error: The file [ " + genotype->bedFile + " ] does not exist or cannot be opened.", 0);
-    const int64_t bpr = ((int64_t)genotype->nBEDIndividuals + 3) / 4;
-    const int64_t slab = std::max<int64_t>(1, (64ll << 20) / bpr);
-    std::vector<uint8_t> buf((size_t)(slab * bpr));   // pageable: the copy is staged before the push returns
-    for (int64_t r0 = 0; r0 < genotype->nBEDSNPs; r0 += slab) {
-      const int64_t cnt = std::min<int64_t>(slab, genotype->nBEDSNPs - r0);
-      if ((int64_t)fread(buf.data(), (size_t)bpr, (size_t)cnt, f) != cnt) {
-        fclose(f);
-        misc.error("Error: An internal error has happened when reading the genotypes file.", 0);   // genotype.cpp:693-696
+    for (size_t g = 0; g < genotypes.size(); ++g) {
+      Genotype* gt = genotypes[g];
+      *misc.message << "Reading genotype data from file [ " << gt->bedFile << " ] ..." << std::endl;
+      if (G == 1) {
+        std::vector<int64_t> keepIdx(gt->SNPsBEDIdxsToKeep.begin(), gt->SNPsBEDIdxsToKeep.end());
+        engine_check(eng_, dgrm_load_bed_file(eng_, gt->bedFile.c_str(), gt->nBEDSNPs, keepIdx.empty() ? NULL : keepIdx.data(),
+                                              (int64_t)keepIdx.size()));
+        continue;
       }
-      for (int r = 0; r < G; ++r)
-        engine_check(engs_[r], dgrm_push_bed_host(engs_[r], buf.data(), bpr, cnt, keep.empty() ? NULL : keep.data() + r0));
+      // several engines: the .bed is read once and every slab of rows is handed to every engine
+      engine_check(eng_, dgrm_validate_bed_header(eng_, gt->bedFile.c_str()));   // genotype.cpp:578-605
+      std::vector<uint8_t> keep;
+      if (!gt->SNPsBEDIdxsToKeep.empty()) {
+        keep.assign((size_t)gt->nBEDSNPs, 0);
+        for (size_t k = 0; k < gt->SNPsBEDIdxsToKeep.size(); ++k) keep[(size_t)gt->SNPsBEDIdxsToKeep[k]] = 1;
+      }
+      FILE* f = fopen(gt->bedFile.c_str(), "rb");
+      if (!f || fseek(f, 3, SEEK_SET) != 0) misc.error("Error: The file [ " + gt->bedFile + " ] does not exist or cannot be opened.", 0);
+      const int64_t bpr = ((int64_t)gt->nBEDIndividuals + 3) / 4;
+      const int64_t slab = std::max<int64_t>(1, (64ll << 20) / bpr);
+      std::vector<uint8_t> buf((size_t)(slab * bpr));   // pageable: the copy is staged before the push returns
+      for (int64_t r0 = 0; r0 < gt->nBEDSNPs; r0 += slab) {
+        const int64_t cnt = std::min<int64_t>(slab, gt->nBEDSNPs - r0);
+        if ((int64_t)fread(buf.data(), (size_t)bpr, (size_t)cnt, f) != cnt) {
+          fclose(f);
+          misc.error("Error: An internal error has happened when reading the genotypes file.", 0);   // genotype.cpp:693-696
+        }
+        for (int r = 0; r < G; ++r)
+          engine_check(engs_[r], dgrm_push_bed_host(engs_[r], buf.data(), bpr, cnt, keep.empty() ? NULL : keep.data() + r0));
+      }
+      fclose(f);
     }
-    fclose(f);
   }
   int rc = DGRM_OK;
   for (size_t r = 0; r < engs_.size(); ++r) {
@@ -490,15 +532,17 @@ Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
   }
   // per-SNP records, as gatherSNPData leaves them on the root (genotype.cpp:859-870)
   {
-    const int m = genotype->nSNPs;
+    const int m = totalSNPs;
     std::vector<int32_t> freq((size_t)m * 4), nn(m);
     std::vector<double> p1(m), p2(m), sd(m);
     engine_check(eng_, dgrm_snp_stats(eng_, freq.data(), nn.data(), p1.data(), p2.data(), sd.data()));
-    for (int k = 0; k < m; ++k) {
-      SNP& s = genotype->SNPs[k];
-      for (int c = 0; c < 4; ++c) s.frequencies[c] = freq[(size_t)k * 4 + c];
-      s.nNonMissing = nn[k]; s.p1 = p1[k]; s.p2 = p2[k]; s.standardDev = sd[k];
-    }
+    int k = 0;
+    for (size_t g = 0; g < genotypes.size(); ++g)
+      for (int q = 0; q < genotypes[g]->nSNPs; ++q, ++k) {
+        SNP& s = genotypes[g]->SNPs[q];
+        for (int c = 0; c < 4; ++c) s.frequencies[c] = freq[(size_t)k * 4 + c];
+        s.nNonMissing = nn[k]; s.p1 = p1[k]; s.p2 = p2[k]; s.standardDev = sd[k];
+      }
   }
   if (rc == DGRM_E_BADSNP) {
     // genotype.cpp:924-939: list the offenders in <out>.badsnps, then fail
@@ -506,18 +550,52 @@ Kernel::Kernel(Genotype* genotype, bool normalizeGRM)
     std::vector<int64_t> idx(65536);
     dgrm_bad_snps(eng_, idx.data(), (int64_t)idx.size(), &cnt);
     std::ofstream bad((options.outFile + ".badsnps").c_str());
-    for (int64_t i = 0; i < std::min<int64_t>(cnt, (int64_t)idx.size()); ++i) bad << genotype->SNPs[(size_t)idx[i]].name << std::endl;
+    for (int64_t i = 0; i < std::min<int64_t>(cnt, (int64_t)idx.size()); ++i) bad << randomVarNames[(size_t)idx[i]] << std::endl;
     *misc.message << "The SNPs are stored in the file [ " << options.outFile + ".badsnps" << " ]." << std::endl;
   }
   engine_check(eng_, rc);
-  genotype->normalized = true;  // the standardised values exist (on the GPU) from here on
+  for (size_t g = 0; g < genotypes.size(); ++g) genotypes[g]->normalized = true;  // the standardised values exist (on the GPU) from here on
   if (!options.flatGRMNormalization)
     *misc.message << "GRM will be normalized using the individuals shared non-missing SNPs." << std::endl;
   else
-    *misc.message << "GRM will be normalized for all individuals by the total number of SNPs: " << double(genotype->nSNPs) << "." << std::endl;
+    *misc.message << "GRM will be normalized for all individuals by the total number of SNPs: " << double(totalSNPs) << "." << std::endl;
   normalized = normalizeGRM;
   if (!options.lazyHostMatrices) fetch();
   *misc.message << "GRM computation finished." << std::endl;
+}
+
+// loadGRMUsingOptions (auxiliar.cpp:581-700) for the genotype sources of --make-grm: one file (--bfile) or a list
+// (--bfile-list, with --grm-join-method 0 = add per-file GRMs, 1 = join the genotypes first).
+Kernel* loadGRMUsingOptions() {
+  if (options.genotypeListFile.empty()) {
+    if (options.genotypeFile.empty()) misc.error("Error: No genotype file(s) specified.", 0);
+    Genotype* genotype = new Genotype(options.genotypeFile);
+    Kernel* grm = new Kernel(genotype);
+    delete genotype;
+    return grm;
+  }
+  if (options.GRMJoinMethod == 0)
+    *misc.message << "Computing GRM using a list of genotype files. Method 0: First compute GRMs for each genotype, then add GRMs." << std::endl;
+  else
+    *misc.message << "Computing GRM using a list of genotype files. Method 1: First join genotypes, then compute GRM." << std::endl;
+  std::ifstream file(options.genotypeListFile.c_str());
+  if (!file) misc.error("Error: The file [ " + options.genotypeListFile + " ] does not exist or cannot be opened.", 0);
+  std::vector<Genotype*> genotypes;
+  std::set<std::string> seenFiles;
+  std::string line;
+  while (std::getline(file, line)) {
+    std::istringstream ss(line);
+    std::string partialFileName;
+    if (!(ss >> partialFileName)) continue;
+    if (!seenFiles.insert(partialFileName).second)   // genotype.cpp:397-400
+      misc.error("Error: The file [ " + partialFileName + ".bim/bed/fam ] appears defined twice.", 0);
+    if (!genotypes.empty()) *misc.message << (options.GRMJoinMethod == 0 ? "Adding GRM..." : "Adding genotype...") << std::endl;
+    genotypes.push_back(new Genotype(partialFileName));
+  }
+  Kernel* grm = new Kernel(genotypes, true);
+  for (size_t g = 0; g < genotypes.size(); ++g) delete genotypes[g];
+  *misc.message << "Genotype loading and GRM computation finished." << std::endl;
+  return grm;
 }
 
 Kernel::Kernel()

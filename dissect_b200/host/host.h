@@ -32,6 +32,7 @@ enum GroupBy { ungrouped, byPosition, byGene, byGroup, byOrderedFixedSize, byAll
 struct Options {
   bool makeGRM;
   std::string genotypeFile;            // --bfile
+  std::string genotypeListFile;        // --bfile-list F: one genotype file prefix per line (options.cpp:414-417)
   std::string outFile;                 // --out            (default "dissect", options.cpp:60)
   std::string fileSNPsToKeep;          // --extract
   std::string fileIndividualsToKeep;   // --keep
@@ -54,6 +55,7 @@ struct Options {
   bool lazyHostMatrices;               // --gpu-lazy-host: kernel / N are only brought to the host when asked for
                                        // (ensureHost); --make-grm itself needs files only, so a 50k or 100k GRM never
                                        // has to fit the INT_MAX local-matrix limit of a 1 x 1 grid (matrix.cpp:1773-1779)
+  int GRMJoinMethod;                   // --grm-join-method 0 | 1 (options.cpp:76, 497-500; auxiliar.cpp:615-690)
   Options();
   void parseOptions(int argc, char** argv);
 };
@@ -163,6 +165,7 @@ class Kernel {
   std::map<std::string, int> individualIdsIdx;
   std::vector<std::string> randomVarNames;  // = genotype->SNPIds (kernel.cpp:85)
   Kernel(Genotype* genotype, bool normalizeGRM = true);  // kernel.cpp:61-125, computed on the GPU
+  Kernel(const std::vector<Genotype*>& genotypes, bool normalizeGRM);  // one GRM over the SNPs of several files (--bfile-list)
   explicit Kernel(const std::string& f);                 // kernel.cpp:127-... -> readGRM :1023-1196 (host only)
   Kernel();                                              // empty, for addKernels results
   ~Kernel();
@@ -185,11 +188,15 @@ class Kernel {
   bool ownsEngine_, isView_;
   std::vector<long long> subset_;  // individuals (positions) still in the kernel after sanitizeKernel
   void fetch();
+  void compute(const std::vector<Genotype*>& genotypes, bool normalizeGRM);
   std::vector<std::string> minimumIndividualsRemovePairs(const std::vector<int>& i1, const std::vector<int>& i2);
   void filterIndividuals(const std::vector<std::string>& keepIds);
   Kernel(const Kernel&);
   Kernel& operator=(const Kernel&);
 };
+
+// auxiliar.cpp:581-700 for the genotype sources of --make-grm (--bfile, or --bfile-list with --grm-join-method)
+Kernel* loadGRMUsingOptions();
 
 }  // namespace dgrm_host
 #endif

@@ -12,11 +12,9 @@ int main(int argc, char** argv) {
     options.parseOptions(argc, argv);
     communicator->nDefaultBlockRows = communicator->nDefaultBlockCols = options.defaultBlockSize;
     if (!options.makeGRM) misc.error("Error: only --make-grm is implemented by this adapter.", 0);
-    if (options.genotypeFile.empty()) misc.error("Error: No genotype file(s) specified.", 0);
+    if (options.genotypeFile.empty() && options.genotypeListFile.empty()) misc.error("Error: No genotype file(s) specified.", 0);
     if (!options.regionalAnalysis) {
-      Genotype* genotype = new Genotype(options.genotypeFile);
-      Kernel* grm = new Kernel(genotype);
-      delete genotype;
+      Kernel* grm = loadGRMUsingOptions();   // analysis.cpp:45-47
       const bool sanitized = grm->sanitizeKernel();
       if (sanitized) grm->writeGRM(options.outFile);
       else *misc.message << "Sorry, a problem was happened while computing the GRM. Please, check the logs." << std::endl;

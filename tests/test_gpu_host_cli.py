@@ -167,3 +167,41 @@ def test_cli_lazy_and_eager_host_matrices_agree(tmp_path):
     assert run_cli(c["dir"], a).returncode == 0
     assert run_cli(c["dir"], b, ["--gpu-eager-host"]).returncode == 0
     assert open(a + ".grm.dat", "rb").read() == open(b + ".grm.dat", "rb").read()
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_cli_bfile_list_matches_reference_join(method, tmp_path):
+    """--bfile-list + --grm-join-method (loadGRMUsingOptions, auxiliar.cpp:615-690): two genotype files with the same
+    individuals and disjoint SNPs against the file the reference itself wrote through `--bfile-list ... --grm-join-method 0`
+    (per-file kernels joined with Kernel::addKernels; tests/golden/parts/joined.*)."""
+    from dissect_b200 import bedio
+    d = os.path.join(GOLDEN, "parts")
+    n, split = 48, 70
+    pk = bedio.read_bed(os.path.join(d, "in"), n)
+    bim = open(os.path.join(d, "in.bim")).read().splitlines()
+    fam = open(os.path.join(d, "in.fam")).read()
+    for name, (a, b) in (("pa", (0, split)), ("pb", (split, pk.shape[0]))):
+        sub = str(tmp_path / name)
+        bedio.write_bed(sub, pk[a:b], n)
+        open(sub + ".fam", "w").write(fam)
+        open(sub + ".bim", "w").write("\n".join(bim[a:b]) + "\n")
+    lst = str(tmp_path / "list.txt")
+    open(lst, "w").write(str(tmp_path / "pa") + "\n" + str(tmp_path / "pb") + "\n")
+    out = str(tmp_path / "joined")
+    r = subprocess.run([CLI, "--make-grm", "--bfile-list", lst, "--grm-join-method", str(method), "--out", out],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert f"Method {method}:" in r.stdout
+    for ext in (".grm.ids", ".grm.snps"):
+        assert open(out + ext).read() == open(os.path.join(d, "joined" + ext)).read(), ext
+    ref_A, ref_N = orc.unpack_grm_dat(open(os.path.join(d, "joined.grm.dat"), "rb").read(), n)
+    A, N = orc.unpack_grm_dat(open(out + ".grm.dat", "rb").read(), n)
+    low = lower_mask(n)
+    assert np.array_equal(N[low], ref_N[low])
+    assert np.max(np.abs(A[low] - ref_A[low])) <= 3e-4 * (1000.0 / 160) ** 0.5
+    # the same SNP in two files is an error, with the reference's message (auxiliar.cpp:651-655)
+    open(lst, "w").write(str(tmp_path / "pa") + "\n" + str(tmp_path / "pa2") + "\n")
+    for ext in (".bed", ".bim", ".fam"):
+        open(str(tmp_path / "pa2") + ext, "wb").write(open(str(tmp_path / "pa") + ext, "rb").read())
+    r = subprocess.run([CLI, "--make-grm", "--bfile-list", lst, "--out", out], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "There are SNPs repeated in different files" in r.stderr
