@@ -291,9 +291,15 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     chunk = args.chunk
+    # Transport of the streamed outputs (e2e leg).  Narrow transports (A as fp32, N as 16-bit deficiencies) cut the PCIe
+    # bytes but are widened to the caller's doubles by host threads; with only a few host cores per rank that widening is
+    # the bottleneck (measured r2, 2 ranks on 24 vCPUs), so then the copy engine delivers doubles directly.
+    threads_per_rank = max(1, cpu_threads() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    a_tr = args.a_transport if args.a_transport != "auto" else ("fp32" if threads_per_rank >= 12 else "fp64")
+    n_tr = args.n_transport if args.n_transport != "auto" else ("narrow" if threads_per_rank >= 6 else "fp64")
     mg = MultiGpuGrm(n, rank=rank, world=world, device=local, chunk_snps=chunk, xg=args.xg, exchange=args.exchange,
                      operand=args.operand, count_method=args.count, cta_group=args.cg, profile=True,
-                     resident_chunks=args.resident, resident_mb=args.resident_mb, a_transport=args.a_transport)
+                     resident_chunks=args.resident, resident_mb=args.resident_mb, a_transport=a_tr, n_transport=n_tr)
     eng = mg.eng
     # ---- synthetic cohort (same seed on every rank -> identical data; a rank only READS its own row shards) ----
     pk_raw, maf = synth_packed_cuda(n, m_file, seed, maf_lo=MAF_LO, maf_hi=MAF_HI, missing=MISSING)
@@ -398,6 +404,19 @@ def run_gpu(args):
                * n_pad * ((m_kept + 255) // 256 * 256)}                # operands are materialised: listed (§8d)
         names = {"decode": ("gather", "count"), "expand": ("expand",)}
         peaks1 = load_peaks()
+        # write-only stream in the same run (cudaMemset of 4 GiB): bed_expand writes 10x what it reads, and a pure write
+        # stream does not reach the read+write figure that MEASURED_PEAKS.json's copy test gives
+        wbuf = torch.empty(4 << 30, dtype=torch.uint8, device="cuda")
+        wbuf.zero_()
+        torch.cuda.synchronize()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(3):
+            wbuf.zero_()
+        w1.record()
+        torch.cuda.synchronize()
+        write_only_gbs = 3 * wbuf.numel() / (w0.elapsed_time(w1) * 1e-3) / 1e9
+        del wbuf
         kern = {}
         for k, parts in names.items():
             ms = sum(kt1[p][0] for p in parts) / reps
@@ -405,7 +424,11 @@ def run_gpu(args):
                 kern[k] = {"ms_per_step": ms, "algorithmic_bytes": alg[k], "achieved": alg[k] / (ms * 1e-3) / 1e9,
                            "frac": alg[k] / (ms * 1e-3) / 1e9 / peaks1["hbm_gbs"],
                            "launches_per_step": sum(kt1[p][1] for p in parts) / reps}
+        if "expand" in kern:
+            kern["expand"]["frac_of_write_only_stream"] = kern["expand"]["achieved"] / write_only_gbs
         k1 = {"bound": "hbm", "peak": peaks1["hbm_gbs"], "unit": "GB/s", "overlap": "off for this measurement",
+              "write_only_stream_gbs": write_only_gbs,
+              "write_only_note": "cudaMemset of 4 GiB timed in this run; `peak` is the copy (read + write) figure of MEASURED_PEAKS.json",
               "kernels": kern}
 
     # ---- e2e: host buffers in, A and N (lower triangle / this rank's tiles) out, every step ------------------
@@ -439,8 +462,9 @@ def run_gpu(args):
         e2e = {"value": ke * W / dte, "unit": "pair*SNP/s", "ms_per_step": 1e3 * dte / ke, "steps": ke,
                "h2d_bytes_per_step": int(m_file * bpr), "d2h_bytes_per_step": int(eng.last_d2h_bytes),
                "result": "A and N lower triangles as fp64 in pinned block-cyclic Matrix::m buffers (bs 256, 1x1 grid); "
-                         "d2h_bytes_per_step = bytes the copy engine really moved (A as " + args.a_transport +
-                         ", N as 16-bit deficiencies m - N or int32, widened to fp64 by host threads)",
+                         "d2h_bytes_per_step = bytes the copy engine really moved (A as " + a_tr +
+                         (", N as 16-bit deficiencies m - N or int32, widened to fp64 by host threads)" if n_tr == "narrow" else ", N as fp64)"),
+               "host_threads_per_rank": threads_per_rank,
                "check_trace_A": float(np.trace(A_host.array[:2000, :2000]))}
         eng.unbind_outputs()
         del A_host, N_host
@@ -473,8 +497,9 @@ def run_gpu(args):
                "h2d_bytes_per_step": int(plan.rows_of(rank) * bpr), "d2h_bytes_per_step": int(eng.last_d2h_bytes),
                "bytes_are": "this rank's; every rank moves about the same",
                "result": "per rank: its packed row shards in, its owned 128x256 tiles of A and N as fp64 in bound pinned "
-                         "buffers; d2h_bytes_per_step = bytes the copy engine really moved (A as " + args.a_transport +
-                         ", N as 16-bit deficiencies or int32, widened by host threads)"}
+                         "buffers; d2h_bytes_per_step = bytes the copy engine really moved (A as " + a_tr +
+                         (", N as 16-bit deficiencies or int32, widened by host threads)" if n_tr == "narrow" else ", N as fp64)"),
+               "host_threads_per_rank": threads_per_rank}
         eng.unbind_outputs()
 
     # ---- correctness of what was just timed (outside the timed regions) --------------------------------------
@@ -622,9 +647,13 @@ def main():
     ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--xg", type=int, default=0, help="engine chunks per all-gather (multi-GPU exchange granularity); "
                                                       "0 = as many as a 2 GB exchange-buffer budget allows")
-    ap.add_argument("--a-transport", default="fp32", choices=["fp64", "fp32"],
+    ap.add_argument("--a-transport", default="auto", choices=["auto", "fp64", "fp32"],
                     help="how streamed A values cross PCIe on the e2e path: fp32 (+ the exact fp64 diagonal; adds <= 6e-8 "
-                         "relative, the caller still receives fp64) or fp64")
+                         "relative, the caller still receives fp64), fp64, or auto = fp32 when a rank has >= 12 host threads "
+                         "for the widening, else fp64")
+    ap.add_argument("--n-transport", default="auto", choices=["auto", "narrow", "fp64"],
+                    help="how streamed pair counts cross PCIe: narrow (16-bit deficiencies / int32, widened by host threads), "
+                         "fp64 (doubles by the copy engine, no host work), auto = narrow when a rank has >= 6 host threads")
     ap.add_argument("--no-k1", action="store_true", help="skip the stand-alone decode-kernel measurement")
     ap.add_argument("--no-check", action="store_true", help="skip the parity block and the full-size checks")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],

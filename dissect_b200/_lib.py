@@ -11,7 +11,7 @@ K_NAMES = ("count", "expand", "syrk", "paircnt", "final", "fetch", "gather", "d2
 OPERANDS = {"fp16": 0, "bf16": 1, "fp16x2": 2}
 COUNT_METHODS = {"mma": 0, "popc": 1, "fp4": 2}
 FETCH = {"A": 0, "S": 1, "N": 2}
-TRANSPORT = {"fp64": 0, "fp32": 1}
+TRANSPORT = {"fp64": 0, "fp32": 1, "narrow": 2}
 
 # every symbol include/dgrm.h declares
 SYMBOLS = (
@@ -33,7 +33,7 @@ class Config(C.Structure):
         ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("operand", C.c_int32),
         ("count_method", C.c_int32), ("flat_norm", C.c_int32), ("chunk_snps", C.c_int32),
         ("cta_group", C.c_int32), ("profile", C.c_int32), ("resident_chunks", C.c_int32), ("resident_mb", C.c_int32),
-        ("reserve_sms", C.c_int32), ("a_transport", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("reserve_sms", C.c_int32), ("a_transport", C.c_int32), ("n_transport", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 

@@ -1049,6 +1049,8 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
         for (int32_t v : miss) mx = std::max<int64_t>(mx, v);
         e->n_u16 = 2 * mx <= 65534 && !getenv("DGRM_NO_U16");
       }
+      // DGRM_TRANSPORT_FP64 (a zero-initialised config reads as that too): counts leave as doubles, no host widening
+      const bool narrow_n = e->cfg.n_transport == DGRM_TRANSPORT_NARROW;
       // output jobs: one per (raster row group, streaming binding), in the order the row groups finish
       e->jobs.clear();
       e->jobs_issued = e->jobs_done = 0;
@@ -1066,7 +1068,7 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
           j.lr1 = first_local_ge(row1, bd.g.nloc_r, bd.g.bs_r, bd.g.my_row, bd.g.R);
           j.lc1 = first_local_ge(row1, bd.g.nloc_c, bd.g.bs_c, bd.g.my_col, bd.g.C);
           if (j.lr1 <= j.lr0 || j.lc1 <= 0) continue;
-          j.ntype = (bd.which == DGRM_FETCH_N && !e->cfg.flat_norm) ? (e->n_u16 ? 2 : 1)
+          j.ntype = (bd.which == DGRM_FETCH_N && !e->cfg.flat_norm && narrow_n) ? (e->n_u16 ? 2 : 1)
                     : (bd.which == DGRM_FETCH_A && e->cfg.a_transport == DGRM_TRANSPORT_FP32) ? 3 : 0;
           j.direct = bd.dev != nullptr && j.ntype == 0;
           j.tiles = false;
@@ -1084,7 +1086,7 @@ int flush_super(dgrm_engine* e, bool final, bool wrap) {
           for (int b = 0; b < e->ntbind; ++b) {
             dgrm_engine::OutJob j{};
             j.b = b; j.ev = (int)gi; j.tiles = true;
-            j.ntype = (e->tbind[b].which == DGRM_FETCH_N && !e->cfg.flat_norm) ? (e->n_u16 ? 2 : 1)
+            j.ntype = (e->tbind[b].which == DGRM_FETCH_N && !e->cfg.flat_norm && narrow_n) ? (e->n_u16 ? 2 : 1)
                       : (e->tbind[b].which == DGRM_FETCH_A && e->cfg.a_transport == DGRM_TRANSPORT_FP32) ? 3 : 0;
             j.direct = e->tbind[b].pinned && j.ntype == 0;
             j.t0 = (int64_t)w0g * per_work;
@@ -1405,6 +1407,7 @@ int dgrm_default_config(dgrm_config* cfg) {
   cfg->resident_mb = 16384;
   cfg->reserve_sms = -1;
   cfg->a_transport = DGRM_TRANSPORT_FP64;
+  cfg->n_transport = DGRM_TRANSPORT_NARROW;
   return DGRM_OK;
 }
 
@@ -1427,6 +1430,8 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
     return fail(nullptr, DGRM_E_INVALID, "dgrm_create: bad operand/count_method");
   if (cfg->a_transport != DGRM_TRANSPORT_FP64 && cfg->a_transport != DGRM_TRANSPORT_FP32)
     return fail(nullptr, DGRM_E_INVALID, "dgrm_create: bad a_transport");
+  if (cfg->n_transport != DGRM_TRANSPORT_FP64 && cfg->n_transport != DGRM_TRANSPORT_NARROW && cfg->n_transport != 0)
+    return fail(nullptr, DGRM_E_INVALID, "dgrm_create: bad n_transport");
   int ndev = 0;
   cudaError_t st = cudaGetDeviceCount(&ndev);
   if (st != cudaSuccess || ndev == 0)

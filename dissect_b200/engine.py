@@ -56,7 +56,7 @@ class PinnedArray:
 class GrmEngine:
     def __init__(self, device=0, rank=0, world=1, operand="fp16", count_method="fp4", flat_norm=False,
                  chunk_snps=16384, cta_group=2, profile=False, resident_chunks=0, resident_mb=16384,
-                 reserve_sms=-1, a_transport="fp64"):
+                 reserve_sms=-1, a_transport="fp64", n_transport="narrow"):
         self._lib = _lib.load()
         cfg = _lib.Config()
         self._lib.dgrm_default_config(C.byref(cfg))
@@ -71,6 +71,7 @@ class GrmEngine:
         cfg.resident_mb = resident_mb
         cfg.reserve_sms = reserve_sms
         cfg.a_transport = _lib.TRANSPORT[a_transport]
+        cfg.n_transport = _lib.TRANSPORT[n_transport]
         self.cfg = cfg
         h = C.c_void_p()
         rc = self._lib.dgrm_create(C.byref(cfg), C.byref(h))

@@ -52,6 +52,7 @@ extern "C" {
  * <= 2^-24 = 6e-8 to A_ij (three orders below the operand tolerance) and halves the bytes of the largest stream. */
 #define DGRM_TRANSPORT_FP64 0
 #define DGRM_TRANSPORT_FP32 1
+#define DGRM_TRANSPORT_NARROW 2   /* pair counts only */
 
 /* which matrix dgrm_fetch_* returns */
 #define DGRM_FETCH_A  0  /* normalised GRM  A = S * (1/N)     (matrix.cpp:4096)               */
@@ -88,7 +89,11 @@ typedef struct dgrm_config {
                             no net gain (the contraction loses what the exchange wins), so the default is 0 */
   int32_t a_transport;   /* DGRM_TRANSPORT_*: how STREAMED values of A (dgrm_bind_output / dgrm_bind_tiles) cross
                             PCIe; the caller's buffer always receives doubles                                 */
-  int32_t reserved[3];
+  int32_t n_transport;   /* how STREAMED pair counts cross PCIe: DGRM_TRANSPORT_NARROW (default: 16-bit deficiencies
+                            m - N or int32, widened to double by the library's host threads) or DGRM_TRANSPORT_FP64
+                            (doubles straight into a pinned caller buffer by the copy engine: 4x the PCIe bytes, no
+                            host CPU work; the better choice when an engine has only a few host cores to itself)     */
+  int32_t reserved[2];
 } dgrm_config;
 
 /* Fill *cfg with defaults (device 0, rank 0/1, fp16 operands, fp4 pair count, chunk 16384, cta_group 2). */

@@ -206,3 +206,41 @@ def test_two_rank_run_matches_oracle(exchange, tmp_path):
            str(tmp_path)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("tiles", [False, True])
+def test_pair_count_transport_fp64_equals_narrow(tiles):
+    """cfg.n_transport: doubles straight from the copy engine vs 16-bit deficiencies widened by host threads — the
+    caller sees the same exact counts either way; the direct form moves 4x the bytes and needs no host work."""
+    n, m = 900, 600
+    pk = bedio.synth_packed(n, m, 43, missing=0.03)
+    res, moved = {}, {}
+    for tr in ("narrow", "fp64"):
+        eng = GrmEngine(chunk_snps=256, n_transport=tr, rank=0, world=2 if tiles else 1)
+        eng.set_individuals(n)
+        if tiles:
+            N = PinnedArray((eng.num_tiles, 256, 128), np.float64)
+            eng.bind_tiles("N", N.ptr)
+        else:
+            N = PinnedArray((n, n), np.float64, order="F")
+            N.array[:] = -1.0
+            eng.bind_output("N", N.ptr, n, bs=(n, n))
+        eng.begin(m)
+        eng.push_bed_host(pk)
+        eng.finish()
+        moved[tr] = eng.last_d2h_bytes
+        want = eng.fetch_tiles("N") if tiles else eng.fetch_block_cyclic("N", bs=(n, n))
+        got = N.array.copy()
+        if tiles:
+            assert np.array_equal(got, want)
+        else:
+            low = lower_mask(n)
+            assert np.array_equal(got[low], want[low])
+        res[tr] = got
+        eng.close()
+    if tiles:
+        assert np.array_equal(res["narrow"], res["fp64"])
+    else:
+        low = lower_mask(n)
+        assert np.array_equal(res["narrow"][low], res["fp64"][low])
+    assert moved["fp64"] > 2 * moved["narrow"] > 0
