@@ -295,7 +295,7 @@ def run_gpu(args):
     # bytes but are widened to the caller's doubles by host threads; with only a few host cores per rank that widening is
     # the bottleneck (measured r2, 2 ranks on 24 vCPUs), so then the copy engine delivers doubles directly.
     threads_per_rank = max(1, cpu_threads() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
-    a_tr = args.a_transport if args.a_transport != "auto" else ("fp32" if threads_per_rank >= 12 else "fp64")
+    a_tr = args.a_transport if args.a_transport != "auto" else ("fp32" if threads_per_rank >= 16 else "fp64")
     n_tr = args.n_transport if args.n_transport != "auto" else ("narrow" if threads_per_rank >= 6 else "fp64")
     mg = MultiGpuGrm(n, rank=rank, world=world, device=local, chunk_snps=chunk, xg=args.xg, exchange=args.exchange,
                      operand=args.operand, count_method=args.count, cta_group=args.cg, profile=True,
@@ -506,8 +506,9 @@ def run_gpu(args):
     checks = None
     if not args.no_check and groups is None:
         from tools import fullsize_checks
-        if tiles_A is None:       # no e2e leg (or one GPU): take the tiles of the last timed GRM
-            tA, tN = eng.fetch_tiles("A"), eng.fetch_tiles("N")
+        if tiles_A is None:       # no e2e leg (or one GPU): take the tiles of the last timed GRM, slab by slab
+            tA = lambda t0, t1: eng.fetch_tiles_range("A", t0, t1 - t0)      # noqa: E731
+            tN = lambda t0, t1: eng.fetch_tiles_range("N", t0, t1 - t0)      # noqa: E731
         else:
             tA, tN = tiles_A.array, tiles_N.array
         checks = fullsize_checks.run(pk_all, keep, n, m_kept, eng.tile_coords(), tA, tN, eng.snp_stats(), rank, world,
@@ -649,8 +650,8 @@ def main():
                                                       "0 = as many as a 2 GB exchange-buffer budget allows")
     ap.add_argument("--a-transport", default="auto", choices=["auto", "fp64", "fp32"],
                     help="how streamed A values cross PCIe on the e2e path: fp32 (+ the exact fp64 diagonal; adds <= 6e-8 "
-                         "relative, the caller still receives fp64), fp64, or auto = fp32 when a rank has >= 12 host threads "
-                         "for the widening, else fp64")
+                         "relative, the caller still receives fp64), fp64, or auto = fp32 when a rank has >= 16 host threads "
+                         "for the widening, else fp64 (r2: 1 rank x 16 threads 56 vs 69 ms; 2 ranks x 12 threads 86 vs 73 ms)")
     ap.add_argument("--n-transport", default="auto", choices=["auto", "narrow", "fp64"],
                     help="how streamed pair counts cross PCIe: narrow (16-bit deficiencies / int32, widened by host threads), "
                          "fp64 (doubles by the copy engine, no host work), auto = narrow when a rank has >= 6 host threads")

@@ -19,7 +19,7 @@ SYMBOLS = (
     "dgrm_set_individuals", "dgrm_begin", "dgrm_push_bed_host", "dgrm_push_bed_device", "dgrm_release_inputs",
     "dgrm_load_bed_file", "dgrm_finish", "dgrm_sync", "dgrm_num_snps", "dgrm_num_individuals",
     "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_fetch_block_cyclic_cols", "dgrm_bind_output", "dgrm_unbind_outputs", "dgrm_bind_tiles", "dgrm_low_overlap_pairs",
-    "dgrm_set_output_subset", "dgrm_write_grm_dat", "dgrm_write_grm_dat_part", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles",
+    "dgrm_set_output_subset", "dgrm_write_grm_dat", "dgrm_write_grm_dat_part", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles", "dgrm_fetch_tiles_range",
     "dgrm_host_alloc", "dgrm_host_free", "dgrm_kernel_times",
     "dgrm_store_bed_file", "dgrm_store_bed_host", "dgrm_store_bed_device", "dgrm_last_d2h_bytes", "dgrm_store_clear", "dgrm_stored_snps", "dgrm_push_stored",
     "dgrm_fetch_standardised", "dgrm_save", "dgrm_set_view", "dgrm_ld_begin", "dgrm_ld_pairs",
@@ -88,6 +88,7 @@ def load():
     lib.dgrm_num_tiles.restype = i64
     lib.dgrm_tile_coords.argtypes = [vp, vp]
     lib.dgrm_fetch_tiles.argtypes = [vp, i32, vp]
+    lib.dgrm_fetch_tiles_range.argtypes = [vp, i32, vp, i64, i64]
     lib.dgrm_host_alloc.argtypes = [i64]
     lib.dgrm_host_alloc.restype = vp
     lib.dgrm_host_free.argtypes = [vp]

@@ -2337,47 +2337,57 @@ int dgrm_tile_coords(const dgrm_engine* e, int32_t* tile_rc) {
   return DGRM_OK;
 }
 
-int dgrm_fetch_tiles(dgrm_engine* e, int which, double* tiles) {
+int dgrm_fetch_tiles_range(dgrm_engine* e, int which, double* tiles, int64_t tile0, int64_t count) {
   int rc = check_ready(e, true);
   if (rc) return rc;
-  if (!tiles || which < 0 || which > 2) return fail(e, DGRM_E_INVALID, "dgrm_fetch_tiles: bad arguments");
-  if (e->ntiles == 0) return DGRM_OK;
+  if (!tiles || which < 0 || which > 2 || tile0 < 0 || count < 0 || tile0 + count > e->ntiles)
+    return fail(e, DGRM_E_INVALID, "dgrm_fetch_tiles: bad arguments");
+  if (count == 0) return DGRM_OK;
   CK(cudaSetDevice(e->cfg.device));
-  const int64_t total = e->ntiles * kTileElems;
+  const int64_t first = tile0 * kTileElems;
+  const int64_t total = count * kTileElems;
   const int64_t slab = 32ll << 20;  // elements per pass (256 MB), two staging buffers
-  double* d_tmp[2] = {nullptr, nullptr};
-  cudaEvent_t done[2];
+  struct Stage {
+    double* d[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    ~Stage() {
+      for (int i = 0; i < 2; ++i) {
+        if (d[i]) cudaFree(d[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+      }
+    }
+  } st;
   for (int i = 0; i < 2; ++i) {
-    CK(cudaMalloc(&d_tmp[i], (size_t)std::min(total, slab) * sizeof(double)));
-    CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    CK(cudaMalloc(&st.d[i], (size_t)std::min(total, slab) * sizeof(double)));
+    CK(cudaEventCreateWithFlags(&st.done[i], cudaEventDisableTiming));
   }
   TileStore ts = tile_store(e);
   int sl = 0;
   for (int64_t o = 0; o < total; o += slab, sl ^= 1) {
     const int64_t cnt = std::min(slab, total - o);
     TileStore t2 = ts;
-    t2.S = ts.S + o;
-    t2.N = ts.N ? ts.N + o : nullptr;
-    t2.S2 = ts.S2 ? ts.S2 + o : nullptr;
-    t2.N2 = ts.N2 ? ts.N2 + o : nullptr;
-    CK(cudaStreamWaitEvent(e->stream, done[sl], 0));
+    t2.S = ts.S + first + o;
+    t2.N = ts.N ? ts.N + first + o : nullptr;
+    t2.S2 = ts.S2 ? ts.S2 + first + o : nullptr;
+    t2.N2 = ts.N2 ? ts.N2 + first + o : nullptr;
+    CK(cudaStreamWaitEvent(e->stream, st.done[sl], 0));
     {
       Prof pr(e, DGRM_K_FETCH);
-      export_tiles_kernel<double><<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(t2, which, cnt, d_tmp[sl], e->d_tile_rc,
-                                                                               o / kTileElems, e->d_diag);
+      export_tiles_kernel<double><<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(t2, which, cnt, st.d[sl], e->d_tile_rc,
+                                                                               (first + o) / kTileElems, e->d_diag);
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->stage_packed[sl], e->stream));
     CK(cudaStreamWaitEvent(e->d2h_stream, e->stage_packed[sl], 0));
-    CK(cudaMemcpyAsync(tiles + o, d_tmp[sl], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, e->d2h_stream));
-    CK(cudaEventRecord(done[sl], e->d2h_stream));
+    CK(cudaMemcpyAsync(tiles + o, st.d[sl], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, e->d2h_stream));
+    CK(cudaEventRecord(st.done[sl], e->d2h_stream));
   }
   CK(cudaStreamSynchronize(e->d2h_stream));
-  for (int i = 0; i < 2; ++i) {
-    cudaFree(d_tmp[i]);
-    cudaEventDestroy(done[i]);
-  }
   return DGRM_OK;
+}
+
+int dgrm_fetch_tiles(dgrm_engine* e, int which, double* tiles) {
+  return dgrm_fetch_tiles_range(e, which, tiles, 0, e ? e->ntiles : 0);
 }
 
 // ---- resident cohort -------------------------------------------------------------------------------------

@@ -319,6 +319,13 @@ class GrmEngine:
             self._ck(self._lib.dgrm_fetch_tiles(self._h, _lib.FETCH[which], t.ctypes.data))
         return t
 
+    def fetch_tiles_range(self, which, tile0, count):
+        """Tiles [tile0, tile0 + count) of this engine as doubles, [tile][col][row]."""
+        t = np.zeros((count, 256, 128), np.float64)
+        if count:
+            self._ck(self._lib.dgrm_fetch_tiles_range(self._h, _lib.FETCH[which], t.ctypes.data, int(tile0), int(count)))
+        return t
+
     def kernel_times(self):
         ms = (C.c_double * _lib.K_NUM)()
         ln = (C.c_int64 * _lib.K_NUM)()

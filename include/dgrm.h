@@ -233,6 +233,8 @@ int dgrm_write_grm_dat_part(dgrm_engine *e, const char *path, int create);
 int64_t dgrm_num_tiles(const dgrm_engine *e);
 int dgrm_tile_coords(const dgrm_engine *e, int32_t *tile_rc);
 int dgrm_fetch_tiles(dgrm_engine *e, int which, double *tiles /* [ntiles][128*256] */);
+/* tiles [tile0, tile0 + count) of the same export (a 100k-individual tile set is tens of GB: move it in pieces) */
+int dgrm_fetch_tiles_range(dgrm_engine *e, int which, double *tiles, int64_t tile0, int64_t count);
 
 /* ---- resident cohort: the packed .bed stays in HBM (2 bits per genotype: 12.5 GB at 100k x 500k) ----------
  * The reference loads a Genotype once and then builds many kernels from it: one per SNP group

@@ -119,18 +119,32 @@ def test_grm_vs_oracle_seeded(operand, count, cg):
     eng.close()
 
 
-def test_config1_2000x10000():
-    """BASELINE.json configs[0]: 2,000 x 10,000, no missing — the reference's own CPU-runnable case."""
+# Stated tolerance per BASELINE.json configuration, max |dA| over the lower triangle (mean diag(A) ~ 1).  Operand
+# rounding falls as m^-1/2, so the one-pass fp16 operands meet the north star's 1e-5 from m ~ 1e5 on; below that the
+# hi+lo split (cfg.operand = fp16x2, three MMA passes) does.  "mode for 1e-5" is the cheapest mode that meets 1e-5.
+#   config                      m (SNPs per GRM)      fp16 (default)   fp16x2        mode for 1e-5
+#   C1  2,000 x 10,000          1.0e4                 <= 5e-5 (1.9e-5) <= 5e-6       fp16x2
+#   C2  20,000 x 100,000        9.8e4                 <= 1e-5 (7e-6)   <= 5e-6       fp16
+#   C3  100,000 x 500,000       4.9e5                 <= 1e-5          <= 5e-6       fp16
+#   C4  50,000 x 22 partitions  4.4e3 .. 2.4e4 each   <= 1e-4          <= 5e-6       fp16x2 (fp16 for the global GRM)
+#   C5  50,000 x 200,000        2.0e5                 <= 1e-5          <= 5e-6       fp16
+CONFIG_TOL = {"C1": {"fp16": 5e-5, "fp16x2": 5e-6}, "C2": {"fp16": 1e-5, "fp16x2": 5e-6}}
+
+
+@pytest.mark.parametrize("operand", ["fp16", "fp16x2"])
+def test_config1_2000x10000(operand):
+    """BASELINE.json configs[0]: 2,000 x 10,000, no missing — the reference's own CPU-runnable case.  With the hi+lo
+    split the north star's example tolerance (1e-5) holds here as well."""
     n, m = 2000, 10000
     pk = bedio.synth_packed(n, m, 1, missing=0.0)
     ref = orc.grm(orc.decode_rows(pk, n))
-    eng = build(pk, n)
+    eng = build(pk, n, operand=operand)
     check_stats(eng.snp_stats(), ref["stats"])
     got = fetch_all(eng)
     low = lower_mask(n)
     assert np.array_equal(got["N"][low], ref["N"][low]) and np.all(got["N"][low] == m)
     err = np.max(np.abs(got["A"][low] - ref["A"][low]))
-    assert err <= 5e-5, err      # measured 1.9e-5 (fp16 operands, m = 1e4)
+    assert err <= CONFIG_TOL["C1"][operand], err      # measured 1.9e-5 (fp16), 1.9e-6 (fp16x2) at m = 1e4
     eng.close()
 
 

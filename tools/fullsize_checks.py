@@ -67,7 +67,8 @@ def reference_matvecs(pk, keep, n, w_pm, w01, rank=0, world=1, rows_per_block=0)
 
 
 def tile_matvecs(tile_rc, tiles_A, tiles_N, n, w_pm, w01, device, slab=512):
-    """Left-hand sides from this rank's tiles.  tiles_*: numpy [ntiles, 256, 128] ([tile][col][row]), fp64."""
+    """Left-hand sides from this rank's tiles.  tiles_*: numpy [ntiles, 256, 128] ([tile][col][row]), fp64, or a
+    callable (t0, t1) -> that slab (so that a 100k-individual tile set never has to sit in host memory at once)."""
     n_pad = (n + 255) // 256 * 256
     wS = torch.zeros(n_pad, dtype=torch.float64, device=device)
     wN = torch.zeros(n_pad, dtype=torch.float64, device=device)
@@ -82,8 +83,8 @@ def tile_matvecs(tile_rc, tiles_A, tiles_N, n, w_pm, w01, device, slab=512):
         t1 = min(t0 + slab, rc.shape[0])
         r0 = torch.as_tensor(rc[t0:t1, 0].astype(np.int64) * 128, device=device)
         c0 = torch.as_tensor(rc[t0:t1, 1].astype(np.int64) * 256, device=device)
-        A = torch.from_numpy(np.ascontiguousarray(tiles_A[t0:t1])).to(device)
-        N = torch.from_numpy(np.ascontiguousarray(tiles_N[t0:t1])).to(device)
+        A = torch.from_numpy(np.ascontiguousarray(tiles_A(t0, t1) if callable(tiles_A) else tiles_A[t0:t1])).to(device)
+        N = torch.from_numpy(np.ascontiguousarray(tiles_N(t0, t1) if callable(tiles_N) else tiles_N[t0:t1])).to(device)
         gr = (r0[:, None] + ar[None, :])[:, None, :]          # [t, 1, 128]
         gc = (c0[:, None] + ac[None, :])[:, :, None]          # [t, 256, 1]
         valid = (gr < n) & (gc < n)
