@@ -296,7 +296,7 @@ def run_gpu(args):
     # the bottleneck (measured r2, 2 ranks on 24 vCPUs), so then the copy engine delivers doubles directly.
     threads_per_rank = max(1, cpu_threads() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     a_tr = args.a_transport if args.a_transport != "auto" else ("fp32" if threads_per_rank >= 16 else "fp64")
-    n_tr = args.n_transport if args.n_transport != "auto" else ("narrow" if threads_per_rank >= 6 else "fp64")
+    n_tr = args.n_transport if args.n_transport != "auto" else ("narrow" if threads_per_rank >= 2 else "fp64")
     mg = MultiGpuGrm(n, rank=rank, world=world, device=local, chunk_snps=chunk, xg=args.xg, exchange=args.exchange,
                      operand=args.operand, count_method=args.count, cta_group=args.cg, profile=True,
                      resident_chunks=args.resident, resident_mb=args.resident_mb, a_transport=a_tr, n_transport=n_tr)
@@ -502,6 +502,24 @@ def run_gpu(args):
                "host_threads_per_rank": threads_per_rank}
         eng.unbind_outputs()
 
+    # ---- e2e against the host link: bytes that really crossed / the measured concurrent-copy ceiling --------------
+    if e2e is not None:
+        pj = os.path.join(ROOT, "profiles", "r2_d2h_concurrency_n8.json")
+        if os.path.exists(pj):
+            rows = [r for r in json.load(open(pj))["rows"] if r["direction"] == "d2h"]
+            near = min(rows, key=lambda r: abs(r["ranks_active"] - G))
+            tot = torch.tensor([float(e2e["d2h_bytes_per_step"])], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            floor_ms = float(tot.item()) / (near["aggregate_GBps"] * 1e9) * 1e3
+            e2e["roofline_e2e"] = {
+                "bound": "host link, device->host", "d2h_bytes_all_ranks": float(tot.item()),
+                "ceiling_gbs": near["aggregate_GBps"], "ceiling_ranks": near["ranks_active"],
+                "ceiling_source": "profiles/r2_d2h_concurrency_n8.json: plain pinned cudaMemcpy D2H issued concurrently on k ranks of "
+                                  "an 8-GPU box of this pool (56 / 69 / 72 / 93 GB/s aggregate at 1 / 2 / 4 / 8 ranks: the GPUs share the link)",
+                "floor_ms": floor_ms, "frac": floor_ms / e2e["ms_per_step"],
+                "note": "floor = D2H bytes of all ranks / ceiling; the step also has to compute (ms_per_step of `value`) and upload"}
+
     # ---- correctness of what was just timed (outside the timed regions) --------------------------------------
     checks = None
     if not args.no_check and groups is None:
@@ -654,7 +672,8 @@ def main():
                          "for the widening, else fp64 (r2: 1 rank x 16 threads 56 vs 69 ms; 2 ranks x 12 threads 86 vs 73 ms)")
     ap.add_argument("--n-transport", default="auto", choices=["auto", "narrow", "fp64"],
                     help="how streamed pair counts cross PCIe: narrow (16-bit deficiencies / int32, widened by host threads), "
-                         "fp64 (doubles by the copy engine, no host work), auto = narrow when a rank has >= 6 host threads")
+                         "fp64 (doubles by the copy engine, no host work), auto = narrow unless a rank has a single host thread (r2, 8 ranks x 4 "
+                         "threads: the shared host link, 93 GB/s for all 8 GPUs, is the bound, so fewer bytes win)")
     ap.add_argument("--no-k1", action="store_true", help="skip the stand-alone decode-kernel measurement")
     ap.add_argument("--no-check", action="store_true", help="skip the parity block and the full-size checks")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
