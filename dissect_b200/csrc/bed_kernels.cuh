@@ -611,6 +611,7 @@ struct ExpandTArgs {
   double* diag_part;   // [ktiles][n_pad]
   int32_t* miss_part;  // [ktiles][n_pad] or NULL
   int n_pad;
+  const int32_t* blocks;  // 128-individual blocks to expand (blockIdx.x indexes it), NULL = all of them
 };
 
 constexpr int kExpTThreads = 512;    // 16 warps per block: the 64 KB of staging then carry 48 warps per SM
@@ -635,7 +636,7 @@ __global__ void __launch_bounds__(kExpTThreads) bed_expand_t_kernel(const Expand
   extern __shared__ __align__(16) uint8_t expand_smem_raw[];
   ExpandTSmem<QK, SPLIT>& sm = *reinterpret_cast<ExpandTSmem<QK, SPLIT>*>(expand_smem_raw);
   const int tid = threadIdx.x;
-  const int i0 = blockIdx.x * kExpI;
+  const int i0 = (a.blocks ? a.blocks[blockIdx.x] : (int)blockIdx.x) * kExpI;
   const int k0 = blockIdx.y * kExpK;
   if (tid < kExpK) {
     double z[4] = {0., 0., 0., 0.};

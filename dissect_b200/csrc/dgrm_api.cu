@@ -67,6 +67,8 @@ struct dgrm_engine {
   std::vector<int32_t> tile_rc; // [ntiles][2]
   std::vector<int32_t> h_index; // host copy of d_index: [nrb][ncp] -> storage tile or -1 (not owned)
   std::vector<int32_t> h_subset; // host copy of d_subset
+  std::vector<int32_t> need_blocks;  // 128-individual blocks that this engine's tiles touch (ascending)
+  int32_t* d_need_blocks = nullptr;
   int4* d_work = nullptr;
   int4* d_work_cg1 = nullptr;
   int32_t* d_index = nullptr;
@@ -267,6 +269,7 @@ void release_geometry(dgrm_engine* e) {
   free_dev(e->d_work); e->d_work = nullptr;
   free_dev(e->d_work_cg1); e->d_work_cg1 = nullptr;
   free_dev(e->d_index); e->d_index = nullptr;
+  free_dev(e->d_need_blocks); e->d_need_blocks = nullptr;
   free_dev(e->d_tile_rc); e->d_tile_rc = nullptr;
   free_dev(e->d_S); e->d_S = nullptr;
   free_dev(e->d_N); e->d_N = nullptr;
@@ -324,11 +327,18 @@ int make_tmap(dgrm_engine* e, CUtensorMap* map, void* base, int elem_bytes, int6
   return DGRM_OK;
 }
 
-// Lower-triangle supertiles (256x256) in an L2-friendly raster: groups of 8 supertile rows, swept
-// column by column.  Engine r of a partition of G owns the contiguous raster segment [r*K/G, (r+1)*K/G) of the
-// K supertiles: equal work (every tile costs the same), and its concurrent CTAs share A/B panels exactly as on
-// one GPU (dealing tiles round-robin gave each engine one row of every column: 1 + 74 panels per k-block
-// instead of 8 + 9, and the contraction ran 20 % slower at 8 GPUs).
+// Lower-triangle supertiles (256x256) in an L2-friendly raster: groups of 8 supertile rows, swept column by column.
+// Engine r of a partition of G owns the contiguous raster segment [r*K/G, (r+1)*K/G) of the K supertiles: equal work
+// (every tile costs the same), and its concurrent CTAs share A/B panels exactly as on one GPU (dealing tiles
+// round-robin gave each engine one row of every column: 1 + 74 panels per k-block instead of 8 + 9, and the
+// contraction ran 20 % slower at 8 GPUs).
+// With four or more engines the raster is additionally cut into a 4 x 4 grid of macro blocks that are visited one
+// after the other (6 full squares + 4 diagonal halves = 8 units of area, ordered so that the diagonal halves come in
+// pairs: every unit-sized piece of the order is one square or two triangles), so that a contiguous segment is a
+// COMPACT region of the triangle instead of a band of rows across all columns: with 8 engines an engine's tiles touch
+// only about half of the individuals (a quarter as rows, a quarter as columns), and bed_expand writes tensor-core
+// operands for those only.  The decode is the one part of the path that is replicated on every
+// engine (it costs n*m per engine while the contraction costs n^2 m / G), so this halves what limits weak scaling.
 int build_tiles(dgrm_engine* e) {
   const int T = (int)(e->n_pad / 256);
   const int GR = 8;
@@ -344,31 +354,54 @@ int build_tiles(dgrm_engine* e) {
   int64_t s = 0, ls = 0;
   const int64_t total = (int64_t)T * (T + 1) / 2;
   const int64_t own0 = total * e->cfg.rank / e->cfg.world, own1 = total * (e->cfg.rank + 1) / e->cfg.world;
-  for (int g = 0; g < T; g += GR) {
-    const int imax = std::min(g + GR, T) - 1;
-    if (g > 0) e->rg_end.push_back((int)(e->cfg.cta_group == 2 ? e->work.size() : e->work_cg1.size()));
-    for (int J = 0; J <= imax; ++J) {
-      for (int I = std::max(g, J); I <= imax; ++I, ++s) {
-        if (s < own0 || s >= own1) continue;
-        const int s0 = (int)(2 * ls), s1 = (int)(2 * ls + 1);
-        index[(size_t)(2 * I) * e->ncp + J] = s0;
-        index[(size_t)(2 * I + 1) * e->ncp + J] = s1;
-        e->tile_rc.push_back(2 * I); e->tile_rc.push_back(J);
-        e->tile_rc.push_back(2 * I + 1); e->tile_rc.push_back(J);
-        e->work_cg1.push_back(make_int4(I * 256, J * 256, s0, s0));
-        e->work_cg1.push_back(make_int4(I * 256 + 128, J * 256, s1, s1));
-        if (e->cfg.cta_group == 2) e->work.push_back(make_int4(I * 256, J * 256, s0, s1));
-        ++ls;
+  const int MB = e->cfg.world >= 4 ? 4 : 1;                 // macro blocks per side
+  const int mb_size = (T + MB - 1) / MB;                    // supertile rows per macro block
+  static const int kOrder4[10][2] = {{0, 0}, {1, 1}, {1, 0}, {2, 0}, {2, 1}, {2, 2}, {3, 3}, {3, 0}, {3, 1}, {3, 2}};
+  static const int kOrder1[1][2] = {{0, 0}};
+  const int (*order)[2] = MB == 4 ? kOrder4 : kOrder1;
+  const int norder = MB == 4 ? 10 : 1;
+  std::vector<uint8_t> need((size_t)2 * T, 0);              // 128-row blocks of individuals this engine's tiles touch
+  for (int ob = 0; ob < norder; ++ob) {
+    {
+      const int bI = order[ob][0], bJ = order[ob][1];
+      if (bI * mb_size >= T) continue;
+      const int i_lo = bI * mb_size, i_hi = std::min(T, i_lo + mb_size);
+      const int j_lo = bJ * mb_size, j_hi = std::min(T, j_lo + mb_size);
+      for (int g = i_lo; g < i_hi; g += GR) {
+        const int imax = std::min(g + GR, i_hi) - 1;
+        if (!(ob == 0 && g == 0)) e->rg_end.push_back((int)(e->cfg.cta_group == 2 ? e->work.size() : e->work_cg1.size()));
+        for (int J = j_lo; J < j_hi && J <= imax; ++J) {
+          for (int I = std::max(g, J); I <= imax; ++I, ++s) {
+            if (s < own0 || s >= own1) continue;
+            const int s0 = (int)(2 * ls), s1 = (int)(2 * ls + 1);
+            index[(size_t)(2 * I) * e->ncp + J] = s0;
+            index[(size_t)(2 * I + 1) * e->ncp + J] = s1;
+            e->tile_rc.push_back(2 * I); e->tile_rc.push_back(J);
+            e->tile_rc.push_back(2 * I + 1); e->tile_rc.push_back(J);
+            e->work_cg1.push_back(make_int4(I * 256, J * 256, s0, s0));
+            e->work_cg1.push_back(make_int4(I * 256 + 128, J * 256, s1, s1));
+            if (e->cfg.cta_group == 2) e->work.push_back(make_int4(I * 256, J * 256, s0, s1));
+            need[(size_t)2 * I] = need[(size_t)2 * I + 1] = need[(size_t)2 * J] = need[(size_t)2 * J + 1] = 1;
+            ++ls;
+          }
+        }
       }
     }
   }
   if (e->cfg.cta_group == 1) e->work = e->work_cg1;
   e->rg_end.push_back((int)e->work.size());
-  for (int g = 0; g < T; g += GR) e->rg_row1.push_back(std::min(g + GR, T) * 256);
+  for (int g = 0; g < T; g += GR) e->rg_row1.push_back(std::min(g + GR, T) * 256);   // (rectangle jobs: world == 1, MB == 1)
   e->ntiles = 2 * ls;
+  e->need_blocks.clear();
+  for (int b2 = 0; b2 < 2 * T; ++b2)
+    if (need[(size_t)b2]) e->need_blocks.push_back(b2);
   // upload
   CK(cudaMalloc(&e->d_index, index.size() * sizeof(int32_t)));
   CK(cudaMemcpy(e->d_index, index.data(), index.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (!e->need_blocks.empty()) {
+    CK(cudaMalloc(&e->d_need_blocks, e->need_blocks.size() * sizeof(int32_t)));
+    CK(cudaMemcpy(e->d_need_blocks, e->need_blocks.data(), e->need_blocks.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   if (!e->work_cg1.empty()) {
     std::vector<int2> rc(e->work_cg1.size());
     for (size_t t = 0; t < e->work_cg1.size(); ++t) rc[(size_t)e->work_cg1[t].z] = make_int2(e->work_cg1[t].x, e->work_cg1[t].y);
@@ -483,10 +516,14 @@ int process_chunk(dgrm_engine* e) {
   }
   {
     Prof pr(e, DGRM_K_EXPAND, e->prep);
-    const dim3 grid((unsigned)(e->n_pad / kExpI), (unsigned)(kc_pad / kExpK));
+    dim3 grid((unsigned)(e->n_pad / kExpI), (unsigned)(kc_pad / kExpK));
     const int qk = count_mma ? 1 : count_fp4 ? 2 : count_popc ? 3 : 0;
     if (transposed) {
       ExpandTArgs a;
+      // operands only for the individuals this engine's tiles touch (all of them unless the partition is compact)
+      a.blocks = (e->need_blocks.size() < (size_t)(e->n_pad / kExpI)) ? e->d_need_blocks : nullptr;
+      if (a.blocks) grid.x = (unsigned)e->need_blocks.size();
+      if (grid.x == 0) grid.x = 1, a.blocks = nullptr;
       a.T = e->d_chunkT; a.t_pitch = e->t_pitch; a.kc = kc; a.n = (int)e->n_row; a.zt = e->d_zt;
       a.Z = e->d_Z + col0; a.z_pitch = e->z_pitch; a.lo_off = (int64_t)e->slots * e->kc_max;
       a.Q = count_mma ? e->d_Q + col0 : nullptr; a.q_pitch = e->q_pitch;
@@ -1620,8 +1657,10 @@ static int setup_geometry(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mas
     CK(cudaMalloc(&e->d_chunkT, (size_t)(kc / 16) * e->t_pitch * sizeof(uint32_t)));
     CK(cudaMalloc(&e->d_counts, (size_t)kc * 4 * sizeof(int32_t)));
     CK(cudaMalloc(&e->d_miss_part, (size_t)(kc / kExpK) * e->n_pad * sizeof(int32_t)));
+    CK(cudaMemset(e->d_miss_part, 0, (size_t)(kc / kExpK) * e->n_pad * sizeof(int32_t)));
   }
   CK(cudaMalloc(&e->d_diag_part, (size_t)(kc / kExpK) * e->n_pad * sizeof(double)));
+  CK(cudaMemset(e->d_diag_part, 0, (size_t)(kc / kExpK) * e->n_pad * sizeof(double)));   // blocks nobody expands stay 0
   e->slots = 0;  // operand slots are sized by dgrm_begin, once the SNP count is known
   // host staging: slabs of up to kc rows
   e->stage_rows = kc;

@@ -56,15 +56,14 @@ class ShardPlan:
 
 
 def auto_xg(n, world, chunk_snps, m_file, exchange="nccl", budget_bytes=4 << 30):
-    """Engine chunks per exchange.  The copy-engine exchange (p2p) runs underneath the contraction, so one chunk per
-    exchange pipelines best.  An NCCL all-gather is a kernel and cannot run underneath the persistent contraction:
-    every exchange is then a bubble in the MMA stream, and for large cohorts (>= 128 MB per chunk) fewer, larger
-    exchanges win (measured r1: C3 on 8 GPUs 779 -> 696 ms with 4 chunks per all-gather; for the 28k-individual
-    2-GPU case one chunk per exchange is 2.5 % faster than six, r2)."""
-    if world == 1 or exchange == "p2p":
+    """Engine chunks per exchange.  For large cohorts (>= 256 MB of packed rows per chunk) fewer, larger exchanges
+    win with either exchange — measured on one 8-GPU box at C3 (r2): copy-engine exchange 722 ms with one chunk per
+    exchange, 664 ms with four; NCCL all-gather 700 ms with four (779 ms with one, r1) — for small ones one chunk per
+    exchange pipelines best (28k individuals on 2 GPUs: 2.5 % faster than six)."""
+    if world == 1:
         return 1
     pitch = ((n + 3) // 4 + 15) // 16 * 16
-    if chunk_snps * pitch < (128 << 20):
+    if chunk_snps * pitch < (256 << 20):
         return 1
     per_chunk = 2 * (1 + 1.0 / world) * chunk_snps * pitch
     nchunks = max(1, math.ceil(m_file / chunk_snps))

@@ -2,16 +2,28 @@
 driver (pure index arithmetic; the kernels consume the same tables built in csrc/dgrm_api.cu:build_tiles)."""
 
 
-def supertile_order(n_pad, group_rows=8):
+_ORDER4 = [(0, 0), (1, 1), (1, 0), (2, 0), (2, 1), (2, 2), (3, 3), (3, 0), (3, 1), (3, 2)]
+
+
+def supertile_order(n_pad, group_rows=8, world=1):
     """Lower-triangle 256x256 supertiles (I, J), J <= I, in the engine's raster: groups of `group_rows`
-    supertile rows swept column by column."""
+    supertile rows swept column by column; with four or more engines inside a 4 x 4 grid of macro blocks visited in
+    an order that pairs the diagonal halves (every unit of area is one square or two triangles), so that a contiguous
+    segment is a compact region (csrc/dgrm_api.cu:build_tiles)."""
     T = n_pad // 256
+    MB = 4 if world >= 4 else 1
+    mb = (T + MB - 1) // MB
     out = []
-    for g in range(0, T, group_rows):
-        imax = min(g + group_rows, T) - 1
-        for J in range(0, imax + 1):
-            for I in range(max(g, J), imax + 1):
-                out.append((I, J))
+    for bI, bJ in (_ORDER4 if MB == 4 else [(0, 0)]):
+        if bI * mb >= T:
+            continue
+        i_lo, i_hi = bI * mb, min(T, bI * mb + mb)
+        j_lo, j_hi = bJ * mb, min(T, bJ * mb + mb)
+        for g in range(i_lo, i_hi, group_rows):
+            imax = min(g + group_rows, i_hi) - 1
+            for J in range(j_lo, min(j_hi, imax + 1)):
+                for I in range(max(g, J), imax + 1):
+                    out.append((I, J))
     return out
 
 
@@ -20,7 +32,7 @@ def tiles_of_rank(n, rank, world):
     [rank*K/world, (rank+1)*K/world) of the K supertiles."""
     n_pad = (n + 255) // 256 * 256
     tiles = []
-    order = supertile_order(n_pad)
+    order = supertile_order(n_pad, world=world)
     total = len(order)
     s0, s1 = total * rank // world, total * (rank + 1) // world
     for s, (I, J) in enumerate(order):
@@ -28,6 +40,16 @@ def tiles_of_rank(n, rank, world):
             tiles.append((2 * I, J))
             tiles.append((2 * I + 1, J))
     return tiles
+
+
+def individuals_touched(n, rank, world):
+    """Fraction of the (padded) individuals whose operands `rank` needs: rows and columns of its supertiles."""
+    n_pad = (n + 255) // 256 * 256
+    need = set()
+    for rb, cp in tiles_of_rank(n, rank, world):
+        need.add(rb // 2)
+        need.add(cp)
+    return len(need) * 256 / n_pad
 
 
 def row_shards(m_file, chunk, world):
