@@ -370,7 +370,17 @@ def run_gpu(args):
     dt = ev0.elapsed_time(ev1) * 1e-3
     clocks = sampler.stop()
     kt = eng.kernel_times()
+    per_rank = None
     if world > 1:
+        # every rank's own device time and kernel-class times (imbalance is visible in the line), then the max
+        mine_t = torch.tensor([dt * 1e3 / args.steps, kt["syrk"][0] / args.steps, kt["paircnt"][0] / args.steps,
+                               kt["expand"][0] / args.steps, kt["gather"][0] / args.steps, float(len(eng.tile_coords()))],
+                              dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(allt, mine_t)
+        per_rank = {"ms_per_step": [round(float(x[0]), 3) for x in allt], "syrk_ms": [round(float(x[1]), 3) for x in allt],
+                    "paircnt_ms": [round(float(x[2]), 3) for x in allt], "expand_ms": [round(float(x[3]), 3) for x in allt],
+                    "decode_ms": [round(float(x[4]), 3) for x in allt], "tiles": [int(x[5]) for x in allt]}
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
@@ -601,6 +611,7 @@ def run_gpu(args):
                          "pair*SNP: nominal ratio, no fp4 GEMM measurement exists in MEASURED_PEAKS.json",
             "launches": pc_launches, "avg_launch_ms": pc_ms / max(pc_launches, 1)},
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()},
+        "per_rank": per_rank,
         "kernel_ms_note": "decode kernels (gather/count/expand) run on a second stream underneath the contraction: "
                           "their times here are inflated by the overlap, see roofline_k1 for them alone",
         "roofline_k1": k1,
