@@ -55,6 +55,7 @@ struct dgrm_engine {
   int64_t n_fam = 0, n = 0, n_pad = 0;   // n = dimension of the output matrices (individuals; SNPs of the group in LD mode)
   int64_t n_row = 0;        // individuals per compacted packed row (== n except in LD mode)
   bool ld_mode = false;     // dgrm_ld_begin: SNP x SNP correlations, the contraction runs over the individuals
+  std::vector<int32_t> ld_keep;  // keep mask of the current LD geometry (to recognise an unchanged dgrm_ld_begin)
   int64_t b_fam = 0;        // bytes per raw .bed row
   int64_t b_row = 0;        // bytes per compacted row
   int64_t chunk_pitch = 0;  // device chunk row pitch (multiple of 128)
@@ -1698,8 +1699,16 @@ int dgrm_ld_begin(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mask, int64
   if (!e) return DGRM_E_INVALID;
   if (m_group <= 0 || m_group > (1 << 30)) return fail(e, DGRM_E_INVALID, "dgrm_ld_begin: bad m_group");
   if (e->cfg.flat_norm) return fail(e, DGRM_E_INVALID, "dgrm_ld_begin: flat normalisation does not exist for SNP correlations");
-  int rc = setup_geometry(e, n_fam, keep_mask, m_group);
-  if (rc) return rc;
+  // GWAS calls this once per SNP group: keep the geometry (tile store, operand buffers, staging) when nothing changed
+  std::vector<int32_t> km;
+  if (keep_mask) km.assign(keep_mask, keep_mask + n_fam);
+  const bool same = e->have_ind && e->ld_mode && e->n_fam == n_fam && e->n == m_group && e->ld_keep == km &&
+                    e->nbind == 0 && e->ntbind == 0;
+  if (!same) {
+    int rc = setup_geometry(e, n_fam, keep_mask, m_group);
+    if (rc) return rc;
+    e->ld_keep.swap(km);
+  }
   return begin_common(e, m_group);
 }
 

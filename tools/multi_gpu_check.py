@@ -1,7 +1,7 @@
 """Multi-GPU parity check, run under torchrun with one rank per GPU:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/multi_gpu_check.py [--exchange nccl|p2p] [--n 1500 --m 3000 --chunk 1024] [--out DIR]
+        tools/multi_gpu_check.py [--exchange nccl|p2p] [--individuals 1500 --snps 3000 --chunk 1024] [--out DIR]
 
 Drives dissect_b200.multi.MultiGpuGrm — the same exchange loop bench.py times — and checks, against the numpy
 oracle: per-SNP statistics bit-exact, N exact and A within tolerance over the whole lower triangle (tiles gathered
@@ -26,8 +26,8 @@ from dissect_b200.partition import tiles_of_rank  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--exchange", default=os.environ.get("DGRM_EXCHANGE", "nccl"), choices=["nccl", "p2p"])
-    ap.add_argument("--n", type=int, default=1500)
-    ap.add_argument("--m", type=int, default=3000)
+    ap.add_argument("--individuals", "--n", dest="n", type=int, default=1500)   # (torchrun rejects a bare --n as ambiguous)
+    ap.add_argument("--snps", "--m", dest="m", type=int, default=3000)
     ap.add_argument("--chunk", type=int, default=1024)
     ap.add_argument("--xg", type=int, default=1)
     ap.add_argument("--out", default="")
