@@ -2245,23 +2245,42 @@ int dgrm_ld_pairs(dgrm_engine* e, double threshold, int64_t* pairs, int64_t cap,
   return DGRM_OK;
 }
 
+// Boundaries, in VISIBLE index space, at which the 128-row block / 256-column panel of the individual behind a visible
+// index changes (the output subset is ascending, so each block is one run of visible indices).  Without a subset these
+// are the multiples of 128 / 256.
+static void visible_block_starts(const dgrm_engine* e, int n, std::vector<int>* rb, std::vector<int>* cp) {
+  rb->clear();
+  cp->clear();
+  int last_rb = -1, last_cp = -1;
+  for (int v = 0; v < n; ++v) {
+    const int ind = e->h_subset.empty() ? v : e->h_subset[(size_t)v];
+    if ((ind >> 7) != last_rb) { rb->push_back(v); last_rb = ind >> 7; }
+    if ((ind >> 8) != last_cp) { cp->push_back(v); last_cp = ind >> 8; }
+  }
+  rb->push_back(n);
+  cp->push_back(n);
+}
+
 // Owned runs of file column c of the packed (n+1) x n array: rows pr <= c hold N[c][pr] (tile of (c, pr)), rows
-// pr > c hold A[pr-1][c] (tile of (pr-1, c)).  Appends [begin, end) row ranges, merged where adjacent.
-static void grm_dat_owned_runs(const dgrm_engine* e, int n, int c, std::vector<std::pair<int, int>>* runs) {
+// pr > c hold A[pr-1][c] (tile of (pr-1, c)).  Appends [begin, end) row ranges, merged where adjacent.  Ownership is
+// constant between two block starts, so a column costs O(n / 128) tests.
+static void grm_dat_owned_runs(const dgrm_engine* e, int n, int c, const std::vector<int>& rb, const std::vector<int>& cp,
+                               std::vector<std::pair<int, int>>* runs) {
   auto add = [&](int a, int b) {
+    if (b <= a) return;
     if (!runs->empty() && runs->back().second == a) runs->back().second = b;
     else runs->push_back({a, b});
   };
   if (e->cfg.world == 1) { add(0, n + 1); return; }
-  if (!e->h_subset.empty()) {  // ownership follows the individuals behind the subset: element by element
-    for (int pr = 0; pr <= n; ++pr)
-      if (pr <= c ? owns_element(e, c, pr) : owns_element(e, pr - 1, c)) add(pr, pr + 1);
-    return;
+  // N part: visible columns pr in [0, c], cut at the 256-panel starts
+  for (size_t k = 0; k + 1 < cp.size() && cp[k] <= c; ++k)
+    if (owns_element(e, c, cp[k])) add(cp[k], std::min(cp[k + 1], c + 1));
+  // A part: visible rows r in [c, n), cut at the 128-block starts; P row = r + 1
+  size_t k = std::upper_bound(rb.begin(), rb.end(), c) - rb.begin() - 1;   // block that contains row c
+  for (; k + 1 < rb.size(); ++k) {
+    const int r0 = std::max(rb[k], c), r1 = rb[k + 1];
+    if (r0 < r1 && owns_element(e, r0, c)) add(r0 + 1, r1 + 1);
   }
-  for (int pr = 0; pr <= c; pr += 256)
-    if (owns_element(e, c, pr)) add(pr, std::min(pr + 256, c + 1));
-  for (int r = c; r < n; r = (r | 127) + 1)
-    if (owns_element(e, r, c)) add(r + 1, std::min((r | 127) + 1, n) + 1);
 }
 
 int dgrm_write_grm_dat_part(dgrm_engine* e, const char* path, int create) {
@@ -2299,6 +2318,8 @@ int dgrm_write_grm_dat_part(dgrm_engine* e, const char* path, int create) {
   CK(cudaHostAlloc(&rs.h_panel, (size_t)PC * col_elems * sizeof(double), cudaHostAllocDefault));
   const TileStore ts = tile_store(e);
   std::vector<std::vector<std::pair<int, int>>> runs((size_t)PC);
+  std::vector<int> rb_starts, cp_starts;
+  visible_block_starts(e, n, &rb_starts, &cp_starts);
   for (int c0 = 0; c0 < n; c0 += PC) {
     const int c1 = std::min(c0 + PC, n);
     // the row range of P this engine has anything in, over the panel's columns (the whole column when world == 1)
@@ -2306,7 +2327,7 @@ int dgrm_write_grm_dat_part(dgrm_engine* e, const char* path, int create) {
     for (int c = c0; c < c1; ++c) {
       auto& rv = runs[(size_t)(c - c0)];
       rv.clear();
-      grm_dat_owned_runs(e, n, c, &rv);
+      grm_dat_owned_runs(e, n, c, rb_starts, cp_starts, &rv);
       if (!rv.empty()) { pr0 = std::min(pr0, rv.front().first); pr1 = std::max(pr1, rv.back().second); }
     }
     if (pr1 <= pr0) continue;

@@ -222,7 +222,7 @@ int dgrm_write_grm_dat(dgrm_engine *e, const char *path);
 
 /* Multi-engine form of the writer (the reference funnels every block through rank 0: packMatrices
  * matrix.cpp:2262-2349 + writeMatrixMPI :2168-2219).  Every engine of a partition writes, at their offsets in
- * the same file, exactly the entries whose tiles it owns (per file column at most a few contiguous runs), so an
+ * the same file, exactly the entries whose tiles it owns (per file column a few contiguous runs), so an
  * 80 GB result needs no gather.  Exactly one engine calls it with create != 0 FIRST (creates / truncates the
  * file, writes the header, sizes the file); the others call it with create == 0 after that call has returned
  * (the caller's barrier).  With world == 1 and create != 0 it is dgrm_write_grm_dat. */
