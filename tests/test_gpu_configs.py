@@ -138,3 +138,43 @@ def test_config4_geometry_groups_and_loco_views_vs_oracle():
         assert np.max(np.abs(A[low] - ((S_all - S_g) * (1.0 / (N_all - N_g)))[low])) <= 3e-5, g
         eng.set_view("current")
     eng.close()
+
+
+def test_config3_geometry_subset_vs_oracle_whole_and_one_of_eight_engines():
+    """configs[2]: 100,000 individuals (391 x 391 supertiles, 49 raster row groups; a 40 GB fp64 + 20 GB int32 tile store
+    on one GPU), SNPs cut from 500,000 to 8,192.  Checked on a random 384-individual sub-block for (a) the whole
+    triangle on one engine and (b) engine 5 of an 8-engine partition — the compact macro-block raster at its real size,
+    with operands expanded only for the individuals that engine's tiles touch — on the entries it owns."""
+    n, m = 100000, 8192
+    pk, keep = synth(n, m, 3)
+    host = pk.cpu().numpy()[keep != 0]
+    st = stats_from_packed(host, n)
+    sub = np.sort(np.random.default_rng(13).choice(n, 384, replace=False))
+    S, Nn = sub_block_oracle(host, st, sub)
+    A_ref = S * (1.0 / Nn)
+    low = lower_mask(384)
+    tol = 3e-4 * max(0.25, (1000.0 / host.shape[0]) ** 0.5)
+    for rank, world in ((0, 1), (5, 8)):
+        eng = GrmEngine(rank=rank, world=world)
+        eng.set_individuals(n)
+        eng.begin(m)
+        eng.push_bed_device(pk.data_ptr(), pk.stride(0), m, row_keep=keep)
+        eng.finish()
+        if world == 1:
+            check_stats(eng.snp_stats(), st)
+        owned = np.zeros((384, 384), bool)
+        have = {(int(rb), int(cp)) for rb, cp in eng.tile_coords()}
+        for i, r in enumerate(sub):
+            for j, c in enumerate(sub[: i + 1]):
+                owned[i, j] = (r // 128, c // 256) in have
+        assert owned.any()
+        if world == 1:
+            assert owned[low].all()
+        eng.set_output_subset(sub)
+        N = eng.fetch_block_cyclic("N", bs=(384, 384), fill=-5.0)
+        A = eng.fetch_block_cyclic("A", bs=(384, 384), fill=-5.0)
+        assert np.array_equal(N[owned], Nn[owned]), (rank, world)
+        assert np.max(np.abs(A[owned] - A_ref[owned])) <= tol, (rank, world)
+        assert np.all(N[low & ~owned] == -5.0)            # entries of other engines' tiles are left alone
+        eng.close()
+    del pk
