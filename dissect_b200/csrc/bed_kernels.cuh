@@ -611,7 +611,9 @@ struct ExpandTArgs {
   double* diag_part;   // [ktiles][n_pad]
   int32_t* miss_part;  // [ktiles][n_pad] or NULL
   int n_pad;
-  const int32_t* blocks;  // 128-individual blocks to expand (blockIdx.x indexes it), NULL = all of them
+  const int32_t* blocks;  // 128-individual blocks to expand (the individual-block index indexes it), NULL = all of them
+  int k_fast;             // 1: blockIdx.x runs along the SNP tiles (concurrent blocks write adjacent pieces of the same rows)
+  int stream_stores;      // 1: operand stores bypass L2 retention (st.global.cs)
 };
 
 constexpr int kExpTThreads = 512;    // 16 warps per block: the 64 KB of staging then carry 48 warps per SM
@@ -636,8 +638,9 @@ __global__ void __launch_bounds__(kExpTThreads) bed_expand_t_kernel(const Expand
   extern __shared__ __align__(16) uint8_t expand_smem_raw[];
   ExpandTSmem<QK, SPLIT>& sm = *reinterpret_cast<ExpandTSmem<QK, SPLIT>*>(expand_smem_raw);
   const int tid = threadIdx.x;
-  const int i0 = (a.blocks ? a.blocks[blockIdx.x] : (int)blockIdx.x) * kExpI;
-  const int k0 = blockIdx.y * kExpK;
+  const int bi = a.k_fast ? blockIdx.y : blockIdx.x, bk = a.k_fast ? blockIdx.x : blockIdx.y;
+  const int i0 = (a.blocks ? a.blocks[bi] : bi) * kExpI;
+  const int k0 = bk * kExpK;
   if (tid < kExpK) {
     double z[4] = {0., 0., 0., 0.};
     if (k0 + tid < a.kc) {
@@ -745,7 +748,8 @@ __global__ void __launch_bounds__(kExpTThreads) bed_expand_t_kernel(const Expand
       for (int ps = 0; ps < kExpI / (kExpTThreads / 16); ++ps) {
         const int r = ps * (kExpTThreads / 16) + (tid >> 4);
         const uint4 v = *reinterpret_cast<const uint4*>(&sm.outz[r * kExpZPitch + c * 16]);
-        *reinterpret_cast<uint4*>(zbase + (int64_t)(i0 + r) * a.z_pitch + c * 8) = v;
+        uint4* zdst = reinterpret_cast<uint4*>(zbase + (int64_t)(i0 + r) * a.z_pitch + c * 8);
+        if (a.stream_stores) __stcs(zdst, v); else *zdst = v;
       }
       if (part == 0) {
         if constexpr (QK == 1) {
@@ -776,9 +780,9 @@ __global__ void __launch_bounds__(kExpTThreads) bed_expand_t_kernel(const Expand
           int ms = sm.mpart[0][tid];
 #pragma unroll
           for (int h2 = 1; h2 < kExpTKh; ++h2) { ds = __dadd_rn(ds, sm.dpart[h2][tid]); ms += sm.mpart[h2][tid]; }
-          a.diag_part[(int64_t)blockIdx.y * a.n_pad + i0 + tid] = ds;
+          a.diag_part[(int64_t)bk * a.n_pad + i0 + tid] = ds;
           if (a.miss_part)   // padding individuals and SNP rows past the chunk were read as "missing": not real ones
-            a.miss_part[(int64_t)blockIdx.y * a.n_pad + i0 + tid] =
+            a.miss_part[(int64_t)bk * a.n_pad + i0 + tid] =
                 (i0 + tid < a.n) ? ms - max(0, min(kExpK, k0 + kExpK - a.kc)) : 0;
         }
       }

@@ -186,6 +186,7 @@ struct dgrm_engine {
   bool n_u16 = false;          // streamed pair counts travel as 16-bit deficiencies m - N
   int overlap = 1;  // DGRM_OVERLAP=0: contract only in dgrm_finish (experiments)
   int fused_decode = 1;  // DGRM_FUSED_DECODE=0: separate gather and count kernels (A/B measurements)
+  int expand_k_fast = 0, expand_stream_stores = 0;   // DGRM_EXPAND_KFAST / DGRM_EXPAND_CS (A/B measurements)
   int k1_transposed = 1; // DGRM_K1_TRANSPOSED=0: row-major chunk + bed_expand_kernel (round-1 decode path, A/B measurements)
   uint32_t* d_chunkT = nullptr;   // transposed chunk: [kc_max / 16][t_pitch] words (GRM mode)
   int64_t t_pitch = 0;
@@ -525,6 +526,9 @@ int process_chunk(dgrm_engine* e) {
       a.blocks = (e->need_blocks.size() < (size_t)(e->n_pad / kExpI)) ? e->d_need_blocks : nullptr;
       if (a.blocks) grid.x = (unsigned)e->need_blocks.size();
       if (grid.x == 0) grid.x = 1, a.blocks = nullptr;
+      a.k_fast = e->expand_k_fast;
+      a.stream_stores = e->expand_stream_stores;
+      if (a.k_fast) std::swap(grid.x, grid.y);
       a.T = e->d_chunkT; a.t_pitch = e->t_pitch; a.kc = kc; a.n = (int)e->n_row; a.zt = e->d_zt;
       a.Z = e->d_Z + col0; a.z_pitch = e->z_pitch; a.lo_off = (int64_t)e->slots * e->kc_max;
       a.Q = count_mma ? e->d_Q + col0 : nullptr; a.q_pitch = e->q_pitch;
@@ -1491,6 +1495,8 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   if (const char* ov = getenv("DGRM_OVERLAP")) e->overlap = atoi(ov);
   if (const char* fd = getenv("DGRM_FUSED_DECODE")) e->fused_decode = atoi(fd);
   if (const char* kt = getenv("DGRM_K1_TRANSPOSED")) e->k1_transposed = atoi(kt);
+  if (const char* kf = getenv("DGRM_EXPAND_KFAST")) e->expand_k_fast = atoi(kf);
+  if (const char* cs = getenv("DGRM_EXPAND_CS")) e->expand_stream_stores = atoi(cs);
   if (const char* pp = getenv("DGRM_PREFIX_PCT")) e->prefix_pct = std::max(0, std::min(90, atoi(pp)));
   e->reserve_sms = cfg->reserve_sms > 0 ? cfg->reserve_sms : 0;
   if (const char* rs = getenv("DGRM_RESERVE_SMS")) e->reserve_sms = atoi(rs);
