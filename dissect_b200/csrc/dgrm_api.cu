@@ -358,7 +358,7 @@ int build_tiles(dgrm_engine* e) {
   const int64_t own0 = total * e->cfg.rank / e->cfg.world, own1 = total * (e->cfg.rank + 1) / e->cfg.world;
   const int MB = e->cfg.world >= 4 ? 4 : 1;                 // macro blocks per side
   const int mb_size = (T + MB - 1) / MB;                    // supertile rows per macro block
-  static const int kOrder4[10][2] = {{0, 0}, {1, 1}, {1, 0}, {2, 0}, {2, 1}, {2, 2}, {3, 3}, {3, 0}, {3, 1}, {3, 2}};
+  static const int kOrder4[10][2] = {{0, 0}, {1, 1}, {1, 0}, {2, 0}, {2, 1}, {2, 2}, {3, 3}, {3, 2}, {3, 0}, {3, 1}};
   static const int kOrder1[1][2] = {{0, 0}};
   const int (*order)[2] = MB == 4 ? kOrder4 : kOrder1;
   const int norder = MB == 4 ? 10 : 1;

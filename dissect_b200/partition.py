@@ -2,7 +2,7 @@
 driver (pure index arithmetic; the kernels consume the same tables built in csrc/dgrm_api.cu:build_tiles)."""
 
 
-_ORDER4 = [(0, 0), (1, 1), (1, 0), (2, 0), (2, 1), (2, 2), (3, 3), (3, 0), (3, 1), (3, 2)]
+_ORDER4 = [(0, 0), (1, 1), (1, 0), (2, 0), (2, 1), (2, 2), (3, 3), (3, 2), (3, 0), (3, 1)]
 
 
 def supertile_order(n_pad, group_rows=8, world=1):
