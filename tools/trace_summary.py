@@ -15,9 +15,13 @@ def main(path):
         m = pat.search(line)
         if m:
             per[int(m.group(1))].append((float(m.group(2)), float(m.group(3)), m.group(4)))
-    print(f"# {path}: DGRM_TRACE=1 launch timeline, all timed steps of the run together")
+    print(f"# {path}: DGRM_TRACE=1 launch timeline; the last timeline each rank printed (= the timed steps)")
     for r in sorted(per):
         ev = per[r]
+        # every dgrm_kernel_times call prints one timeline sorted by start time, with its own time base: keep the last
+        cuts = [i for i in range(1, len(ev)) if ev[i][0] < ev[i - 1][0]]
+        if cuts:
+            ev = ev[cuts[-1]:]
         mma = sorted((t, d) for t, d, k in ev if k in ("syrk", "paircnt"))
         dec = sorted((t, d) for t, d, k in ev if k in ("expand", "gather", "count"))
         if not mma:
