@@ -224,8 +224,10 @@ class MultiGpuGrm:
         xch, sends = self._xch, self._bufs["send"]
         cs = xch.copy_stream.cuda_stream
         ng, posted = len(plan.groups), 0
-        for gi in range(ng):
-            while posted < min(ng, gi + NBUF):
+
+        def post_until(limit):
+            nonlocal posted
+            while posted < min(ng, limit):
                 a, b = plan.groups[posted][1][self.rank]
                 sb = sends[posted % len(sends)]
                 if isinstance(source, DeviceRows) and source.pk.stride(0) == self.pitch:
@@ -237,7 +239,11 @@ class MultiGpuGrm:
                     ptr = sb.data_ptr()
                 xch.post(ptr, b - a)
                 posted += 1
-            xch.consume(self.eng, plan.groups[gi][2])
+
+        for gi in range(ng):
+            post_until(gi + 1)                 # this group's shard is on its way ...
+            xch.consume(self.eng, plan.groups[gi][2])   # ... its decode is queued behind the arrival flags ...
+            post_until(gi + NBUF)              # ... and only then does the host run ahead with the next groups
 
     # -- egress -----------------------------------------------------------------------------------------------
     def gather_tiles(self, which, dst=0):
