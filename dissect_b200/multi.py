@@ -28,23 +28,36 @@ class ShardPlan:
     """Pure index arithmetic of the exchange: which file rows every rank keeps per chunk group, and which of the
     G * shard gathered rows of a group are real, kept SNPs (shards are padded to `shard` rows).
 
+    Groups are cut by KEPT rows: every group but the last delivers exactly `xchunk` kept SNPs, i.e. whole engine
+    chunks, so a chunk never has to wait for the first rows of the next exchange (with an --extract list that drops 2 %
+    of the SNPs, groups cut by file rows left every chunk 2 % short until the next group arrived: 0.5 ms of idle MMA
+    stream at the head of each GRM on 8 GPUs, profiles/r2_trace_n8_rank0_tail.txt).
+
     groups[g] = (first file row, [(row0, row1) per rank], row_keep uint8[G * shard])"""
 
     def __init__(self, m_file, world, chunk_snps, xg=1, keep=None):
         self.m_file, self.world = int(m_file), int(world)
         self.xchunk = int(chunk_snps) * max(1, int(xg))
-        self.shard = (self.xchunk + world - 1) // world
         keep = np.ones(m_file, np.uint8) if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
         assert keep.shape == (m_file,)
         self.keep = keep
         self.m_kept = int(np.count_nonzero(keep))
+        # file-row boundaries: after every xchunk-th kept row
+        kept_idx = np.flatnonzero(keep)
+        cuts = [0]
+        for k in range(self.xchunk, len(kept_idx), self.xchunk):
+            cuts.append(int(kept_idx[k - 1]) + 1)
+        if cuts[-1] != m_file:
+            cuts.append(m_file)
+        spans = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
+        self.shard = max([(c1 - c0 + world - 1) // world for c0, c1 in spans] + [1])
         self.groups = []
-        for c0 in range(0, m_file, self.xchunk):
-            c1 = min(c0 + self.xchunk, m_file)
+        for c0, c1 in spans:
+            per = (c1 - c0 + world - 1) // world
             ranges, rk = [], np.zeros(world * self.shard, np.uint8)
             for g in range(world):
-                a = min(c0 + g * self.shard, c1)
-                b = min(a + self.shard, c1)
+                a = min(c0 + g * per, c1)
+                b = min(a + per, c1)
                 ranges.append((a, b))
                 if b > a:
                     rk[g * self.shard: g * self.shard + (b - a)] = keep[a:b] != 0
