@@ -22,6 +22,7 @@
 
 #include "../../include/dgrm.h"
 #include "bed_kernels.cuh"
+#include "dosage_kernels.cuh"
 #include "finalize_kernels.cuh"
 #include "paircount_popc.cuh"
 #include "syrk_tcgen05.cuh"
@@ -193,6 +194,21 @@ struct dgrm_engine {
   int32_t* d_counts = nullptr;    // [kc_max][4] per-row pattern counts being accumulated
   int32_t* d_miss_part = nullptr; // [kc_max / 128][n_pad]
 
+  // real-valued genotype rows (dgrm_push_dosage_host): pinned host staging (transfer pieces) -> device staging (up to a
+  // whole chunk of rows, so that one statistics launch carries many rows) -> operands
+  double* h_dos[2] = {nullptr, nullptr};
+  uint8_t* h_dmiss[2] = {nullptr, nullptr};
+  int h_cap = 0, h_fill = 0, dos_i = 0;   // rows per pinned buffer, rows staged in the current one
+  bool h_any_missing = false;             // a row staged in the current pinned buffer came with a missing mask
+  double* d_dos = nullptr;
+  uint8_t* d_dmiss = nullptr;
+  int dev_cap = 0, dev_fill = 0;          // rows of the device staging buffer, rows copied (or being copied) into it
+  bool dev_any_missing = false;
+  double *d_dos_mean = nullptr, *d_dos_sd = nullptr;
+  cudaEvent_t dos_copied[2] = {nullptr, nullptr}, dos_ready = nullptr, dos_read = nullptr;
+  int dosage_stage_mb = 2048;             // DGRM_DOSAGE_STAGE_MB: size of the device staging buffer
+  bool fill_dosage = false;               // the `fill` rows of the open chunk are already expanded (dosage rows)
+
   bool have_ind = false, begun = false, finished = false;
 
   // resident packed cohort (dgrm_store_*): SNP-major rows of ceil(n_fam/4) bytes at pitch bed_pitch
@@ -266,6 +282,19 @@ void free_dev(void* p) {
   if (p) cudaFree(p);
 }
 
+void release_dosage_staging(dgrm_engine* e) {
+  for (int i = 0; i < 2; ++i) {
+    if (e->h_dos[i]) cudaFreeHost(e->h_dos[i]);
+    if (e->h_dmiss[i]) cudaFreeHost(e->h_dmiss[i]);
+    e->h_dos[i] = nullptr; e->h_dmiss[i] = nullptr;
+  }
+  free_dev(e->d_dos); e->d_dos = nullptr;
+  free_dev(e->d_dmiss); e->d_dmiss = nullptr;
+  free_dev(e->d_dos_mean); e->d_dos_mean = nullptr;
+  free_dev(e->d_dos_sd); e->d_dos_sd = nullptr;
+  e->h_cap = e->h_fill = e->dev_cap = e->dev_fill = 0;
+}
+
 void release_geometry(dgrm_engine* e) {
   free_dev(e->d_src_ind); e->d_src_ind = nullptr;
   free_dev(e->d_work); e->d_work = nullptr;
@@ -288,6 +317,7 @@ void release_geometry(dgrm_engine* e) {
   e->saved = false;
   e->view = DGRM_VIEW_CURRENT;
   free_dev(e->d_chunk); e->d_chunk = nullptr;
+  release_dosage_staging(e);
   free_dev(e->d_chunkT); e->d_chunkT = nullptr;
   free_dev(e->d_counts); e->d_counts = nullptr;
   free_dev(e->d_miss_part); e->d_miss_part = nullptr;
@@ -460,8 +490,35 @@ int launch_syrk(dgrm_engine* e, const CUtensorMap& tmap, const SyrkParams& p) {
 constexpr int kCountMergeSnps = 32768;  // SNPs per pair-count accumulation (exact in fp32: << 2^24)
 
 int flush_super(dgrm_engine* e, bool final, bool wrap = false);
+int flush_dosage(dgrm_engine* e);
+int process_chunk(dgrm_engine* e);
 int flush_prefix(dgrm_engine* e);
 bool streaming_bound(const dgrm_engine* e);
+
+// The next resident operand slot (`chunks_in_super`) becomes writable on the decode stream.
+int acquire_slot(dgrm_engine* e) {
+  if (e->chunks_in_super == e->slots) {  // every resident slot is taken: contract them before reusing slot 0
+    const int rc = flush_super(e, false, true);
+    if (rc) return rc;
+  }
+  if (e->supers_done > 0) CK(cudaStreamWaitEvent(e->prep, e->slot_ev[e->chunks_in_super], 0));  // the slot's previous chunk is contracted
+  return DGRM_OK;
+}
+
+// The open slot holds a finished chunk of kc SNPs (kc_pad operand columns).
+int close_chunk(dgrm_engine* e, int kc, int kc_pad) {
+  e->slot_kpad[e->chunks_in_super] = kc_pad;
+  e->m += kc;
+  e->chunks_done++;
+  e->fill = 0;
+  ++e->chunks_in_super;
+  // Without streaming output bindings the chunk is contracted right away on the MMA stream, so that the decode of
+  // the next chunk (prep stream) overlaps it; with them the contraction waits for dgrm_finish, which walks the
+  // tiles group by group so that finished groups leave the device early.
+  if (e->overlap && !streaming_bound(e)) return flush_super(e, false);
+  if (e->overlap) return flush_prefix(e);
+  return DGRM_OK;
+}
 
 // One chunk of packed rows: per-SNP statistics, then expansion into resident operand slot `chunks_in_super`.
 int process_chunk(dgrm_engine* e) {
@@ -495,13 +552,18 @@ int process_chunk(dgrm_engine* e) {
   const bool count_mma = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_MMA;
   const bool count_fp4 = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_FP4;
   const bool count_popc = !e->cfg.flat_norm && e->cfg.count_method == DGRM_COUNT_POPC;
-  if (e->chunks_in_super == e->slots) {  // every resident slot is taken: contract them before reusing slot 0
-    const int rc = flush_super(e, false, true);
-    if (rc) return rc;
+  if (e->fill_dosage) {
+    // dosage rows were expanded into the open slot as they arrived (expand_dosage_rows): only the diagonal is left
+    diag_reduce_kernel<<<(unsigned)((e->n_pad + 31) / 32), 256, 0, e->prep>>>(e->d_diag_part, kc_pad / kExpK, (int)e->n_pad,
+                                                                             e->d_diag);
+    CK(cudaGetLastError());
+    e->fill_dosage = false;
+    return close_chunk(e, kc, kc_pad);
   }
+  int rc0 = acquire_slot(e);
+  if (rc0) return rc0;
   const int slot = e->chunks_in_super;
   const int64_t col0 = (int64_t)slot * e->kc_max;
-  if (e->supers_done > 0) CK(cudaStreamWaitEvent(e->prep, e->slot_ev[slot], 0));  // the slot's previous chunk is contracted
 
   // (per-SNP counts, statistics and the zt table of these rows were produced while the rows were gathered into the
   // chunk buffer: bed_decode_kernel in push_device_rows)
@@ -576,17 +638,7 @@ int process_chunk(dgrm_engine* e) {
       CK(cudaGetLastError());
     }
   }
-  e->slot_kpad[slot] = kc_pad;
-  e->m += kc;
-  e->chunks_done++;
-  e->fill = 0;
-  ++e->chunks_in_super;
-  // Without streaming output bindings the chunk is contracted right away on the MMA stream, so that the decode of
-  // the next chunk (prep stream) overlaps it; with them the contraction waits for dgrm_finish, which walks the
-  // tiles group by group so that finished groups leave the device early.
-  if (e->overlap && !streaming_bound(e)) return flush_super(e, false);
-  if (e->overlap) return flush_prefix(e);
-  return DGRM_OK;
+  return close_chunk(e, kc, kc_pad);
 }
 
 // Rectangles of a block-cyclic binding stream out row group by row group only when this engine owns the whole
@@ -1232,6 +1284,12 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
       if (row_keep[r]) idx.push_back((int32_t)r);
     kept = (int64_t)idx.size();
   }
+  if (e->h_fill > 0 || e->dev_fill > 0 || e->fill_dosage) {  // real-valued rows came before: they end their chunk
+    int rc = flush_dosage(e);
+    if (rc) return rc;
+    if (e->fill_dosage) rc = process_chunk(e);
+    if (rc) return rc;
+  }
   if (e->m + e->fill + kept > e->m_cap)
     return fail(e, DGRM_E_INVALID, "more SNPs pushed (%lld) than dgrm_begin's capacity (%lld)",
                 (long long)(e->m + e->fill + kept), (long long)e->m_cap);
@@ -1324,6 +1382,156 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
     }
   }
   return DGRM_OK;
+}
+
+// Staging for real-valued rows: two pinned host buffers of 64 MB of dosages (the caller's rows are copied here, so the
+// row-at-a-time pushes of a variant parser still cross the bus in large pieces) and a device buffer of dev_cap rows, up
+// to one chunk: the statistics kernel runs one sequential chain per row, so a launch should carry many rows.
+int ensure_dosage_staging(dgrm_engine* e) {
+  if (e->dev_cap > 0) return DGRM_OK;
+  const int64_t row_bytes = std::max<int64_t>(1, e->n * (int64_t)sizeof(double));
+  const int64_t hrows = std::max<int64_t>(1, std::min<int64_t>((64ll << 20) / row_bytes, e->kc_max));
+  int64_t drows = ((int64_t)e->dosage_stage_mb << 20) / (row_bytes + e->n);
+  drows = std::max<int64_t>(256, std::min<int64_t>(drows / 256 * 256, e->kc_max));
+  for (int i = 0; i < 2; ++i) {
+    if (cudaHostAlloc(&e->h_dos[i], (size_t)hrows * e->n * sizeof(double), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc(&e->h_dmiss[i], (size_t)hrows * e->n, cudaHostAllocDefault) != cudaSuccess) {
+      release_dosage_staging(e);
+      return fail(e, DGRM_E_NOMEM, "dgrm_push_dosage_host: no pinned memory for %lld staged rows", (long long)hrows);
+    }
+    if (!e->dos_copied[i]) CK(cudaEventCreateWithFlags(&e->dos_copied[i], cudaEventDisableTiming));
+  }
+  if (!e->dos_read) CK(cudaEventCreateWithFlags(&e->dos_read, cudaEventDisableTiming));
+  if (!e->dos_ready) CK(cudaEventCreateWithFlags(&e->dos_ready, cudaEventDisableTiming));
+  CK(cudaMalloc(&e->d_dos, (size_t)drows * e->n * sizeof(double)));
+  CK(cudaMalloc(&e->d_dmiss, (size_t)drows * e->n));
+  CK(cudaMalloc(&e->d_dos_mean, (size_t)drows * sizeof(double)));
+  CK(cudaMalloc(&e->d_dos_sd, (size_t)drows * sizeof(double)));
+  e->h_cap = (int)hrows;
+  e->dev_cap = (int)drows;
+  e->h_fill = e->dev_fill = 0;
+  e->h_any_missing = e->dev_any_missing = false;
+  return DGRM_OK;
+}
+
+// The dev_fill rows of the device staging buffer: missing mask folded in, statistics, then expansion into the open
+// operand slot at column `fill`.  Full buffers are multiples of 256 rows, so the open chunk only ever ends on a
+// partial k-block when this is the last batch before something else (packed rows, dgrm_finish): that batch closes
+// the chunk.
+int process_dosage_device(dgrm_engine* e) {
+  const int rows = e->dev_fill;
+  if (rows == 0) return DGRM_OK;
+  CK(cudaEventRecord(e->dos_ready, e->copy_stream));
+  CK(cudaStreamWaitEvent(e->prep, e->dos_ready, 0));
+  {
+    Prof pr(e, DGRM_K_COUNT, e->prep);
+    if (e->dev_any_missing) {
+      const int64_t count = (int64_t)rows * e->n;
+      dosage_fold_mask_kernel<<<(unsigned)std::min<int64_t>((count + 255) / 256, 148 * 16), 256, 0, e->prep>>>(e->d_dos, e->d_dmiss,
+                                                                                                             count);
+      CK(cudaGetLastError());
+    }
+    DosageStatsOut so{e->d_freq, e->d_nn, e->d_p1, e->d_p2, e->d_sd, e->d_bad_count + 3};
+    dosage_stats_kernel<<<(rows + kStatRows - 1) / kStatRows, kStatThreads, sizeof(DosageStatSmem), e->prep>>>(
+        e->d_dos, e->n, rows, (int)e->n, e->m + e->fill, so, e->d_dos_mean, e->d_dos_sd);
+    CK(cudaGetLastError());
+  }
+  e->dev_fill = 0;
+  e->dev_any_missing = false;
+  const bool split = e->cfg.operand == DGRM_OPERAND_FP16X2;
+  const bool bf16 = e->cfg.operand == DGRM_OPERAND_BF16;
+  const int qk = e->cfg.flat_norm ? 0
+                 : e->cfg.count_method == DGRM_COUNT_MMA ? 1
+                 : e->cfg.count_method == DGRM_COUNT_FP4 ? 2
+                 : e->cfg.count_method == DGRM_COUNT_POPC ? 3 : 0;
+  int pos = 0;
+  while (pos < rows) {
+    if (e->fill == 0) {
+      const int rc = acquire_slot(e);
+      if (rc) return rc;
+    }
+    const int take = std::min(rows - pos, e->kc_max - e->fill);
+    const int64_t col = (int64_t)e->chunks_in_super * e->kc_max + e->fill;
+    DosageExpandArgs a;
+    a.dos = e->d_dos + (int64_t)pos * e->n; a.pitch = e->n;
+    a.mean = e->d_dos_mean + pos; a.sd = e->d_dos_sd + pos;
+    a.kc = take; a.n = (int)e->n;
+    a.Z = e->d_Z + col; a.z_pitch = e->z_pitch; a.lo_off = (int64_t)e->slots * e->kc_max;
+    a.Q = qk == 1 ? e->d_Q + col : nullptr; a.q_pitch = e->q_pitch;
+    a.Q4 = qk == 2 ? e->d_Q4 + col / 2 : nullptr; a.q4_pitch = e->q4_pitch;
+    a.MB = qk == 3 ? e->d_MB + col / 32 : nullptr; a.mb_pitch = e->mb_pitch;
+    a.diag_part = e->d_diag_part + (int64_t)(e->fill / kExpK) * e->n_pad; a.n_pad = (int)e->n_pad;
+    const dim3 grid((unsigned)(e->n_pad / kExpI), (unsigned)(round_up(take, 256) / kExpK));
+    {
+      Prof pr(e, DGRM_K_EXPAND, e->prep);
+#define DGRM_DOSAGE(B, S, K) dosage_expand_kernel<B, S, K><<<grid, 256, sizeof(DosageSmem), e->prep>>>(a)
+#define DGRM_DOSAGE_Q(B, S)                                                     \
+  do {                                                                          \
+    if (qk == 0) DGRM_DOSAGE(B, S, 0); else if (qk == 1) DGRM_DOSAGE(B, S, 1);  \
+    else if (qk == 2) DGRM_DOSAGE(B, S, 2); else DGRM_DOSAGE(B, S, 3);          \
+  } while (0)
+      if (bf16) DGRM_DOSAGE_Q(true, false);
+      else if (split) DGRM_DOSAGE_Q(false, true);
+      else DGRM_DOSAGE_Q(false, false);
+#undef DGRM_DOSAGE_Q
+#undef DGRM_DOSAGE
+      CK(cudaGetLastError());
+    }
+    e->fill += take;
+    e->fill_dosage = true;
+    pos += take;
+    if (e->fill == e->kc_max || e->fill % 256 != 0) {
+      const int rc = process_chunk(e);  // diagonal + bookkeeping of the finished chunk
+      if (rc) return rc;
+    }
+  }
+  CK(cudaEventRecord(e->dos_read, e->prep));
+  // per-individual missing counts are not kept for real-valued rows: streamed pair counts travel as int32
+  if (!e->cfg.flat_norm) e->miss_valid = false;
+  return DGRM_OK;
+}
+
+// The h_fill rows of the current pinned buffer go to the device staging buffer (asynchronously, copy stream); every
+// time that buffer is full it is processed.
+int send_dosage(dgrm_engine* e) {
+  const int rows = e->h_fill;
+  if (rows == 0) return DGRM_OK;
+  const int s = e->dos_i;
+  const bool with_miss = e->h_any_missing;
+  const int64_t n = e->n;
+  int off = 0;
+  while (off < rows) {
+    if (e->dev_fill == 0) CK(cudaStreamWaitEvent(e->copy_stream, e->dos_read, 0));  // the kernels of the previous batch have read it
+    const int take = std::min(rows - off, e->dev_cap - e->dev_fill);
+    CK(cudaMemcpyAsync(e->d_dos + (int64_t)e->dev_fill * n, e->h_dos[s] + (int64_t)off * n, (size_t)take * n * sizeof(double),
+                       cudaMemcpyHostToDevice, e->copy_stream));
+    if (with_miss) {
+      if (!e->dev_any_missing && e->dev_fill > 0) CK(cudaMemsetAsync(e->d_dmiss, 0, (size_t)e->dev_fill * n, e->copy_stream));
+      CK(cudaMemcpyAsync(e->d_dmiss + (int64_t)e->dev_fill * n, e->h_dmiss[s] + (int64_t)off * n, (size_t)take * n,
+                         cudaMemcpyHostToDevice, e->copy_stream));
+      e->dev_any_missing = true;
+    } else if (e->dev_any_missing) {
+      CK(cudaMemsetAsync(e->d_dmiss + (int64_t)e->dev_fill * n, 0, (size_t)take * n, e->copy_stream));
+    }
+    e->dev_fill += take;
+    off += take;
+    if (e->dev_fill == e->dev_cap) {
+      const int rc = process_dosage_device(e);
+      if (rc) return rc;
+    }
+  }
+  CK(cudaEventRecord(e->dos_copied[s], e->copy_stream));
+  e->dos_i ^= 1;
+  e->h_fill = 0;
+  e->h_any_missing = false;
+  return DGRM_OK;
+}
+
+// everything staged so far reaches the operands
+int flush_dosage(dgrm_engine* e) {
+  int rc = send_dosage(e);
+  if (rc) return rc;
+  return process_dosage_device(e);
 }
 
 // (Re)allocate the resident operand buffers for `slots` chunks of kc_max SNPs.
@@ -1498,6 +1706,7 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   if (const char* kf = getenv("DGRM_EXPAND_KFAST")) e->expand_k_fast = atoi(kf);
   if (const char* cs = getenv("DGRM_EXPAND_CS")) e->expand_stream_stores = atoi(cs);
   if (const char* pp = getenv("DGRM_PREFIX_PCT")) e->prefix_pct = std::max(0, std::min(90, atoi(pp)));
+  if (const char* ds = getenv("DGRM_DOSAGE_STAGE_MB")) e->dosage_stage_mb = std::max(1, std::min(65536, atoi(ds)));
   e->reserve_sms = cfg->reserve_sms > 0 ? cfg->reserve_sms : 0;
   if (const char* rs = getenv("DGRM_RESERVE_SMS")) e->reserve_sms = atoi(rs);
   e->reserve_sms = std::max(0, std::min(e->reserve_sms, e->sm_count - 2));
@@ -1567,6 +1776,13 @@ int dgrm_create(const dgrm_config* cfg, dgrm_engine** out) {
   DGRM_EXPAND_T_ATTR(true, false, 0); DGRM_EXPAND_T_ATTR(true, false, 1); DGRM_EXPAND_T_ATTR(true, false, 2); DGRM_EXPAND_T_ATTR(true, false, 3);
   DGRM_EXPAND_T_ATTR(false, true, 0); DGRM_EXPAND_T_ATTR(false, true, 1); DGRM_EXPAND_T_ATTR(false, true, 2); DGRM_EXPAND_T_ATTR(false, true, 3);
 #undef DGRM_EXPAND_T_ATTR
+#define DGRM_DOSAGE_ATTR(B, S, K)                                                                          \
+  CKC(cudaFuncSetAttribute(dosage_expand_kernel<B, S, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DosageSmem)))
+  DGRM_DOSAGE_ATTR(false, false, 0); DGRM_DOSAGE_ATTR(false, false, 1); DGRM_DOSAGE_ATTR(false, false, 2); DGRM_DOSAGE_ATTR(false, false, 3);
+  DGRM_DOSAGE_ATTR(true, false, 0); DGRM_DOSAGE_ATTR(true, false, 1); DGRM_DOSAGE_ATTR(true, false, 2); DGRM_DOSAGE_ATTR(true, false, 3);
+  DGRM_DOSAGE_ATTR(false, true, 0); DGRM_DOSAGE_ATTR(false, true, 1); DGRM_DOSAGE_ATTR(false, true, 2); DGRM_DOSAGE_ATTR(false, true, 3);
+#undef DGRM_DOSAGE_ATTR
+  CKC(cudaFuncSetAttribute(dosage_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DosageStatSmem)));
 #undef CKC
   *out = e;
   return DGRM_OK;
@@ -1589,6 +1805,10 @@ void dgrm_destroy(dgrm_engine* e) {
     if (e->rowidx_free[i]) cudaEventDestroy(e->rowidx_free[i]);
   }
   if (e->producer_ev) cudaEventDestroy(e->producer_ev);
+  for (int i = 0; i < 2; ++i)
+    if (e->dos_copied[i]) cudaEventDestroy(e->dos_copied[i]);
+  if (e->dos_read) cudaEventDestroy(e->dos_read);
+  if (e->dos_ready) cudaEventDestroy(e->dos_ready);
   if (e->bed_ev) cudaEventDestroy(e->bed_ev);
   free_dev(e->d_bed);
   free_dev(e->d_grm_rows);
@@ -1763,6 +1983,9 @@ static int begin_common(dgrm_engine* e, int64_t m_capacity) {
   }
   e->m = 0;
   e->fill = 0;
+  e->h_fill = e->dev_fill = 0;
+  e->h_any_missing = e->dev_any_missing = false;
+  e->fill_dosage = false;
   e->chunks_done = 0;
   e->chunks_in_super = 0;
   e->launched_s = e->launched_n = 0;
@@ -1848,6 +2071,52 @@ int dgrm_push_bed_host(dgrm_engine* e, const uint8_t* rows, int64_t pitch, int64
   return DGRM_OK;
 }
 
+int dgrm_push_dosage_host(dgrm_engine* e, const double* dosage, int64_t pitch, const uint8_t* missing, int64_t missing_pitch,
+                          int64_t nrows) {
+  int rc = check_ready(e, false);
+  if (rc) return rc;
+  if (e->finished) return fail(e, DGRM_E_INVALID, "dgrm_push_dosage_host after dgrm_finish");
+  if (e->ld_mode) return fail(e, DGRM_E_INVALID, "dgrm_push_dosage_host: not available in LD mode");
+  if (!dosage || nrows < 0 || pitch < e->n || (missing && missing_pitch < e->n))
+    return fail(e, DGRM_E_INVALID, "dgrm_push_dosage_host: bad rows/pitch (rows hold the %lld kept individuals)", (long long)e->n);
+  const int64_t pending = e->m + e->fill + e->dev_fill + e->h_fill;
+  if (pending + nrows > e->m_cap)
+    return fail(e, DGRM_E_INVALID, "more SNPs pushed (%lld) than dgrm_begin's capacity (%lld)", (long long)(pending + nrows),
+                (long long)e->m_cap);
+  CK(cudaSetDevice(e->cfg.device));
+  rc = ensure_dosage_staging(e);
+  if (rc) return rc;
+  e->grm_from_store = false;
+  if (e->fill > 0 && !e->fill_dosage) {  // packed rows came before: they end their chunk
+    rc = process_chunk(e);
+    if (rc) return rc;
+  }
+  const int64_t n = e->n;
+  for (int64_t r = 0; r < nrows;) {
+    const int s = e->dos_i;
+    if (e->h_fill == 0) CK(cudaEventSynchronize(e->dos_copied[s]));  // the copies that last read this pinned buffer are done
+    const int64_t take = std::min<int64_t>(nrows - r, e->h_cap - e->h_fill);
+    double* hd = e->h_dos[s] + (size_t)e->h_fill * n;
+    uint8_t* hm = e->h_dmiss[s] + (size_t)e->h_fill * n;
+    if (missing && !e->h_any_missing && e->h_fill > 0) memset(e->h_dmiss[s], 0, (size_t)e->h_fill * n);
+    const bool clear_mask = !missing && e->h_any_missing;
+#pragma omp parallel for schedule(static) if (take * n >= (1 << 20))
+    for (int64_t k = 0; k < take; ++k) {
+      memcpy(hd + k * n, dosage + (r + k) * pitch, (size_t)n * sizeof(double));
+      if (missing) memcpy(hm + k * n, missing + (r + k) * missing_pitch, (size_t)n);
+      else if (clear_mask) memset(hm + k * n, 0, (size_t)n);
+    }
+    if (missing) e->h_any_missing = true;
+    e->h_fill += (int)take;
+    r += take;
+    if (e->h_fill == e->h_cap) {
+      rc = send_dosage(e);
+      if (rc) return rc;
+    }
+  }
+  return DGRM_OK;
+}
+
 int dgrm_load_bed_file(dgrm_engine* e, const char* bed_path, int64_t m_file, const int64_t* snp_keep_idx,
                        int64_t m_keep) {
   int rc = check_ready(e, false);
@@ -1904,6 +2173,8 @@ int dgrm_finish(dgrm_engine* e) {
   if (rc) return rc;
   CK(cudaSetDevice(e->cfg.device));
   if (!e->finished) {
+    rc = flush_dosage(e);
+    if (rc) return rc;
     rc = process_chunk(e);
     if (rc) return rc;
     if (e->ld_mode) {   // every individual chunk is resident: contract them all now
@@ -1954,6 +2225,11 @@ int dgrm_finish(dgrm_engine* e) {
                 bad[0]);
   if (bad[1] > 0)
     return fail(e, DGRM_E_NANSNP, "Error: %d SNPs have no non-missing genotype (allele frequency is 0/0).", bad[1]);
+  if (bad[3] > 0 && e->cfg.flat_norm)
+    return fail(e, DGRM_E_BADSNP,
+                "Error: %d dosage SNPs have zero variance; under --grm-flat-norm they change the SNP count the GRM is "
+                "divided by (removeSNPsWithZeroVariance): filter them (dgrm_snp_stats: std_dev == 0) and rebuild.",
+                bad[3]);
   return DGRM_OK;
 }
 
@@ -2025,7 +2301,7 @@ int dgrm_bind_tiles(dgrm_engine* e, int which, double* tiles) {
   return DGRM_OK;
 }
 
-int64_t dgrm_num_snps(const dgrm_engine* e) { return e ? e->m + e->fill : 0; }
+int64_t dgrm_num_snps(const dgrm_engine* e) { return e ? e->m + e->fill + e->dev_fill + e->h_fill : 0; }
 int64_t dgrm_num_individuals(const dgrm_engine* e) { return e ? e->n : 0; }
 
 int dgrm_snp_stats(dgrm_engine* e, int32_t* freq, int32_t* nn, double* p1, double* p2, double* sd) {

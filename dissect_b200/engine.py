@@ -140,6 +140,19 @@ class GrmEngine:
         self._ck(self._lib.dgrm_push_bed_host(self._h, ptr, pitch, nrows, rk.ctypes.data if rk is not None else None))
         self._keep.append((rows, rk))  # the copy is asynchronous: keep the sources alive
 
+    def push_dosage_host(self, dosage, missing=None):
+        """dosage: float64 [nrows, n] expected allele counts of the kept individuals; missing: uint8/bool [nrows, n],
+        non-zero where the sample has no probabilities (the rows the reference's BGEN reader forms,
+        genotypebgen.cpp:183-236).  The rows are copied before the call returns."""
+        d = np.ascontiguousarray(dosage, dtype=np.float64)
+        assert d.ndim == 2
+        mk = None
+        if missing is not None:
+            mk = np.ascontiguousarray(np.asarray(missing) != 0, dtype=np.uint8)
+            assert mk.shape == d.shape
+        self._ck(self._lib.dgrm_push_dosage_host(self._h, d.ctypes.data, d.shape[1], mk.ctypes.data if mk is not None else None,
+                                                 d.shape[1], d.shape[0]))
+
     def push_bed_device(self, ptr, pitch, nrows, row_keep=None, stream=None):
         rk = None
         if row_keep is not None:

@@ -8,6 +8,8 @@
 #include <fstream>
 #include <sstream>
 
+#include <zlib.h>
+
 namespace dgrm_host {
 
 Communicator* communicator = new Communicator();
@@ -45,7 +47,8 @@ Options::Options()
     : makeGRM(false), outFile("dissect"), flatGRMNormalization(false), minimumNumberOverlapingSNPs(10.),
       maximumProportionOfElimitaedIndividuals(0.9), defaultBlockSize(256), regionalAnalysis(false), regionBy(ungrouped),
       regionSize(-1), regionOverlapping(0), minSNPsInRegions(1), writeLOCO(false), device(0), operand(DGRM_OPERAND_FP16),
-      countMethod(DGRM_COUNT_FP4), chunkSNPs(16384), ctaGroup(2), engines(1), lazyHostMatrices(false), GRMJoinMethod(0) {}
+      countMethod(DGRM_COUNT_FP4), chunkSNPs(16384), ctaGroup(2), engines(1), lazyHostMatrices(false), GRMJoinMethod(0),
+      allowBGENLayout1(false) {}
 
 void Options::parseOptions(int argc, char** argv) {
   auto need = [&](int i) -> std::string {
@@ -58,6 +61,8 @@ void Options::parseOptions(int argc, char** argv) {
     if (a == "--make-grm") makeGRM = true;
     else if (a == "--bfile") genotypeFile = need(i++);
     else if (a == "--bfile-list") genotypeListFile = need(i++);                 // options.cpp:414-417
+    else if (a == "--bgen") bgenGenotypeFile = need(i++);                       // options.cpp:418-423
+    else if (a == "--bgen-l1") allowBGENLayout1 = true;                         // options.cpp:1117-1121
     else if (a == "--grm-join-method") {                                        // options.cpp:497-500
       GRMJoinMethod = atoi(need(i++).c_str());
       seenJoin = true;
@@ -106,6 +111,8 @@ void Options::parseOptions(int argc, char** argv) {
     misc.error("Error: A genotype file and a genotype list of files can not be specified at the same time.", 0);
   if (seenJoin && genotypeListFile.empty())                   // options.cpp:1288-1291
     misc.error("Error: The option --grm-join-method can only be used together with --bfile-list.", 0);
+  if (!bgenGenotypeFile.empty() && (!genotypeFile.empty() || !genotypeListFile.empty()))
+    misc.error("Error: A genotype file and a genotype list of files can not be specified at the same time.", 0);
   if (regionalAnalysis && genotypeFile.empty())
     misc.error("Error: To perform a regional analysis, a genotype file must be specified.", 0);
   if (writeLOCO && !regionalAnalysis) misc.error("Error: --gpu-loco needs a regional option (e.g. --groups).", 0);
@@ -202,8 +209,8 @@ static std::vector<std::vector<std::string> > read_table(const std::string& path
 }
 
 Genotype::Genotype()
-    : nSNPs(0), nIndividuals(0), normalized(false), nBEDSNPs(0), nBEDIndividuals(0), groupedBy(ungrouped), eng_(NULL),
-      ownsEngine_(false) {}
+    : nSNPs(0), nIndividuals(0), normalized(false), nBEDSNPs(0), nBEDIndividuals(0), type(GenotypeAttributes::calls),
+      bgenLayout(0), bgenCompression(0), bgenFirstVariant(0), groupedBy(ungrouped), eng_(NULL), ownsEngine_(false) {}
 
 Genotype::~Genotype() {
   if (eng_ && ownsEngine_) dgrm_destroy(eng_);
@@ -211,7 +218,8 @@ Genotype::~Genotype() {
 
 Genotype::Genotype(const std::string& fname)
     : nSNPs(0), nIndividuals(0), normalized(false), bedFile(fname + ".bed"), nBEDSNPs(0), nBEDIndividuals(0),
-      groupedBy(ungrouped), eng_(NULL), ownsEngine_(false) {
+      type(GenotypeAttributes::calls), bgenLayout(0), bgenCompression(0), bgenFirstVariant(0), groupedBy(ungrouped), eng_(NULL),
+      ownsEngine_(false) {
   std::set<std::string> keepSNPs, keepInds;
   if (!options.fileSNPsToKeep.empty()) {
     *misc.message << "Only SNPs specified in file [ " << options.fileSNPsToKeep << " ] will be kept." << std::endl;
@@ -228,6 +236,248 @@ Genotype::Genotype(const std::string& fname)
   for (int k = 0; k < nSNPs; ++k) SNPIdsIdx[SNPIds[k]] = k;
 }
 
+
+// ------------------------------------------------------------------------------------------- BGEN
+// The reference reads BGEN through genfile::bgen (genotypebgen.cpp:284-559), which its tree does not vendor.  What
+// follows restates the published v1.1 / v1.2 container for the subset the reference accepts (biallelic, diploid,
+// unphased; ProbabilitiesSetter::initialise / set_min_max_ploidy / set_number_of_entries, genotypebgen.cpp:99-172).
+namespace {
+
+struct BgenReader {
+  FILE* f;
+  std::string name;
+  explicit BgenReader(const std::string& path) : f(fopen(path.c_str(), "rb")), name(path) {
+    if (!f) misc.error("Error: Unable to read the file [ " + path + " ].", 0);   // genotypebgen.cpp:320-322
+  }
+  ~BgenReader() { if (f) fclose(f); }
+  void bytes(void* dst, size_t n) {
+    if (n && fread(dst, 1, n, f) != n) misc.error("Error: Unexpected end of the BGEN file [ " + name + " ].", 0);
+  }
+  uint32_t u32() { unsigned char b[4]; bytes(b, 4); return b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24); }
+  uint16_t u16() { unsigned char b[2]; bytes(b, 2); return (uint16_t)(b[0] | (b[1] << 8)); }
+  std::string str(size_t n) { std::string s(n, '\0'); bytes(&s[0], n); return s; }
+  void skip(long long n) { if (fseeko(f, n, SEEK_CUR) != 0) misc.error("Error: Unexpected end of the BGEN file [ " + name + " ].", 0); }
+};
+
+struct BgenVariant { std::string chr, rsid; uint32_t position; std::vector<std::string> alleles; };
+
+// identifying data of the next variant (genfile::bgen::read_snp_identifying_data)
+BgenVariant read_variant_id(BgenReader& r, int layout, uint32_t nSamples) {
+  BgenVariant v;
+  if (layout == 1 && r.u32() != nSamples) misc.error("Error: Unexpected number of samples in a BGEN variant block.", 0);
+  r.skip(r.u16());                 // variant identifier (the reference passes a dummy, genotypebgen.cpp:467-472)
+  v.rsid = r.str(r.u16());
+  v.chr = r.str(r.u16());
+  v.position = r.u32();
+  const int k = layout == 2 ? r.u16() : 2;
+  for (int a = 0; a < k; ++a) v.alleles.push_back(r.str(r.u32()));
+  if (k != 2)   // genotypebgen.cpp:107-110
+    misc.error("Error: The bgen file contains non-biallelic genotypes. DISSECT currently can only work with biallelic genotypes.", 0);
+  return v;
+}
+
+// length in bytes of the genotype data block that follows the identifying data
+long long genotype_block_bytes(BgenReader& r, int layout, int compression, uint32_t nSamples) {
+  if (layout == 1 && !compression) return 6ll * nSamples;
+  return r.u32();
+}
+
+}  // namespace
+
+Genotype::Genotype(const std::string& fname, GenotypeAttributes::Type t)
+    : nSNPs(0), nIndividuals(0), normalized(false), nBEDSNPs(0), nBEDIndividuals(0), type(t), bgenFile(fname + ".bgen"),
+      bgenLayout(0), bgenCompression(0), bgenFirstVariant(0), groupedBy(ungrouped), eng_(NULL), ownsEngine_(false) {
+  if (t != GenotypeAttributes::probabilities) misc.error("Error: An internal error was happened. Unexpected genotype type.", 0);
+  std::set<std::string> keepSNPs, keepInds;
+  if (!options.fileSNPsToKeep.empty()) {
+    *misc.message << "Only SNPs specified in file [ " << options.fileSNPsToKeep << " ] will be kept." << std::endl;
+    for (auto& r : read_table(options.fileSNPsToKeep, 1)) keepSNPs.insert(r[0]);
+  }
+  if (!options.fileIndividualsToKeep.empty()) {
+    *misc.message << "Only individuals specified in file [ " << options.fileIndividualsToKeep << " ] will be kept." << std::endl;
+    for (auto& r : read_table(options.fileIndividualsToKeep, 2)) keepInds.insert(r[0] + "@" + r[1]);
+  }
+  *misc.message << "Reading genotype data from file [ " << fname << " ] ..." << std::endl;
+  BgenReader r(bgenFile);
+  const uint32_t offset = r.u32();
+  const uint32_t headerLength = r.u32();
+  const uint32_t nVariants = r.u32();
+  const uint32_t nSamples = r.u32();
+  const std::string magic = r.str(4);
+  if (magic != "bgen" && magic != std::string(4, '\0')) misc.error("Error: The file [ " + bgenFile + " ] is not a valid BGEN file.", 0);
+  r.skip((long long)headerLength - 20);
+  const uint32_t flags = r.u32();
+  bgenCompression = (int)(flags & 3u);
+  bgenLayout = (int)((flags >> 2) & 15u);
+  // genotypebgen.cpp:330-351
+  if (bgenLayout == 0) misc.error("Error: The BGEN file is in Layout 0. Currently DISSECT only supports Layout 1 and Layout 2.", 0);
+  if (bgenLayout == 1 && !options.allowBGENLayout1)
+    misc.error("Error: The BGEN file is using Layout 1. Currently DISSECT only supports Layout 1 for testing purposes. You can use the option --bgen-l1 to enable reading BGEN layout 1 files. But we recommend to update the file to Layout 2.", 0);
+  if (bgenLayout > 2) misc.error("Error: Unrecognized BGEN layout type. Supported types are Layout 1 and Layout 2.", 0);
+  if (bgenCompression == 2) misc.error("Error: zstd-compressed BGEN files are not supported by this adapter (no zstd library in the build).", 0);
+  std::vector<std::pair<std::string, std::string> > ids;
+  if (flags >> 31) {
+    r.u32();
+    const uint32_t n2 = r.u32();
+    for (uint32_t i = 0; i < n2; ++i) { const std::string id = r.str(r.u16()); ids.push_back(std::make_pair(id, id)); }   // genotypebgen.cpp:353-359
+  } else {
+    // genotypebgen.cpp:360-365, 414-441: F.sample, header lines `ID_1 ID_2 ...` and `0 0 ...`
+    *misc.message << "There are no individual identifiers in the [ " << bgenFile << " ] file. Trying to read them from [ " << fname << ".sample file ]." << std::endl;
+    std::vector<std::vector<std::string> > tab = read_table(fname + ".sample", 2);
+    if (tab.size() <= 2) misc.error("Error: The file [ " + fname + ".sample ] is empty.", 0);
+    if (tab[0][0] != "ID_1" || tab[0][1] != "ID_2" || tab[1][0] != "0" || tab[1][1] != "0")
+      misc.error("Error: Unexpected header in the file [" + fname + ".sample].", 0);
+    for (size_t i = 2; i < tab.size(); ++i) ids.push_back(std::make_pair(tab[i][0], tab[i][1]));
+  }
+  if (ids.size() != nSamples) misc.error("Error: An error has happened whe reading bgen file. Unexpected number of individual Ids.", 0);
+  nBEDIndividuals = (int)nSamples;
+  for (size_t i = 0; i < ids.size(); ++i) {
+    const std::string key = ids[i].first + "@" + ids[i].second;
+    const bool keep = keepInds.empty() || keepInds.count(key);
+    individualBEDIdxsMaskToKeep.push_back(keep ? 1 : 0);
+    if (!keep) continue;
+    Individual ind;   // genotypebgen.cpp:578-598
+    ind.familyID = ids[i].first; ind.individualID = ids[i].second;
+    ind.paternalID = ind.maternalID = ind.sex = "NA";
+    ind.phenotype = -1;
+    if (std::find(individualIds.begin(), individualIds.end(), key) != individualIds.end())
+      misc.error("Error: The individual with id: " + ind.individualID + " appears more than one time in the genotypes BGEN file.", 0);
+    individuals.push_back(ind);
+    individualIds.push_back(key);
+  }
+  nIndividuals = (int)individuals.size();
+  *misc.message << "Reading bgen file [ " << fname << " ] (" << (bgenLayout == 2 ? "v1.2 layout" : "v1.1 layout") << ", " << bgenLayout << ", "
+                << (bgenCompression ? "compressed" : "uncompressed") << ") with " << nSamples << " individuals and " << nVariants
+                << " variants." << std::endl;
+  bgenFirstVariant = (long long)offset + 4;
+  if (fseeko(r.f, bgenFirstVariant, SEEK_SET) != 0) misc.error("Error: Unexpected end of the BGEN file [ " + bgenFile + " ].", 0);
+  nBEDSNPs = (int)nVariants;
+  bgenKeepVariant.assign(nVariants, 0);
+  for (uint32_t v = 0; v < nVariants; ++v) {
+    const BgenVariant bv = read_variant_id(r, bgenLayout, nSamples);
+    r.skip(genotype_block_bytes(r, bgenLayout, bgenCompression, nSamples));
+    if (!keepSNPs.empty() && !keepSNPs.count(bv.rsid)) continue;   // genotypebgen.cpp:655-659
+    bgenKeepVariant[v] = 1;
+    SNP s;
+    s.chr = bv.chr; s.name = bv.rsid; s.position = (int)bv.position; s.allele1 = bv.alleles[0]; s.allele2 = bv.alleles[1];
+    s.nNonMissing = 0; s.p1 = s.p2 = s.standardDev = 0.;
+    for (int c = 0; c < 4; ++c) s.frequencies[c] = 0;
+    if (SNPIdsIdx.count(s.name))
+      misc.error("Error: The SNP with name: " + s.name + " appears more than one time in the genotypes BGEN file.", 0);
+    SNPIdsIdx[s.name] = (int)SNPs.size();
+    SNPs.push_back(s);
+    SNPIds.push_back(s.name);
+  }
+  nSNPs = (int)SNPs.size();
+  if (nSNPs == 0 || nIndividuals == 0)
+    misc.error("Error: There are 0 SNPs and/or 0 individuals kept for the analysis. Aborting...", 0);
+}
+
+void Genotype::streamBGEN(BGENSink sink, void* ctx) const {
+  BgenReader r(bgenFile);
+  if (fseeko(r.f, bgenFirstVariant, SEEK_SET) != 0) misc.error("Error: Unexpected end of the BGEN file [ " + bgenFile + " ].", 0);
+  const uint32_t nSamples = (uint32_t)nBEDIndividuals;
+  const size_t nk = (size_t)nIndividuals;
+  std::vector<int> cols;
+  for (uint32_t i = 0; i < nSamples; ++i) if (individualBEDIdxsMaskToKeep[i]) cols.push_back((int)i);
+  const size_t blockRows = std::max<size_t>(1, std::min<size_t>(4096, (64u << 20) / (nk * sizeof(double))));
+  std::vector<double> dosage(blockRows * nk);
+  std::vector<unsigned char> missing(blockRows * nk);
+  std::vector<unsigned char> raw, data;
+  size_t rows = 0;
+  for (size_t v = 0; v < bgenKeepVariant.size(); ++v) {
+    read_variant_id(r, bgenLayout, nSamples);
+    const long long len = genotype_block_bytes(r, bgenLayout, bgenCompression, nSamples);
+    if (!bgenKeepVariant[v]) { r.skip(len); continue; }   // ignoreProbabilities
+    // probability data of this variant, decompressed
+    size_t dataLen;
+    if (bgenLayout == 2 && bgenCompression) {
+      dataLen = r.u32();
+      raw.resize((size_t)len - 4);
+    } else if (bgenLayout == 1 && bgenCompression) {
+      dataLen = 6u * (size_t)nSamples;
+      raw.resize((size_t)len);
+    } else {
+      dataLen = (size_t)len;
+      raw.resize(0);
+    }
+    data.assign(dataLen + 8, 0);   // 8 bytes of slack for the bit reader
+    if (bgenCompression) {
+      r.bytes(raw.data(), raw.size());
+      uLongf got = (uLongf)dataLen;
+      if (uncompress(data.data(), &got, raw.data(), (uLong)raw.size()) != Z_OK || got != dataLen)
+        misc.error("Error: A genotype block of the BGEN file [ " + bgenFile + " ] could not be decompressed.", 0);
+    } else {
+      r.bytes(data.data(), dataLen);
+    }
+    double* drow = &dosage[rows * nk];
+    unsigned char* mrow = &missing[rows * nk];
+    if (bgenLayout == 1) {
+      for (size_t c = 0; c < nk; ++c) {
+        const unsigned char* p = &data[(size_t)cols[c] * 6];
+        const double aa = (double)(p[0] | (p[1] << 8)) / 32768.0, ab = (double)(p[2] | (p[3] << 8)) / 32768.0,
+                     bb = (double)(p[4] | (p[5] << 8)) / 32768.0;
+        mrow[c] = (aa + ab + bb) == 0. ? 1 : 0;     // genotypebgen.cpp:208-214
+        drow[c] = ab + 2. * bb;                      // genotypebgen.cpp:199-205
+      }
+    } else {
+      const unsigned char* p = data.data();
+      const uint32_t n2 = p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
+      const int k2 = p[4] | (p[5] << 8), pmin = p[6], pmax = p[7];
+      if (n2 != nSamples || k2 != 2) misc.error("Error: An internal error has happened. Unexpected small number of samples.", 0);
+      if (pmin != 2 || pmax != 2)   // genotypebgen.cpp:120-123
+        misc.error("Error: The bgen file contains non-diploid genotypes. DISSECT currently can only work with diploid genotypes.", 0);
+      const unsigned char* ploidy = p + 8;
+      const int phased = p[8 + nSamples], bits = p[9 + nSamples];
+      if (phased)                   // genotypebgen.cpp:168-171
+        misc.error("Error: Currently can only load unphased genotypes. If you are interested on loading phased genotypes, please, contact us.", 0);
+      if (bits < 1 || bits > 32) misc.error("Error: Unexpected number of bits per probability in the BGEN file.", 0);
+      const unsigned char* pr = p + 10 + nSamples;
+      const uint64_t mask = bits == 32 ? 0xFFFFFFFFull : ((1ull << bits) - 1ull);
+      const double scale = (double)mask;
+      for (size_t c = 0; c < nk; ++c) {
+        const size_t i = (size_t)cols[c];
+        if ((ploidy[i] & 0x3F) != 2)
+          misc.error("Error: The bgen file contains non-diploid genotypes. DISSECT currently can only work with diploid genotypes.", 0);
+        uint64_t val[2];
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t bit = (uint64_t)(2 * i + h) * (uint64_t)bits;
+          uint64_t w;
+          memcpy(&w, pr + (bit >> 3), 8);   // little-endian host
+          val[h] = (w >> (bit & 7)) & mask;
+        }
+        const double aa = (double)val[0] / scale, ab = (double)val[1] / scale;
+        const double bb = 1.0 - (aa + ab);           // the implied last probability of the format
+        mrow[c] = (ploidy[i] & 0x80) ? 1 : 0;       // set_value(MissingValue), genotypebgen.cpp:229-236
+        drow[c] = ab + 2. * bb;
+      }
+    }
+    if (++rows == blockRows) { sink(ctx, dosage.data(), missing.data(), (long long)rows); rows = 0; }
+  }
+  if (rows) sink(ctx, dosage.data(), missing.data(), (long long)rows);
+}
+
+// genotypebgen.cpp:739-779: SNPs whose standard deviation is 0 are listed in <out>.snps.novariance and dropped.  The
+// device never let their rows into S or N (dgrm_push_dosage_host), so only the records go here.
+void Genotype::removeSNPsWithZeroVariance() {
+  std::vector<std::string> removeSNPs;
+  std::vector<SNP> keptSNPs;
+  std::vector<std::string> keptIds;
+  for (int k = 0; k < nSNPs; ++k) {
+    if (SNPs[(size_t)k].standardDev != 0.) { keptSNPs.push_back(SNPs[(size_t)k]); keptIds.push_back(SNPIds[(size_t)k]); }
+    else removeSNPs.push_back(SNPIds[(size_t)k]);
+  }
+  if (removeSNPs.empty()) return;
+  std::ofstream out((options.outFile + ".snps.novariance").c_str());
+  for (size_t i = 0; i < removeSNPs.size(); ++i) out << removeSNPs[i] << std::endl;
+  *misc.message << "Warning: There are " << removeSNPs.size() << " SNPs which have zero variance and will be removed. They are stored in file [ "
+                << (options.outFile + ".snps.novariance") << " ]." << std::endl;
+  SNPs.swap(keptSNPs);
+  SNPIds.swap(keptIds);
+  nSNPs = (int)SNPs.size();
+  SNPIdsIdx.clear();
+  for (int k = 0; k < nSNPs; ++k) SNPIdsIdx[SNPIds[(size_t)k]] = k;
+}
 
 // readBEDFile's role (genotype.cpp:548-724) for a Genotype that will feed several kernels: validate the header
 // and keep all rows of the file packed in HBM; nothing is decoded to fp64.
@@ -494,6 +744,20 @@ void Kernel::compute(const std::vector<Genotype*>& genotypes, bool normalizeGRM)
     eng_ = engs_[0];
     for (size_t g = 0; g < genotypes.size(); ++g) {
       Genotype* gt = genotypes[g];
+      if (gt->type == GenotypeAttributes::probabilities) {
+        // readBGENFile's probability loop (genotypebgen.cpp:639-689): every block of dosage rows goes to every engine,
+        // which standardises it (ProbabilitiesSetter::finalise) and contracts its own tiles
+        struct Ctx { std::vector<dgrm_engine*>* engs; } ctx = {&engs_};
+        gt->streamBGEN(
+            [](void* c, const double* dosage, const unsigned char* missing, long long rows) {
+              std::vector<dgrm_engine*>& es = *static_cast<Ctx*>(c)->engs;
+              const long long n = dgrm_num_individuals(es[0]);
+              for (size_t r = 0; r < es.size(); ++r)
+                engine_check(es[r], dgrm_push_dosage_host(es[r], dosage, n, missing, n, rows));
+            },
+            &ctx);
+        continue;
+      }
       *misc.message << "Reading genotype data from file [ " << gt->bedFile << " ] ..." << std::endl;
       if (G == 1) {
         std::vector<int64_t> keepIdx(gt->SNPsBEDIdxsToKeep.begin(), gt->SNPsBEDIdxsToKeep.end());
@@ -555,6 +819,21 @@ void Kernel::compute(const std::vector<Genotype*>& genotypes, bool normalizeGRM)
   }
   engine_check(eng_, rc);
   for (size_t g = 0; g < genotypes.size(); ++g) genotypes[g]->normalized = true;  // the standardised values exist (on the GPU) from here on
+  {
+    // BGEN sources: readBGENFile ends with removeSNPsWithZeroVariance (genotypebgen.cpp:717), before the Kernel
+    // constructor copies SNPIds into randomVarNames (kernel.cpp:85)
+    bool any = false;
+    for (size_t g = 0; g < genotypes.size(); ++g)
+      if (genotypes[g]->type == GenotypeAttributes::probabilities) { genotypes[g]->removeSNPsWithZeroVariance(); any = true; }
+    if (any) {
+      randomVarNames.clear();
+      totalSNPs = 0;
+      for (size_t g = 0; g < genotypes.size(); ++g) {
+        randomVarNames.insert(randomVarNames.end(), genotypes[g]->SNPIds.begin(), genotypes[g]->SNPIds.end());
+        totalSNPs += genotypes[g]->nSNPs;
+      }
+    }
+  }
   if (!options.flatGRMNormalization)
     *misc.message << "GRM will be normalized using the individuals shared non-missing SNPs." << std::endl;
   else
@@ -568,8 +847,10 @@ void Kernel::compute(const std::vector<Genotype*>& genotypes, bool normalizeGRM)
 // (--bfile-list, with --grm-join-method 0 = add per-file GRMs, 1 = join the genotypes first).
 Kernel* loadGRMUsingOptions() {
   if (options.genotypeListFile.empty()) {
-    if (options.genotypeFile.empty()) misc.error("Error: No genotype file(s) specified.", 0);
-    Genotype* genotype = new Genotype(options.genotypeFile);
+    if (options.genotypeFile.empty() && options.bgenGenotypeFile.empty()) misc.error("Error: No genotype file(s) specified.", 0);
+    // analysis.cpp:515-522: --bfile -> calls, --bgen -> probabilities
+    Genotype* genotype = options.bgenGenotypeFile.empty() ? new Genotype(options.genotypeFile)
+                                                          : new Genotype(options.bgenGenotypeFile, GenotypeAttributes::probabilities);
     Kernel* grm = new Kernel(genotype);
     delete genotype;
     return grm;

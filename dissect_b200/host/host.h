@@ -33,6 +33,7 @@ struct Options {
   bool makeGRM;
   std::string genotypeFile;            // --bfile
   std::string genotypeListFile;        // --bfile-list F: one genotype file prefix per line (options.cpp:414-417)
+  std::string bgenGenotypeFile;        // --bgen F: F.bgen (+ F.sample when the file holds no sample identifiers), options.cpp:418-423
   std::string outFile;                 // --out            (default "dissect", options.cpp:60)
   std::string fileSNPsToKeep;          // --extract
   std::string fileIndividualsToKeep;   // --keep
@@ -56,6 +57,7 @@ struct Options {
                                        // (ensureHost); --make-grm itself needs files only, so a 50k or 100k GRM never
                                        // has to fit the INT_MAX local-matrix limit of a 1 x 1 grid (matrix.cpp:1773-1779)
   int GRMJoinMethod;                   // --grm-join-method 0 | 1 (options.cpp:76, 497-500; auxiliar.cpp:615-690)
+  bool allowBGENLayout1;               // --bgen-l1 (options.cpp:1117-1121)
   Options();
   void parseOptions(int argc, char** argv);
 };
@@ -113,6 +115,8 @@ struct Individual {  // genotype.h:85-95
   int phenotype;
 };
 
+struct GenotypeAttributes { enum Type { calls, probabilities }; };  // genotype.h: how the genotypes of a file are coded
+
 class Genotype {
  public:
   int nSNPs, nIndividuals;
@@ -127,6 +131,21 @@ class Genotype {
   std::vector<int> SNPsBEDIdxsToKeep;            // empty = all (genotype.cpp:452-456)
   std::vector<int> individualBEDIdxsMaskToKeep;  // one flag per .fam line (genotype.cpp:750)
   explicit Genotype(const std::string& fname);   // genotype.cpp:110 -> load :276 (metadata; rows stream later)
+  // genotype.cpp:110-130 with GenotypeAttributes::probabilities -> readBGENFile (genotypebgen.cpp:561-721): header,
+  // sample identifiers (or F.sample), --keep / --extract, and the identifying data of every kept variant; the
+  // probabilities are read when a Kernel is computed (Genotype::streamBGEN).
+  Genotype(const std::string& fname, GenotypeAttributes::Type type);
+  GenotypeAttributes::Type type;
+  std::string bgenFile;
+  int bgenLayout, bgenCompression;
+  long long bgenFirstVariant;                    // file position of the first variant data block (offset + 4)
+  std::vector<unsigned char> bgenKeepVariant;    // one flag per variant of the file (--extract)
+  // Calls sink(dosage, missing, rows) for blocks of kept variants: dosage / missing are [rows][nIndividuals] arrays of
+  // the kept samples, dosage = P(AB) + 2 P(BB), missing != 0 where the sample has no probabilities
+  // (ProbabilitiesSetter::set_value, genotypebgen.cpp:183-236).
+  typedef void (*BGENSink)(void* ctx, const double* dosage, const unsigned char* missing, long long rows);
+  void streamBGEN(BGENSink sink, void* ctx) const;
+  void removeSNPsWithZeroVariance();             // genotypebgen.cpp:739-779 (on the SNP records; the device drops the rows)
   Genotype();                                    // genotype.cpp:82-91, filled by genotypeOfSNPsGroup
   ~Genotype();
   // SNP groups (genotype.cpp:1293-1470) and the genotype of one group (genotype.cpp:1596-1621)

@@ -12,7 +12,8 @@ int main(int argc, char** argv) {
     options.parseOptions(argc, argv);
     communicator->nDefaultBlockRows = communicator->nDefaultBlockCols = options.defaultBlockSize;
     if (!options.makeGRM) misc.error("Error: only --make-grm is implemented by this adapter.", 0);
-    if (options.genotypeFile.empty() && options.genotypeListFile.empty()) misc.error("Error: No genotype file(s) specified.", 0);
+    if (options.genotypeFile.empty() && options.genotypeListFile.empty() && options.bgenGenotypeFile.empty())
+      misc.error("Error: No genotype file(s) specified.", 0);
     if (!options.regionalAnalysis) {
       Kernel* grm = loadGRMUsingOptions();   // analysis.cpp:45-47
       const bool sanitized = grm->sanitizeKernel();

@@ -6,6 +6,10 @@
 //   selftest add <a> <b> <out>            out = a + b
 //   selftest sub <all> <part> <out>       out = all - part
 //   selftest layout n bsR bsC R C r c     Matrix::initParameters / local2global for process (r, c) of an R x C grid
+//   selftest bgen <options...>            parse the options (--bgen F [--bgen-l1] [--keep] [--extract]), read the BGEN
+//                                         container on the host and print `IND fam ind`, `SNP chr rsid pos a1 a2` and,
+//                                         per kept variant, `ROW` followed by `dosage(hex float):missing` per kept
+//                                         sample -- the rows Kernel::compute hands to dgrm_push_dosage_host
 //   selftest groups <options...>          parse the options, load the .bim/.fam metadata, group the SNPs
 //                                         (Genotype::groupSNPs, genotype.cpp:1293-1470) and print `group: snps...`
 #include <cstdio>
@@ -27,6 +31,26 @@ int main(int argc, char** argv) {
       Kernel a(argv[2]), b(argv[3]), r;
       r.addKernels(1., &a, !strcmp(argv[1], "add") ? 1. : -1., &b);
       r.writeGRM(argv[4]);
+      return 0;
+    }
+    if (argc >= 2 && !strcmp(argv[1], "bgen")) {
+      options.parseOptions(argc - 1, argv + 1);
+      Genotype g(options.bgenGenotypeFile, GenotypeAttributes::probabilities);
+      for (int i = 0; i < g.nIndividuals; ++i) printf("IND %s %s\n", g.individuals[i].familyID.c_str(), g.individuals[i].individualID.c_str());
+      for (int k = 0; k < g.nSNPs; ++k)
+        printf("SNP %s %s %d %s %s\n", g.SNPs[k].chr.c_str(), g.SNPs[k].name.c_str(), g.SNPs[k].position, g.SNPs[k].allele1.c_str(),
+               g.SNPs[k].allele2.c_str());
+      int n = g.nIndividuals;
+      g.streamBGEN(
+          [](void* ctx, const double* dosage, const unsigned char* missing, long long rows) {
+            const int nn = *static_cast<int*>(ctx);
+            for (long long r = 0; r < rows; ++r) {
+              printf("ROW");
+              for (int i = 0; i < nn; ++i) printf(" %a:%d", dosage[r * nn + i], (int)missing[r * nn + i]);
+              printf("\n");
+            }
+          },
+          &n);
       return 0;
     }
     if (argc >= 2 && !strcmp(argv[1], "groups")) {
@@ -55,7 +79,7 @@ int main(int argc, char** argv) {
       for (int l = 0; l < m.nCols; ++l) printf("C %d %d\n", l, m.local2globalCol(l));
       return 0;
     }
-    fprintf(stderr, "usage: selftest roundtrip|add|sub|groups|layout ...\n");
+    fprintf(stderr, "usage: selftest roundtrip|add|sub|groups|bgen|layout ...\n");
     return 2;
   } catch (const DissectError&) {
     return 1;

@@ -135,6 +135,22 @@ int dgrm_push_bed_host(dgrm_engine *e, const uint8_t *rows, int64_t pitch, int64
 int dgrm_push_bed_device(dgrm_engine *e, const uint8_t *d_rows, int64_t pitch, int64_t nrows,
                          const uint8_t *row_keep, void *producer_stream);
 
+/* Feed real-valued genotype rows (expected allele counts, "dosages"): the rows the reference's BGEN reader forms per
+ * variant, d_i = P_i(AB) + 2 P_i(BB), with missing[r][i] != 0 where sample i has no probabilities
+ * (ProbabilitiesSetter::set_value, genotypebgen.cpp:183-236).  Row r starts at dosage + r*pitch (elements) and holds
+ * the KEPT individuals only (dgrm_num_individuals of them; the reader already skips the others,
+ * genotypebgen.cpp:139-150); missing may be NULL (nothing missing), its rows start at missing + r*missing_pitch.
+ * Replaces ProbabilitiesSetter::finalise (mean over the present samples, std with ALL samples in the divisor,
+ * z = (d - mean)/std, 0 where missing; genotypebgen.cpp:239-282), parseBGENSNP's SNP record (p2 = mean/2,
+ * p1 = 1 - mean/2, standardDev = std, nNonMissing = -1, zero frequencies; genotypebgen.cpp:723-736; read them with
+ * dgrm_snp_stats) and both pdsyrk_ calls for these rows.  Rows whose std is 0 contribute nothing to S or N, which is
+ * what removeSNPsWithZeroVariance (genotypebgen.cpp:739-779) achieves by dropping them; the adapter lists them
+ * (std_dev == 0) in <out>.snps.novariance.  The rows are copied before the call returns.  Packed and real-valued
+ * rows may alternate within one GRM (--bfile-list style joins); each switch ends the open chunk.
+ * Parsing the BGEN container itself (the un-vendored `genfile` library in the reference) stays with the caller. */
+int dgrm_push_dosage_host(dgrm_engine *e, const double *dosage, int64_t pitch, const uint8_t *missing,
+                          int64_t missing_pitch, int64_t nrows);
+
 /* Make `consumer_stream` (a cudaStream_t; NULL = legacy default stream) wait until the engine has read every
  * buffer handed to dgrm_push_bed_device / dgrm_push_bed_host so far, so that the caller may overwrite those
  * buffers (e.g. with the next NCCL all-gather) without a host synchronisation. */
