@@ -16,7 +16,7 @@ TRANSPORT = {"fp64": 0, "fp32": 1, "narrow": 2}
 # every symbol include/dgrm.h declares
 SYMBOLS = (
     "dgrm_default_config", "dgrm_device_count", "dgrm_validate_bed_header", "dgrm_create", "dgrm_destroy", "dgrm_last_error", "dgrm_abi_version",
-    "dgrm_set_individuals", "dgrm_begin", "dgrm_push_bed_host", "dgrm_push_dosage_host", "dgrm_push_bed_device", "dgrm_release_inputs",
+    "dgrm_set_individuals", "dgrm_begin", "dgrm_push_bed_host", "dgrm_push_dosage_host", "dgrm_push_bgen_blocks_host", "dgrm_push_bed_device", "dgrm_release_inputs",
     "dgrm_load_bed_file", "dgrm_finish", "dgrm_sync", "dgrm_num_snps", "dgrm_num_individuals",
     "dgrm_snp_stats", "dgrm_bad_snps", "dgrm_fetch_block_cyclic", "dgrm_fetch_block_cyclic_cols", "dgrm_bind_output", "dgrm_unbind_outputs", "dgrm_bind_tiles", "dgrm_low_overlap_pairs",
     "dgrm_set_output_subset", "dgrm_write_grm_dat", "dgrm_write_grm_dat_part", "dgrm_num_tiles", "dgrm_tile_coords", "dgrm_fetch_tiles", "dgrm_fetch_tiles_range",
@@ -65,6 +65,7 @@ def load():
     lib.dgrm_begin.argtypes = [vp, i64]
     lib.dgrm_push_bed_host.argtypes = [vp, vp, i64, i64, vp]
     lib.dgrm_push_dosage_host.argtypes = [vp, vp, i64, vp, i64, i64]
+    lib.dgrm_push_bgen_blocks_host.argtypes = [vp, vp, vp, i64, C.c_int, i64, vp]
     lib.dgrm_push_bed_device.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.dgrm_release_inputs.argtypes = [vp, vp]
     lib.dgrm_load_bed_file.argtypes = [vp, C.c_char_p, i64, vp, i64]

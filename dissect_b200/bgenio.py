@@ -74,8 +74,9 @@ def _unpack_bits(buf, count, bits):
     return (b << np.arange(bits, dtype=np.uint64)).sum(axis=1, dtype=np.uint64)
 
 
-def _variant_rows(f, hdr):
-    """Yields (chromosome, position, rsid, alleles, dosage[n], missing[n]) per variant, file order."""
+def _variant_blocks(f, hdr):
+    """Yields (chromosome, position, rsid, alleles, block) per variant in file order; block = the inflated
+    probability data (layout 2: from the N field on; layout 1: the 6N bytes), a bytes object."""
     n = hdr.n_samples
     for _ in range(hdr.n_variants):
         if hdr.layout == 1:
@@ -99,9 +100,6 @@ def _variant_rows(f, hdr):
                 data = zlib.decompress(f.read(c))
             else:
                 data = f.read(6 * n)
-            v = np.frombuffer(data, dtype="<u2", count=3 * n).reshape(n, 3).astype(np.float64) / 32768.0
-            missing = (v[:, 0] + v[:, 1] + v[:, 2]) == 0.0
-            dosage = v[:, 1] + 2.0 * v[:, 2]
         else:
             (c,) = struct.unpack("<I", f.read(4))
             if hdr.compression:
@@ -111,6 +109,18 @@ def _variant_rows(f, hdr):
                     raise BgenError("Error: A BGEN genotype block does not decompress to its stated length.")
             else:
                 data = f.read(c)
+        yield chrom, pos, rsid, alleles, data
+
+
+def _variant_rows(f, hdr):
+    """Yields (chromosome, position, rsid, alleles, dosage[n], missing[n]) per variant, file order."""
+    n = hdr.n_samples
+    for chrom, pos, rsid, alleles, data in _variant_blocks(f, hdr):
+        if hdr.layout == 1:
+            v = np.frombuffer(data, dtype="<u2", count=3 * n).reshape(n, 3).astype(np.float64) / 32768.0
+            missing = (v[:, 0] + v[:, 1] + v[:, 2]) == 0.0
+            dosage = v[:, 1] + 2.0 * v[:, 2]
+        else:
             n_here, k2, pmin, pmax = struct.unpack_from("<IHBB", data, 0)
             if n_here != n or k2 != 2:
                 raise BgenError("Error: Unexpected sample or allele count in a BGEN genotype block.")
@@ -161,9 +171,36 @@ def iter_dosage_blocks(path, keep_mask=None, keep_snps=None, block=1024):
             yield meta, np.vstack(dos), np.vstack(mis).astype(np.uint8)
 
 
-def push_bgen(engine, path, keep_mask=None, keep_snps=None, block=1024):
-    """Feed every kept variant of a BGEN file to an engine that has been begun; returns the variants' metadata."""
+def iter_raw_blocks(path, keep_snps=None, block=1024):
+    """Blocks of variants as (meta, data uint8[...], offsets int64[rows + 1], header): the inflated probability blocks
+    back to back, for GrmEngine.push_bgen_blocks_host (the device unpacks them)."""
+    with open(path, "rb") as f:
+        hdr = _read_header(f)
+        meta, parts = [], []
+        for chrom, pos, rsid, alleles, data in _variant_blocks(f, hdr):
+            if keep_snps is not None and rsid not in keep_snps:
+                continue
+            meta.append((chrom, pos, rsid, alleles[0], alleles[1]))
+            parts.append(data)
+            if len(meta) == block:
+                off = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int64)
+                yield meta, np.frombuffer(b"".join(parts), dtype=np.uint8), off, hdr
+                meta, parts = [], []
+        if meta:
+            off = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int64)
+            yield meta, np.frombuffer(b"".join(parts), dtype=np.uint8), off, hdr
+
+
+def push_bgen(engine, path, keep_mask=None, keep_snps=None, block=1024, device_unpack=True):
+    """Feed every kept variant of a BGEN file to an engine that has been begun; returns the variants' metadata.
+    device_unpack: hand the inflated probability blocks to the device (dgrm_push_bgen_blocks_host); otherwise the rows
+    are unpacked here and pushed as dosages (dgrm_push_dosage_host).  Both give bit-identical results."""
     out = []
+    if device_unpack:
+        for meta, data, offsets, hdr in iter_raw_blocks(path, keep_snps, block):
+            engine.push_bgen_blocks_host(data, offsets, hdr.layout, hdr.n_samples, keep_mask)
+            out.extend(meta)
+        return out
     for meta, dosage, missing in iter_dosage_blocks(path, keep_mask, keep_snps, block):
         engine.push_dosage_host(dosage, missing if missing.any() else None)
         out.extend(meta)

@@ -207,6 +207,19 @@ struct dgrm_engine {
   double *d_dos_mean = nullptr, *d_dos_sd = nullptr;
   cudaEvent_t dos_copied[2] = {nullptr, nullptr}, dos_ready = nullptr, dos_read = nullptr;
   int dosage_stage_mb = 2048;             // DGRM_DOSAGE_STAGE_MB: size of the device staging buffer
+  // BGEN probability blocks (dgrm_push_bgen_blocks_host): pinned raw pieces -> device raw buffer -> bgen_unpack_kernel -> d_dos
+  uint8_t* h_raw[2] = {nullptr, nullptr};
+  int64_t* h_boff[2] = {nullptr, nullptr};
+  uint8_t* d_raw = nullptr;
+  int64_t* d_boff = nullptr;
+  int64_t raw_cap = 0, raw_fill = 0;      // bytes per raw buffer, bytes staged in the current pinned one
+  int raw_rows_cap = 0, raw_rows = 0, raw_i = 0;
+  int raw_layout = 0;
+  int64_t raw_samples = 0;                // samples per block of the file being pushed
+  cudaEvent_t raw_copied[2] = {nullptr, nullptr}, raw_read = nullptr;
+  std::vector<int32_t> bgen_keep;         // the sample mask the device column list was built from
+  int32_t* d_bgen_cols = nullptr;
+  bool bgen_all = true;                   // every sample of the file is kept (no column list)
   bool fill_dosage = false;               // the `fill` rows of the open chunk are already expanded (dosage rows)
 
   bool have_ind = false, begun = false, finished = false;
@@ -293,6 +306,18 @@ void release_dosage_staging(dgrm_engine* e) {
   free_dev(e->d_dos_mean); e->d_dos_mean = nullptr;
   free_dev(e->d_dos_sd); e->d_dos_sd = nullptr;
   e->h_cap = e->h_fill = e->dev_cap = e->dev_fill = 0;
+  for (int i = 0; i < 2; ++i) {
+    if (e->h_raw[i]) cudaFreeHost(e->h_raw[i]);
+    if (e->h_boff[i]) cudaFreeHost(e->h_boff[i]);
+    e->h_raw[i] = nullptr; e->h_boff[i] = nullptr;
+  }
+  free_dev(e->d_raw); e->d_raw = nullptr;
+  free_dev(e->d_boff); e->d_boff = nullptr;
+  free_dev(e->d_bgen_cols); e->d_bgen_cols = nullptr;
+  e->bgen_keep.clear();
+  e->bgen_all = true;
+  e->raw_cap = e->raw_fill = 0;
+  e->raw_rows_cap = e->raw_rows = 0;
 }
 
 void release_geometry(dgrm_engine* e) {
@@ -1284,7 +1309,7 @@ int push_device_rows(dgrm_engine* e, const uint8_t* d_rows, int64_t pitch, int64
       if (row_keep[r]) idx.push_back((int32_t)r);
     kept = (int64_t)idx.size();
   }
-  if (e->h_fill > 0 || e->dev_fill > 0 || e->fill_dosage) {  // real-valued rows came before: they end their chunk
+  if (e->h_fill > 0 || e->raw_rows > 0 || e->dev_fill > 0 || e->fill_dosage) {  // real-valued rows came before: they end their chunk
     int rc = flush_dosage(e);
     if (rc) return rc;
     if (e->fill_dosage) rc = process_chunk(e);
@@ -1527,9 +1552,79 @@ int send_dosage(dgrm_engine* e) {
   return DGRM_OK;
 }
 
+// Raw staging for BGEN probability blocks: two pinned pieces and one device piece of raw_cap bytes (at least one block).
+int ensure_bgen_staging(dgrm_engine* e, int64_t block_bytes) {
+  const int64_t want = std::max<int64_t>(64ll << 20, block_bytes);
+  if (e->raw_cap >= want) return DGRM_OK;
+  CK(cudaStreamSynchronize(e->copy_stream));
+  CK(cudaStreamSynchronize(e->prep));
+  for (int i = 0; i < 2; ++i) {
+    if (e->h_raw[i]) cudaFreeHost(e->h_raw[i]);
+    if (e->h_boff[i]) cudaFreeHost(e->h_boff[i]);
+    e->h_raw[i] = nullptr; e->h_boff[i] = nullptr;
+  }
+  free_dev(e->d_raw); e->d_raw = nullptr;
+  free_dev(e->d_boff); e->d_boff = nullptr;
+  e->raw_cap = 0;
+  const int rows_cap = 16384;
+  for (int i = 0; i < 2; ++i) {
+    if (cudaHostAlloc(&e->h_raw[i], (size_t)want, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc(&e->h_boff[i], (size_t)(rows_cap + 1) * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess)
+      return fail(e, DGRM_E_NOMEM, "dgrm_push_bgen_blocks_host: no pinned memory for %lld bytes of blocks", (long long)want);
+    if (!e->raw_copied[i]) CK(cudaEventCreateWithFlags(&e->raw_copied[i], cudaEventDisableTiming));
+  }
+  if (!e->raw_read) CK(cudaEventCreateWithFlags(&e->raw_read, cudaEventDisableTiming));
+  CK(cudaMalloc(&e->d_raw, (size_t)want));
+  CK(cudaMalloc(&e->d_boff, (size_t)(rows_cap + 1) * sizeof(int64_t)));
+  e->raw_cap = want;
+  e->raw_rows_cap = rows_cap;
+  return DGRM_OK;
+}
+
+// The raw_rows blocks of the current pinned piece go to the device and are unpacked into the device staging buffer,
+// which is processed every time it is full.
+int send_bgen(dgrm_engine* e) {
+  const int rows = e->raw_rows;
+  if (rows == 0) return DGRM_OK;
+  const int s = e->raw_i;
+  CK(cudaStreamWaitEvent(e->copy_stream, e->raw_read, 0));   // the unpack kernels of the previous piece have read d_raw
+  CK(cudaMemcpyAsync(e->d_raw, e->h_raw[s], (size_t)e->raw_fill, cudaMemcpyHostToDevice, e->copy_stream));
+  CK(cudaMemcpyAsync(e->d_boff, e->h_boff[s], (size_t)(rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, e->copy_stream));
+  CK(cudaEventRecord(e->raw_copied[s], e->copy_stream));
+  CK(cudaStreamWaitEvent(e->prep, e->raw_copied[s], 0));
+  e->raw_i ^= 1;
+  e->raw_rows = 0;
+  e->raw_fill = 0;
+  const int64_t n = e->n;
+  int off = 0;
+  while (off < rows) {
+    const int take = std::min(rows - off, e->dev_cap - e->dev_fill);
+    {
+      Prof pr(e, DGRM_K_GATHER, e->prep);
+      BgenUnpackArgs a;
+      a.raw = e->d_raw; a.offsets = e->d_boff; a.row0 = off; a.layout = e->raw_layout; a.n_samples = (int)e->raw_samples;
+      a.cols = e->bgen_all ? nullptr : e->d_bgen_cols; a.n = (int)n;
+      a.dos = e->d_dos + (int64_t)e->dev_fill * n; a.errors = e->d_bad_count + 4;
+      bgen_unpack_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)take), 256, 0, e->prep>>>(a);
+      CK(cudaGetLastError());
+      if (e->dev_any_missing) CK(cudaMemsetAsync(e->d_dmiss + (int64_t)e->dev_fill * n, 0, (size_t)take * n, e->prep));
+    }
+    e->dev_fill += take;
+    off += take;
+    if (e->dev_fill == e->dev_cap) {
+      const int rc = process_dosage_device(e);
+      if (rc) return rc;
+    }
+  }
+  CK(cudaEventRecord(e->raw_read, e->prep));
+  return DGRM_OK;
+}
+
 // everything staged so far reaches the operands
 int flush_dosage(dgrm_engine* e) {
   int rc = send_dosage(e);
+  if (rc) return rc;
+  rc = send_bgen(e);
   if (rc) return rc;
   return process_dosage_device(e);
 }
@@ -1809,6 +1904,9 @@ void dgrm_destroy(dgrm_engine* e) {
     if (e->dos_copied[i]) cudaEventDestroy(e->dos_copied[i]);
   if (e->dos_read) cudaEventDestroy(e->dos_read);
   if (e->dos_ready) cudaEventDestroy(e->dos_ready);
+  for (int i = 0; i < 2; ++i)
+    if (e->raw_copied[i]) cudaEventDestroy(e->raw_copied[i]);
+  if (e->raw_read) cudaEventDestroy(e->raw_read);
   if (e->bed_ev) cudaEventDestroy(e->bed_ev);
   free_dev(e->d_bed);
   free_dev(e->d_grm_rows);
@@ -1898,7 +1996,7 @@ static int setup_geometry(dgrm_engine* e, int64_t n_fam, const int32_t* keep_mas
     CK(cudaHostAlloc(&e->h_rowidx[i], (size_t)kc * sizeof(int32_t), cudaHostAllocDefault));
   }
   if (!e->d_bad_count) {
-    CK(cudaMalloc(&e->d_bad_count, 4 * sizeof(int32_t)));
+    CK(cudaMalloc(&e->d_bad_count, 8 * sizeof(int32_t)));
     CK(cudaMalloc(&e->d_bad_list, (size_t)dgrm_engine::kBadCap * sizeof(int64_t)));
   }
   e->have_ind = true;
@@ -1984,6 +2082,8 @@ static int begin_common(dgrm_engine* e, int64_t m_capacity) {
   e->m = 0;
   e->fill = 0;
   e->h_fill = e->dev_fill = 0;
+  e->raw_rows = 0;
+  e->raw_fill = 0;
   e->h_any_missing = e->dev_any_missing = false;
   e->fill_dosage = false;
   e->chunks_done = 0;
@@ -2009,7 +2109,7 @@ static int begin_common(dgrm_engine* e, int64_t m_capacity) {
   CK(cudaMemsetAsync(e->d_miss, 0, (size_t)e->n_pad * sizeof(int32_t), e->prep));
   e->miss_valid = !e->ld_mode;
   e->n_u16 = false;
-  CK(cudaMemsetAsync(e->d_bad_count, 0, 4 * sizeof(int32_t), e->prep));
+  CK(cudaMemsetAsync(e->d_bad_count, 0, 8 * sizeof(int32_t), e->prep));
   CK(cudaMemsetAsync(e->d_diag, 0, (size_t)e->n_pad * sizeof(double), e->prep));
   e->begun = true;
   return DGRM_OK;
@@ -2079,7 +2179,7 @@ int dgrm_push_dosage_host(dgrm_engine* e, const double* dosage, int64_t pitch, c
   if (e->ld_mode) return fail(e, DGRM_E_INVALID, "dgrm_push_dosage_host: not available in LD mode");
   if (!dosage || nrows < 0 || pitch < e->n || (missing && missing_pitch < e->n))
     return fail(e, DGRM_E_INVALID, "dgrm_push_dosage_host: bad rows/pitch (rows hold the %lld kept individuals)", (long long)e->n);
-  const int64_t pending = e->m + e->fill + e->dev_fill + e->h_fill;
+  const int64_t pending = e->m + e->fill + e->dev_fill + e->h_fill + e->raw_rows;
   if (pending + nrows > e->m_cap)
     return fail(e, DGRM_E_INVALID, "more SNPs pushed (%lld) than dgrm_begin's capacity (%lld)", (long long)(pending + nrows),
                 (long long)e->m_cap);
@@ -2091,6 +2191,8 @@ int dgrm_push_dosage_host(dgrm_engine* e, const double* dosage, int64_t pitch, c
     rc = process_chunk(e);
     if (rc) return rc;
   }
+  rc = send_bgen(e);   // probability blocks pushed before these rows keep their place in the SNP order
+  if (rc) return rc;
   const int64_t n = e->n;
   for (int64_t r = 0; r < nrows;) {
     const int s = e->dos_i;
@@ -2113,6 +2215,112 @@ int dgrm_push_dosage_host(dgrm_engine* e, const double* dosage, int64_t pitch, c
       rc = send_dosage(e);
       if (rc) return rc;
     }
+  }
+  return DGRM_OK;
+}
+
+int dgrm_push_bgen_blocks_host(dgrm_engine* e, const uint8_t* data, const int64_t* offsets, int64_t nrows, int layout,
+                               int64_t n_samples, const int32_t* sample_keep) {
+  int rc = check_ready(e, false);
+  if (rc) return rc;
+  if (e->finished) return fail(e, DGRM_E_INVALID, "dgrm_push_bgen_blocks_host after dgrm_finish");
+  if (e->ld_mode) return fail(e, DGRM_E_INVALID, "dgrm_push_bgen_blocks_host: not available in LD mode");
+  if (!data || !offsets || nrows < 0 || (layout != 1 && layout != 2) || n_samples <= 0 || n_samples > INT32_MAX)
+    return fail(e, DGRM_E_INVALID, "dgrm_push_bgen_blocks_host: bad arguments");
+  const int64_t pending = e->m + e->fill + e->dev_fill + e->h_fill + e->raw_rows;
+  if (pending + nrows > e->m_cap)
+    return fail(e, DGRM_E_INVALID, "more SNPs pushed (%lld) than dgrm_begin's capacity (%lld)", (long long)(pending + nrows),
+                (long long)e->m_cap);
+  // the format conditions the reference's setter checks per variant (genotypebgen.cpp:99-172), on the block headers
+  int64_t max_block = 0;
+  for (int64_t r = 0; r < nrows; ++r) {
+    const int64_t len = offsets[r + 1] - offsets[r];
+    const uint8_t* b = data + offsets[r];
+    max_block = std::max(max_block, len);
+    if (layout == 1) {
+      if (len != 6 * n_samples) return fail(e, DGRM_E_INVALID, "Error: An internal error has happened. Unexpected small number of samples.");
+      continue;
+    }
+    if (len < 10 + n_samples) return fail(e, DGRM_E_INVALID, "Error: An internal error has happened. Unexpected small number of samples.");
+    const uint32_t nb = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
+    const int kb = b[4] | (b[5] << 8), pmin = b[6], pmax = b[7], phased = b[8 + n_samples], bits = b[9 + n_samples];
+    if ((int64_t)nb != n_samples) return fail(e, DGRM_E_INVALID, "Error: An internal error has happened. Unexpected small number of samples.");
+    if (kb != 2)
+      return fail(e, DGRM_E_INVALID, "Error: The bgen file contains non-biallelic genotypes. DISSECT currently can only work with biallelic genotypes.");
+    if (pmin != 2 || pmax != 2)
+      return fail(e, DGRM_E_INVALID, "Error: The bgen file contains non-diploid genotypes. DISSECT currently can only work with diploid genotypes.");
+    if (phased)
+      return fail(e, DGRM_E_INVALID, "Error: Currently can only load unphased genotypes. If you are interested on loading phased genotypes, please, contact us.");
+    if (bits < 1 || bits > 32 || len < 10 + n_samples + (2 * n_samples * bits + 7) / 8)
+      return fail(e, DGRM_E_INVALID, "Error: Unexpected number of probabilities when reading bgen file.");
+  }
+  CK(cudaSetDevice(e->cfg.device));
+  rc = ensure_dosage_staging(e);
+  if (rc) return rc;
+  e->grm_from_store = false;
+  if (e->fill > 0 && !e->fill_dosage) {  // packed rows came before: they end their chunk
+    rc = process_chunk(e);
+    if (rc) return rc;
+  }
+  rc = send_dosage(e);   // dosage rows pushed before these blocks keep their place in the SNP order
+  if (rc) return rc;
+  // the kept samples: a device list of file indices (individualBGENIdxsMaskToKeep, genotypebgen.cpp:367-379)
+  {
+    std::vector<int32_t> km;
+    if (sample_keep) km.assign(sample_keep, sample_keep + n_samples);
+    if (e->raw_rows > 0 && (km != e->bgen_keep || n_samples != e->raw_samples || layout != e->raw_layout)) {
+      rc = send_bgen(e);   // blocks of another file / selection are still staged
+      if (rc) return rc;
+    }
+    if (km != e->bgen_keep || n_samples != e->raw_samples || !e->d_bgen_cols) {
+      std::vector<int32_t> cols;
+      for (int64_t i = 0; i < n_samples; ++i)
+        if (!sample_keep || sample_keep[i]) cols.push_back((int32_t)i);
+      if ((int64_t)cols.size() != e->n)
+        return fail(e, DGRM_E_INVALID, "dgrm_push_bgen_blocks_host: %lld samples are kept, the engine was set up for %lld individuals",
+                    (long long)cols.size(), (long long)e->n);
+      CK(cudaStreamSynchronize(e->prep));
+      free_dev(e->d_bgen_cols);
+      e->d_bgen_cols = nullptr;
+      CK(cudaMalloc(&e->d_bgen_cols, cols.size() * sizeof(int32_t)));
+      CK(cudaMemcpy(e->d_bgen_cols, cols.data(), cols.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      e->bgen_all = (int64_t)cols.size() == n_samples;
+      e->bgen_keep.swap(km);
+    }
+    e->raw_samples = n_samples;
+    e->raw_layout = layout;
+  }
+  if (max_block > e->raw_cap) {
+    rc = send_bgen(e);
+    if (rc) return rc;
+  }
+  rc = ensure_bgen_staging(e, max_block);
+  if (rc) return rc;
+  for (int64_t r = 0; r < nrows;) {
+    const int64_t len0 = offsets[r + 1] - offsets[r];
+    if (e->raw_rows == e->raw_rows_cap || e->raw_fill + len0 > e->raw_cap) {
+      rc = send_bgen(e);
+      if (rc) return rc;
+    }
+    const int s = e->raw_i;
+    if (e->raw_rows == 0) {
+      CK(cudaEventSynchronize(e->raw_copied[s]));   // the copy that last read this pinned piece is done
+      e->h_boff[s][0] = 0;
+    }
+    // the run of blocks [r, r2) that fits into the open piece; the caller's blocks need not be adjacent in `data`
+    int64_t r2 = r, fill = e->raw_fill;
+    while (r2 < nrows && e->raw_rows + (r2 - r) < e->raw_rows_cap && fill + (offsets[r2 + 1] - offsets[r2]) <= e->raw_cap) {
+      fill += offsets[r2 + 1] - offsets[r2];
+      e->h_boff[s][e->raw_rows + (r2 - r) + 1] = fill;
+      ++r2;
+    }
+    const int64_t* pos = e->h_boff[s] + e->raw_rows;
+    uint8_t* dst = e->h_raw[s];
+#pragma omp parallel for schedule(static) if (fill - e->raw_fill >= (1 << 20))
+    for (int64_t k = r; k < r2; ++k) memcpy(dst + pos[k - r], data + offsets[k], (size_t)(offsets[k + 1] - offsets[k]));
+    e->raw_rows += (int)(r2 - r);
+    e->raw_fill = fill;
+    r = r2;
   }
   return DGRM_OK;
 }
@@ -2214,7 +2422,7 @@ int dgrm_finish(dgrm_engine* e) {
       if (rc) return rc;
     }
   }
-  int32_t bad[4];
+  int32_t bad[8];   // {sd == 0, no non-missing, listed, zero-variance dosage rows, BGEN samples that are not diploid, ...}
   CK(cudaMemcpyAsync(bad, e->d_bad_count, sizeof bad, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaGetLastError());
@@ -2225,6 +2433,9 @@ int dgrm_finish(dgrm_engine* e) {
                 bad[0]);
   if (bad[1] > 0)
     return fail(e, DGRM_E_NANSNP, "Error: %d SNPs have no non-missing genotype (allele frequency is 0/0).", bad[1]);
+  if (bad[4] > 0)   // genotypebgen.cpp:120-123
+    return fail(e, DGRM_E_INVALID,
+                "Error: The bgen file contains non-diploid genotypes. DISSECT currently can only work with diploid genotypes.");
   if (bad[3] > 0 && e->cfg.flat_norm)
     return fail(e, DGRM_E_BADSNP,
                 "Error: %d dosage SNPs have zero variance; under --grm-flat-norm they change the SNP count the GRM is "
@@ -2301,7 +2512,7 @@ int dgrm_bind_tiles(dgrm_engine* e, int which, double* tiles) {
   return DGRM_OK;
 }
 
-int64_t dgrm_num_snps(const dgrm_engine* e) { return e ? e->m + e->fill + e->dev_fill + e->h_fill : 0; }
+int64_t dgrm_num_snps(const dgrm_engine* e) { return e ? e->m + e->fill + e->dev_fill + e->h_fill + e->raw_rows : 0; }
 int64_t dgrm_num_individuals(const dgrm_engine* e) { return e ? e->n : 0; }
 
 int dgrm_snp_stats(dgrm_engine* e, int32_t* freq, int32_t* nn, double* p1, double* p2, double* sd) {

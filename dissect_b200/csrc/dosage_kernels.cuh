@@ -27,6 +27,78 @@ struct DosageStatsOut {
   int32_t* removed;  // number of zero-variance dosage SNPs of this GRM
 };
 
+// BGEN probability blocks, as they come out of the container after inflation, unpacked on the device into the same
+// dosage rows (NaN = missing) that dgrm_push_dosage_host stages: 3 bytes per genotype cross the bus instead of 9, and
+// the host does no per-sample work.  One thread per (kept sample, variant).
+//   layout 2 block: N u32 | K u16 | Pmin u8 | Pmax u8 | N ploidy bytes (bit 7 = missing) | phased u8 | B u8 |
+//                   2N probabilities of B bits, little-endian bit order: P(AA), P(AB) numerators over 2^B - 1
+//   layout 1 block: N x (P(AA), P(AB), P(BB)) u16 numerators over 32768; all three zero = missing
+// Arithmetic as the host readers do it (dissect_b200/bgenio.py, host.cpp streamBGEN), so the rows are bit-identical:
+//   aa = v0 / scale, ab = v1 / scale, bb = 1 - (aa + ab) (layout 2) or v2 / scale (layout 1), d = ab + 2 bb
+// which is what genfile hands to ProbabilitiesSetter::set_value and what that forms (genotypebgen.cpp:199-205).
+struct BgenUnpackArgs {
+  const uint8_t* raw;       // the piece's blocks, back to back
+  const int64_t* offsets;   // [rows of the piece + 1] byte offsets into raw
+  int row0;                 // first row of the piece handled by this launch (gridDim.y rows)
+  int layout;
+  int n_samples;            // samples in the file
+  const int32_t* cols;      // [n] file index of every kept sample, NULL = all samples
+  int n;                    // kept samples
+  double* dos;              // [gridDim.y][n]
+  int32_t* errors;          // samples whose ploidy is not 2 (genotypebgen.cpp:120-123)
+};
+
+__global__ void __launch_bounds__(256) bgen_unpack_kernel(const BgenUnpackArgs a) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= a.n) return;
+  const int r = blockIdx.y;
+  const int i = a.cols ? a.cols[c] : c;
+  const int64_t o0 = a.offsets[a.row0 + r], o1 = a.offsets[a.row0 + r + 1];
+  const uint8_t* base = a.raw + o0;
+  const double nan = __longlong_as_double(0x7FF8000000000000ll);
+  double d;
+  if (a.layout == 1) {
+    const uint8_t* p = base + (int64_t)i * 6;
+    const double aa = __ddiv_rn((double)(p[0] | (p[1] << 8)), 32768.), ab = __ddiv_rn((double)(p[2] | (p[3] << 8)), 32768.),
+                 bb = __ddiv_rn((double)(p[4] | (p[5] << 8)), 32768.);
+    const bool missing = __dadd_rn(__dadd_rn(aa, ab), bb) == 0.;            // genotypebgen.cpp:208-214
+    d = missing ? nan : __dadd_rn(ab, __dmul_rn(2., bb));
+  } else {
+    const int N = a.n_samples;
+    const uint32_t ploidy = base[8 + i];
+    const int bits = base[9 + N];
+    const uint8_t* prob = base + 10 + N;
+    const int64_t avail = o1 - o0 - 10 - N;
+    const uint64_t mask = bits == 32 ? 0xFFFFFFFFull : ((1ull << bits) - 1ull);
+    uint64_t v[2];
+    if (bits == 8) {          // the common depths: whole bytes
+      v[0] = prob[2 * (int64_t)i];
+      v[1] = prob[2 * (int64_t)i + 1];
+    } else if (bits == 16) {
+      const uint8_t* q = prob + 4 * (int64_t)i;
+      v[0] = q[0] | (q[1] << 8);
+      v[1] = q[2] | (q[3] << 8);
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t bit = ((int64_t)2 * i + h) * bits;
+        const int64_t byte = bit >> 3;
+        uint64_t w = 0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b)   // (bit & 7) + bits <= 39 bits
+          if (byte + b < avail) w |= (uint64_t)prob[byte + b] << (8 * b);
+        v[h] = (w >> (bit & 7)) & mask;
+      }
+    }
+    const double scale = (double)mask;
+    const double aa = __ddiv_rn((double)v[0], scale), ab = __ddiv_rn((double)v[1], scale);
+    const double bb = __dsub_rn(1., __dadd_rn(aa, ab));
+    if ((ploidy & 0x3Fu) != 2u) atomicAdd(a.errors, 1);
+    d = (ploidy & 0x80u) ? nan : __dadd_rn(ab, __dmul_rn(2., bb));          // genotypebgen.cpp:229-236
+  }
+  a.dos[(int64_t)r * a.n + c] = d;
+}
+
 // Missing genotypes travel inside the staged rows as NaN from here on: one pass folds the caller's byte mask into the
 // dosages, so that the statistics and the expansion read 8 bytes per genotype and nothing else.  (A NaN that the
 // caller put into a dosage row itself therefore also means "missing".)

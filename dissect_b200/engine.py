@@ -153,6 +153,16 @@ class GrmEngine:
         self._ck(self._lib.dgrm_push_dosage_host(self._h, d.ctypes.data, d.shape[1], mk.ctypes.data if mk is not None else None,
                                                  d.shape[1], d.shape[0]))
 
+    def push_bgen_blocks_host(self, data, offsets, layout, n_samples, sample_keep=None):
+        """data: uint8 array holding the inflated probability blocks of BGEN variants back to back; offsets: int64
+        [nrows + 1]; sample_keep: one flag per sample of the file (None = all).  The device unpacks the blocks."""
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        o = np.ascontiguousarray(offsets, dtype=np.int64)
+        sk = None if sample_keep is None else np.ascontiguousarray(np.asarray(sample_keep) != 0, dtype=np.int32)
+        assert sk is None or sk.shape == (n_samples,)
+        self._ck(self._lib.dgrm_push_bgen_blocks_host(self._h, d.ctypes.data, o.ctypes.data, o.shape[0] - 1, int(layout),
+                                                      int(n_samples), sk.ctypes.data if sk is not None else None))
+
     def push_bed_device(self, ptr, pitch, nrows, row_keep=None, stream=None):
         rk = None
         if row_keep is not None:

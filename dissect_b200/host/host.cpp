@@ -48,7 +48,7 @@ Options::Options()
       maximumProportionOfElimitaedIndividuals(0.9), defaultBlockSize(256), regionalAnalysis(false), regionBy(ungrouped),
       regionSize(-1), regionOverlapping(0), minSNPsInRegions(1), writeLOCO(false), device(0), operand(DGRM_OPERAND_FP16),
       countMethod(DGRM_COUNT_FP4), chunkSNPs(16384), ctaGroup(2), engines(1), lazyHostMatrices(false), GRMJoinMethod(0),
-      allowBGENLayout1(false) {}
+      allowBGENLayout1(false), bgenHostDecode(false) {}
 
 void Options::parseOptions(int argc, char** argv) {
   auto need = [&](int i) -> std::string {
@@ -63,6 +63,7 @@ void Options::parseOptions(int argc, char** argv) {
     else if (a == "--bfile-list") genotypeListFile = need(i++);                 // options.cpp:414-417
     else if (a == "--bgen") bgenGenotypeFile = need(i++);                       // options.cpp:418-423
     else if (a == "--bgen-l1") allowBGENLayout1 = true;                         // options.cpp:1117-1121
+    else if (a == "--gpu-bgen-host-decode") bgenHostDecode = true;
     else if (a == "--grm-join-method") {                                        // options.cpp:497-500
       GRMJoinMethod = atoi(need(i++).c_str());
       seenJoin = true;
@@ -282,6 +283,33 @@ long long genotype_block_bytes(BgenReader& r, int layout, int compression, uint3
   return r.u32();
 }
 
+// the probability data of one variant, inflated and appended to `out` (genfile::bgen::read_genotype_data_block +
+// uncompress_probability_data): layout 2 from the N field on, layout 1 the 6N bytes
+void read_probability_block(BgenReader& r, int layout, int compression, uint32_t nSamples, long long len,
+                            std::vector<unsigned char>& raw, std::vector<unsigned char>& out) {
+  size_t dataLen;
+  if (layout == 2 && compression) {
+    dataLen = r.u32();
+    raw.resize((size_t)len - 4);
+  } else if (layout == 1 && compression) {
+    dataLen = 6u * (size_t)nSamples;
+    raw.resize((size_t)len);
+  } else {
+    dataLen = (size_t)len;
+    raw.resize(0);
+  }
+  const size_t at = out.size();
+  out.resize(at + dataLen);
+  if (compression) {
+    r.bytes(raw.data(), raw.size());
+    uLongf got = (uLongf)dataLen;
+    if (uncompress(out.data() + at, &got, raw.data(), (uLong)raw.size()) != Z_OK || got != dataLen)
+      misc.error("Error: A genotype block of the BGEN file [ " + r.name + " ] could not be decompressed.", 0);
+  } else {
+    r.bytes(out.data() + at, dataLen);
+  }
+}
+
 }  // namespace
 
 Genotype::Genotype(const std::string& fname, GenotypeAttributes::Type t)
@@ -389,27 +417,10 @@ void Genotype::streamBGEN(BGENSink sink, void* ctx) const {
     read_variant_id(r, bgenLayout, nSamples);
     const long long len = genotype_block_bytes(r, bgenLayout, bgenCompression, nSamples);
     if (!bgenKeepVariant[v]) { r.skip(len); continue; }   // ignoreProbabilities
-    // probability data of this variant, decompressed
-    size_t dataLen;
-    if (bgenLayout == 2 && bgenCompression) {
-      dataLen = r.u32();
-      raw.resize((size_t)len - 4);
-    } else if (bgenLayout == 1 && bgenCompression) {
-      dataLen = 6u * (size_t)nSamples;
-      raw.resize((size_t)len);
-    } else {
-      dataLen = (size_t)len;
-      raw.resize(0);
-    }
-    data.assign(dataLen + 8, 0);   // 8 bytes of slack for the bit reader
-    if (bgenCompression) {
-      r.bytes(raw.data(), raw.size());
-      uLongf got = (uLongf)dataLen;
-      if (uncompress(data.data(), &got, raw.data(), (uLong)raw.size()) != Z_OK || got != dataLen)
-        misc.error("Error: A genotype block of the BGEN file [ " + bgenFile + " ] could not be decompressed.", 0);
-    } else {
-      r.bytes(data.data(), dataLen);
-    }
+    // probability data of this variant, decompressed (8 bytes of slack for the bit reader)
+    data.clear();
+    read_probability_block(r, bgenLayout, bgenCompression, nSamples, len, raw, data);
+    data.resize(data.size() + 8, 0);
     double* drow = &dosage[rows * nk];
     unsigned char* mrow = &missing[rows * nk];
     if (bgenLayout == 1) {
@@ -455,6 +466,29 @@ void Genotype::streamBGEN(BGENSink sink, void* ctx) const {
     if (++rows == blockRows) { sink(ctx, dosage.data(), missing.data(), (long long)rows); rows = 0; }
   }
   if (rows) sink(ctx, dosage.data(), missing.data(), (long long)rows);
+}
+
+// The same walk over the file, handing on the inflated probability blocks themselves (for the device to unpack,
+// dgrm_push_bgen_blocks_host): pieces of up to 32 MB, block k of a piece at data[offsets[k] .. offsets[k+1]).
+void Genotype::streamBGENBlocks(BGENBlockSink sink, void* ctx) const {
+  BgenReader r(bgenFile);
+  if (fseeko(r.f, bgenFirstVariant, SEEK_SET) != 0) misc.error("Error: Unexpected end of the BGEN file [ " + bgenFile + " ].", 0);
+  const uint32_t nSamples = (uint32_t)nBEDIndividuals;
+  std::vector<unsigned char> raw, data;
+  std::vector<long long> offsets(1, 0);
+  for (size_t v = 0; v < bgenKeepVariant.size(); ++v) {
+    read_variant_id(r, bgenLayout, nSamples);
+    const long long len = genotype_block_bytes(r, bgenLayout, bgenCompression, nSamples);
+    if (!bgenKeepVariant[v]) { r.skip(len); continue; }
+    read_probability_block(r, bgenLayout, bgenCompression, nSamples, len, raw, data);
+    offsets.push_back((long long)data.size());
+    if (data.size() >= (32u << 20) || offsets.size() > 4096) {
+      sink(ctx, data.data(), offsets.data(), (long long)offsets.size() - 1);
+      data.clear();
+      offsets.assign(1, 0);
+    }
+  }
+  if (offsets.size() > 1) sink(ctx, data.data(), offsets.data(), (long long)offsets.size() - 1);
 }
 
 // genotypebgen.cpp:739-779: SNPs whose standard deviation is 0 are listed in <out>.snps.novariance and dropped.  The
@@ -747,7 +781,21 @@ void Kernel::compute(const std::vector<Genotype*>& genotypes, bool normalizeGRM)
       if (gt->type == GenotypeAttributes::probabilities) {
         // readBGENFile's probability loop (genotypebgen.cpp:639-689): every block of dosage rows goes to every engine,
         // which standardises it (ProbabilitiesSetter::finalise) and contracts its own tiles
-        struct Ctx { std::vector<dgrm_engine*>* engs; } ctx = {&engs_};
+        struct Ctx { std::vector<dgrm_engine*>* engs; const Genotype* gt; } ctx = {&engs_, gt};
+        if (!options.bgenHostDecode) {
+          // the inflated blocks go to the device as they are; bgen_unpack_kernel forms the dosage rows there
+          gt->streamBGENBlocks(
+              [](void* c, const unsigned char* data, const long long* offsets, long long rows) {
+                Ctx* cx = static_cast<Ctx*>(c);
+                std::vector<dgrm_engine*>& es = *cx->engs;
+                std::vector<int64_t> off(offsets, offsets + rows + 1);
+                for (size_t r = 0; r < es.size(); ++r)
+                  engine_check(es[r], dgrm_push_bgen_blocks_host(es[r], data, off.data(), rows, cx->gt->bgenLayout,
+                                                                 cx->gt->nBEDIndividuals, cx->gt->individualBEDIdxsMaskToKeep.data()));
+              },
+              &ctx);
+          continue;
+        }
         gt->streamBGEN(
             [](void* c, const double* dosage, const unsigned char* missing, long long rows) {
               std::vector<dgrm_engine*>& es = *static_cast<Ctx*>(c)->engs;

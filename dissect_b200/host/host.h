@@ -58,6 +58,8 @@ struct Options {
                                        // has to fit the INT_MAX local-matrix limit of a 1 x 1 grid (matrix.cpp:1773-1779)
   int GRMJoinMethod;                   // --grm-join-method 0 | 1 (options.cpp:76, 497-500; auxiliar.cpp:615-690)
   bool allowBGENLayout1;               // --bgen-l1 (options.cpp:1117-1121)
+  bool bgenHostDecode;                 // --gpu-bgen-host-decode: unpack the probabilities on the host and push dosage rows
+                                       // (default: the inflated blocks go to the device, dgrm_push_bgen_blocks_host)
   Options();
   void parseOptions(int argc, char** argv);
 };
@@ -145,6 +147,8 @@ class Genotype {
   // (ProbabilitiesSetter::set_value, genotypebgen.cpp:183-236).
   typedef void (*BGENSink)(void* ctx, const double* dosage, const unsigned char* missing, long long rows);
   void streamBGEN(BGENSink sink, void* ctx) const;
+  typedef void (*BGENBlockSink)(void* ctx, const unsigned char* data, const long long* offsets, long long rows);
+  void streamBGENBlocks(BGENBlockSink sink, void* ctx) const;   // the inflated probability blocks, for the device to unpack
   void removeSNPsWithZeroVariance();             // genotypebgen.cpp:739-779 (on the SNP records; the device drops the rows)
   Genotype();                                    // genotype.cpp:82-91, filled by genotypeOfSNPsGroup
   ~Genotype();

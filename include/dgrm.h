@@ -151,6 +151,22 @@ int dgrm_push_bed_device(dgrm_engine *e, const uint8_t *d_rows, int64_t pitch, i
 int dgrm_push_dosage_host(dgrm_engine *e, const double *dosage, int64_t pitch, const uint8_t *missing,
                           int64_t missing_pitch, int64_t nrows);
 
+/* The same rows one step earlier: the probability data blocks of BGEN variants as they come out of the container
+ * (after zlib inflation), unpacked on the device -- 2B/8 + 1 bytes per genotype cross the bus instead of 9 and the host
+ * does no per-sample work.  Block r is data[offsets[r] .. offsets[r+1]):
+ *   layout 2: N u32 | K u16 | Pmin u8 | Pmax u8 | N ploidy/missingness bytes | phased u8 | B u8 | 2N B-bit probabilities
+ *   layout 1: N x 3 u16 probabilities (all zero = missing)
+ * i.e. what genfile::bgen::read_and_parse_genotype_data_block is handed (genotypebgen.cpp:499-518).  n_samples is the
+ * sample count of the file, sample_keep[n_samples] != 0 the samples to keep (individualBGENIdxsMaskToKeep,
+ * genotypebgen.cpp:367-379; NULL = all); as many must be kept as dgrm_num_individuals.  The conditions the reference's
+ * setter refuses (non-biallelic, non-diploid, phased; genotypebgen.cpp:99-172) fail here with the same messages (the
+ * per-sample ploidy check is made on the device and reported by dgrm_finish).  Dosages are formed exactly as
+ * ProbabilitiesSetter::set_value does from genfile's doubles: d = P(AB) + 2 P(BB), P = numerator / (2^B - 1)
+ * (layout 1: / 32768), P(BB) = 1 - (P(AA) + P(AB)) in layout 2; everything after that is dgrm_push_dosage_host.
+ * The blocks are copied before the call returns. */
+int dgrm_push_bgen_blocks_host(dgrm_engine *e, const uint8_t *data, const int64_t *offsets, int64_t nrows,
+                               int layout, int64_t n_samples, const int32_t *sample_keep);
+
 /* Make `consumer_stream` (a cudaStream_t; NULL = legacy default stream) wait until the engine has read every
  * buffer handed to dgrm_push_bed_device / dgrm_push_bed_host so far, so that the caller may overwrite those
  * buffers (e.g. with the next NCCL all-gather) without a host synchronisation. */

@@ -204,8 +204,8 @@ def test_dosage_refused_in_ld_mode_and_over_capacity():
     eng.close()
 
 
-@pytest.mark.parametrize("engines", [1, 3])
-def test_cli_bgen_make_grm(tmp_path, engines):
+@pytest.mark.parametrize("engines,host_decode", [(1, False), (3, False), (1, True)])
+def test_cli_bgen_make_grm(tmp_path, engines, host_decode):
     """`dgrm_make_grm --bgen F --make-grm` (the reference's `dissect --bgen F --make-grm`, analysis.cpp:515-522): the
     C++ host mirror parses the container, the engines standardise and contract, the files follow the reference's
     conventions (ids = (id, id), zero-variance SNPs listed in <out>.snps.novariance and absent from .grm.snps)."""
@@ -225,7 +225,8 @@ def test_cli_bgen_make_grm(tmp_path, engines):
             f.write("id%d id%d\n" % (i, i))
     out = str(tmp_path / "out")
     r = subprocess.run([cli, "--make-grm", "--bgen", prefix, "--keep", prefix + ".keep", "--out", out, "--gpu-chunk-snps", "256",
-                        "--gpu-engines", str(engines)], capture_output=True, text=True, timeout=300)
+                        "--gpu-engines", str(engines)] + (["--gpu-bgen-host-decode"] if host_decode else []),
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "1 SNPs which have zero variance and will be removed" in r.stdout
     assert open(out + ".snps.novariance").read().split() == ["rs17"]
@@ -263,4 +264,96 @@ def test_constant_row_follows_the_reference_rounding():
     check_stats(eng, ref["stats"], m)
     got = fetch_all(eng)
     assert np.array_equal(got["N"][lower_mask(n)], ref["N"][lower_mask(n)])
+    eng.close()
+
+
+@pytest.mark.parametrize("layout,bits", [(2, 8), (2, 16), (2, 11), (2, 3), (2, 32), (1, 16)])
+def test_device_unpack_of_bgen_blocks_is_bit_identical(tmp_path, layout, bits):
+    """dgrm_push_bgen_blocks_host (inflated blocks unpacked by bgen_unpack_kernel) against dgrm_push_dosage_host fed by
+    the host reader: same statistics, S, N and A to the last bit, with a sample selection and missing samples."""
+    m, n = 530, 297
+    denom = 32768 if layout == 1 else (1 << bits) - 1
+    p_aa, p_ab, miss = synth_probs(m, n, 50 + bits, denom)
+    path = str(tmp_path / "u.bgen")
+    bgenio.write_bgen(path, p_aa, p_ab, miss, layout=layout, bits=bits)
+    keep = (np.arange(n) % 6 != 4).astype(np.int32)
+    nk = int(keep.sum())
+    outs = []
+    for device_unpack in (True, False):
+        eng = GrmEngine(chunk_snps=256)
+        eng.set_individuals(nk)
+        eng.begin(m)
+        meta = bgenio.push_bgen(eng, path, keep_mask=keep, block=77, device_unpack=device_unpack)
+        eng.finish()
+        assert len(meta) == m
+        outs.append((fetch_all(eng), eng.snp_stats()))
+        eng.close()
+    low = lower_mask(nk)
+    for k in ("S", "N", "A"):
+        assert np.array_equal(outs[0][0][k][low], outs[1][0][k][low]), k
+    for k in ("p1", "p2", "sd"):
+        assert np.array_equal(outs[0][1][k].view(np.uint64), outs[1][1][k].view(np.uint64)), k
+    blocks = list(bgenio.iter_dosage_blocks(path, keep_mask=keep, block=1 << 20))
+    ref = orc.dosage_grm(blocks[0][1], blocks[0][2] == 0)
+    assert np.array_equal(outs[0][0]["N"][low], ref["N"][low])
+    for k in ("p1", "p2", "sd"):
+        assert np.array_equal(outs[0][1][k][:m].view(np.uint64), ref["stats"][k].view(np.uint64)), k
+
+
+def test_bgen_blocks_mixed_with_dosage_and_bed_rows(tmp_path):
+    n, m = 200, 300
+    p_aa, p_ab, miss = synth_probs(m, n, 61, 255)
+    path = str(tmp_path / "x.bgen")
+    bgenio.write_bgen(path, p_aa, p_ab, miss)
+    _, dos, mis = list(bgenio.iter_dosage_blocks(path, block=1 << 20))[0]
+    raw = list(bgenio.iter_raw_blocks(path, block=1 << 20))[0]
+    data, off, hdr = raw[1], raw[2], raw[3]
+    pk = bedio.synth_packed(n, 120, 5, missing=0.02)
+    eng = GrmEngine(chunk_snps=256)
+    eng.set_individuals(n)
+    eng.begin(m + 120)
+    eng.push_dosage_host(dos[:50], mis[:50])
+    eng.push_bgen_blocks_host(data[off[50]:off[170]], off[50:171] - off[50], hdr.layout, hdr.n_samples)
+    eng.push_bed_host(pk)
+    eng.push_bgen_blocks_host(data[off[170]:off[260]], off[170:261] - off[170], hdr.layout, hdr.n_samples)
+    eng.push_dosage_host(dos[260:], mis[260:])
+    eng.finish()
+    codes = orc.decode_rows(pk, n)
+    st = orc.snp_stats(codes)
+    zb = orc.standardise(codes, st["p2"], st["sd"])
+    # SNP order: dosage[0:170], bed, dosage[170:]; the GRM does not depend on it
+    ref = orc.dosage_grm(dos, mis == 0, extra_z=zb, extra_q=(codes != 0).astype(np.float64))
+    compare(eng, ref, "fp16", m + 120, n)
+    got = eng.snp_stats()
+    rs = orc.dosage_standardise(dos, mis == 0)
+    assert np.array_equal(got["sd"][:170], rs["sd"][:170]) and np.array_equal(got["sd"][170:290], st["sd"])
+    assert np.array_equal(got["sd"][290:m + 120], rs["sd"][170:])
+    eng.close()
+
+
+def test_bgen_blocks_refusals(tmp_path):
+    n, m = 40, 6
+    p = np.full((m, n), 80, np.uint64)
+    path = str(tmp_path / "r.bgen")
+    bgenio.write_bgen(path, p, p, compressed=False)
+    _, data, off, hdr = list(bgenio.iter_raw_blocks(path))[0]
+    data = data.copy()
+    eng = GrmEngine()
+    eng.set_individuals(n)
+    eng.begin(m)
+    bad = data.copy()
+    bad[off[2] + 8 + n] = 1                                  # phased flag of block 2
+    with pytest.raises(DgrmError, match="unphased"):
+        eng.push_bgen_blocks_host(bad, off, 2, n)
+    bad = data.copy()
+    bad[off[1] + 4] = 3                                      # three alleles
+    with pytest.raises(DgrmError, match="non-biallelic"):
+        eng.push_bgen_blocks_host(bad, off, 2, n)
+    with pytest.raises(DgrmError, match="samples are kept"):
+        eng.push_bgen_blocks_host(data, off, 2, n, sample_keep=np.arange(n) % 2)
+    bad = data.copy()
+    bad[off[3] + 8 + 5] = 3                                  # sample 5 of block 3 is triploid: found on the device
+    eng.push_bgen_blocks_host(bad, off, 2, n)
+    with pytest.raises(DgrmError, match="non-diploid"):
+        eng.finish()
     eng.close()

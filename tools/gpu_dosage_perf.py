@@ -69,6 +69,38 @@ def main():
         out["roofline"][k]["frac"] = v / peak if v else None
     print(json.dumps(out))
 
+    # the same genotypes as inflated BGEN layout-2 blocks with 8-bit probabilities, unpacked on the device
+    del d
+    blk = 10 + a.n + 2 * a.n
+    data = np.zeros((a.snps, blk), dtype=np.uint8)
+    data[:, 0:4] = np.frombuffer(np.uint32(a.n).tobytes(), dtype=np.uint8)
+    data[:, 4], data[:, 6], data[:, 7] = 2, 2, 2
+    data[:, 8:8 + a.n] = 2 | (miss << 7)
+    data[:, 9 + a.n] = 8
+    data[:, 10 + a.n:] = rng.integers(0, 128, size=(a.snps, 2 * a.n), dtype=np.uint8)
+    offsets = np.arange(a.snps + 1, dtype=np.int64) * blk
+    flat = data.reshape(-1)
+
+    def step_raw():
+        eng.begin(a.snps)
+        eng.push_bgen_blocks_host(flat, offsets, 2, a.n)
+        eng.finish()
+
+    step_raw()
+    eng.kernel_times()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_raw()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / a.steps
+    ms = {k: v[0] / a.steps for k, v in eng.kernel_times().items()}
+    print(json.dumps({"metric": "bgen_block_ingest", "n": a.n, "snps": a.snps, "bits": 8, "ms_per_step_wall": 1e3 * dt,
+                      "pair_updates_per_s": a.n * (a.n + 1) / 2 * a.snps / dt, "h2d_bytes_per_step": int(flat.nbytes),
+                      "kernel_ms_per_step": ms,
+                      "unpack": {"bytes_per_genotype": 3 + 8, "achieved_GBps": g * 11 / (ms["gather"] * 1e-3) / 1e9 if ms["gather"] else None},
+                      "note": "gather = bgen_unpack_kernel (3 bytes read, 8 written per genotype); count / expand as above"}))
+
 
 if __name__ == "__main__":
     main()
