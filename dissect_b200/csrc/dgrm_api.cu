@@ -1602,10 +1602,10 @@ int send_bgen(dgrm_engine* e) {
     {
       Prof pr(e, DGRM_K_GATHER, e->prep);
       BgenUnpackArgs a;
-      a.raw = e->d_raw; a.offsets = e->d_boff; a.row0 = off; a.layout = e->raw_layout; a.n_samples = (int)e->raw_samples;
+      a.raw = e->d_raw; a.offsets = e->d_boff; a.row0 = off; a.rows = take; a.layout = e->raw_layout; a.n_samples = (int)e->raw_samples;
       a.cols = e->bgen_all ? nullptr : e->d_bgen_cols; a.n = (int)n;
       a.dos = e->d_dos + (int64_t)e->dev_fill * n; a.errors = e->d_bad_count + 4;
-      bgen_unpack_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)take), 256, 0, e->prep>>>(a);
+      bgen_unpack_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)((take + kUnpackRows - 1) / kUnpackRows)), 256, 0, e->prep>>>(a);
       CK(cudaGetLastError());
       if (e->dev_any_missing) CK(cudaMemsetAsync(e->d_dmiss + (int64_t)e->dev_fill * n, 0, (size_t)take * n, e->prep));
     }

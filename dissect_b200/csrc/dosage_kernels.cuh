@@ -39,64 +39,79 @@ struct DosageStatsOut {
 struct BgenUnpackArgs {
   const uint8_t* raw;       // the piece's blocks, back to back
   const int64_t* offsets;   // [rows of the piece + 1] byte offsets into raw
-  int row0;                 // first row of the piece handled by this launch (gridDim.y rows)
+  int row0, rows;           // rows [row0, row0 + rows) of the piece are handled by this launch
   int layout;
   int n_samples;            // samples in the file
   const int32_t* cols;      // [n] file index of every kept sample, NULL = all samples
   int n;                    // kept samples
-  double* dos;              // [gridDim.y][n]
+  double* dos;              // [rows][n]
   int32_t* errors;          // samples whose ploidy is not 2 (genotypebgen.cpp:120-123)
 };
 
+constexpr int kUnpackRows = 16;   // variants per block: the per-block set-up (table of quotients) is shared by them
+
 __global__ void __launch_bounds__(256) bgen_unpack_kernel(const BgenUnpackArgs a) {
+  __shared__ double lut[1024];   // numerator / (2^B - 1) for B <= 10: two table reads instead of two fp64 divisions
   const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= a.n) return;
-  const int r = blockIdx.y;
-  const int i = a.cols ? a.cols[c] : c;
-  const int64_t o0 = a.offsets[a.row0 + r], o1 = a.offsets[a.row0 + r + 1];
-  const uint8_t* base = a.raw + o0;
+  const bool active = c < a.n;
+  const int i = active ? (a.cols ? a.cols[c] : c) : 0;
+  const int N = a.n_samples;
   const double nan = __longlong_as_double(0x7FF8000000000000ll);
-  double d;
-  if (a.layout == 1) {
-    const uint8_t* p = base + (int64_t)i * 6;
-    const double aa = __ddiv_rn((double)(p[0] | (p[1] << 8)), 32768.), ab = __ddiv_rn((double)(p[2] | (p[3] << 8)), 32768.),
-                 bb = __ddiv_rn((double)(p[4] | (p[5] << 8)), 32768.);
-    const bool missing = __dadd_rn(__dadd_rn(aa, ab), bb) == 0.;            // genotypebgen.cpp:208-214
-    d = missing ? nan : __dadd_rn(ab, __dmul_rn(2., bb));
-  } else {
-    const int N = a.n_samples;
-    const uint32_t ploidy = base[8 + i];
-    const int bits = base[9 + N];
-    const uint8_t* prob = base + 10 + N;
-    const int64_t avail = o1 - o0 - 10 - N;
-    const uint64_t mask = bits == 32 ? 0xFFFFFFFFull : ((1ull << bits) - 1ull);
-    uint64_t v[2];
-    if (bits == 8) {          // the common depths: whole bytes
-      v[0] = prob[2 * (int64_t)i];
-      v[1] = prob[2 * (int64_t)i + 1];
-    } else if (bits == 16) {
-      const uint8_t* q = prob + 4 * (int64_t)i;
-      v[0] = q[0] | (q[1] << 8);
-      v[1] = q[2] | (q[3] << 8);
+  int lut_bits = -1;             // depth the table was built for (block-uniform)
+  for (int rr = 0; rr < kUnpackRows; ++rr) {
+    const int r = blockIdx.y * kUnpackRows + rr;
+    if (r >= a.rows) break;
+    const int64_t o0 = a.offsets[a.row0 + r], o1 = a.offsets[a.row0 + r + 1];
+    const uint8_t* base = a.raw + o0;
+    double d;
+    if (a.layout == 1) {
+      const uint8_t* p = base + (int64_t)i * 6;
+      const double aa = __ddiv_rn((double)(p[0] | (p[1] << 8)), 32768.), ab = __ddiv_rn((double)(p[2] | (p[3] << 8)), 32768.),
+                   bb = __ddiv_rn((double)(p[4] | (p[5] << 8)), 32768.);
+      const bool missing = __dadd_rn(__dadd_rn(aa, ab), bb) == 0.;            // genotypebgen.cpp:208-214
+      d = missing ? nan : __dadd_rn(ab, __dmul_rn(2., bb));
     } else {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int64_t bit = ((int64_t)2 * i + h) * bits;
-        const int64_t byte = bit >> 3;
-        uint64_t w = 0;
-#pragma unroll
-        for (int b = 0; b < 5; ++b)   // (bit & 7) + bits <= 39 bits
-          if (byte + b < avail) w |= (uint64_t)prob[byte + b] << (8 * b);
-        v[h] = (w >> (bit & 7)) & mask;
+      const int bits = base[9 + N];
+      const uint64_t mask = bits == 32 ? 0xFFFFFFFFull : ((1ull << bits) - 1ull);
+      const double scale = (double)mask;
+      const bool use_lut = bits <= 10;
+      if (use_lut && bits != lut_bits) {   // block-uniform: bits belongs to the variant
+        __syncthreads();
+        for (int k = threadIdx.x; k <= (int)mask; k += 256) lut[k] = __ddiv_rn((double)k, scale);
+        __syncthreads();
+        lut_bits = bits;
       }
+      const uint32_t ploidy = base[8 + i];
+      const uint8_t* prob = base + 10 + N;
+      const int64_t avail = o1 - o0 - 10 - N;
+      uint64_t v[2];
+      if (bits == 8) {          // the common depths: whole bytes
+        v[0] = prob[2 * (int64_t)i];
+        v[1] = prob[2 * (int64_t)i + 1];
+      } else if (bits == 16) {
+        const uint8_t* q = prob + 4 * (int64_t)i;
+        v[0] = q[0] | (q[1] << 8);
+        v[1] = q[2] | (q[3] << 8);
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int64_t bit = ((int64_t)2 * i + h) * bits;
+          const int64_t byte = bit >> 3;
+          uint64_t w = 0;
+#pragma unroll
+          for (int b = 0; b < 5; ++b)   // (bit & 7) + bits <= 39 bits
+            if (byte + b < avail) w |= (uint64_t)prob[byte + b] << (8 * b);
+          v[h] = (w >> (bit & 7)) & mask;
+        }
+      }
+      const double aa = use_lut ? lut[v[0]] : __ddiv_rn((double)v[0], scale);
+      const double ab = use_lut ? lut[v[1]] : __ddiv_rn((double)v[1], scale);
+      const double bb = __dsub_rn(1., __dadd_rn(aa, ab));
+      if (active && (ploidy & 0x3Fu) != 2u) atomicAdd(a.errors, 1);
+      d = (ploidy & 0x80u) ? nan : __dadd_rn(ab, __dmul_rn(2., bb));          // genotypebgen.cpp:229-236
     }
-    const double scale = (double)mask;
-    const double aa = __ddiv_rn((double)v[0], scale), ab = __ddiv_rn((double)v[1], scale);
-    const double bb = __dsub_rn(1., __dadd_rn(aa, ab));
-    if ((ploidy & 0x3Fu) != 2u) atomicAdd(a.errors, 1);
-    d = (ploidy & 0x80u) ? nan : __dadd_rn(ab, __dmul_rn(2., bb));          // genotypebgen.cpp:229-236
+    if (active) a.dos[(int64_t)r * a.n + c] = d;
   }
-  a.dos[(int64_t)r * a.n + c] = d;
 }
 
 // Missing genotypes travel inside the staged rows as NaN from here on: one pass folds the caller's byte mask into the
@@ -115,11 +130,11 @@ dosage_fold_mask_kernel(double* __restrict__ dos, const uint8_t* __restrict__ mi
 // loops, and so is its `standardDev != 0.` decision about which SNPs are dropped (a constant row whose running sum
 // rounds leaves a tiny non-zero std there, and here).  The chains of different rows are independent, which is all the
 // parallelism this needs: a launch should therefore carry as many rows as possible (the device staging buffer holds up
-// to a whole chunk).  The block streams 128-sample tiles of its rows into shared memory with cp.async (8-byte pieces:
+// to a whole chunk).  The block streams 64-sample tiles of its rows into shared memory with cp.async (8-byte pieces:
 // rows are only 8-byte aligned), one tile ahead of the row threads.
 constexpr int kStatRows = 32;
 constexpr int kStatThreads = 128;
-constexpr int kStatTile = 128;   // samples per tile
+constexpr int kStatTile = 64;    // samples per tile: 33 KB of staging per block, so the row chains of a whole chunk are resident at once
 
 struct DosageStatSmem {
   double v[2][kStatRows][kStatTile + 1];
