@@ -1428,10 +1428,15 @@ int ensure_dosage_staging(dgrm_engine* e) {
   }
   if (!e->dos_read) CK(cudaEventCreateWithFlags(&e->dos_read, cudaEventDisableTiming));
   if (!e->dos_ready) CK(cudaEventCreateWithFlags(&e->dos_ready, cudaEventDisableTiming));
-  CK(cudaMalloc(&e->d_dos, (size_t)drows * e->n * sizeof(double)));
-  CK(cudaMalloc(&e->d_dmiss, (size_t)drows * e->n));
-  CK(cudaMalloc(&e->d_dos_mean, (size_t)drows * sizeof(double)));
-  CK(cudaMalloc(&e->d_dos_sd, (size_t)drows * sizeof(double)));
+  if (cudaMalloc(&e->d_dos, (size_t)drows * e->n * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&e->d_dmiss, (size_t)drows * e->n) != cudaSuccess ||
+      cudaMalloc(&e->d_dos_mean, (size_t)drows * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&e->d_dos_sd, (size_t)drows * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    release_dosage_staging(e);   // nothing half-allocated stays behind
+    return fail(e, DGRM_E_NOMEM, "dgrm_push_dosage_host: no device memory for %lld staged rows (DGRM_DOSAGE_STAGE_MB = %d)",
+                (long long)drows, e->dosage_stage_mb);
+  }
   e->h_cap = (int)hrows;
   e->dev_cap = (int)drows;
   e->h_fill = e->dev_fill = 0;
@@ -1568,14 +1573,26 @@ int ensure_bgen_staging(dgrm_engine* e, int64_t block_bytes) {
   e->raw_cap = 0;
   const int rows_cap = 16384;
   for (int i = 0; i < 2; ++i) {
-    if (cudaHostAlloc(&e->h_raw[i], (size_t)want, cudaHostAllocDefault) != cudaSuccess ||
-        cudaHostAlloc(&e->h_boff[i], (size_t)(rows_cap + 1) * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess)
-      return fail(e, DGRM_E_NOMEM, "dgrm_push_bgen_blocks_host: no pinned memory for %lld bytes of blocks", (long long)want);
     if (!e->raw_copied[i]) CK(cudaEventCreateWithFlags(&e->raw_copied[i], cudaEventDisableTiming));
   }
   if (!e->raw_read) CK(cudaEventCreateWithFlags(&e->raw_read, cudaEventDisableTiming));
-  CK(cudaMalloc(&e->d_raw, (size_t)want));
-  CK(cudaMalloc(&e->d_boff, (size_t)(rows_cap + 1) * sizeof(int64_t)));
+  bool ok = true;
+  for (int i = 0; i < 2 && ok; ++i)
+    ok = cudaHostAlloc(&e->h_raw[i], (size_t)want, cudaHostAllocDefault) == cudaSuccess &&
+         cudaHostAlloc(&e->h_boff[i], (size_t)(rows_cap + 1) * sizeof(int64_t), cudaHostAllocDefault) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_raw, (size_t)want) == cudaSuccess &&
+       cudaMalloc(&e->d_boff, (size_t)(rows_cap + 1) * sizeof(int64_t)) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    for (int i = 0; i < 2; ++i) {   // nothing half-allocated stays behind
+      if (e->h_raw[i]) cudaFreeHost(e->h_raw[i]);
+      if (e->h_boff[i]) cudaFreeHost(e->h_boff[i]);
+      e->h_raw[i] = nullptr; e->h_boff[i] = nullptr;
+    }
+    free_dev(e->d_raw); e->d_raw = nullptr;
+    free_dev(e->d_boff); e->d_boff = nullptr;
+    return fail(e, DGRM_E_NOMEM, "dgrm_push_bgen_blocks_host: no memory for %lld bytes of staged blocks", (long long)want);
+  }
   e->raw_cap = want;
   e->raw_rows_cap = rows_cap;
   return DGRM_OK;
