@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <sstream>
 
@@ -470,25 +471,68 @@ void Genotype::streamBGEN(BGENSink sink, void* ctx) const {
 
 // The same walk over the file, handing on the inflated probability blocks themselves (for the device to unpack,
 // dgrm_push_bgen_blocks_host): pieces of up to 32 MB, block k of a piece at data[offsets[k] .. offsets[k+1]).
+// The file is read sequentially; the zlib inflation of a piece's variants -- the only per-byte host work left on this
+// path -- runs on all host threads (each variant is its own zlib stream with a known inflated size).
 void Genotype::streamBGENBlocks(BGENBlockSink sink, void* ctx) const {
   BgenReader r(bgenFile);
   if (fseeko(r.f, bgenFirstVariant, SEEK_SET) != 0) misc.error("Error: Unexpected end of the BGEN file [ " + bgenFile + " ].", 0);
   const uint32_t nSamples = (uint32_t)nBEDIndividuals;
-  std::vector<unsigned char> raw, data;
-  std::vector<long long> offsets(1, 0);
+  std::vector<unsigned char> comp, data;
+  std::vector<long long> offsets(1, 0), cpos(1, 0);
+  const bool trace = getenv("DGRM_TRACE_BGEN") != NULL;   // seconds spent reading / inflating / in the sink, to stderr
+  double tRead = 0., tInflate = 0., tSink = 0.;
+  auto now = []() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; };
+  double tMark = now();
+  auto flush = [&]() {
+    const long long rows = (long long)offsets.size() - 1;
+    if (rows == 0) return;
+    tRead += now() - tMark;
+    tMark = now();
+    // one allocation for the whole walk where possible: fresh pages are the expensive part of a large buffer
+    if (data.capacity() < (size_t)offsets.back()) data.reserve((size_t)offsets.back() + (size_t)(offsets.back() / rows) * 64);
+    data.resize((size_t)offsets.back());
+    int failed = 0;
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : failed)
+    for (long long k = 0; k < rows; ++k) {
+      const size_t dlen = (size_t)(offsets[(size_t)k + 1] - offsets[(size_t)k]);
+      const size_t clen = (size_t)(cpos[(size_t)k + 1] - cpos[(size_t)k]);
+      unsigned char* dst = data.data() + offsets[(size_t)k];
+      const unsigned char* src = comp.data() + cpos[(size_t)k];
+      if (bgenCompression) {
+        uLongf got = (uLongf)dlen;
+        if (uncompress(dst, &got, src, (uLong)clen) != Z_OK || got != dlen) failed += 1;
+      } else {
+        memcpy(dst, src, dlen);
+      }
+    }
+    if (failed) misc.error("Error: A genotype block of the BGEN file [ " + bgenFile + " ] could not be decompressed.", 0);
+    tInflate += now() - tMark;
+    tMark = now();
+    sink(ctx, data.data(), offsets.data(), rows);
+    tSink += now() - tMark;
+    tMark = now();
+    comp.clear();
+    offsets.assign(1, 0);
+    cpos.assign(1, 0);
+  };
   for (size_t v = 0; v < bgenKeepVariant.size(); ++v) {
     read_variant_id(r, bgenLayout, nSamples);
     const long long len = genotype_block_bytes(r, bgenLayout, bgenCompression, nSamples);
     if (!bgenKeepVariant[v]) { r.skip(len); continue; }
-    read_probability_block(r, bgenLayout, bgenCompression, nSamples, len, raw, data);
-    offsets.push_back((long long)data.size());
-    if (data.size() >= (32u << 20) || offsets.size() > 4096) {
-      sink(ctx, data.data(), offsets.data(), (long long)offsets.size() - 1);
-      data.clear();
-      offsets.assign(1, 0);
-    }
+    // stored and inflated sizes of this variant's probability data (genfile::bgen::read_genotype_data_block)
+    long long dlen = len, clen = len;
+    if (bgenLayout == 2 && bgenCompression) { dlen = r.u32(); clen = len - 4; }
+    else if (bgenLayout == 1 && bgenCompression) dlen = 6ll * nSamples;
+    if (clen < 0) misc.error("Error: Unexpected end of the BGEN file [ " + bgenFile + " ].", 0);
+    const size_t at = comp.size();
+    comp.resize(at + (size_t)clen);
+    r.bytes(comp.data() + at, (size_t)clen);
+    cpos.push_back((long long)comp.size());
+    offsets.push_back(offsets.back() + dlen);
+    if (offsets.back() >= (32ll << 20) || offsets.size() > 4096) flush();
   }
-  if (offsets.size() > 1) sink(ctx, data.data(), offsets.data(), (long long)offsets.size() - 1);
+  flush();
+  if (trace) fprintf(stderr, "[bgen] read %.3f s, inflate %.3f s, sink %.3f s\n", tRead, tInflate, tSink);
 }
 
 // genotypebgen.cpp:739-779: SNPs whose standard deviation is 0 are listed in <out>.snps.novariance and dropped.  The

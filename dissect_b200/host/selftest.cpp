@@ -10,11 +10,17 @@
 //                                         container on the host and print `IND fam ind`, `SNP chr rsid pos a1 a2` and,
 //                                         per kept variant, `ROW` followed by `dosage(hex float):missing` per kept
 //                                         sample -- the rows Kernel::compute hands to dgrm_push_dosage_host
+//   selftest bgenblocks <options...>      the same file as Genotype::streamBGENBlocks hands it to the engines: per kept
+//                                         variant `BLOCK <bytes> <FNV-1a 64 of the inflated probability block>`, then
+//                                         `TIME <seconds>` for the whole walk (parallel inflate)
 //   selftest groups <options...>          parse the options, load the .bim/.fam metadata, group the SNPs
 //                                         (Genotype::groupSNPs, genotype.cpp:1293-1470) and print `group: snps...`
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <utility>
+#include <vector>
 
 #include "host.h"
 
@@ -53,6 +59,30 @@ int main(int argc, char** argv) {
           &n);
       return 0;
     }
+    if (argc >= 2 && !strcmp(argv[1], "bgenblocks")) {
+      options.parseOptions(argc - 1, argv + 1);
+      Genotype g(options.bgenGenotypeFile, GenotypeAttributes::probabilities);
+      struct Out { std::vector<unsigned char> bytes; std::vector<long long> lens; } out;
+      struct timespec t0, t1;
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+      g.streamBGENBlocks(
+          [](void* ctx, const unsigned char* data, const long long* offsets, long long rows) {
+            Out* o = static_cast<Out*>(ctx);
+            o->bytes.insert(o->bytes.end(), data, data + offsets[rows]);
+            for (long long r = 0; r < rows; ++r) o->lens.push_back(offsets[r + 1] - offsets[r]);
+          },
+          &out);
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      size_t at = 0;
+      for (size_t k = 0; k < out.lens.size(); ++k) {   // hashed outside the timed walk
+        unsigned long long h = 1469598103934665603ull;
+        for (long long b = 0; b < out.lens[k]; ++b) { h ^= out.bytes[at + (size_t)b]; h *= 1099511628211ull; }
+        at += (size_t)out.lens[k];
+        printf("BLOCK %lld %016llx\n", out.lens[k], h);
+      }
+      printf("TIME %.6f\n", (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
+      return 0;
+    }
     if (argc >= 2 && !strcmp(argv[1], "groups")) {
       options.parseOptions(argc - 1, argv + 1);
       Genotype g(options.genotypeFile);
@@ -79,7 +109,7 @@ int main(int argc, char** argv) {
       for (int l = 0; l < m.nCols; ++l) printf("C %d %d\n", l, m.local2globalCol(l));
       return 0;
     }
-    fprintf(stderr, "usage: selftest roundtrip|add|sub|groups|bgen|layout ...\n");
+    fprintf(stderr, "usage: selftest roundtrip|add|sub|groups|bgen|bgenblocks|layout ...\n");
     return 2;
   } catch (const DissectError&) {
     return 1;
