@@ -248,17 +248,23 @@ namespace {
 struct BgenReader {
   FILE* f;
   std::string name;
-  explicit BgenReader(const std::string& path) : f(fopen(path.c_str(), "rb")), name(path) {
+  long long size;
+  explicit BgenReader(const std::string& path) : f(fopen(path.c_str(), "rb")), name(path), size(0) {
     if (!f) misc.error("Error: Unable to read the file [ " + path + " ].", 0);   // genotypebgen.cpp:320-322
+    if (fseeko(f, 0, SEEK_END) == 0) size = (long long)ftello(f);
+    fseeko(f, 0, SEEK_SET);
   }
   ~BgenReader() { if (f) fclose(f); }
+  [[noreturn]] void truncated() { misc.error("Error: Unexpected end of the BGEN file [ " + name + " ].", 0); }
+  // every length field of the container is checked against what is left of the file before it is believed
+  void need(long long n) { if (n < 0 || (long long)ftello(f) + n > size) truncated(); }
   void bytes(void* dst, size_t n) {
-    if (n && fread(dst, 1, n, f) != n) misc.error("Error: Unexpected end of the BGEN file [ " + name + " ].", 0);
+    if (n && fread(dst, 1, n, f) != n) truncated();
   }
   uint32_t u32() { unsigned char b[4]; bytes(b, 4); return b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24); }
   uint16_t u16() { unsigned char b[2]; bytes(b, 2); return (uint16_t)(b[0] | (b[1] << 8)); }
-  std::string str(size_t n) { std::string s(n, '\0'); bytes(&s[0], n); return s; }
-  void skip(long long n) { if (fseeko(f, n, SEEK_CUR) != 0) misc.error("Error: Unexpected end of the BGEN file [ " + name + " ].", 0); }
+  std::string str(size_t n) { need((long long)n); std::string s(n, '\0'); bytes(&s[0], n); return s; }
+  void skip(long long n) { need(n); if (fseeko(f, n, SEEK_CUR) != 0) truncated(); }
 };
 
 struct BgenVariant { std::string chr, rsid; uint32_t position; std::vector<std::string> alleles; };
@@ -289,7 +295,9 @@ long long genotype_block_bytes(BgenReader& r, int layout, int compression, uint3
 void read_probability_block(BgenReader& r, int layout, int compression, uint32_t nSamples, long long len,
                             std::vector<unsigned char>& raw, std::vector<unsigned char>& out) {
   size_t dataLen;
+  r.need(len);
   if (layout == 2 && compression) {
+    if (len < 4) r.truncated();
     dataLen = r.u32();
     raw.resize((size_t)len - 4);
   } else if (layout == 1 && compression) {
@@ -334,6 +342,7 @@ Genotype::Genotype(const std::string& fname, GenotypeAttributes::Type t)
   const uint32_t nSamples = r.u32();
   const std::string magic = r.str(4);
   if (magic != "bgen" && magic != std::string(4, '\0')) misc.error("Error: The file [ " + bgenFile + " ] is not a valid BGEN file.", 0);
+  if (headerLength < 20) misc.error("Error: The file [ " + bgenFile + " ] is not a valid BGEN file.", 0);
   r.skip((long long)headerLength - 20);
   const uint32_t flags = r.u32();
   bgenCompression = (int)(flags & 3u);
@@ -523,7 +532,8 @@ void Genotype::streamBGENBlocks(BGENBlockSink sink, void* ctx) const {
     long long dlen = len, clen = len;
     if (bgenLayout == 2 && bgenCompression) { dlen = r.u32(); clen = len - 4; }
     else if (bgenLayout == 1 && bgenCompression) dlen = 6ll * nSamples;
-    if (clen < 0) misc.error("Error: Unexpected end of the BGEN file [ " + bgenFile + " ].", 0);
+    r.need(clen);
+    if (dlen > (1ll << 32)) misc.error("Error: A genotype block of the BGEN file [ " + bgenFile + " ] could not be decompressed.", 0);
     const size_t at = comp.size();
     comp.resize(at + (size_t)clen);
     r.bytes(comp.data() + at, (size_t)clen);

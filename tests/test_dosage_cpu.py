@@ -247,3 +247,25 @@ def test_cpp_block_stream_equals_python_block_stream(tmp_path, layout, bits, com
         for _, data, off, _ in bgenio.iter_raw_blocks(prefix + ".bgen", keep_snps=keep_snps, block=40):
             want += [(int(off[k + 1] - off[k]), fnv1a64(data[off[k]:off[k + 1]])) for k in range(len(off) - 1)]
         assert got == want
+
+
+@needs_selftest
+def test_cpp_bgen_reader_survives_truncated_and_corrupt_files(tmp_path):
+    """Length fields are checked against the file size before they are believed: a cut or corrupted file ends in the
+    reader's error, never in a huge allocation or a crash."""
+    m, n = 12, 33
+    p_aa, p_ab, miss = synth_probs(m, n, 5, 255)
+    prefix = str(tmp_path / "t")
+    bgenio.write_bgen(prefix + ".bgen", p_aa, p_ab, miss, sample_ids=["s%d" % i for i in range(n)])
+    blob = open(prefix + ".bgen", "rb").read()
+    cases = [blob[: len(blob) // 2], blob[: len(blob) - 3], blob[:40]]
+    first = int.from_bytes(blob[:4], "little") + 4           # first variant block: its id length field
+    corrupt = bytearray(blob)
+    corrupt[first + 2 + 3 + 2 + 3 + 2 + 1 + 4 + 2: first + 2 + 3 + 2 + 3 + 2 + 1 + 4 + 2 + 4] = (0xFFFFFFF0).to_bytes(4, "little")
+    cases.append(bytes(corrupt))                             # allele-1 length field of variant 0 = 4 GB
+    for k, data in enumerate(cases):
+        open(prefix + ".bgen", "wb").write(data)
+        for mode in ("bgen", "bgenblocks"):
+            r = subprocess.run([SELFTEST, mode, "--bgen", prefix], capture_output=True, text=True, timeout=60)
+            assert r.returncode == 1, (k, mode, r.returncode, r.stderr[-300:])
+            assert "Error:" in r.stdout + r.stderr
