@@ -1531,7 +1531,9 @@ int send_dosage(dgrm_engine* e) {
   const int64_t n = e->n;
   int off = 0;
   while (off < rows) {
-    if (e->dev_fill == 0) CK(cudaStreamWaitEvent(e->copy_stream, e->dos_read, 0));  // the kernels of the previous batch have read it
+    // the kernels of the previous batch have read the device buffer (also when this batch was opened by unpacked BGEN
+    // rows, which are written on the decode stream and say nothing to the copy stream)
+    CK(cudaStreamWaitEvent(e->copy_stream, e->dos_read, 0));
     const int take = std::min(rows - off, e->dev_cap - e->dev_fill);
     CK(cudaMemcpyAsync(e->d_dos + (int64_t)e->dev_fill * n, e->h_dos[s] + (int64_t)off * n, (size_t)take * n * sizeof(double),
                        cudaMemcpyHostToDevice, e->copy_stream));
